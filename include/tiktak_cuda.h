@@ -1,0 +1,173 @@
+/* tiktak_cuda.h -- C ABI of libtiktak_cuda, the B200 (sm_100a) implementation of TikTak's
+ * data-parallel hot path: the Sobol pre-test stage and the batch of warm-start local searches.
+ *
+ * Every entry point replaces the body of one stage routine of the reference driver
+ * (/root/reference/TiktakGlobalSearch.f90, internal procedures of PROGRAM TiktakGlobalSearch).
+ * The file:line each one stands in for is cited on the declaration.  A Fortran driver reaches
+ * these through ISO_C_BINDING (see INTEGRATION.md for the interface block); the in-tree host
+ * mirror is tiktak_b200/ (ctypes) and driver/TiktakGlobalSearch.cpp.
+ *
+ * Conventions
+ *   - plain C types only: REAL(DP) -> double, INTEGER(I4B) -> int32_t (nrtype.f90:5-7);
+ *     64-bit integers only for Sobol point indices and counts.
+ *   - arrays that mirror Fortran arrays are COLUMN-MAJOR with the reference's shapes, so the
+ *     Fortran side passes them without transposition: p_range(nx,2), p_bound(nx,2)
+ *     (genericParams.f90:353-360), x_starts(p_maxpoints, nx+1) (TiktakGlobalSearch.f90:851).
+ *   - every output buffer is caller-allocated.  A pointer may be host memory OR device memory
+ *     of the handle's GPU (detected with cudaPointerGetAttributes) -- device pointers let a
+ *     multi-GPU host exchange rows with NCCL without staging.
+ *   - the handle owns all device memory; calls block the calling thread; a handle is not
+ *     re-entrant.  The library never exits the process: the reference's `stop 0` / exitState
+ *     (stateControl.f90:203-216) become negative return codes, see tiktak_cuda_strerror().
+ *   - point / restart numbering is 1-based like the reference (whichPoint, k).
+ */
+#ifndef TIKTAK_CUDA_H
+#define TIKTAK_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tiktak_handle tiktak_handle;
+
+/* status codes */
+enum {
+    TIKTAK_OK = 0,
+    TIKTAK_ERR_ARG = -1,       /* bad argument / inconsistent config (reference: `stop 0` in parseConfig) */
+    TIKTAK_ERR_CUDA = -2,      /* CUDA runtime failure; message in tiktak_cuda_last_error() */
+    TIKTAK_ERR_STATE = -3,     /* stage called out of order (e.g. choose before pretest) */
+    TIKTAK_ERR_NOGPU = -4,     /* no CUDA device: the library has NO CPU fallback */
+    TIKTAK_ERR_UNSUPPORTED = -5
+};
+
+/* built-in objective plugins (device code in tiktak_b200/csrc/objectives.cuh; contract in
+ * include/tiktak_obj.cuh).  0 restates the shipped objective.f90:76-142 (sleep removed). */
+enum {
+    TIKTAK_OBJ_TEMPLATE = 0,   /* Griewank/200 template shipped in objective.f90:96-117 */
+    TIKTAK_OBJ_GRIEWANK = 1,   /* 1 + sum x^2/4000 - prod cos(x_i/sqrt(i)) */
+    TIKTAK_OBJ_RASTRIGIN = 2,  /* 10 n + sum (x^2 - 10 cos(2 pi x)) */
+    TIKTAK_OBJ_ROSENBROCK = 3, /* sum 100 (x_{i+1}-x_i^2)^2 + (1-x_i)^2 */
+    TIKTAK_OBJ_SMM = 4         /* synthetic simulated-method-of-moments panel, 1200 moments */
+};
+
+/* local-search algorithm ids = the reference's `alg` (genericParams.f90:12-13) */
+enum { TIKTAK_ALG_DFNLS = 0, TIKTAK_ALG_AMOEBA = 1, TIKTAK_ALG_DFPMIN = 2 };
+
+/* Mirrors the module variables of genericParams.f90:14-21 after parseConfig (:265-450), i.e.
+ * AFTER defaults were applied (maxeval=40(nx+1), legitimate=qr_ndraw+10000, fvalmax=1e8, ...);
+ * tiktak_cuda_config_defaults() applies them for callers holding raw config.txt values. */
+typedef struct tiktak_config {
+    int32_t nx;              /* p_nx */
+    int32_t nm;              /* p_nmom */
+    int32_t maxeval;         /* p_maxeval (DFNLS MAXFUN) */
+    int32_t qr_ndraw;        /* p_qr_ndraw, must be < 2^30 (utilities.f90:937) */
+    int32_t legitimate;      /* p_legitimate */
+    int32_t maxpoints_plus1; /* p_maxpoints = config maxpoints + 1 (genericParams.f90:369) */
+    int32_t search_type;     /* p_searchType: only 0 (best point) is implemented */
+    int32_t lottery_points;  /* p_lotteryPoints (unused while search_type == 0) */
+    double fvalmax;          /* p_fvalmax */
+    const double* range;     /* p_range(nx,2) column-major: lo[0..nx), hi[0..nx) */
+    const double* init;      /* p_init(nx) */
+    const double* bound;     /* p_bound(nx,2) column-major */
+    /* --- knobs that do not exist in the reference (all default to reference behaviour) --- */
+    int32_t objective_id;    /* TIKTAK_OBJ_* */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t rank, world;     /* shard of the Sobol index range / restart set owned by this handle */
+    int32_t nm_itmax;        /* amoeba evaluation cap; reference value 5000 (minimize.f90:27-35) */
+    int32_t nm_shrink_mode;  /* 0 = code behaviour; 1 = README.md:36 simplex bounds from best minima */
+    int32_t sobol_quirk;     /* 1 = reproduce the single-precision rightmost-zero search (utilities.f90:1090) */
+    int32_t text_roundtrip;  /* 1 = values pass through the f40.20 records like the reference's .dat files */
+    int32_t round_size;      /* restarts blended against the same best-so-far; 1 = sequential reference order */
+    double nm_ftol;          /* p_tolf_amoeba = 1e-4 (genericParams.f90:25) */
+    const void* user;        /* objective-specific parameters (e.g. tiktak_smm_params) or NULL */
+} tiktak_config;
+
+/* genericParams.f90:307-338 defaults for negative ("-1") entries, applied in place to the raw
+ * config.txt scalars; `maxpoints` is the raw value (NOT +1).  Returns TIKTAK_ERR_ARG where the
+ * reference stops (maxpoints > qr_ndraw). */
+int tiktak_cuda_config_defaults(int32_t nx, int32_t* maxeval, int32_t* qr_ndraw, int32_t* legitimate,
+                                double* fvalmax, int32_t* maxpoints, int32_t* lottery_points);
+
+/* obj_initialize (objective.f90:31-37) + allocation of device state.  Replaces the in-memory
+ * globals of genericParams / the .dat counters of stateControl.f90 on the hot path. */
+int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg);
+void tiktak_cuda_destroy(tiktak_handle* h);
+
+/* setupSobol (TiktakGlobalSearch.f90:825-838): insobl + I4_SOBOL + affine map, for points
+ * first_1based .. first_1based+count-1.  out is (count, nx) column-major like sobol_trial. */
+int tiktak_cuda_sobol_points(tiktak_handle* h, int64_t first_1based, int64_t count, double* out);
+
+/* objFun (objective.f90:125-142) at n points; x is (n, nx) column-major (host or device). */
+int tiktak_cuda_objfun(tiktak_handle* h, const double* x, int64_t n, double* fval);
+
+/* solveAtSobolPoints (TiktakGlobalSearch.f90:405-471), states 2-5 in one call: evaluate points
+ * 1,2,... of this handle's shard until the `legitimate` cut or qr_ndraw.  With world > 1 the
+ * caller all-gathers per-block valid counts (tiktak_cuda_pretest_counts) and sets the global cut
+ * with tiktak_cuda_pretest_set_cut; with world == 1 the cut is final on return.
+ * n_evaluated = Kcut (the evaluated prefix 1..Kcut), n_legit = #(fval < fvalmax) within it. */
+int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit);
+/* fval of points first..first+count-1 (the rows of sobolFnVal.dat, :467); points this shard
+ * does not own or beyond the cut come back as NaN. */
+int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first_1based, int64_t count, double* fval);
+/* multi-GPU helpers: valid counts per TIKTAK_SOBOL_BLOCK-point block of the GLOBAL index range
+ * (zeros for blocks of other ranks; summing over ranks gives the global histogram). */
+#define TIKTAK_SOBOL_BLOCK 65536
+int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t first_block, int64_t n_blocks); /* evaluate owned blocks */
+int tiktak_cuda_pretest_counts(tiktak_handle* h, int64_t* counts, int64_t nblocks);
+/* exact Sobol index of the `need`-th valid point inside count block `block` (0 unless this rank owns it) */
+int tiktak_cuda_pretest_find(tiktak_handle* h, int64_t block, int64_t need, int64_t* n_out);
+int tiktak_cuda_pretest_set_cut(tiktak_handle* h, int64_t kcut, int64_t n_legit);
+
+/* chooseSobol (TiktakGlobalSearch.f90:840-899): row 1 = [objFun(p_init), p_init]; rows 2..K = the
+ * best K-1 evaluated Sobol points in ascending fval (ties: ascending Sobol index).
+ * x_starts is (K, nx+1) column-major, sobol_idx[K] (0 for row 1).  With world > 1 this selects
+ * the shard-local top K-1; merge with tiktak_cuda_choose_merge. */
+int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx);
+/* merge `world` shard-local candidate lists (each (K-1) rows of [fval, idx] pairs, fval first)
+ * into the replicated x_starts; cand is (world*(K-1), 2) row-major doubles. */
+int tiktak_cuda_choose_merge(tiktak_handle* h, const double* cand, int64_t nrows, double* x_starts,
+                             int32_t* sobol_idx);
+/* export this shard's candidates for the all-gather: (K-1, 2) row-major [fval, (double)idx]. */
+int tiktak_cuda_choose_candidates(tiktak_handle* h, double* cand);
+
+/* LocalMinimizations + completeSearch (TiktakGlobalSearch.f90:473-600) for restarts
+ * first_k .. first_k+n_k-1 of ONE round: starts = getModifiedParam (:683-720) blended against
+ * the best row known to the handle when the call begins; then runAmoeba (:602-633) /
+ * bobyqa_h (:572); then the re-evaluation (:582).  stride = `world`-style dealing is the
+ * caller's business: only restarts with (k - first_k) % world == rank are run, rows of the
+ * others are left untouched (NaN-filled) for the all-gather.
+ * starts  : (n_k, nx)   column-major, the searchStart.dat rows (:557)
+ * results : (n_k, nx+4) column-major = seqNo, k, #improvements, fval, x -- searchResults.dat (:594)
+ * evals   : objective evaluations spent per restart (may be NULL). */
+int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* starts,
+                      double* results, int32_t* evals);
+/* make rows computed elsewhere (other ranks, or a resumed searchResults.dat) known to the handle;
+ * rows is (n, nx+4) column-major.  Rows whose fval is NaN are ignored.  Also how the k=0 row
+ * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */
+int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n);
+
+/* getBestLine (TiktakGlobalSearch.f90:781-802): best row so far. */
+int tiktak_cuda_best(tiktak_handle* h, double* fbest, double* xbest, int32_t* k);
+
+/* lastSearch (TiktakGlobalSearch.f90:635-681): EST_dfpmin polish from the best row. */
+int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* iters);
+
+/* introspection for bench.py / tests */
+int tiktak_cuda_device_buffer(tiktak_handle* h, const char* name, void** ptr, int64_t* bytes);
+int64_t tiktak_cuda_launch_count(tiktak_handle* h);       /* kernels launched so far by this handle */
+int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms); /* CUDA-event time of last run */
+void* tiktak_cuda_stream(tiktak_handle* h);               /* the cudaStream_t all work is queued on */
+
+const char* tiktak_cuda_strerror(int code);
+const char* tiktak_cuda_last_error(void);
+const char* tiktak_cuda_version(void);
+
+/* FP64 DFMA-chain microbenchmark (roofline denominator; not part of the reference). Returns FLOP/s. */
+int tiktak_cuda_fp64_peak(int device, double* flops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIKTAK_CUDA_H */

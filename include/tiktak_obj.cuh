@@ -1,0 +1,86 @@
+/* tiktak_obj.cuh -- the device-side objective plugin contract of libtiktak_cuda.
+ *
+ * Reference contract being replaced: MODULE OBJECTIVE (objective.f90:16-144), which exports
+ *   objFun(theta), dfovec(np,nm,x,Fnout), getPenalty(theta), obj_initialize, GetData, diagnostic
+ * and reads p_nx, p_nmom, p_bound, p_fvalmax from genericParams (objective.f90:17).  As in the
+ * reference, the objective is COMPILED IN: a user edits one plugin struct and rebuilds the library.
+ *
+ * A plugin is a struct with
+ *     static constexpr int kId;                       // TIKTAK_OBJ_* id it registers under
+ *     static void host_init(int nx, double* aux);     // obj_initialize/GetData: fill per-coordinate
+ *                                                     // constants (aux[nx]) once on the host
+ *     template <class X> static __device__ double value(const tk_obj_ctx& c, const X& x);
+ * `value` is the user part of dfovec (objective.f90:96-117): it returns the scalar v_err that the
+ * shipped template replicates over the nm moments.  X is any type with `double operator[](int) const`
+ * -- registers in the Sobol kernel (one point per thread, fully unrolled), shared memory in the
+ * Nelder-Mead kernel -- so ONE definition serves every stage and every stage gets bit-identical
+ * values.  Everything around it (getPenalty, the penalty branch of dfovec, DOT_PRODUCT, objFun) is
+ * framework code below, restating objective.f90:51-74,92-95,125-142 operation for operation.
+ *
+ * Arithmetic rules for plugin authors: use TK_MUL/TK_ADD/... or plain operators (the library is
+ * compiled with -fmad=false, so nothing is contracted behind your back), call tk_cos/tk_sin from
+ * tiktak_math.h instead of cos/sin if you need CPU/GPU trajectories to agree bit for bit, and return
+ * a finite value >= fvalmax where the model is undefined (README.md:34) -- never NaN.
+ *
+ * Objectives with vector-valued, per-moment residuals (DFNLS, TIKTAK_OBJ_SMM) additionally provide
+ * a batched residual kernel; see tiktak_b200/csrc/smm.cuh.
+ */
+#ifndef TIKTAK_OBJ_CUH
+#define TIKTAK_OBJ_CUH
+
+#include "tiktak_math.h"
+
+#define TK_NX_PARAM_MAX 64 /* largest nx whose tables travel as __grid_constant__ kernel parameters */
+
+/* what objective code may read: the module variables of genericParams + the penalty constants of
+ * obj_initialize (objective.f90:35-36).  Pointers are valid in the address space of the caller. */
+struct tk_obj_ctx {
+    int nx, nm;
+    const double* bl;  /* p_bound(:,1) */
+    const double* bu;  /* p_bound(:,2) */
+    const double* aux; /* plugin constants from host_init */
+    double fvalmax, penalty0, penaltyc, max_penalty;
+    double sqrt_nm;    /* DSQRT(DBLE(nm)), objective.f90:94 */
+    const void* user;
+};
+
+#define TK_MYEPS 2.220446049250313e-16 /* EPSILON(1.0_DP), objective.f90:24 */
+
+#ifdef __CUDACC__
+
+/* getPenalty (objective.f90:51-74).  When every coordinate is inside its bounds each term is an
+ * exact +0, so the sum is skipped; otherwise the full sum is formed in index order. */
+template <class X>
+__device__ __forceinline__ double tk_get_penalty(const tk_obj_ctx& c, const X& x) {
+    bool out = false;
+#pragma unroll
+    for (int i = 0; i < c.nx; i++) out = out || (x[i] < c.bl[i]) || (x[i] > c.bu[i]);
+    if (!out) return 0.0;
+    double penalty = 0.0;
+    for (int i = 0; i < c.nx; i++) {
+        const double xi = x[i];
+        const double a = TK_DIV(fmax(0.0, TK_SUB(c.bl[i], xi)), fmax(0.1, fabs(c.bl[i])));
+        const double b = TK_DIV(fmax(0.0, TK_SUB(xi, c.bu[i])), fmax(0.1, fabs(c.bu[i])));
+        const double temp = TK_ADD(TK_MUL(c.penaltyc, TK_MUL(a, a)), TK_MUL(c.penaltyc, TK_MUL(b, b)));
+        penalty = TK_ADD(penalty, temp);
+    }
+    if (penalty > TK_MYEPS) return fmin(c.max_penalty, TK_ADD(c.penalty0, penalty));
+    return 0.0;
+}
+
+/* objFun (objective.f90:125-142) for plugins whose moments are nm copies of one value
+ * (the shipped template): DOT_PRODUCT in index order, then + getPenalty. */
+template <class Obj, class X>
+__device__ __forceinline__ double tk_objfun(const tk_obj_ctx& c, const X& x) {
+    const double pen = tk_get_penalty(c, x);
+    double f;
+    if (pen > TK_MYEPS) f = TK_DIV(pen, c.sqrt_nm); /* objective.f90:93-94 */
+    else f = Obj::value(c, x);
+    const double ff = TK_MUL(f, f);
+    double dot = 0.0;
+    for (int m = 0; m < c.nm; m++) dot = TK_ADD(dot, ff);
+    return TK_ADD(dot, pen);
+}
+
+#endif /* __CUDACC__ */
+#endif /* TIKTAK_OBJ_CUH */

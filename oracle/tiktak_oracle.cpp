@@ -1,0 +1,759 @@
+/* tiktak_oracle.cpp -- CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle for libtiktak_cuda.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it; the product never does.
+ *
+ * The reference (/root/reference, Fortran 90, ifort-only) cannot be compiled in this image (no
+ * Fortran compiler; SHARE='DENYRW' is Intel-specific), so this is a line-faithful C++ restatement of
+ * the single-instance (seqNo = 1) run, serial, values kept in memory.  Each function cites the
+ * reference lines it follows.  PARITY PINNING: the reference ships no tests, golden vectors or sample
+ * outputs, so the oracle is pinned by the known-answer vectors derived from the
+ * reference's formulas (tests/test_oracle_kat.py) and by an independent numpy
+ * restatement of the small pieces (tests/golden/make_golden.py).  With respect to outputs of the
+ * reference binary itself: "parity unpinned".
+ *
+ * Build: make -C oracle   (g++ -O2 -ffp-contract=off: no FMA contraction, like the reference build)
+ *
+ * Floating-point conventions restated from the reference:
+ *   - all stage arithmetic is unfused and evaluated left to right as written;
+ *   - Fortran SUM / DOT_PRODUCT are taken in index order;
+ *   - MINLOC / MAXLOC return the first occurrence;
+ *   - REAL() is single precision (nrtype.f90:5): w11 and itratio go through float.
+ * math_mode 0 uses libm cos (what the reference's intrinsic COS is); math_mode 1 uses the
+ * deterministic tk_cos of include/tiktak_math.h so that GPU and CPU trajectories can be compared
+ * bit for bit (the two modes agree to <= 2 ulp per cos; tests check objective values to 1e-12).
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#include "../include/tiktak_cuda.h" /* tiktak_config layout only */
+#include "../include/tiktak_math.h" /* tk_cos for math_mode 1, tk_* bit casts */
+#include "../tables/sobol_bf1111.inc"
+
+namespace {
+
+/* ------------------------------------------------------------------------------------------
+ * Sobol generator: insobl (utilities.f90:883-1043) and i4_sobol (utilities.f90:1045-1116)
+ * ------------------------------------------------------------------------------------------ */
+struct Sobol {
+    int s = 0, maxcol = 0, scount = 0;
+    double recipd = 0.0;
+    std::vector<int> lastq;            /* 1-based [1..s] */
+    std::vector<std::vector<int>> v;   /* v[i][j], 1-based, i<=s, j<=maxcol */
+    int insobl(int dim_num, int atmost) {
+        const int maxdim = 1111, maxdeg = 13, maxbit = 30;
+        s = dim_num;
+        if (dim_num < 1 || maxdim < dim_num || atmost <= 0 || (1 << maxbit) <= atmost) return -1; /* :921-955 */
+        int i = atmost; /* :959-964 number of bits in atmost */
+        maxcol = 0;
+        do { maxcol++; i = i / 2; } while (i > 0);
+        v.assign(s + 1, std::vector<int>(maxcol + 1, 0));
+        for (int j = 1; j <= maxcol; j++) v[1][j] = 1; /* :977 */
+        for (i = 2; i <= s; i++) {                      /* :981-1024 */
+            int j = tk_sobol_poly[i - 2], m = 0;
+            for (;;) { j = j / 2; if (j > 0) m++; else break; }
+            bool includ[maxdeg + 1];
+            j = tk_sobol_poly[i - 2];
+            for (int k = m; k >= 1; k--) { includ[k] = (j % 2 == 1); j = j / 2; }
+            for (int jj = 1; jj <= m && jj <= maxcol; jj++) v[i][jj] = tk_sobol_vinit[i - 2][jj - 1];
+            for (int jj = m + 1; jj <= maxcol; jj++) {
+                int newv = v[i][jj - m], l = 1;
+                for (int k = 1; k <= m; k++) {
+                    l = 2 * l;
+                    if (includ[k]) newv = newv ^ (l * v[i][jj - k]);
+                }
+                v[i][jj] = newv;
+            }
+        }
+        int l = 1; /* :1027-1031 multiply columns by powers of 2 */
+        for (int j = maxcol - 1; j >= 1; j--) {
+            l = 2 * l;
+            for (int ii = 1; ii <= s; ii++) v[ii][j] = v[ii][j] * l;
+        }
+        recipd = 0.5 / (double)l; /* :1035 */
+        scount = 0;
+        lastq.assign(s + 1, 0);
+        return 0;
+    }
+    /* quirk = 1: literal `i = floor(real(i/2))` with single-precision REAL (utilities.f90:1090);
+     * quirk = 0: exact integer halving (identical for Scount <= 33,554,433). */
+    int next(double* quasi, int quirk) {
+        int i = scount, l = 1;
+        while (i % 2 == 1) {
+            l = l + 1;
+            if (quirk) i = (int)floorf((float)(i / 2));
+            else i = i / 2;
+        }
+        if (maxcol < l) return -1; /* :1095-1102 */
+        for (int d = 1; d <= s; d++) {
+            lastq[d] = lastq[d] ^ v[d][l];
+            quasi[d - 1] = (double)lastq[d] * recipd;
+        }
+        scount++;
+        return 0;
+    }
+};
+
+/* ------------------------------------------------------------------------------------------
+ * indexx (utilities.f90:1334-1424): NR index quicksort, NN=15, NSTACK=50.  1-based inside.
+ * ------------------------------------------------------------------------------------------ */
+int indexx(int n, const double* arr0, int* index0) {
+    const int NN = 15, NSTACK = 50;
+    const double* arr = arr0 - 1; /* arr[1..n] */
+    int* index = index0 - 1;
+    int istack[NSTACK + 1];
+    for (int i = 1; i <= n; i++) index[i] = i;
+    int jstack = 0, l = 1, r = n;
+    auto icomp_xchg = [&](int& i, int& j) { if (arr[j] < arr[i]) { int s = i; i = j; j = s; } };
+    for (;;) {
+        if (r - l < NN) {
+            for (int j = l + 1; j <= r; j++) {
+                int indext = index[j];
+                double a = arr[indext];
+                int i;
+                for (i = j - 1; i >= l; i--) {
+                    if (arr[index[i]] <= a) break;
+                    index[i + 1] = index[i];
+                }
+                index[i + 1] = indext;
+            }
+            if (jstack == 0) return 0;
+            r = istack[jstack];
+            l = istack[jstack - 1];
+            jstack -= 2;
+        } else {
+            int k = (l + r) / 2;
+            std::swap(index[k], index[l + 1]);
+            icomp_xchg(index[l], index[r]);
+            icomp_xchg(index[l + 1], index[r]);
+            icomp_xchg(index[l], index[l + 1]);
+            int i = l + 1, j = r;
+            int indext = index[l + 1];
+            double a = arr[indext];
+            for (;;) {
+                do { i++; } while (!(arr[index[i]] >= a));
+                do { j--; } while (!(arr[index[j]] <= a));
+                if (j < i) break;
+                std::swap(index[i], index[j]);
+            }
+            index[l + 1] = index[j];
+            index[j] = indext;
+            jstack += 2;
+            if (jstack > NSTACK) return -1; /* 'indexx: NSTACK too small' -> stop 0 */
+            if (r - i + 1 >= j - l) {
+                istack[jstack] = r;
+                istack[jstack - 1] = i;
+                r = j - 1;
+            } else {
+                istack[jstack] = j - 1;
+                istack[jstack - 1] = l;
+                l = i;
+            }
+        }
+    }
+}
+
+/* value as re-read from a '200f40.20' record (independent of tk_f4020_roundtrip: real text) */
+double text4020(double x) {
+    if (!std::isfinite(x)) return x;
+    char buf[512];
+    snprintf(buf, sizeof buf, "%40.20f", x);
+    return strtod(buf, nullptr);
+}
+
+struct Row { /* one searchResults.dat record (TiktakGlobalSearch.f90:594) */
+    int seq, k, imp;
+    double fval;
+    std::vector<double> x;
+};
+
+struct Oracle {
+    tiktak_config c;
+    std::vector<double> range, init, bound; /* column-major copies */
+    int math_mode = 0;
+    double penalty0 = 0, penaltyc = 0, max_penalty = 0; /* objective.f90:35-36 */
+    const double myeps = 2.220446049250313e-16;         /* EPSILON(1.0_DP), objective.f90:24 */
+    std::vector<double> rsq;                            /* 1/sqrt(i) for the Griewank plugin */
+    long nfev = 0;
+    /* pre-test state */
+    int64_t kcut = 0, nlegit = 0;
+    std::vector<double> sob_f;   /* fval of points 1..kcut */
+    std::vector<double> sob_x;   /* (kcut, nx) row-major */
+    /* chooseSobol output */
+    std::vector<double> x_starts; /* (K, nx+1) row-major: fval, x */
+    std::vector<int> start_idx;
+    int n_start_rows = 0;         /* rows actually filled (reference leaves the rest uninitialised) */
+    bool tie_straddle = false;
+    /* local stage */
+    std::vector<Row> rows;
+    long best_tie_events = 0;
+
+    double COS(double a) const { return math_mode ? tk_cos(a) : cos(a); }
+    const double* lo_r() const { return range.data(); }
+    const double* hi_r() const { return range.data() + c.nx; }
+    const double* bl() const { return bound.data(); }
+    const double* bu() const { return bound.data() + c.nx; }
+
+    /* getPenalty (objective.f90:51-74) */
+    double getPenalty(const double* theta) const {
+        double penalty = 0.0;
+        for (int i = 0; i < c.nx; i++) {
+            double a = std::max(0.0, bl()[i] - theta[i]) / std::max(0.1, fabs(bl()[i]));
+            double b = std::max(0.0, theta[i] - bu()[i]) / std::max(0.1, fabs(bu()[i]));
+            double temp = penaltyc * (a * a) + penaltyc * (b * b);
+            penalty = penalty + temp;
+        }
+        if (penalty > myeps) return std::min(max_penalty, penalty0 + penalty);
+        return 0.0;
+    }
+
+    /* the scalar v_err that the template replicates over the nm moments (objective.f90:96-117),
+     * for each synthetic objective.  Plain unfused arithmetic, index order. */
+    double model_value(const double* x) const {
+        const int n = c.nx;
+        switch (c.objective_id) {
+            case TIKTAK_OBJ_TEMPLATE: { /* objective.f90:98-109, literally */
+                double val1 = (x[0] * x[0]) / 200.0;
+                for (int ii = 2; ii <= n; ii++) val1 = val1 + (x[ii - 1] * x[ii - 1]) / 200.0;
+                double val2 = COS(x[0]);
+                for (int ii = 2; ii <= n; ii++) val2 = val2 * COS(x[ii - 1] / sqrt(ii + 0.0));
+                double v = val1 - val2 + 1.0;
+                return v + 1.0;
+            }
+            case TIKTAK_OBJ_GRIEWANK: {
+                double s = 0.0, p = 1.0;
+                for (int i = 0; i < n; i++) {
+                    s = s + (x[i] * x[i]) * 2.5e-4;
+                    p = p * COS(x[i] * rsq[i]);
+                }
+                double v = s - p + 1.0;
+                return v + 1.0;
+            }
+            case TIKTAK_OBJ_RASTRIGIN: {
+                double s = 10.0 * (double)n;
+                for (int i = 0; i < n; i++) s = s + (x[i] * x[i] - 10.0 * COS(6.283185307179586 * x[i]));
+                return s + 1.0;
+            }
+            case TIKTAK_OBJ_ROSENBROCK: {
+                double s = 0.0;
+                for (int i = 0; i + 1 < n; i++) {
+                    double t = x[i + 1] - x[i] * x[i];
+                    double u = 1.0 - x[i];
+                    s = s + (100.0 * (t * t) + u * u);
+                }
+                return s + 1.0;
+            }
+        }
+        return NAN;
+    }
+
+    /* dfovec (objective.f90:76-123) */
+    void dfovec(const double* x, double* F) const {
+        double v_err = getPenalty(x);
+        if (v_err > myeps) {
+            double f = v_err / sqrt((double)c.nm);
+            for (int m = 0; m < c.nm; m++) F[m] = f;
+        } else {
+            double v = model_value(x);
+            for (int m = 0; m < c.nm; m++) F[m] = v;
+        }
+    }
+    /* objFun (objective.f90:125-142) */
+    double objFun(const double* theta) {
+        nfev++;
+        std::vector<double> F(c.nm);
+        dfovec(theta, F.data());
+        double dot = 0.0;
+        for (int m = 0; m < c.nm; m++) dot = dot + F[m] * F[m];
+        return dot + getPenalty(theta);
+    }
+
+    /* setupSobol (TiktakGlobalSearch.f90:825-838) + solveAtSobolPoints (:405-471) */
+    int pretest() {
+        Sobol sb;
+        if (c.qr_ndraw <= 0) { kcut = 0; nlegit = 0; return 0; }
+        if (sb.insobl(c.nx, c.qr_ndraw)) return -1;
+        std::vector<double> q(c.nx), x(c.nx);
+        sob_f.clear(); sob_x.clear();
+        int64_t whichPoint = 1, legit = 0; /* counters lastSobol.dat / legitSobol.dat */
+        while (whichPoint <= c.qr_ndraw && legit < c.legitimate) { /* :429 */
+            if (sb.next(q.data(), c.sobol_quirk)) return -2;
+            for (int i = 0; i < c.nx; i++) x[i] = lo_r()[i] + q[i] * (hi_r()[i] - lo_r()[i]); /* :834 */
+            double fval = objFun(x.data());                                                   /* :437 */
+            if (fval < c.fvalmax) legit++;                                                     /* :438-439 */
+            sob_f.push_back(fval);
+            sob_x.insert(sob_x.end(), x.begin(), x.end());
+            whichPoint++;
+        }
+        kcut = whichPoint - 1;
+        nlegit = legit;
+        return 0;
+    }
+
+    /* chooseSobol (TiktakGlobalSearch.f90:840-899).  mode 0: the reference's indexx (unstable
+     * among equal keys); mode 1: ascending fval then ascending Sobol index (what the GPU does). */
+    int choose(int mode) {
+        const int K = c.maxpoints_plus1, nx = c.nx;
+        x_starts.assign((size_t)K * (nx + 1), NAN);
+        start_idx.assign(K, 0);
+        x_starts[0] = objFun(init.data()); /* :853 */
+        for (int i = 0; i < nx; i++) x_starts[1 + i] = init[i];
+        n_start_rows = 1;
+        tie_straddle = false;
+        if (c.qr_ndraw > 0 && kcut > 0 && K > 1) {
+            const int numrows = (int)kcut;
+            /* the rows as re-read from sobolFnVal.dat (:860) */
+            std::vector<double> fv(numrows);
+            for (int r = 0; r < numrows; r++) fv[r] = c.text_roundtrip ? text4020(sob_f[r]) : sob_f[r];
+            std::vector<int> idx(numrows);
+            if (mode == 0) {
+                if (indexx(numrows, fv.data(), idx.data())) return -1; /* :882 */
+            } else {
+                for (int r = 0; r < numrows; r++) idx[r] = r + 1;
+                std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return fv[a - 1] < fv[b - 1]; });
+            }
+            auto put = [&](int j /*1-based row*/, int src /*1-based sobol row*/) {
+                double* row = &x_starts[(size_t)(j - 1) * (nx + 1)];
+                row[0] = fv[src - 1];
+                for (int i = 0; i < nx; i++) {
+                    double xv = sob_x[(size_t)(src - 1) * nx + i];
+                    row[1 + i] = c.text_roundtrip ? text4020(xv) : xv;
+                }
+                start_idx[j - 1] = src;
+            };
+            put(2, idx[0]); /* :884 */
+            int j = 3;
+            for (int i = 2; i <= numrows; i++) { /* :886-892 */
+                if (j > K) break;                /* (the reference tests after the copy; same effect) */
+                if (idx[i - 1] != idx[i - 2]) { put(j, idx[i - 1]); j++; }
+            }
+            n_start_rows = std::min(j - 1, K);
+            /* does a run of equal keys cross the selection boundary? then the SET depends on tie order */
+            const int M = K - 1;
+            if (numrows > M && M >= 1) {
+                std::vector<double> s(fv);
+                std::nth_element(s.begin(), s.begin() + (M - 1), s.end());
+                double kth = s[M - 1];
+                long below = 0, equal = 0;
+                for (double f : fv) { if (f < kth) below++; else if (f == kth) equal++; }
+                if (below + equal > M && equal > 1) tie_straddle = true;
+            }
+        }
+        return 0;
+    }
+
+    /* getSortedResults (:804-823) + getBestLine (:781-802) on a given set of rows */
+    int best_row(const std::vector<Row>& rs, int upto) {
+        if (upto <= 0) return -1;
+        std::vector<double> fv(upto);
+        for (int i = 0; i < upto; i++) fv[i] = rs[i].fval;
+        std::vector<int> idx(upto);
+        indexx(upto, fv.data(), idx.data());
+        int b = idx[0] - 1;
+        for (int i = 0; i < upto; i++)
+            if (i != b && rs[i].fval == rs[b].fval) { best_tie_events++; break; }
+        return b;
+    }
+
+    /* simplex_coordinates2 (simplex.f90:346-438); x is (n, n+1) column-major */
+    static void simplex_coordinates2(int n, std::vector<double>& x) {
+        x.assign((size_t)n * (n + 1), 0.0);
+        auto X = [&](int i, int j) -> double& { return x[(size_t)(j - 1) * n + (i - 1)]; };
+        for (int j = 1; j <= n; j++) X(j, j) = 1.0;
+        double a = (1.0 - sqrt(1.0 + (double)n)) / (double)n;
+        for (int i = 1; i <= n; i++) X(i, n + 1) = a;
+        std::vector<double> cvec(n + 1);
+        for (int i = 1; i <= n; i++) {
+            double sum = 0.0;
+            for (int j = 1; j <= n + 1; j++) sum = sum + X(i, j);
+            cvec[i] = sum / (double)(n + 1);
+        }
+        for (int j = 1; j <= n + 1; j++)
+            for (int i = 1; i <= n; i++) X(i, j) = X(i, j) - cvec[i];
+        double ss = 0.0;
+        for (int i = 1; i <= n; i++) ss = ss + X(i, 1) * X(i, 1);
+        double s = sqrt(ss);
+        for (int j = 1; j <= n + 1; j++)
+            for (int i = 1; i <= n; i++) X(i, j) = X(i, j) / s;
+    }
+
+    /* amoeba + amotry (minimize.f90:7-135).  p is (ndim+1, ndim) ROW-major here (p[i][j]). */
+    void amoeba(std::vector<double>& p, std::vector<double>& y, double ftol, int& iter, int ITMAX) {
+        const double TINY = (double)1.0e-10f; /* REAL(dp), PARAMETER :: TINY=1.0e-10 -- SP literal (:28) */
+        const int ndim = c.nx, np = ndim + 1;
+        auto P = [&](int i, int j) -> double& { return p[(size_t)i * ndim + j]; };
+        std::vector<double> psum(ndim), ptry(ndim);
+        auto iminloc = [&]() { int b = 0; for (int i = 1; i < np; i++) if (y[i] < y[b]) b = i; return b; };
+        auto imaxloc = [&]() { int b = 0; for (int i = 1; i < np; i++) if (y[i] > y[b]) b = i; return b; };
+        auto sum_psum = [&]() {
+            for (int j = 0; j < ndim; j++) { double s = 0.0; for (int i = 0; i < np; i++) s = s + P(i, j); psum[j] = s; }
+        };
+        int ihi = 0;
+        auto amotry = [&](double fac) {
+            double fac1 = (1.0 - fac) / ndim;
+            double fac2 = fac1 - fac;
+            for (int j = 0; j < ndim; j++) ptry[j] = psum[j] * fac1 - P(ihi, j) * fac2;
+            double ytry = objFun(ptry.data());
+            if (ytry < y[ihi]) {
+                y[ihi] = ytry;
+                for (int j = 0; j < ndim; j++) { psum[j] = psum[j] - P(ihi, j) + ptry[j]; P(ihi, j) = ptry[j]; }
+            }
+            return ytry;
+        };
+        iter = 0;
+        sum_psum();
+        for (;;) {
+            int ilo = iminloc();
+            ihi = imaxloc();
+            double ytmp = y[ihi];
+            y[ihi] = y[ilo];
+            int inhi = imaxloc();
+            y[ihi] = ytmp;
+            double rtol = 2.0 * fabs(y[ihi] - y[ilo]) / (fabs(y[ihi]) + fabs(y[ilo]) + TINY);
+            if (rtol < ftol || iter >= ITMAX) { /* :85-96 */
+                std::swap(y[0], y[ilo]);
+                for (int j = 0; j < ndim; j++) std::swap(P(0, j), P(ilo, j));
+                return;
+            }
+            double ytry = amotry(-1.0);
+            iter++;
+            if (ytry <= y[ilo]) {
+                ytry = amotry(2.0);
+                iter++;
+            } else if (ytry >= y[inhi]) {
+                double ysave = y[ihi];
+                ytry = amotry(0.5);
+                iter++;
+                if (ytry >= ysave) {
+                    for (int i = 0; i < np; i++)
+                        for (int j = 0; j < ndim; j++) P(i, j) = 0.5 * (P(i, j) + P(ilo, j));
+                    /* NB: row ilo is its own fixed point, so updating rows in order is the same as
+                     * the array expression with spread() (:107) */
+                    for (int i = 0; i < np; i++)
+                        if (i != ilo) y[i] = objFun(&P(i, 0));
+                    iter += ndim;
+                    sum_psum();
+                }
+            }
+        }
+    }
+
+    /* per-coordinate width that scales the initial simplex: p_range (:623) or, in shrink mode 1, the
+     * README.md:36 rule (bounds of the best local minima so far) -- see DESIGN.md "nm_shrink_mode". */
+    void simplex_width(int k, const std::vector<Row>& snapshot, int count, std::vector<double>& w) {
+        const int nx = c.nx;
+        w.resize(nx);
+        for (int i = 0; i < nx; i++) w[i] = hi_r()[i] - lo_r()[i];
+        if (c.nm_shrink_mode != 1) return;
+        float itratio = (float)k / (float)c.maxpoints_plus1;
+        if (!(itratio > 0.5f)) return;
+        /* rows that are local-search outcomes (k >= 1) */
+        std::vector<int> cand;
+        for (int i = 0; i < count; i++) if (snapshot[i].k >= 1) cand.push_back(i);
+        if ((int)cand.size() < 2) return;
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+            if (snapshot[a].fval != snapshot[b].fval) return snapshot[a].fval < snapshot[b].fval;
+            return snapshot[a].k < snapshot[b].k; });
+        int T = std::min<int>((int)cand.size(), 10);
+        for (int i = 0; i < nx; i++) {
+            double mn = snapshot[cand[0]].x[i], mx = mn;
+            for (int t = 1; t < T; t++) { double v = snapshot[cand[t]].x[i]; mn = std::min(mn, v); mx = std::max(mx, v); }
+            double ww = mx - mn;
+            if (ww > 0.0) w[i] = ww;
+        }
+    }
+
+    /* runAmoeba (TiktakGlobalSearch.f90:602-633) */
+    void runAmoeba(std::vector<double>& pt, const std::vector<double>& width, int& iters) {
+        const int nx = c.nx, K = c.maxpoints_plus1;
+        std::vector<double> x;
+        simplex_coordinates2(nx, x);
+        std::vector<double> xT((size_t)(nx + 1) * nx), fnVals(nx + 1), temp(nx);
+        const double scale = pow((double)K, 1.0 / nx); /* DBLE(p_maxpoints)**(1.0_dp/p_nx) */
+        for (int ia = 1; ia <= nx + 1; ia++) {
+            for (int i = 0; i < nx; i++) {
+                double t = pt[i] + x[(size_t)(ia - 1) * nx + i] * width[i] / scale; /* :623 */
+                t = std::max(std::min(t, bu()[i]), bl()[i]);                          /* :624 */
+                temp[i] = t;
+            }
+            fnVals[ia - 1] = objFun(temp.data());
+            for (int i = 0; i < nx; i++) xT[(size_t)(ia - 1) * nx + i] = temp[i];
+        }
+        amoeba(xT, fnVals, c.nm_ftol, iters, c.nm_itmax); /* the 5th positional is `iter`; ITMAX stays 5000 */
+        int ia = 0;
+        for (int i = 1; i <= nx; i++) if (fnVals[i] < fnVals[ia]) ia = i; /* minloc, first occurrence */
+        for (int i = 0; i < nx; i++) pt[i] = xT[(size_t)ia * nx + i];
+    }
+
+    void write_row(int seq, int k, int imp, double fval, const double* x) {
+        Row r;
+        r.seq = seq; r.k = k; r.imp = imp;
+        r.fval = c.text_roundtrip ? text4020(fval) : fval;
+        r.x.resize(c.nx);
+        for (int i = 0; i < c.nx; i++) r.x[i] = c.text_roundtrip ? text4020(x[i]) : x[i];
+        rows.push_back(r);
+    }
+
+    /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
+     * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
+    int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out);
+    int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
+};
+
+int Oracle::local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out) {
+    const int K = c.maxpoints_plus1, nx = c.nx;
+    if ((int)x_starts.size() != K * (nx + 1)) return -1;
+    if (round_size < 1) round_size = 1;
+    rows.clear();
+    best_tie_events = 0;
+    const int seqNo = 1;
+    write_row(seqNo, 0, 0, x_starts[0], &x_starts[1]); /* :496-501, whichPoint == 1 */
+    for (int k0 = 1; k0 <= K; k0 += round_size) {
+        const int k1 = std::min(K, k0 + round_size - 1);
+        const int count = (int)rows.size(); /* rows visible to this round */
+        const std::vector<Row> snapshot(rows.begin(), rows.end());
+        int bsnap = best_row(snapshot, count);
+        for (int k = k0; k <= k1; k++) {
+            std::vector<double> evalParam(nx);
+            const double* evalPoint = &x_starts[(size_t)(k - 1) * (nx + 1) + 1];
+            if (count <= 1) { /* :701-705 */
+                for (int i = 0; i < nx; i++) evalParam[i] = evalPoint[i];
+            } else {
+                const std::vector<double>& base = snapshot[bsnap].x;
+                float wf = sqrtf((float)k / (float)K); /* :718, single precision */
+                wf = std::min(std::max(0.10f, wf), 0.95f);
+                double w11 = (double)wf;
+                for (int i = 0; i < nx; i++) evalParam[i] = w11 * base[i] + (1.0 - w11) * evalPoint[i]; /* :719 */
+            }
+            if (starts_out) for (int i = 0; i < nx; i++) starts_out[(size_t)i * K + (k - 1)] = evalParam[i];
+            long nfev0 = nfev;
+            if (alg == TIKTAK_ALG_AMOEBA) {
+                std::vector<double> width;
+                simplex_width(k, snapshot, count, width);
+                int iters = 0;
+                runAmoeba(evalParam, width, iters);
+            } else if (alg == TIKTAK_ALG_DFNLS) {
+                /* :564 itratio is REAL(DP) but the quotient REAL(k)/REAL(K) is single precision */
+                double itratio = (double)((float)k / (float)K);
+                double mn = bu()[0] - bl()[0];
+                for (int i = 1; i < nx; i++) mn = std::min(mn, bu()[i] - bl()[i]);
+                double rhobeg, rhoend;
+                if (itratio > 0.5) { /* :565-571 */
+                    rhobeg = (mn / 2.5) / (4 * itratio);
+                    rhoend = 1.0e-3 / (4 * itratio);
+                } else {
+                    rhobeg = mn / 2.50;
+                    rhoend = 1.0e-3;
+                }
+                int nf = 0, nresc = 0;
+                dfnls(evalParam, rhobeg, rhoend, c.maxeval, nf, nresc);
+            } else return -2;
+            double fn_val = objFun(evalParam.data()); /* :582 */
+            if (evals_out) evals_out[k - 1] = (int32_t)(nfev - nfev0);
+            int b = best_row(rows, (int)rows.size()); /* getBestLine :585 */
+            int imp = rows[b].imp;
+            if (fn_val < rows[b].fval) imp++;
+            write_row(seqNo, k, imp, fn_val, evalParam.data()); /* :594 */
+        }
+    }
+    if (results_out) {
+        for (int k = 1; k <= K; k++) {
+            const Row& r = rows[k]; /* rows[0] is the k=0 record */
+            results_out[(size_t)0 * K + (k - 1)] = r.seq;
+            results_out[(size_t)1 * K + (k - 1)] = r.k;
+            results_out[(size_t)2 * K + (k - 1)] = r.imp;
+            results_out[(size_t)3 * K + (k - 1)] = r.fval;
+            for (int i = 0; i < nx; i++) results_out[(size_t)(4 + i) * K + (k - 1)] = r.x[i];
+        }
+    }
+    return 0;
+}
+
+#include "dfnls_oracle.inc"
+
+} /* namespace */
+
+/* ------------------------------------------------------------------------------------------
+ * C API (ctypes).  Mirrors include/tiktak_cuda.h entry for entry where that makes sense.
+ * ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+void* orc_create(const tiktak_config* cfg, int math_mode) {
+    if (!cfg || cfg->nx < 1 || cfg->nx > 1111 || cfg->nm < 1) return nullptr;
+    Oracle* o = new Oracle();
+    o->c = *cfg;
+    const int nx = cfg->nx;
+    o->range.assign(cfg->range, cfg->range + 2 * nx);
+    o->init.assign(cfg->init, cfg->init + nx);
+    o->bound.assign(cfg->bound, cfg->bound + 2 * nx);
+    o->c.range = o->range.data(); o->c.init = o->init.data(); o->c.bound = o->bound.data();
+    o->math_mode = math_mode;
+    o->penalty0 = cfg->fvalmax; /* objective.f90:35-36 */
+    o->penaltyc = 10 * cfg->fvalmax;
+    o->max_penalty = 1000.0 * o->penalty0;
+    o->rsq.resize(nx);
+    for (int i = 0; i < nx; i++) o->rsq[i] = 1.0 / sqrt((double)(i + 1));
+    return o;
+}
+void orc_destroy(void* h) { delete (Oracle*)h; }
+
+/* (count, nx) column-major, points first..first+count-1 (generated from point 1: the reference's
+ * generator is sequential) */
+int orc_sobol_points(void* h, int64_t first, int64_t count, double* out, int quirk, int atmost) {
+    Oracle* o = (Oracle*)h;
+    Sobol sb;
+    if (sb.insobl(o->c.nx, atmost > 0 ? atmost : (int)std::max<int64_t>(first + count - 1, 1))) return -1;
+    std::vector<double> q(o->c.nx);
+    for (int64_t n = 1; n < first + count; n++) {
+        if (sb.next(q.data(), quirk)) return -2;
+        if (n >= first)
+            for (int i = 0; i < o->c.nx; i++)
+                out[(size_t)i * count + (n - first)] = o->lo_r()[i] + q[i] * (o->hi_r()[i] - o->lo_r()[i]);
+    }
+    return 0;
+}
+/* raw unit-cube points + the l sequence, for the KATs */
+int orc_sobol_unit(int nx, int atmost, int64_t count, double* out, int quirk) {
+    Sobol sb;
+    if (sb.insobl(nx, atmost)) return -1;
+    std::vector<double> q(nx);
+    for (int64_t n = 0; n < count; n++) {
+        if (sb.next(q.data(), quirk)) return -2;
+        for (int i = 0; i < nx; i++) out[(size_t)n * nx + i] = q[i];
+    }
+    return 0;
+}
+/* rightmost-zero column l for a given Scount under both rules (finding 2 of SURVEY.md) */
+int orc_sobol_l(int scount, int quirk) {
+    int i = scount, l = 1;
+    while (i % 2 == 1) { l++; if (quirk) i = (int)floorf((float)(i / 2)); else i = i / 2; }
+    return l;
+}
+int orc_sobol_maxcol(int nx, int atmost) { Sobol sb; if (sb.insobl(nx, atmost)) return -1; return sb.maxcol; }
+/* direction numbers v(i, j) scaled to 32 bits (v * 2^(32-maxcol)), row-major (nx, 32): lets the
+ * tests compare the library's table without going through points */
+int orc_sobol_dirnums(int nx, int atmost, uint32_t* out) {
+    Sobol sb;
+    if (sb.insobl(nx, atmost)) return -1;
+    for (int i = 1; i <= nx; i++)
+        for (int j = 1; j <= 32; j++)
+            out[(size_t)(i - 1) * 32 + (j - 1)] = j <= sb.maxcol ? ((uint32_t)sb.v[i][j]) << (32 - sb.maxcol) : 0u;
+    return 0;
+}
+
+int orc_objfun(void* h, const double* x, int64_t n, double* fval) { /* x (n, nx) column-major */
+    Oracle* o = (Oracle*)h;
+    std::vector<double> t(o->c.nx);
+    for (int64_t r = 0; r < n; r++) {
+        for (int i = 0; i < o->c.nx; i++) t[i] = x[(size_t)i * n + r];
+        fval[r] = o->objFun(t.data());
+    }
+    return 0;
+}
+int orc_dfovec(void* h, const double* x, double* F) { ((Oracle*)h)->dfovec(x, F); return 0; }
+double orc_penalty(void* h, const double* x) { return ((Oracle*)h)->getPenalty(x); }
+
+int orc_pretest(void* h, int64_t* n_eval, int64_t* n_legit) {
+    Oracle* o = (Oracle*)h;
+    int rc = o->pretest();
+    if (n_eval) *n_eval = o->kcut;
+    if (n_legit) *n_legit = o->nlegit;
+    return rc;
+}
+int orc_pretest_values(void* h, int64_t first, int64_t count, double* fval) {
+    Oracle* o = (Oracle*)h;
+    for (int64_t i = 0; i < count; i++) {
+        int64_t n = first + i;
+        fval[i] = (n >= 1 && n <= o->kcut) ? o->sob_f[n - 1] : NAN;
+    }
+    return 0;
+}
+/* x_starts (K, nx+1) column-major; idx[K]; returns rows filled; *tie = 1 when equal keys straddle the cut */
+int orc_choose(void* h, int mode, double* x_starts, int32_t* idx, int* tie) {
+    Oracle* o = (Oracle*)h;
+    if (o->choose(mode)) return -1;
+    const int K = o->c.maxpoints_plus1, nx = o->c.nx;
+    for (int k = 0; k < K; k++) {
+        for (int j = 0; j <= nx; j++) x_starts[(size_t)j * K + k] = o->x_starts[(size_t)k * (nx + 1) + j];
+        if (idx) idx[k] = o->start_idx[k];
+    }
+    if (tie) *tie = o->tie_straddle ? 1 : 0;
+    return o->n_start_rows;
+}
+/* overwrite x_starts (e.g. with the GPU's, to test the local stage from identical starts) */
+int orc_set_starts(void* h, const double* x_starts) {
+    Oracle* o = (Oracle*)h;
+    const int K = o->c.maxpoints_plus1, nx = o->c.nx;
+    o->x_starts.resize((size_t)K * (nx + 1));
+    for (int k = 0; k < K; k++)
+        for (int j = 0; j <= nx; j++) o->x_starts[(size_t)k * (nx + 1) + j] = x_starts[(size_t)j * K + k];
+    o->n_start_rows = K;
+    return 0;
+}
+/* starts (K, nx), results (K, nx+4) column-major, evals[K] */
+int orc_local(void* h, int alg, int round_size, double* starts, double* results, int32_t* evals) {
+    return ((Oracle*)h)->local(alg, round_size, starts, results, evals);
+}
+int orc_best(void* h, double* fbest, double* xbest, int32_t* k) {
+    Oracle* o = (Oracle*)h;
+    if (o->rows.empty()) return -1;
+    int b = o->best_row(o->rows, (int)o->rows.size());
+    if (fbest) *fbest = o->rows[b].fval;
+    if (xbest) for (int i = 0; i < o->c.nx; i++) xbest[i] = o->rows[b].x[i];
+    if (k) *k = o->rows[b].k;
+    return 0;
+}
+long orc_nfev(void* h) { return ((Oracle*)h)->nfev; }
+long orc_best_tie_events(void* h) { return ((Oracle*)h)->best_tie_events; }
+
+/* one Nelder-Mead restart from `start` exactly as runAmoeba does it for restart k (width = p_range) */
+int orc_run_amoeba(void* h, double* pt, int32_t* iters) {
+    Oracle* o = (Oracle*)h;
+    std::vector<double> p(pt, pt + o->c.nx), w(o->c.nx);
+    for (int i = 0; i < o->c.nx; i++) w[i] = o->hi_r()[i] - o->lo_r()[i];
+    int it = 0;
+    o->runAmoeba(p, w, it);
+    for (int i = 0; i < o->c.nx; i++) pt[i] = p[i];
+    if (iters) *iters = it;
+    return 0;
+}
+int orc_simplex_coordinates2(int n, double* x) { /* (n, n+1) column-major */
+    std::vector<double> v;
+    Oracle::simplex_coordinates2(n, v);
+    memcpy(x, v.data(), v.size() * sizeof(double));
+    return 0;
+}
+int orc_indexx(int n, const double* arr, int32_t* index) {
+    std::vector<int> idx(n);
+    int rc = indexx(n, arr, idx.data());
+    for (int i = 0; i < n; i++) index[i] = idx[i];
+    return rc;
+}
+double orc_text4020(double x) { return text4020(x); }
+float orc_w11(int k, int K) { float wf = sqrtf((float)k / (float)K); return std::min(std::max(0.10f, wf), 0.95f); }
+/* one DFNLS run (bobyqa_h) from x with explicit radii */
+int orc_dfnls(void* h, double* x, double rhobeg, double rhoend, int maxfun, int32_t* nf, int32_t* nrescue) {
+    Oracle* o = (Oracle*)h;
+    std::vector<double> p(x, x + o->c.nx);
+    int n1 = 0, n2 = 0;
+    int rc = o->dfnls(p, rhobeg, rhoend, maxfun, n1, n2);
+    for (int i = 0; i < o->c.nx; i++) x[i] = p[i];
+    if (nf) *nf = n1;
+    if (nrescue) *nrescue = n2;
+    return rc;
+}
+/* runtime self-check that this build does not contract a*b+c (the reference build has no FMA) */
+int orc_unfused_selfcheck(void) {
+    volatile double a = 1.0 + ldexp(1.0, -30), b = 1.0 - ldexp(1.0, -30), cc = -1.0;
+    double unf = a * b + cc;      /* a*b rounds to 1 - 2^-60 -> 1.0?  exact a*b = 1 - 2^-60; rounds to 1.0 */
+    double fus = fma(a, b, cc);   /* exact: -2^-60 */
+    return (unf == 0.0 && fus != 0.0) ? 0 : -1;
+}
+
+} /* extern "C" */

@@ -1,0 +1,654 @@
+/* api.cu -- the C ABI of libtiktak_cuda (include/tiktak_cuda.h): handle, config, stage drivers.
+ *
+ * Host-side restatements in this file (small, run once per handle):
+ *   - insobl's direction-number recurrence (utilities.f90:981-1031) -> 32-bit scaled table V
+ *   - the blend weight w11 (TiktakGlobalSearch.f90:718, single precision)
+ *   - simplex_coordinates2 (simplex.f90:346-438) and the simplex scale K**(1/nx) (:623)
+ *   - parseConfig's defaults (genericParams.f90:307-338)
+ * There is no CPU fallback: without a CUDA device tiktak_cuda_create fails with TIKTAK_ERR_NOGPU.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "tk_common.cuh"
+#include "../../tables/sobol_bf1111.inc"
+
+static thread_local char g_err[1024] = "";
+void tk_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int tk_sort_candidates(tiktak_handle* h, const double* d_f, const unsigned int* d_i, int64_t n, double* d_sf,
+                       unsigned int* d_si);
+
+namespace {
+
+/* direction numbers m_{d,j} (odd, < 2^j) from the primitive polynomial + initial values, then
+ * V[d][j-1] = m_{d,j} * 2^(32-j): the reference's v(d,j)*2^(maxcol-j) and recipd = 2^-maxcol
+ * (utilities.f90:1027-1035) give the same dyadic rational for every maxcol. */
+void build_dirnums(int nx, std::vector<uint32_t>& V) {
+    V.assign((size_t)nx * 32, 0u);
+    for (int d = 0; d < nx; d++) {
+        uint64_t m[33];
+        if (d == 0) {
+            for (int j = 1; j <= 32; j++) m[j] = 1; /* :977 */
+        } else {
+            const unsigned poly = tk_sobol_poly[d - 1];
+            int deg = 0;
+            for (unsigned t = poly >> 1; t; t >>= 1) deg++;
+            for (int j = 1; j <= deg; j++) m[j] = tk_sobol_vinit[d - 1][j - 1];
+            for (int j = deg + 1; j <= 32; j++) {
+                uint64_t nv = m[j - deg];
+                for (int k = 1; k <= deg; k++)
+                    if ((poly >> (deg - k)) & 1u) nv ^= (m[j - k] << k); /* includ(k), :1013-1021 */
+                m[j] = nv;
+            }
+        }
+        for (int j = 1; j <= 32; j++) V[(size_t)d * 32 + (j - 1)] = (uint32_t)(m[j] << (32 - j));
+    }
+}
+
+void build_simplex(int n, std::vector<double>& x) { /* simplex.f90:412-435; (n, n+1) column-major */
+    x.assign((size_t)n * (n + 1), 0.0);
+    for (int j = 0; j < n; j++) x[(size_t)j * n + j] = 1.0;
+    const double a = (1.0 - sqrt(1.0 + (double)n)) / (double)n;
+    for (int i = 0; i < n; i++) x[(size_t)n * n + i] = a;
+    std::vector<double> c(n);
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int j = 0; j <= n; j++) s += x[(size_t)j * n + i];
+        c[i] = s / (double)(n + 1);
+    }
+    for (int j = 0; j <= n; j++)
+        for (int i = 0; i < n; i++) x[(size_t)j * n + i] -= c[i];
+    double ss = 0.0;
+    for (int i = 0; i < n; i++) ss += x[i] * x[i];
+    const double s = sqrt(ss);
+    for (size_t e = 0; e < x.size(); e++) x[e] /= s;
+}
+
+template <class T>
+int dalloc(T** p, size_t n) {
+    TK_CUDA(cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)));
+    return TIKTAK_OK;
+}
+template <class T>
+int upload(T** p, const std::vector<T>& v, cudaStream_t s) {
+    int rc = dalloc(p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) TK_CUDA(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return TIKTAK_OK;
+}
+
+int begin_timer(tiktak_handle* h) { TK_CUDA(cudaEventRecord(h->ev0, h->stream)); return TIKTAK_OK; }
+int end_timer(tiktak_handle* h, double* ms) {
+    TK_CUDA(cudaEventRecord(h->ev1, h->stream));
+    TK_CUDA(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    TK_CUDA(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = f;
+    return TIKTAK_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+} /* namespace */
+
+extern "C" {
+
+const char* tiktak_cuda_last_error(void) { return g_err; }
+const char* tiktak_cuda_version(void) { return "tiktak_b200 0.1 (sm_100a)"; }
+const char* tiktak_cuda_strerror(int code) {
+    switch (code) {
+        case TIKTAK_OK: return "ok";
+        case TIKTAK_ERR_ARG: return "invalid argument or inconsistent configuration";
+        case TIKTAK_ERR_CUDA: return "CUDA runtime error";
+        case TIKTAK_ERR_STATE: return "stage called out of order";
+        case TIKTAK_ERR_NOGPU: return "no CUDA device available (libtiktak_cuda has no CPU fallback)";
+        case TIKTAK_ERR_UNSUPPORTED: return "feature not supported by this build";
+    }
+    return "unknown status";
+}
+
+int tiktak_cuda_config_defaults(int32_t nx, int32_t* maxeval, int32_t* qr_ndraw, int32_t* legitimate,
+                                double* fvalmax, int32_t* maxpoints, int32_t* lottery_points) {
+    if (!maxeval || !qr_ndraw || !legitimate || !fvalmax || !maxpoints || !lottery_points) return TIKTAK_ERR_ARG;
+    if (*maxeval < 0) *maxeval = 40 * (nx + 1);             /* genericParams.f90:307-309 */
+    if (*qr_ndraw < 0) *qr_ndraw = 500;                      /* :313-315 */
+    if (*legitimate < 0) *legitimate = *qr_ndraw + 10000;    /* :317-319 */
+    if (*fvalmax < 0.0) *fvalmax = 100000000.0;              /* :321-323 */
+    if (*qr_ndraw == 0) *maxpoints = 0;                      /* :325-326 */
+    else if (*maxpoints < 0) *maxpoints = std::min(200, *qr_ndraw); /* :328-329 */
+    else if (*maxpoints > *qr_ndraw) {                       /* :331-333 `stop 0` */
+        tk_set_error("config: maxpoints > # sobol points");
+        return TIKTAK_ERR_ARG;
+    }
+    if (*lottery_points < 0) *lottery_points = *maxpoints;   /* :336-338 */
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
+    if (!out || !cfg) return TIKTAK_ERR_ARG;
+    *out = nullptr;
+    if (cfg->nx < 1 || cfg->nx > TK_SOBOL_MAXDIM || cfg->nm < 1 || !cfg->range || !cfg->init || !cfg->bound ||
+        cfg->maxpoints_plus1 < 1 || cfg->qr_ndraw < 0 || cfg->qr_ndraw >= (1 << TK_MAXBIT) || cfg->world < 1 ||
+        cfg->rank < 0 || cfg->rank >= cfg->world) {
+        tk_set_error("create: invalid configuration");
+        return TIKTAK_ERR_ARG;
+    }
+    if (cfg->maxpoints_plus1 - 1 > cfg->qr_ndraw) { tk_set_error("create: maxpoints > qr_ndraw"); return TIKTAK_ERR_ARG; }
+    if (cfg->search_type != 0) { tk_set_error("create: only selectType 0 (best point) is implemented"); return TIKTAK_ERR_UNSUPPORTED; }
+    if (cfg->nx > TK_NX_GENERIC_MAX) { tk_set_error("create: nx > %d not supported by this build", TK_NX_GENERIC_MAX); return TIKTAK_ERR_UNSUPPORTED; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        tk_set_error("create: no CUDA device; libtiktak_cuda has no CPU fallback");
+        return TIKTAK_ERR_NOGPU;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { tk_set_error("create: device %d of %d", cfg->device, ndev); return TIKTAK_ERR_ARG; }
+    TK_CUDA(cudaSetDevice(cfg->device));
+    tiktak_handle* h = new tiktak_handle();
+    h->cfg = *cfg;
+    const int nx = cfg->nx, K = cfg->maxpoints_plus1;
+    h->range.assign(cfg->range, cfg->range + 2 * nx);
+    h->init.assign(cfg->init, cfg->init + nx);
+    h->bound.assign(cfg->bound, cfg->bound + 2 * nx);
+    h->cfg.range = h->range.data(); h->cfg.init = h->init.data(); h->cfg.bound = h->bound.data();
+    if (h->cfg.nm_itmax <= 0) h->cfg.nm_itmax = 5000;
+    if (!(h->cfg.nm_ftol > 0)) h->cfg.nm_ftol = 1.0e-4;
+    if (h->cfg.round_size < 1) h->cfg.round_size = 1;
+    h->device = cfg->device;
+    cudaDeviceProp prop;
+    TK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TK_CUDA(cudaEventCreate(&h->ev0));
+    TK_CUDA(cudaEventCreate(&h->ev1));
+    /* obj_initialize (objective.f90:31-37) */
+    h->sc.nx = nx; h->sc.nm = cfg->nm;
+    h->sc.fvalmax = cfg->fvalmax;
+    h->sc.penalty0 = cfg->fvalmax;
+    h->sc.penaltyc = 10 * cfg->fvalmax;
+    h->sc.max_penalty = 1000.0 * h->sc.penalty0;
+    h->sc.sqrt_nm = sqrt((double)cfg->nm);
+    h->sc.user = nullptr;
+    h->aux.assign(nx, 0.0);
+    int rc = tk_dispatch_obj(cfg->objective_id, [&]<class Obj>() -> int { Obj::host_init(nx, h->aux.data()); return TIKTAK_OK; });
+    if (rc) { delete h; return rc; }
+    build_dirnums(nx, h->V);
+    build_simplex(nx, h->simplex);
+    h->nm_scale = pow((double)K, 1.0 / nx); /* DBLE(p_maxpoints)**(1.0_dp/p_nx), :623 */
+    h->w11.assign(K + 1, 0.0);
+    for (int k = 1; k <= K; k++) { /* :718 -- REAL() is single precision */
+        float wf = sqrtf((float)k / (float)K);
+        wf = std::min(std::max(0.10f, wf), 0.95f);
+        h->w11[k] = (double)wf;
+    }
+    std::vector<double> lo(h->range.begin(), h->range.begin() + nx), w(nx), bl(h->bound.begin(), h->bound.begin() + nx),
+        bu(h->bound.begin() + nx, h->bound.end());
+    for (int d = 0; d < nx; d++) w[d] = h->range[nx + d] - h->range[d];
+#define TK_TRY(x) do { rc = (x); if (rc) { tiktak_cuda_destroy(h); return rc; } } while (0)
+    TK_TRY(upload(&h->d_V, h->V, h->stream));
+    TK_TRY(upload(&h->d_lo, lo, h->stream));
+    TK_TRY(upload(&h->d_w, w, h->stream));
+    TK_TRY(upload(&h->d_width, w, h->stream));
+    TK_TRY(upload(&h->d_bl, bl, h->stream));
+    TK_TRY(upload(&h->d_bu, bu, h->stream));
+    TK_TRY(upload(&h->d_aux, h->aux, h->stream));
+    TK_TRY(upload(&h->d_init, h->init, h->stream));
+    TK_TRY(upload(&h->d_simplex, h->simplex, h->stream));
+    TK_TRY(upload(&h->d_w11, h->w11, h->stream));
+    h->n_cblocks = (int64_t)cfg->qr_ndraw / TIKTAK_SOBOL_BLOCK + 1; /* n = 0..N */
+    h->n_local_cblocks = (h->n_cblocks > cfg->rank) ? (h->n_cblocks - cfg->rank + cfg->world - 1) / cfg->world : 0;
+    TK_TRY(dalloc(&h->d_fval, (size_t)h->n_local_cblocks * TIKTAK_SOBOL_BLOCK));
+    TK_TRY(dalloc(&h->d_counts, (size_t)h->n_cblocks + 1));
+    h->h_counts.assign(h->n_cblocks, 0ULL);
+    TK_TRY(dalloc(&h->d_hist, 256));
+    TK_TRY(dalloc(&h->d_selstate, 8));
+    const size_t ncand = (size_t)std::max(K - 1, 1) * (size_t)std::max(cfg->world, 1);
+    TK_TRY(dalloc(&h->d_cand_f, ncand));
+    TK_TRY(dalloc(&h->d_cand_i, ncand));
+    TK_TRY(dalloc(&h->d_cand_n, 1));
+    TK_TRY(dalloc(&h->d_sorted_f, ncand));
+    TK_TRY(dalloc(&h->d_sorted_i, ncand));
+    TK_TRY(dalloc(&h->d_xstarts, (size_t)K * (nx + 1)));
+    TK_TRY(dalloc(&h->d_res, (size_t)(K + 1) * (nx + 1)));
+    TK_TRY(dalloc(&h->d_res_valid, (size_t)K + 1));
+    TK_CUDA(cudaMemsetAsync(h->d_res_valid, 0, (size_t)(K + 1) * sizeof(int), h->stream));
+    h->h_res_f.assign(K + 1, 0.0);
+    h->h_res_valid.assign(K + 1, 0);
+    h->h_res_imp.assign(K + 1, 0);
+    TK_TRY(dalloc(&h->d_best, (size_t)nx + 4));
+    TK_TRY(dalloc(&h->d_starts, (size_t)K * nx));
+    TK_TRY(dalloc(&h->d_out_x, (size_t)K * nx));
+    TK_TRY(dalloc(&h->d_out_f, (size_t)K));
+    TK_TRY(dalloc(&h->d_out_evals, (size_t)K));
+#undef TK_TRY
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return TIKTAK_OK;
+}
+
+void tiktak_cuda_destroy(tiktak_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
+                    h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
+                    h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
+                    h->d_out_f, h->d_width, h->d_out_evals};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+void* tiktak_cuda_stream(tiktak_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t tiktak_cuda_launch_count(tiktak_handle* h) { return h ? h->launches : 0; }
+
+int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms) {
+    if (!h || !stage || !ms) return TIKTAK_ERR_ARG;
+    if (!strcmp(stage, "pretest")) *ms = h->ms_pretest;
+    else if (!strcmp(stage, "pretest_eval")) *ms = h->ms_pretest_eval;
+    else if (!strcmp(stage, "choose")) *ms = h->ms_choose;
+    else if (!strcmp(stage, "local")) *ms = h->ms_local;
+    else return TIKTAK_ERR_ARG;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_device_buffer(tiktak_handle* h, const char* name, void** ptr, int64_t* bytes) {
+    if (!h || !name || !ptr) return TIKTAK_ERR_ARG;
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
+    int64_t b = 0;
+    if (!strcmp(name, "fval")) { *ptr = h->d_fval; b = h->n_local_cblocks * (int64_t)TIKTAK_SOBOL_BLOCK * 8; }
+    else if (!strcmp(name, "counts")) { *ptr = h->d_counts; b = h->n_cblocks * 8; }
+    else if (!strcmp(name, "x_starts")) { *ptr = h->d_xstarts; b = (int64_t)K * (nx + 1) * 8; }
+    else if (!strcmp(name, "results")) { *ptr = h->d_res; b = (int64_t)(K + 1) * (nx + 1) * 8; }
+    else return TIKTAK_ERR_ARG;
+    if (bytes) *bytes = b;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_sobol_points(tiktak_handle* h, int64_t first, int64_t count, double* out) {
+    if (!h || !out || first < 1 || count < 0 || first + count - 1 >= ((int64_t)1 << TK_MAXBIT)) return TIKTAK_ERR_ARG;
+    if (count == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)count * h->cfg.nx * sizeof(double);
+    if (is_device_ptr(out)) {
+        int rc = tk_launch_sobol_points(h, first, count, out);
+        if (rc) return rc;
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        return TIKTAK_OK;
+    }
+    double* d = nullptr;
+    TK_CUDA(cudaMalloc(&d, bytes));
+    int rc = tk_launch_sobol_points(h, first, count, d);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { tk_set_error("sobol_points copy: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int tiktak_cuda_objfun(tiktak_handle* h, const double* x, int64_t n, double* fval) {
+    if (!h || !x || !fval || n < 0) return TIKTAK_ERR_ARG;
+    if (n == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    const size_t xb = (size_t)n * h->cfg.nx * sizeof(double), fb = (size_t)n * sizeof(double);
+    const bool xdev = is_device_ptr(x), fdev = is_device_ptr(fval);
+    double *dx = nullptr, *df = nullptr;
+    int rc = TIKTAK_OK;
+    if (!xdev) {
+        TK_CUDA(cudaMalloc(&dx, xb));
+        TK_CUDA(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!fdev) TK_CUDA(cudaMalloc(&df, fb));
+    rc = tk_launch_objfun(h, xdev ? x : dx, n, fdev ? fval : df);
+    if (!rc && !fdev) {
+        cudaError_t e = cudaMemcpyAsync(fval, df, fb, cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) { tk_set_error("objfun copy: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess && !rc) { tk_set_error("objfun: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
+    if (dx) cudaFree(dx);
+    if (df) cudaFree(df);
+    return rc;
+}
+
+/* evaluate the owned count blocks of [cb0, cb0+ncb) */
+int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
+    if (!h || cb0 < 0 || ncb < 0 || cb0 + ncb > h->n_cblocks) return TIKTAK_ERR_ARG;
+    TK_CUDA(cudaSetDevice(h->device));
+    if (cb0 == 0) {
+        TK_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
+        h->cblocks_done = 0; h->kcut = -1; h->pretest_done = false; h->starts_ready = false;
+    }
+    if (ncb == 0) return TIKTAK_OK;
+    TkWave wv;
+    wv.N = h->cfg.qr_ndraw; wv.cb0 = cb0; wv.ncb = ncb; wv.rank = h->cfg.rank; wv.world = h->cfg.world;
+    wv.fval = h->d_fval; wv.counts = h->d_counts;
+    int rc = tk_launch_sobol_wave(h, wv);
+    if (rc) return rc;
+    h->cblocks_done = std::max(h->cblocks_done, cb0 + ncb);
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_pretest_counts(tiktak_handle* h, int64_t* counts, int64_t nblocks) {
+    if (!h || !counts || nblocks < 0 || nblocks > h->n_cblocks) return TIKTAK_ERR_ARG;
+    TK_CUDA(cudaSetDevice(h->device));
+    static_assert(sizeof(int64_t) == sizeof(unsigned long long), "count width");
+    TK_CUDA(cudaMemcpyAsync(counts, h->d_counts, (size_t)nblocks * 8, cudaMemcpyDefault, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return TIKTAK_OK;
+}
+
+/* exact index of the `need`-th valid point of count block cb (owner only; others get 0) */
+int tiktak_cuda_pretest_find(tiktak_handle* h, int64_t cb, int64_t need, int64_t* n_out) {
+    if (!h || !n_out || cb < 0 || cb >= h->n_cblocks || need < 1) return TIKTAK_ERR_ARG;
+    *n_out = 0;
+    if (cb % h->cfg.world != h->cfg.rank) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc = tk_launch_find_cut(h, cb, (unsigned long long)need, h->d_selstate);
+    if (rc) return rc;
+    unsigned long long r = 0;
+    TK_CUDA(cudaMemcpyAsync(&r, h->d_selstate, 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    *n_out = (int64_t)r;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_pretest_set_cut(tiktak_handle* h, int64_t kcut, int64_t n_legit) {
+    if (!h || kcut < 0 || kcut > h->cfg.qr_ndraw) return TIKTAK_ERR_ARG;
+    h->kcut = kcut;
+    h->nlegit = n_legit;
+    h->pretest_done = true;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit) {
+    if (!h) return TIKTAK_ERR_ARG;
+    TK_CUDA(cudaSetDevice(h->device));
+    const int64_t N = h->cfg.qr_ndraw, L = h->cfg.legitimate;
+    int rc = begin_timer(h);
+    if (rc) return rc;
+    if (N == 0 || L <= 0) { /* :429: nothing is evaluated */
+        tiktak_cuda_pretest_wave(h, 0, 0);
+        h->kcut = 0; h->nlegit = 0; h->pretest_done = true;
+        if (n_evaluated) *n_evaluated = 0;
+        if (n_legit) *n_legit = 0;
+        return end_timer(h, &h->ms_pretest);
+    }
+    const bool can_cut = (L <= N) && h->cfg.world == 1;
+    const int64_t wave = can_cut ? 64 : h->n_cblocks;
+    int64_t cum = 0, kcut = -1, nleg = 0;
+    h->ms_pretest_eval = 0;
+    for (int64_t cb0 = 0; cb0 < h->n_cblocks && kcut < 0; cb0 += wave) {
+        const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
+        cudaEvent_t w0, w1;
+        TK_CUDA(cudaEventCreate(&w0)); TK_CUDA(cudaEventCreate(&w1));
+        TK_CUDA(cudaEventRecord(w0, h->stream));
+        rc = tiktak_cuda_pretest_wave(h, cb0, ncb);
+        TK_CUDA(cudaEventRecord(w1, h->stream));
+        if (rc) return rc;
+        TK_CUDA(cudaMemcpyAsync(h->h_counts.data() + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        float wms = 0; cudaEventElapsedTime(&wms, w0, w1); h->ms_pretest_eval += wms;
+        cudaEventDestroy(w0); cudaEventDestroy(w1);
+        if (h->cfg.world > 1) continue;
+        for (int64_t cb = cb0; cb < cb0 + ncb; cb++) {
+            const int64_t c = (int64_t)h->h_counts[cb];
+            if (can_cut && cum + c >= L) { /* the L-th valid point lives in this count block */
+                int64_t n = 0;
+                rc = tiktak_cuda_pretest_find(h, cb, L - cum, &n);
+                if (rc) return rc;
+                kcut = n; nleg = L;
+                break;
+            }
+            cum += c;
+        }
+    }
+    if (h->cfg.world == 1) {
+        if (kcut < 0) { kcut = N; nleg = cum; }
+        h->kcut = kcut; h->nlegit = nleg; h->pretest_done = true;
+    }
+    if (n_evaluated) *n_evaluated = h->cfg.world == 1 ? kcut : -1;
+    if (n_legit) *n_legit = h->cfg.world == 1 ? nleg : -1;
+    return end_timer(h, &h->ms_pretest);
+}
+
+int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first, int64_t count, double* fval) {
+    if (!h || !fval || first < 1 || count < 0) return TIKTAK_ERR_ARG;
+    if (!h->pretest_done) return TIKTAK_ERR_STATE;
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> tmp((size_t)count, NAN);
+    int64_t n = first;
+    while (n < first + count) {
+        const int64_t cb = n / TIKTAK_SOBOL_BLOCK;
+        const int64_t end = std::min<int64_t>((cb + 1) * (int64_t)TIKTAK_SOBOL_BLOCK, first + count);
+        const int64_t hi = std::min<int64_t>(end, h->kcut + 1);
+        if (cb % h->cfg.world == h->cfg.rank && hi > n && cb < h->cblocks_done)
+            TK_CUDA(cudaMemcpy(tmp.data() + (n - first), h->d_fval + tk_local_index(n, h->cfg.world), (size_t)(hi - n) * 8,
+                               cudaMemcpyDeviceToHost));
+        n = end;
+    }
+    TK_CUDA(cudaMemcpy(fval, tmp.data(), (size_t)count * 8, cudaMemcpyDefault));
+    return TIKTAK_OK;
+}
+
+/* the k=0 record [seqNo, 0, 0, fval(p_init), p_init] (TiktakGlobalSearch.f90:496-501) */
+static int push_init_row(tiktak_handle* h) {
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
+    std::vector<double> row0(nx + 1);
+    TK_CUDA(cudaMemcpyAsync(&row0[0], h->d_xstarts, 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    for (int d = 0; d < nx; d++) row0[1 + d] = h->init[d];
+    std::vector<double> rows(nx + 4);
+    rows[0] = 1; rows[1] = 0; rows[2] = 0;
+    rows[3] = h->cfg.text_roundtrip ? tk_f4020_roundtrip(row0[0]) : row0[0];
+    for (int d = 0; d < nx; d++) rows[4 + d] = h->cfg.text_roundtrip ? tk_f4020_roundtrip(row0[1 + d]) : row0[1 + d];
+    std::fill(h->h_res_valid.begin(), h->h_res_valid.end(), 0);
+    TK_CUDA(cudaMemsetAsync(h->d_res_valid, 0, (size_t)(K + 1) * sizeof(int), h->stream));
+    return tiktak_cuda_push_results(h, rows.data(), 1);
+}
+
+static int export_starts(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
+    if (x_starts) TK_CUDA(cudaMemcpyAsync(x_starts, h->d_xstarts, (size_t)K * (nx + 1) * 8, cudaMemcpyDefault, h->stream));
+    std::vector<unsigned int> si(std::max<int64_t>(h->n_cand, 1));
+    if (sobol_idx && h->n_cand > 0)
+        TK_CUDA(cudaMemcpyAsync(si.data(), h->d_sorted_i, (size_t)h->n_cand * 4, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (sobol_idx) {
+        std::vector<int32_t> idx(K, 0);
+        for (int r = 0; r < K - 1 && r < h->n_cand; r++) idx[r + 1] = (int32_t)si[r];
+        TK_CUDA(cudaMemcpy(sobol_idx, idx.data(), (size_t)K * 4, cudaMemcpyDefault));
+    }
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
+    if (!h) return TIKTAK_ERR_ARG;
+    if (!h->pretest_done) { tk_set_error("choose: pretest has not completed"); return TIKTAK_ERR_STATE; }
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc = begin_timer(h);
+    if (rc) return rc;
+    rc = tk_select_top(h, h->cfg.maxpoints_plus1 - 1);
+    if (rc) return rc;
+    rc = tk_build_starts(h);
+    if (rc) return rc;
+    rc = end_timer(h, &h->ms_choose);
+    if (rc) return rc;
+    h->starts_ready = true;
+    rc = push_init_row(h);
+    if (rc) return rc;
+    return export_starts(h, x_starts, sobol_idx);
+}
+
+int tiktak_cuda_choose_candidates(tiktak_handle* h, double* cand) {
+    if (!h || !cand) return TIKTAK_ERR_ARG;
+    if (!h->starts_ready) return TIKTAK_ERR_STATE;
+    const int M = h->cfg.maxpoints_plus1 - 1;
+    std::vector<double> f(std::max(M, 1)); std::vector<unsigned int> si(std::max(M, 1));
+    if (h->n_cand > 0) {
+        TK_CUDA(cudaMemcpyAsync(f.data(), h->d_sorted_f, (size_t)h->n_cand * 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaMemcpyAsync(si.data(), h->d_sorted_i, (size_t)h->n_cand * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> out((size_t)2 * std::max(M, 1), NAN);
+    for (int r = 0; r < M; r++)
+        if (r < h->n_cand) { out[2 * r] = f[r]; out[2 * r + 1] = (double)si[r]; }
+    TK_CUDA(cudaMemcpy(cand, out.data(), (size_t)2 * M * 8, cudaMemcpyDefault));
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_choose_merge(tiktak_handle* h, const double* cand, int64_t nrows, double* x_starts, int32_t* sobol_idx) {
+    if (!h || !cand || nrows < 0) return TIKTAK_ERR_ARG;
+    const int M = h->cfg.maxpoints_plus1 - 1;
+    if (nrows > (int64_t)M * h->cfg.world) return TIKTAK_ERR_ARG;
+    TK_CUDA(cudaSetDevice(h->device));
+    std::vector<double> host((size_t)2 * std::max<int64_t>(nrows, 1));
+    TK_CUDA(cudaMemcpy(host.data(), cand, (size_t)2 * nrows * 8, cudaMemcpyDefault));
+    std::vector<double> f; std::vector<unsigned int> si;
+    for (int64_t r = 0; r < nrows; r++)
+        if (host[2 * r] == host[2 * r] && host[2 * r + 1] >= 1) { f.push_back(host[2 * r]); si.push_back((unsigned int)host[2 * r + 1]); }
+    const int64_t n = (int64_t)f.size();
+    if (n > 0) {
+        TK_CUDA(cudaMemcpyAsync(h->d_cand_f, f.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaMemcpyAsync(h->d_cand_i, si.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+        int rc = tk_sort_candidates(h, h->d_cand_f, h->d_cand_i, n, h->d_sorted_f, h->d_sorted_i);
+        if (rc) return rc;
+    }
+    h->n_cand = std::min<int64_t>(n, M);
+    int rc = tk_build_starts(h);
+    if (rc) return rc;
+    h->starts_ready = true;
+    rc = push_init_row(h);
+    if (rc) return rc;
+    return export_starts(h, x_starts, sobol_idx);
+}
+
+int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
+    if (!h || !rows || n < 0) return TIKTAK_ERR_ARG;
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
+    TK_CUDA(cudaSetDevice(h->device));
+    std::vector<double> host((size_t)n * (nx + 4));
+    if (n == 0) return TIKTAK_OK;
+    TK_CUDA(cudaMemcpy(host.data(), rows, host.size() * 8, cudaMemcpyDefault));
+    /* running best, for the #improvements column (completeSearch :585-589) */
+    double best_f = 1.0e7; /* pos_miss, getBestLine :791-796 */
+    int best_imp = 0;
+    bool any = false;
+    for (int k = 0; k <= K; k++)
+        if (h->h_res_valid[k] && (!any || h->h_res_f[k] < best_f)) { best_f = h->h_res_f[k]; best_imp = h->h_res_imp[k]; any = true; }
+    std::vector<double> rec(nx + 1);
+    for (int r = 0; r < n; r++) {
+        const double fv = host[(size_t)3 * n + r];
+        const int k = (int)host[(size_t)1 * n + r];
+        if (!(fv == fv) || k < 0 || k > K) continue;
+        int imp = best_imp;
+        if (k > 0 && fv < best_f) imp = best_imp + 1;
+        if (!any || fv < best_f) { best_f = fv; best_imp = imp; any = true; }
+        h->h_res_f[k] = fv; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
+        rec[0] = fv;
+        for (int d = 0; d < nx; d++) rec[1 + d] = host[(size_t)(4 + d) * n + r];
+        const int one = 1;
+        TK_CUDA(cudaMemcpyAsync(h->d_res + (size_t)k * (nx + 1), rec.data(), (size_t)(nx + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaMemcpyAsync(h->d_res_valid + k, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream)); /* rec/one are reused */
+    }
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* starts, double* results,
+                      int32_t* evals) {
+    if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
+    if (alg != TIKTAK_ALG_AMOEBA) { tk_set_error("local: algorithm %d not available in this build", alg); return TIKTAK_ERR_UNSUPPORTED; }
+    if (n_k == 0) return TIKTAK_OK;
+    const int nx = h->cfg.nx;
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc = begin_timer(h);
+    if (rc) return rc;
+    /* rows of restarts this rank does not run stay NaN */
+    std::vector<double> nanf(n_k, NAN);
+    TK_CUDA(cudaMemcpyAsync(h->d_out_f, nanf.data(), (size_t)n_k * 8, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemsetAsync(h->d_out_evals, 0, (size_t)n_k * sizeof(int), h->stream));
+    TK_CUDA(cudaMemsetAsync(h->d_out_x, 0, (size_t)n_k * nx * 8, h->stream));
+    if ((rc = tk_launch_best(h))) return rc;
+    if ((rc = tk_launch_blend(h, first_k, n_k))) return rc;
+    if ((rc = tk_launch_nm(h, first_k, n_k))) return rc;
+    std::vector<double> hs((size_t)n_k * nx), hx((size_t)n_k * nx), hf(n_k);
+    std::vector<int> he(n_k);
+    TK_CUDA(cudaMemcpyAsync(hs.data(), h->d_starts, hs.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hx.data(), h->d_out_x, hx.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hf.data(), h->d_out_f, hf.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(he.data(), h->d_out_evals, he.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = end_timer(h, &h->ms_local))) return rc; /* synchronises the stream */
+    /* searchResults.dat records (:594): seqNo, k, #improvements, fval, x -- as re-read from the file */
+    std::vector<double> rows((size_t)n_k * (nx + 4));
+    const bool rt = h->cfg.text_roundtrip != 0;
+    for (int s = 0; s < n_k; s++) {
+        rows[(size_t)0 * n_k + s] = 1.0;
+        rows[(size_t)1 * n_k + s] = (double)(first_k + s);
+        rows[(size_t)2 * n_k + s] = 0.0;
+        rows[(size_t)3 * n_k + s] = rt ? tk_f4020_roundtrip(hf[s]) : hf[s];
+        for (int d = 0; d < nx; d++) {
+            const double xv = hx[(size_t)d * n_k + s];
+            rows[(size_t)(4 + d) * n_k + s] = (hf[s] == hf[s]) ? (rt ? tk_f4020_roundtrip(xv) : xv) : NAN;
+        }
+    }
+    if (h->cfg.world == 1) {
+        if ((rc = tiktak_cuda_push_results(h, rows.data(), n_k))) return rc;
+        for (int s = 0; s < n_k; s++) rows[(size_t)2 * n_k + s] = (double)h->h_res_imp[first_k + s];
+    }
+    if (starts) TK_CUDA(cudaMemcpy(starts, hs.data(), hs.size() * 8, cudaMemcpyDefault));
+    if (results) TK_CUDA(cudaMemcpy(results, rows.data(), rows.size() * 8, cudaMemcpyDefault));
+    if (evals) TK_CUDA(cudaMemcpy(evals, he.data(), he.size() * sizeof(int), cudaMemcpyDefault));
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_best(tiktak_handle* h, double* fbest, double* xbest, int32_t* k) {
+    if (!h) return TIKTAK_ERR_ARG;
+    const int nx = h->cfg.nx;
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc = tk_launch_best(h);
+    if (rc) return rc;
+    std::vector<double> b(nx + 3);
+    TK_CUDA(cudaMemcpyAsync(b.data(), h->d_best, b.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (b[1] < 0) { /* getBestLine with no rows (:791-796) */
+        if (fbest) *fbest = 1.0e7;
+        if (xbest) for (int d = 0; d < nx; d++) xbest[d] = h->init[d];
+        if (k) *k = 0;
+        return TIKTAK_OK;
+    }
+    if (fbest) *fbest = b[0];
+    if (k) *k = (int32_t)b[1];
+    if (xbest) for (int d = 0; d < nx; d++) xbest[d] = b[3 + d];
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* iters) {
+    (void)h; (void)fval; (void)x; (void)iters;
+    tk_set_error("last_search (EST_dfpmin polish) is not built yet");
+    return TIKTAK_ERR_UNSUPPORTED;
+}
+
+int tiktak_cuda_fp64_peak(int device, double* flops_per_s, double* ms) { return tk_fp64_peak(device, flops_per_s, ms); }
+
+} /* extern "C" */

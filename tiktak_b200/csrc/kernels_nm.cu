@@ -1,0 +1,313 @@
+/* kernels_nm.cu -- batched warm-start Nelder-Mead: one restart per warp.
+ *
+ * Replaces, per restart k: getBestLine/getModifiedParam (TiktakGlobalSearch.f90:683-720, 781-823: the
+ * theta-blend toward the best local minimum so far, which the reference obtains by re-reading and
+ * re-sorting searchResults.dat), runAmoeba (:602-633: regular simplex from simplex_coordinates2 scaled
+ * by range/K^(1/nx), clamped to the bounds, nx+1 evaluations) and amoeba/amotry (minimize.f90:7-135).
+ *
+ * Mapping: a warp owns a restart.  The simplex (nx+1 vertices x nx), y, psum live in the warp's slice
+ * of shared memory; lanes parallelise the coordinate-wise vector updates, warp shuffles give
+ * argmin/argmax (first occurrence, like MINLOC/MAXLOC) and the shrink re-evaluates its nx vertices on
+ * nx lanes at once.  The sequential part of amoeba -- reflect, then expand OR contract -- is collapsed
+ * into one evaluation phase per iteration by evaluating the four possible trial points (reflection R,
+ * expansion from R, contraction after an accepted R, contraction after a rejected R) on four lanes at
+ * once; which of them count, and the `iter` bookkeeping, follow minimize.f90:97-114 exactly, so the
+ * trajectory is the sequential one.  All arithmetic is unfused, in the reference's order; psum is
+ * updated incrementally (minimize.f90:130) and only re-summed after a shrink (:112).
+ */
+#include <float.h>
+
+#include "tk_common.cuh"
+
+namespace {
+
+struct NmArgs {
+    int n_run;            /* restarts this launch runs */
+    int n_k;              /* restarts of the round (column length of starts/out_x) */
+    int rank, world;      /* restart slot = rank + r*world */
+    const double* starts; /* (n_k, nx) column-major */
+    const double* width;  /* nx: p_range(:,2)-p_range(:,1), or (n_k, nx) column-major if per_restart_width */
+    int per_restart_width;
+    const double* simplex; /* (nx, nx+1) column-major unit simplex */
+    double scale;          /* DBLE(p_maxpoints)**(1/nx) */
+    double ftol;
+    int itmax;
+    double fac1r, fac2r, fac1e, fac2e, fac1c, fac2c; /* amotry's fac1/fac2 for fac = -1, 2, 0.5 */
+    double tiny;
+    double* out_x; /* (n_k, nx) column-major */
+    double* out_f; /* n_k */
+    int* out_evals;
+};
+
+__device__ __forceinline__ void warp_argmin(const double* y, int np, int lane, int& idx) {
+    double v = DBL_MAX; int bi = 0x7fffffff;
+    bool has = false;
+    for (int i = lane; i < np; i += 32) {
+        const double yi = y[i];
+        if (!has || yi < v) { v = yi; bi = i; has = true; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (i2 != 0x7fffffff && (bi == 0x7fffffff || v2 < v || (v2 == v && i2 < bi))) { v = v2; bi = i2; }
+    }
+    idx = bi;
+}
+/* argmax with y[skip] read as `subst` (amoeba's y(ihi)=y(ilo) trick, minimize.f90:80-83); skip<0: none */
+__device__ __forceinline__ void warp_argmax(const double* y, int np, int lane, int skip, double subst, int& idx) {
+    double v = -DBL_MAX; int bi = 0x7fffffff;
+    bool has = false;
+    for (int i = lane; i < np; i += 32) {
+        const double yi = (i == skip) ? subst : y[i];
+        if (!has || yi > v) { v = yi; bi = i; has = true; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (i2 != 0x7fffffff && (bi == 0x7fffffff || v2 > v || (v2 == v && i2 < bi))) { v = v2; bi = i2; }
+    }
+    idx = bi;
+}
+
+template <class Obj>
+__global__ void __launch_bounds__(128) nm_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int r = blockIdx.x * wpb + warp;
+    if (r >= a.n_run) return;
+    const int slot = a.rank + r * a.world;
+    const int nx = sc.nx, np = nx + 1;
+    const int per_warp = np * nx + np + nx + 4 * nx + 4;
+    double* p = smem + (size_t)warp * per_warp; /* p[i*nx + j] */
+    double* y = p + np * nx;
+    double* psum = y + np;
+    double* cand = psum + nx; /* cand[c*nx + j], c = R, E, Cout, Cin */
+    double* ycand = cand + 4 * nx;
+    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, T.bl, T.bu, T.aux);
+
+    /* runAmoeba :622-627 -- initial simplex around the blended start */
+    for (int e = lane; e < np * nx; e += 32) {
+        const int ia = e / nx, i = e - ia * nx;
+        const double wd = a.per_restart_width ? a.width[(size_t)i * a.n_k + slot] : a.width[i];
+        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wd), a.scale));
+        t = fmax(fmin(t, T.bu[i]), T.bl[i]);
+        p[e] = t;
+    }
+    __syncwarp();
+    for (int ia = lane; ia < np; ia += 32) y[ia] = tk_objfun<Obj>(ctx, TkMemX{p + (size_t)ia * nx, 1});
+    __syncwarp();
+    /* amoeba :49 psum = sum(p, dim=1), index order */
+    for (int j = lane; j < nx; j += 32) {
+        double s = 0.0;
+        for (int i = 0; i < np; i++) s = TK_ADD(s, p[i * nx + j]);
+        psum[j] = s;
+    }
+    __syncwarp();
+
+    int iter = 0, ilo = 0;
+    for (;;) {
+        int ihi, inhi;
+        warp_argmin(y, np, lane, ilo);
+        warp_argmax(y, np, lane, -1, 0.0, ihi);
+        const double ylo = y[ilo], yhi = y[ihi];
+        warp_argmax(y, np, lane, ihi, ylo, inhi);
+        const double ynhi = y[inhi];
+        const double rtol = TK_DIV(TK_MUL(2.0, fabs(TK_SUB(yhi, ylo))), TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny));
+        if (rtol < a.ftol || iter >= a.itmax) break; /* :85-96 */
+
+        /* the four possible trial points of this iteration (amotry :124-126, unfused) */
+        for (int j = lane; j < nx; j += 32) {
+            const double ps = psum[j], ph = p[ihi * nx + j];
+            const double R = TK_SUB(TK_MUL(ps, a.fac1r), TK_MUL(ph, a.fac2r));
+            const double ps1 = TK_ADD(TK_SUB(ps, ph), R); /* psum after R is accepted (:130) */
+            cand[j] = R;
+            cand[nx + j] = TK_SUB(TK_MUL(ps1, a.fac1e), TK_MUL(R, a.fac2e));
+            cand[2 * nx + j] = TK_SUB(TK_MUL(ps1, a.fac1c), TK_MUL(R, a.fac2c));
+            cand[3 * nx + j] = TK_SUB(TK_MUL(ps, a.fac1c), TK_MUL(ph, a.fac2c));
+        }
+        __syncwarp();
+        if (lane < 4) ycand[lane] = tk_objfun<Obj>(ctx, TkMemX{cand + (size_t)lane * nx, 1});
+        __syncwarp();
+        const double yR = ycand[0];
+        const bool accR = yR < yhi; /* :128 */
+        if (accR) {
+            for (int j = lane; j < nx; j += 32) {
+                const double R = cand[j];
+                psum[j] = TK_ADD(TK_SUB(psum[j], p[ihi * nx + j]), R);
+                p[ihi * nx + j] = R;
+            }
+            if (lane == 0) y[ihi] = yR;
+        }
+        iter++;
+        __syncwarp();
+        if (yR <= ylo) { /* :99 expansion */
+            double yE = ycand[1];
+            if (!accR) { /* only if every y was equal; not speculated -- evaluate from the live state */
+                for (int j = lane; j < nx; j += 32)
+                    cand[nx + j] = TK_SUB(TK_MUL(psum[j], a.fac1e), TK_MUL(p[ihi * nx + j], a.fac2e));
+                __syncwarp();
+                if (lane == 0) ycand[1] = tk_objfun<Obj>(ctx, TkMemX{cand + nx, 1});
+                __syncwarp();
+                yE = ycand[1];
+            }
+            iter++;
+            if (yE < y[ihi]) {
+                __syncwarp();
+                for (int j = lane; j < nx; j += 32) {
+                    const double E = cand[nx + j];
+                    psum[j] = TK_ADD(TK_SUB(psum[j], p[ihi * nx + j]), E);
+                    p[ihi * nx + j] = E;
+                }
+                if (lane == 0) y[ihi] = yE;
+            }
+            __syncwarp();
+        } else if (yR >= ynhi) { /* :102 contraction */
+            const double ysave = accR ? yR : yhi; /* y(ihi) at :103 */
+            const int cc = accR ? 2 : 3;
+            const double yC = ycand[cc];
+            iter++;
+            if (yC < ysave) {
+                for (int j = lane; j < nx; j += 32) {
+                    const double C = cand[cc * nx + j];
+                    psum[j] = TK_ADD(TK_SUB(psum[j], p[ihi * nx + j]), C);
+                    p[ihi * nx + j] = C;
+                }
+                if (lane == 0) y[ihi] = yC;
+                __syncwarp();
+            } else { /* :106-113 shrink toward the best vertex, re-evaluate, re-sum */
+                for (int e = lane; e < np * nx; e += 32) {
+                    const int i = e / nx, j = e - i * nx;
+                    if (i != ilo) p[e] = TK_MUL(0.5, TK_ADD(p[e], p[ilo * nx + j]));
+                }
+                __syncwarp();
+                for (int i = lane; i < np; i += 32)
+                    if (i != ilo) y[i] = tk_objfun<Obj>(ctx, TkMemX{p + (size_t)i * nx, 1});
+                iter += nx;
+                __syncwarp();
+                for (int j = lane; j < nx; j += 32) {
+                    double s = 0.0;
+                    for (int i = 0; i < np; i++) s = TK_ADD(s, p[i * nx + j]);
+                    psum[j] = s;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    /* runAmoeba :631-632 returns the first minimal vertex = p(ilo) (amoeba swapped it into row 1);
+     * completeSearch :582 re-evaluates objFun there: same point, same value. */
+    for (int j = lane; j < nx; j += 32) a.out_x[(size_t)j * a.n_k + slot] = p[ilo * nx + j];
+    if (lane == 0) {
+        a.out_f[slot] = y[ilo];
+        a.out_evals[slot] = np + iter + 1;
+    }
+}
+
+/* getSortedResults/getBestLine (:781-823) over the device-resident result rows.
+ * res: rows 0..K, each [fval, x(nx)]; best: [0]=fval [1]=row [2]=#rows, [3..] = x */
+__global__ void best_kernel(const double* res, const int* valid, int nrows, int nx, double* best) {
+    __shared__ double sv[256];
+    __shared__ int si[256];
+    __shared__ int sc[256];
+    double v = DBL_MAX; int bi = 0x7fffffff, cnt = 0;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+        if (!valid[r]) continue;
+        cnt++;
+        const double f = res[(size_t)r * (nx + 1)];
+        if (bi == 0x7fffffff || f < v) { v = f; bi = r; }
+    }
+    sv[threadIdx.x] = v; si[threadIdx.x] = bi; sc[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double v2 = sv[threadIdx.x + o]; const int i2 = si[threadIdx.x + o];
+            if (i2 != 0x7fffffff && (si[threadIdx.x] == 0x7fffffff || v2 < sv[threadIdx.x] ||
+                                     (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x]))) {
+                sv[threadIdx.x] = v2; si[threadIdx.x] = i2;
+            }
+            sc[threadIdx.x] += sc[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const int b = si[0];
+    if (threadIdx.x == 0) { best[0] = sv[0]; best[1] = (b == 0x7fffffff) ? -1.0 : (double)b; best[2] = (double)sc[0]; }
+    if (b != 0x7fffffff)
+        for (int d = threadIdx.x; d < nx; d += blockDim.x) best[3 + d] = res[(size_t)b * (nx + 1) + 1 + d];
+}
+
+/* getModifiedParam (:683-720): start = w11*best + (1-w11)*x_starts(k), unfused; w11 is the
+ * single-precision weight widened to double (computed on the host, h->w11). */
+__global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11,
+                             const double* best, double* starts) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_k * nx) return;
+    const int d = e / n_k, s = e - d * n_k, k = first_k + s; /* k is 1-based */
+    const double ev = xs[(size_t)(d + 1) * K + (k - 1)];
+    double out = ev;
+    if (best[2] > 1.0) { /* count <= 1: no finished local minimisation yet (:701) */
+        const double w = w11[k];
+        out = TK_ADD(TK_MUL(w, best[3 + d]), TK_MUL(TK_SUB(1.0, w), ev));
+    }
+    starts[(size_t)d * n_k + s] = out;
+}
+
+} /* namespace */
+
+int tk_launch_best(tiktak_handle* h) {
+    best_kernel<<<1, 256, 0, h->stream>>>(h->d_res, h->d_res_valid, h->cfg.maxpoints_plus1 + 1, h->cfg.nx, h->d_best);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_launch_blend(tiktak_handle* h, int first_k, int n_k) {
+    const int tot = n_k * h->cfg.nx;
+    blend_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, h->cfg.maxpoints_plus1, h->cfg.nx, first_k, n_k,
+                                                            h->d_w11, h->d_best, h->d_starts);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
+    const int nx = h->cfg.nx, np = nx + 1;
+    NmArgs a;
+    a.n_k = n_k;
+    a.rank = h->cfg.rank;
+    a.world = h->cfg.world;
+    a.n_run = (n_k > a.rank) ? (n_k - a.rank + a.world - 1) / a.world : 0;
+    if (a.n_run <= 0) return TIKTAK_OK;
+    a.starts = h->d_starts;
+    a.width = h->d_width;
+    a.per_restart_width = 0;
+    a.simplex = h->d_simplex;
+    a.scale = h->nm_scale;
+    a.ftol = h->cfg.nm_ftol;
+    a.itmax = h->cfg.nm_itmax;
+    const double ndim = (double)nx;
+    a.fac1r = (1.0 - (-1.0)) / ndim; a.fac2r = a.fac1r - (-1.0);
+    a.fac1e = (1.0 - 2.0) / ndim;    a.fac2e = a.fac1e - 2.0;
+    a.fac1c = (1.0 - 0.5) / ndim;    a.fac2c = a.fac1c - 0.5;
+    a.tiny = (double)1.0e-10f; /* TINY=1.0e-10 is a single-precision literal (minimize.f90:28) */
+    a.out_x = h->d_out_x;
+    a.out_f = h->d_out_f;
+    a.out_evals = h->d_out_evals;
+    (void)first_k;
+    const size_t per_warp = (size_t)(np * nx + np + nx + 4 * nx + 4) * sizeof(double);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb > 227 * 1024) {
+        tk_set_error("nx=%d: Nelder-Mead simplex does not fit in shared memory", nx);
+        return TIKTAK_ERR_UNSUPPORTED;
+    }
+    /* spread the restarts over the SMs before stacking warps in a block */
+    while (wpb > 1 && (a.n_run + wpb - 1) / wpb < h->sm_count) wpb >>= 1;
+    const size_t shmem = per_warp * wpb;
+    const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
+    return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
+        TK_CUDA(cudaFuncSetAttribute(nm_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        nm_kernel<Obj><<<(a.n_run + wpb - 1) / wpb, wpb * 32, shmem, h->stream>>>(T, h->sc, a);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+        return TIKTAK_OK;
+    });
+}

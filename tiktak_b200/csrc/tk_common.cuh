@@ -1,0 +1,157 @@
+/* tk_common.cuh -- shared declarations of libtiktak_cuda's translation units. */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tiktak_cuda.h"
+#include "../../include/tiktak_obj.cuh"
+
+#define TK_MAXBIT 30          /* utilities.f90:54: atmost < 2^30 */
+#define TK_NX_GENERIC_MAX 128 /* largest nx of the runtime-nx fallback kernels */
+
+void tk_set_error(const char* fmt, ...);
+#define TK_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            tk_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return TIKTAK_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+/* tables that ride along as __grid_constant__ kernel parameters (constant bank, broadcast reads) */
+template <int NX>
+struct TkTables {
+    uint32_t V[NX][32]; /* V[d][j]: direction number of Gray-code bit j, scaled so that q = lastq * 2^-32 */
+    double lo[NX], w[NX], bl[NX], bu[NX], aux[NX];
+};
+struct TkScalars {
+    int nx, nm;
+    double fvalmax, penalty0, penaltyc, max_penalty, sqrt_nm;
+    const void* user;
+};
+
+/* pointers to the same tables in global memory, for the runtime-nx kernels */
+struct TkTablesG {
+    const uint32_t* V; /* [nx][32] */
+    const double *lo, *w, *bl, *bu, *aux;
+};
+
+/* one evaluation wave of the pre-test stage: the points n (1-based Sobol index; n = 0 is the
+ * skipped all-zero vector) of count blocks [cb0, cb0+ncb) that belong to this rank */
+struct TkWave {
+    int64_t N;            /* qr_ndraw */
+    int64_t cb0, ncb;     /* global count-block range of the wave */
+    int rank, world;
+    double* fval;         /* local store, indexed by local n (see tk_local_index) */
+    unsigned long long* counts; /* per GLOBAL count block */
+};
+
+__host__ __device__ inline int64_t tk_local_index(int64_t n, int world) {
+    const int64_t cb = n / TIKTAK_SOBOL_BLOCK;
+    return (cb / world) * TIKTAK_SOBOL_BLOCK + (n % TIKTAK_SOBOL_BLOCK);
+}
+
+struct tiktak_handle {
+    tiktak_config cfg;
+    std::vector<double> range, init, bound, aux;
+    std::vector<uint32_t> V; /* [nx][32] */
+    std::vector<double> w11; /* blend weight per restart k (index k, 1-based) */
+    std::vector<double> simplex; /* simplex_coordinates2, (nx, nx+1) column-major */
+    double nm_scale = 1.0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+    TkScalars sc;
+    /* device copies */
+    uint32_t* d_V = nullptr;
+    double *d_lo = nullptr, *d_w = nullptr, *d_bl = nullptr, *d_bu = nullptr, *d_aux = nullptr, *d_init = nullptr;
+    double *d_simplex = nullptr, *d_w11 = nullptr;
+    /* pre-test state */
+    int64_t n_cblocks = 0, n_local_cblocks = 0;
+    double* d_fval = nullptr;             /* local fvals */
+    unsigned long long* d_counts = nullptr; /* [n_cblocks] */
+    std::vector<unsigned long long> h_counts;
+    int64_t cblocks_done = 0;
+    int64_t kcut = -1, nlegit = 0;
+    bool pretest_done = false;
+    /* selection state */
+    unsigned long long* d_hist = nullptr; /* 256 bins */
+    unsigned long long* d_selstate = nullptr;
+    double* d_cand_f = nullptr;           /* K-1 candidates */
+    unsigned int* d_cand_i = nullptr;
+    unsigned int* d_cand_n = nullptr;
+    double* d_sorted_f = nullptr;
+    unsigned int* d_sorted_i = nullptr;
+    int64_t n_cand = 0;
+    /* starts + results */
+    double* d_xstarts = nullptr; /* (K, nx+1) column-major */
+    bool starts_ready = false;
+    double* d_res = nullptr;     /* (K+1) rows x (nx+1): [fval, x], row k (row 0 = the k=0 record) */
+    int* d_res_valid = nullptr;
+    std::vector<double> h_res_f;
+    std::vector<int> h_res_valid, h_res_imp;
+    double* d_best = nullptr;    /* [0]=fval [1]=k [2]=count, [3..3+nx) = x */
+    /* local stage scratch */
+    double *d_starts = nullptr, *d_out_x = nullptr, *d_out_f = nullptr, *d_width = nullptr;
+    int* d_out_evals = nullptr;
+    /* stage timings */
+    double ms_pretest = 0, ms_choose = 0, ms_local = 0, ms_pretest_eval = 0;
+};
+
+/* kernel launchers (one per translation unit) */
+int tk_launch_sobol_wave(tiktak_handle* h, const TkWave& wv);
+int tk_launch_sobol_points(tiktak_handle* h, int64_t first, int64_t count, double* d_out);
+int tk_launch_objfun(tiktak_handle* h, const double* d_x, int64_t n, double* d_f);
+int tk_launch_find_cut(tiktak_handle* h, int64_t cb, unsigned long long need, unsigned long long* d_result);
+int tk_select_top(tiktak_handle* h, int64_t M);
+int tk_build_starts(tiktak_handle* h);
+int tk_launch_best(tiktak_handle* h);
+int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
+int tk_launch_nm(tiktak_handle* h, int first_k, int n_k);
+int tk_fp64_peak(int device, double* flops, double* ms);
+
+/* objective dispatch: calls f.template operator()<Obj>() for the configured plugin */
+#include "objectives.cuh"
+template <class F>
+inline int tk_dispatch_obj(int id, F&& f) {
+    switch (id) {
+        case TIKTAK_OBJ_TEMPLATE: return f.template operator()<ObjTemplate>();
+        case TIKTAK_OBJ_GRIEWANK: return f.template operator()<ObjGriewank>();
+        case TIKTAK_OBJ_RASTRIGIN: return f.template operator()<ObjRastrigin>();
+        case TIKTAK_OBJ_ROSENBROCK: return f.template operator()<ObjRosenbrock>();
+    }
+    tk_set_error("objective id %d has no scalar plugin", id);
+    return TIKTAK_ERR_UNSUPPORTED;
+}
+
+#ifdef __CUDACC__
+/* accessors handed to Obj::value */
+template <int NX>
+struct TkRegX {
+    double v[NX];
+    __device__ __forceinline__ double operator[](int i) const { return v[i]; }
+};
+struct TkMemX { /* strided memory (shared or global) */
+    const double* p;
+    int64_t stride;
+    __device__ __forceinline__ double operator[](int i) const { return p[(int64_t)i * stride]; }
+};
+__device__ __forceinline__ tk_obj_ctx tk_make_ctx(const TkScalars& s, int nx, const double* bl, const double* bu,
+                                                  const double* aux) {
+    tk_obj_ctx c;
+    c.nx = nx; c.nm = s.nm; c.bl = bl; c.bu = bu; c.aux = aux;
+    c.fvalmax = s.fvalmax; c.penalty0 = s.penalty0; c.penaltyc = s.penaltyc; c.max_penalty = s.max_penalty;
+    c.sqrt_nm = s.sqrt_nm; c.user = s.user;
+    return c;
+}
+/* 32-bit Sobol numerator -> double in [0,1), exact: build 1.q in [1,2) and subtract 1 */
+__device__ __forceinline__ double tk_q2unit(uint32_t q) {
+    return __dsub_rn(__hiloint2double((int)(0x3ff00000u | (q >> 12)), (int)(q << 20)), 1.0);
+}
+#endif
