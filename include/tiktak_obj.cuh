@@ -6,16 +6,27 @@
  * reference, the objective is COMPILED IN: a user edits one plugin struct and rebuilds the library.
  *
  * A plugin is a struct with
- *     static constexpr int kId;                       // TIKTAK_OBJ_* id it registers under
- *     static void host_init(int nx, double* aux);     // obj_initialize/GetData: fill per-coordinate
- *                                                     // constants (aux[nx]) once on the host
- *     template <class X> static __device__ double value(const tk_obj_ctx& c, const X& x);
- * `value` is the user part of dfovec (objective.f90:96-117): it returns the scalar v_err that the
- * shipped template replicates over the nm moments.  X is any type with `double operator[](int) const`
- * -- registers in the Sobol kernel (one point per thread, fully unrolled), shared memory in the
- * Nelder-Mead kernel -- so ONE definition serves every stage and every stage gets bit-identical
- * values.  Everything around it (getPenalty, the penalty branch of dfovec, DOT_PRODUCT, objFun) is
- * framework code below, restating objective.f90:51-74,92-95,125-142 operation for operation.
+ *     static constexpr int kId;                          // TIKTAK_OBJ_* id it registers under
+ *     static void host_init(int nx, double* aux);        // obj_initialize/GetData: per-coordinate
+ *                                                        // constants aux[nx], computed once on the host
+ *     static __device__ int    nterms(int nx);           // how many per-coordinate terms
+ *     template <class X>
+ *     static __device__ void   term(const tk_obj_ctx&, const X& x, int i, double& a, double& b);
+ *     static __device__ void   fold_init(const tk_obj_ctx&, double& s, double& p);
+ *     static __device__ void   fold(double& s, double& p, double a, double b);
+ *     static __device__ double finish(const tk_obj_ctx&, double s, double p);
+ * Together they are the user part of dfovec (objective.f90:96-117), i.e. the scalar v_err that the
+ * shipped template replicates over the nm moments:
+ *     fold_init(s,p); for i = 0 .. nterms-1 { term(x,i,a,b); fold(s,p,a,b); }  v_err = finish(s,p)
+ * `term` holds the expensive independent work of coordinate i (a cos, a square ...); `fold` is the
+ * cheap accumulation, ALWAYS applied in index order.  The split lets every stage pick its own
+ * parallelism without changing a single rounding: the Sobol kernel runs the loop in one thread with
+ * x in registers; the Nelder-Mead kernel spreads the `term`s of its trial points over the lanes of a
+ * warp and folds them in order on one lane -- so all stages, and the CPU oracle, see bit-identical
+ * objective values.  X is any type with `double operator[](int) const`.  Everything around this
+ * (getPenalty, the penalty branch of dfovec, DOT_PRODUCT, objFun) is framework code below,
+ * restating objective.f90:51-74,92-95,125-142 operation for operation.  A plugin that cannot be
+ * decomposed sets nterms = 1 and does everything in term(.,0,.).
  *
  * Arithmetic rules for plugin authors: use TK_MUL/TK_ADD/... or plain operators (the library is
  * compiled with -fmad=false, so nothing is contracted behind your back), call tk_cos/tk_sin from
@@ -68,18 +79,47 @@ __device__ __forceinline__ double tk_get_penalty(const tk_obj_ctx& c, const X& x
     return 0.0;
 }
 
-/* objFun (objective.f90:125-142) for plugins whose moments are nm copies of one value
- * (the shipped template): DOT_PRODUCT in index order, then + getPenalty. */
+/* bounds test only: true when some coordinate is outside [bl, bu] */
+template <class X>
+__device__ __forceinline__ bool tk_out_of_bounds(const tk_obj_ctx& c, const X& x) {
+    bool out = false;
+#pragma unroll
+    for (int i = 0; i < c.nx; i++) out = out || (x[i] < c.bl[i]) || (x[i] > c.bu[i]);
+    return out;
+}
+
+/* the user part of dfovec, evaluated sequentially by one thread */
+template <class Obj, class X>
+__device__ __forceinline__ double tk_value_seq(const tk_obj_ctx& c, const X& x) {
+    double s, p;
+    Obj::fold_init(c, s, p);
+    const int nt = Obj::nterms(c.nx);
+#pragma unroll
+    for (int i = 0; i < nt; i++) {
+        double a, b;
+        Obj::term(c, x, i, a, b);
+        Obj::fold(s, p, a, b);
+    }
+    return Obj::finish(c, s, p);
+}
+
+/* objFun (objective.f90:125-142) given dfovec's common moment value f and getPenalty:
+ * DOT_PRODUCT over the nm identical moments in index order, then + getPenalty. */
+__device__ __forceinline__ double tk_objfun_finish(const tk_obj_ctx& c, double f, double pen) {
+    const double ff = TK_MUL(f, f);
+    double dot = 0.0;
+    for (int m = 0; m < c.nm; m++) dot = TK_ADD(dot, ff);
+    return TK_ADD(dot, pen);
+}
+
+/* objFun for plugins whose moments are nm copies of one value (the shipped template) */
 template <class Obj, class X>
 __device__ __forceinline__ double tk_objfun(const tk_obj_ctx& c, const X& x) {
     const double pen = tk_get_penalty(c, x);
     double f;
     if (pen > TK_MYEPS) f = TK_DIV(pen, c.sqrt_nm); /* objective.f90:93-94 */
-    else f = Obj::value(c, x);
-    const double ff = TK_MUL(f, f);
-    double dot = 0.0;
-    for (int m = 0; m < c.nm; m++) dot = TK_ADD(dot, ff);
-    return TK_ADD(dot, pen);
+    else f = tk_value_seq<Obj>(c, x);
+    return tk_objfun_finish(c, f, pen);
 }
 
 #endif /* __CUDACC__ */

@@ -555,7 +555,19 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
     bool any = false;
     for (int k = 0; k <= K; k++)
         if (h->h_res_valid[k] && (!any || h->h_res_f[k] < best_f)) { best_f = h->h_res_f[k]; best_imp = h->h_res_imp[k]; any = true; }
-    std::vector<double> rec(nx + 1);
+    /* rows usually arrive with consecutive k: stage runs of consecutive rows and copy each run once */
+    std::vector<double> stage;
+    std::vector<int> ones;
+    int run_k0 = -1, run_len = 0;
+    auto flush = [&]() -> int {
+        if (run_len == 0) return TIKTAK_OK;
+        ones.assign(run_len, 1);
+        TK_CUDA(cudaMemcpyAsync(h->d_res + (size_t)run_k0 * (nx + 1), stage.data(), stage.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaMemcpyAsync(h->d_res_valid + run_k0, ones.data(), (size_t)run_len * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream)); /* staging buffers are reused */
+        stage.clear(); run_len = 0; run_k0 = -1;
+        return TIKTAK_OK;
+    };
     for (int r = 0; r < n; r++) {
         const double fv = host[(size_t)3 * n + r];
         const int k = (int)host[(size_t)1 * n + r];
@@ -564,14 +576,13 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
         if (k > 0 && fv < best_f) imp = best_imp + 1;
         if (!any || fv < best_f) { best_f = fv; best_imp = imp; any = true; }
         h->h_res_f[k] = fv; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
-        rec[0] = fv;
-        for (int d = 0; d < nx; d++) rec[1 + d] = host[(size_t)(4 + d) * n + r];
-        const int one = 1;
-        TK_CUDA(cudaMemcpyAsync(h->d_res + (size_t)k * (nx + 1), rec.data(), (size_t)(nx + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-        TK_CUDA(cudaMemcpyAsync(h->d_res_valid + k, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        TK_CUDA(cudaStreamSynchronize(h->stream)); /* rec/one are reused */
+        if (run_len > 0 && k != run_k0 + run_len) { int rc = flush(); if (rc) return rc; }
+        if (run_len == 0) run_k0 = k;
+        stage.push_back(fv);
+        for (int d = 0; d < nx; d++) stage.push_back(host[(size_t)(4 + d) * n + r]);
+        run_len++;
     }
-    return TIKTAK_OK;
+    return flush();
 }
 
 int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* starts, double* results,

@@ -73,17 +73,26 @@ template <class Obj>
 __global__ void __launch_bounds__(128) nm_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int nx = sc.nx, np = nx + 1;
+    const int nt = Obj::nterms(nx);
+    /* block-shared copies of the bounds and plugin constants */
+    double* sbl = smem;
+    double* sbu = sbl + nx;
+    double* saux = sbu + nx;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
+    __syncthreads();
     const int r = blockIdx.x * wpb + warp;
     if (r >= a.n_run) return;
     const int slot = a.rank + r * a.world;
-    const int nx = sc.nx, np = nx + 1;
-    const int per_warp = np * nx + np + nx + 4 * nx + 4;
-    double* p = smem + (size_t)warp * per_warp; /* p[i*nx + j] */
+    const int per_warp = np * nx + np + nx + 4 * nx + 4 + 8 * nx;
+    double* p = smem + 3 * nx + (size_t)warp * per_warp; /* p[i*nx + j] */
     double* y = p + np * nx;
     double* psum = y + np;
     double* cand = psum + nx; /* cand[c*nx + j], c = R, E, Cout, Cin */
     double* ycand = cand + 4 * nx;
-    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, T.bl, T.bu, T.aux);
+    double* ta = ycand + 4;   /* per-term partials of the four trial points */
+    double* tb = ta + 4 * nx;
+    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
 
     /* runAmoeba :622-627 -- initial simplex around the blended start */
     for (int e = lane; e < np * nx; e += 32) {
@@ -126,7 +135,37 @@ __global__ void __launch_bounds__(128) nm_kernel(const TkTablesG T, const TkScal
             cand[3 * nx + j] = TK_SUB(TK_MUL(ps, a.fac1c), TK_MUL(ph, a.fac2c));
         }
         __syncwarp();
-        if (lane < 4) ycand[lane] = tk_objfun<Obj>(ctx, TkMemX{cand + (size_t)lane * nx, 1});
+        /* objFun at the four trial points: the independent per-coordinate `term`s are spread over the
+         * lanes, the in-order `fold` runs on one lane per point (tiktak_obj.cuh) -- same roundings as a
+         * single-thread evaluation.  A point outside the bounds takes the full getPenalty path. */
+        unsigned oob = 0;
+        for (int e = lane; e < 4 * nx; e += 32) {
+            const int c = e / nx, i = e - c * nx;
+            const double xv = cand[e];
+            if (xv < sbl[i] || xv > sbu[i]) oob |= 1u << c;
+        }
+        oob = __reduce_or_sync(0xffffffffu, oob);
+        for (int e = lane; e < 4 * nt; e += 32) {
+            const int c = e / nt, i = e - c * nt;
+            if ((oob >> c) & 1u) continue;
+            double ta_, tb_;
+            Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, i, ta_, tb_);
+            ta[c * nx + i] = ta_;
+            tb[c * nx + i] = tb_;
+        }
+        __syncwarp();
+        if (lane < 4) {
+            double yv;
+            if ((oob >> lane) & 1u) {
+                yv = tk_objfun<Obj>(ctx, TkMemX{cand + (size_t)lane * nx, 1});
+            } else {
+                double s_, p_;
+                Obj::fold_init(ctx, s_, p_);
+                for (int i = 0; i < nt; i++) Obj::fold(s_, p_, ta[lane * nx + i], tb[lane * nx + i]);
+                yv = tk_objfun_finish(ctx, Obj::finish(ctx, s_, p_), 0.0);
+            }
+            ycand[lane] = yv;
+        }
         __syncwarp();
         const double yR = ycand[0];
         const bool accR = yR < yhi; /* :128 */
@@ -292,16 +331,17 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     a.out_f = h->d_out_f;
     a.out_evals = h->d_out_evals;
     (void)first_k;
-    const size_t per_warp = (size_t)(np * nx + np + nx + 4 * nx + 4) * sizeof(double);
+    const size_t per_warp = (size_t)(np * nx + np + nx + 4 * nx + 4 + 8 * nx) * sizeof(double);
+    const size_t per_block = (size_t)3 * nx * sizeof(double);
     int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
-    if (per_warp * wpb > 227 * 1024) {
+    while (wpb > 1 && per_warp * wpb + per_block > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb + per_block > 227 * 1024) {
         tk_set_error("nx=%d: Nelder-Mead simplex does not fit in shared memory", nx);
         return TIKTAK_ERR_UNSUPPORTED;
     }
     /* spread the restarts over the SMs before stacking warps in a block */
     while (wpb > 1 && (a.n_run + wpb - 1) / wpb < h->sm_count) wpb >>= 1;
-    const size_t shmem = per_warp * wpb;
+    const size_t shmem = per_warp * wpb + per_block;
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
         TK_CUDA(cudaFuncSetAttribute(nm_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -11,74 +11,85 @@
 #include "../../include/tiktak_cuda.h"
 #include "../../include/tiktak_obj.cuh"
 
-struct ObjTemplate {
+struct ObjTemplate { /* val1 = sum x^2/200 ; val2 = cos(x1) * prod cos(x_i/sqrt(i)) ; v = val1 - val2 + 1 + 1 */
     static constexpr int kId = TIKTAK_OBJ_TEMPLATE;
     static void host_init(int nx, double* aux) {
-        for (int i = 0; i < nx; i++) aux[i] = sqrt((double)(i + 1) + 0.0); /* sqrt(ii+0.0D0) */
+        for (int i = 0; i < nx; i++) aux[i] = sqrt((double)(i + 1) + 0.0); /* sqrt(ii+0.0D0), :106 */
     }
+    static __device__ __forceinline__ int nterms(int nx) { return nx; }
     template <class X>
-    static __device__ __forceinline__ double value(const tk_obj_ctx& c, const X& x) {
-        double val1 = TK_DIV(TK_MUL(x[0], x[0]), 200.0);
-        double val2 = tk_cos(x[0]);
-#pragma unroll
-        for (int i = 1; i < c.nx; i++) {
-            val1 = TK_ADD(val1, TK_DIV(TK_MUL(x[i], x[i]), 200.0));
-            val2 = TK_MUL(val2, tk_cos(TK_DIV(x[i], c.aux[i])));
-        }
-        const double v = TK_ADD(TK_SUB(val1, val2), 1.0);
-        return TK_ADD(v, 1.0);
+    static __device__ __forceinline__ void term(const tk_obj_ctx& c, const X& x, int i, double& a, double& b) {
+        const double xi = x[i];
+        a = TK_DIV(TK_MUL(xi, xi), 200.0);
+        b = (i == 0) ? tk_cos(xi) : tk_cos(TK_DIV(xi, c.aux[i])); /* x/sqrt(1) == x exactly anyway */
+    }
+    static __device__ __forceinline__ void fold_init(const tk_obj_ctx&, double& s, double& p) { s = 0.0; p = 1.0; }
+    static __device__ __forceinline__ void fold(double& s, double& p, double a, double b) {
+        s = TK_ADD(s, a); /* 0 + a0 and 1 * b0 are exact, so this equals the reference's seeded loops */
+        p = TK_MUL(p, b);
+    }
+    static __device__ __forceinline__ double finish(const tk_obj_ctx&, double s, double p) {
+        return TK_ADD(TK_ADD(TK_SUB(s, p), 1.0), 1.0);
     }
 };
 
-struct ObjGriewank {
+struct ObjGriewank { /* f = 1 + sum x^2/4000 - prod cos(x_i/sqrt(i)) */
     static constexpr int kId = TIKTAK_OBJ_GRIEWANK;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 1.0 / sqrt((double)(i + 1));
     }
+    static __device__ __forceinline__ int nterms(int nx) { return nx; }
     template <class X>
-    static __device__ __forceinline__ double value(const tk_obj_ctx& c, const X& x) {
-        double s = 0.0, p = 1.0;
-#pragma unroll
-        for (int i = 0; i < c.nx; i++) {
-            s = TK_ADD(s, TK_MUL(TK_MUL(x[i], x[i]), 2.5e-4));
-            p = TK_MUL(p, tk_cos(TK_MUL(x[i], c.aux[i])));
-        }
-        const double v = TK_ADD(TK_SUB(s, p), 1.0);
-        return TK_ADD(v, 1.0);
+    static __device__ __forceinline__ void term(const tk_obj_ctx& c, const X& x, int i, double& a, double& b) {
+        const double xi = x[i];
+        a = TK_MUL(TK_MUL(xi, xi), 2.5e-4);
+        b = tk_cos(TK_MUL(xi, c.aux[i]));
+    }
+    static __device__ __forceinline__ void fold_init(const tk_obj_ctx&, double& s, double& p) { s = 0.0; p = 1.0; }
+    static __device__ __forceinline__ void fold(double& s, double& p, double a, double b) {
+        s = TK_ADD(s, a);
+        p = TK_MUL(p, b);
+    }
+    static __device__ __forceinline__ double finish(const tk_obj_ctx&, double s, double p) {
+        return TK_ADD(TK_ADD(TK_SUB(s, p), 1.0), 1.0);
     }
 };
 
-struct ObjRastrigin {
+struct ObjRastrigin { /* f = 10 n + sum (x^2 - 10 cos(2 pi x)) */
     static constexpr int kId = TIKTAK_OBJ_RASTRIGIN;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }
+    static __device__ __forceinline__ int nterms(int nx) { return nx; }
     template <class X>
-    static __device__ __forceinline__ double value(const tk_obj_ctx& c, const X& x) {
-        double s = TK_MUL(10.0, (double)c.nx);
-#pragma unroll
-        for (int i = 0; i < c.nx; i++) {
-            const double t = TK_SUB(TK_MUL(x[i], x[i]), TK_MUL(10.0, tk_cos(TK_MUL(6.283185307179586, x[i]))));
-            s = TK_ADD(s, t);
-        }
-        return TK_ADD(s, 1.0);
+    static __device__ __forceinline__ void term(const tk_obj_ctx&, const X& x, int i, double& a, double& b) {
+        const double xi = x[i];
+        a = TK_SUB(TK_MUL(xi, xi), TK_MUL(10.0, tk_cos(TK_MUL(6.283185307179586, xi))));
+        b = 0.0;
     }
+    static __device__ __forceinline__ void fold_init(const tk_obj_ctx& c, double& s, double& p) {
+        s = TK_MUL(10.0, (double)c.nx);
+        p = 0.0;
+    }
+    static __device__ __forceinline__ void fold(double& s, double&, double a, double) { s = TK_ADD(s, a); }
+    static __device__ __forceinline__ double finish(const tk_obj_ctx&, double s, double) { return TK_ADD(s, 1.0); }
 };
 
-struct ObjRosenbrock {
+struct ObjRosenbrock { /* f = sum_{i<n} 100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2 */
     static constexpr int kId = TIKTAK_OBJ_ROSENBROCK;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }
+    static __device__ __forceinline__ int nterms(int nx) { return nx - 1; }
     template <class X>
-    static __device__ __forceinline__ double value(const tk_obj_ctx& c, const X& x) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i + 1 < c.nx; i++) {
-            const double t = TK_SUB(x[i + 1], TK_MUL(x[i], x[i]));
-            const double u = TK_SUB(1.0, x[i]);
-            s = TK_ADD(s, TK_ADD(TK_MUL(100.0, TK_MUL(t, t)), TK_MUL(u, u)));
-        }
-        return TK_ADD(s, 1.0);
+    static __device__ __forceinline__ void term(const tk_obj_ctx&, const X& x, int i, double& a, double& b) {
+        const double x0 = x[i];
+        const double t = TK_SUB(x[i + 1], TK_MUL(x0, x0));
+        const double u = TK_SUB(1.0, x0);
+        a = TK_ADD(TK_MUL(100.0, TK_MUL(t, t)), TK_MUL(u, u));
+        b = 0.0;
     }
+    static __device__ __forceinline__ void fold_init(const tk_obj_ctx&, double& s, double& p) { s = 0.0; p = 0.0; }
+    static __device__ __forceinline__ void fold(double& s, double&, double a, double) { s = TK_ADD(s, a); }
+    static __device__ __forceinline__ double finish(const tk_obj_ctx&, double s, double) { return TK_ADD(s, 1.0); }
 };

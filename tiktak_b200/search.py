@@ -117,14 +117,13 @@ class TikTakSearch:
         return self._solve_sharded()
 
     def _solve_sharded(self):
-        import torch
+        from . import dist as D
 
-        dist = self._dist()
         N, Lg = self.cfg.qr_ndraw, self.cfg.legitimate
         nblocks = N // SOBOL_BLOCK + 1
         can_cut = Lg <= N
         wave = 64 * self.world if can_cut else nblocks
-        dev = torch.device("cuda", self.device)
+        dev = f"cuda:{self.device}"
         cum, kcut, nleg = 0, -1, 0
         cb0 = 0
         if N == 0 or Lg <= 0:
@@ -133,19 +132,15 @@ class TikTakSearch:
         while cb0 < nblocks and kcut < 0:
             ncb = min(wave, nblocks - cb0)
             _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, cb0, ncb), "pretest_wave")
-            counts = torch.zeros(nblocks, dtype=torch.int64, device=dev)
-            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), nblocks), "pretest_counts")
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)  # one exchange per wave
-            cc = counts[cb0:cb0 + ncb].cpu().numpy()
-            for i, c in enumerate(cc):
-                if can_cut and cum + int(c) >= Lg:
-                    n = C.c_int64()
-                    _lib.check(self._L.tiktak_cuda_pretest_find(self._h, cb0 + i, Lg - cum, C.byref(n)), "pretest_find")
-                    t = torch.tensor([n.value], dtype=torch.int64, device=dev)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-                    kcut, nleg = int(t.item()), Lg
-                    break
-                cum += int(c)
+            counts = np.zeros(nblocks, dtype=np.int64)
+            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.ctypes.data, nblocks), "pretest_counts")
+            counts[cb0 + ncb:] = 0
+            # one exchange per wave: all-reduce of the per-block valid counts
+            _, b, need, cum = D.global_cut(counts, cb0, Lg if can_cut else 2**62, cum, self.group, dev)
+            if b >= 0:
+                n = C.c_int64()
+                _lib.check(self._L.tiktak_cuda_pretest_find(self._h, b, need, C.byref(n)), "pretest_find")
+                kcut, nleg = D.agree_max(n.value, self.group, dev), Lg
             cb0 += ncb
         if kcut < 0:
             kcut, nleg = N, cum
@@ -167,17 +162,12 @@ class TikTakSearch:
         idx = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
         if self.world > 1 and K > 1:
-            import torch
+            from . import dist as D
 
-            dist = self._dist()
             M = K - 1
             cand = np.empty((M, 2), dtype=np.float64)
             _lib.check(self._L.tiktak_cuda_choose_candidates(self._h, cand.ctypes.data), "choose_candidates")
-            dev = torch.device("cuda", self.device)
-            mine = torch.from_numpy(cand).to(dev)
-            allc = torch.empty((self.world * M, 2), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(allc, mine, group=self.group)
-            allh = np.ascontiguousarray(allc.cpu().numpy())
+            allh = D.gather_candidates(cand, self.world, self.group, f"cuda:{self.device}")
             _lib.check(self._L.tiktak_cuda_choose_merge(self._h, allh.ctypes.data, allh.shape[0], xs.ctypes.data,
                                                         idx.ctypes.data), "choose_merge")
         self.x_starts = xs.T.copy()  # (K, nx+1) = [fval, x]
@@ -217,22 +207,14 @@ class TikTakSearch:
 
     def _exchange_round(self, r, e, n_k):
         """one all-gather of this round's rows over NVLink; every rank then ingests all of them."""
-        import torch
+        from . import dist as D
 
-        dist = self._dist()
-        dev = torch.device("cuda", self.device)
         nx = self.cfg.nx
         pack = np.concatenate([r, e[None, :].astype(np.float64)], axis=0)  # (nx+5, n_k)
-        mine = torch.from_numpy(np.ascontiguousarray(pack)).to(dev)
-        allr = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allr, mine, group=self.group)
-        allh = allr.cpu().numpy()
-        merged = np.empty_like(pack)
-        for s in range(n_k):
-            merged[:, s] = allh[s % self.world, :, s]  # restart slot s was run by rank s % world
+        merged = D.exchange_rows(pack, self.world, self.group, f"cuda:{self.device}")
         rows = np.ascontiguousarray(merged[: nx + 4])
         _lib.check(self._L.tiktak_cuda_push_results(self._h, rows.ctypes.data, n_k), "push_results")
-        # the #improvements column is assigned at ingestion (identically on every rank); read it back
+        # the #improvements column is assigned at ingestion (identically on every rank)
         out = rows.copy()
         out[2] = self._improvements(rows)
         return out, merged[nx + 4].astype(np.int32)
