@@ -68,12 +68,50 @@ TK_HD double tk_u2d(uint64_t u) {
 #define TK_2OPI 0.6366197723675814          /* 0x3fe45f306dc9c883 */
 #define TK_RMAGIC 6755399441055744.0        /* 1.5 * 2^52 */
 
-/* Shared core: reduce x = k*pi/2 + r, |r| <= pi/4(1+eps); evaluate the sine polynomial when
- * (k + shift) is odd ... see tk_cos / tk_sin.  `shift` = 1 for cos, 0 for sin:
- *   sin(x) with n = k     : n&1 ? cos(r) : sin(r), negated when n&2
- *   cos(x) = sin(x + pi/2): n = k+1. */
+/* Shared core: reduce x = k*pi/2 + r, |r| <= pi/4(1+eps), n = k + shift (shift = 1 for cos, 0 for
+ * sin: cos(x) = sin(x + pi/2)); then sin(x + shift*pi/2) = (n&1 ? cos(r) : sin(r)), negated when n&2.
+ *     sin(r) = r + (z*r)*S(z)        cos(r) = (1 - z/2) + (z*z)*C(z)        z = r*r
+ * Host and device run the same operations on the branch that is selected.  The device version
+ * evaluates BOTH polynomials and selects the result: that costs 5 more DFMA but removes ~24 per-thread
+ * coefficient selects, which is what bounded the Sobol kernel (issue slots, not the FP64 pipe), and it
+ * reads the coefficients from one __constant__ table (two doubles per LDCU.128). */
+#if defined(__CUDACC__)
+static __constant__ double tk_sc_tab[16] = {
+    /* S1..S6 */ -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    /* C1..C6 */ 4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+    /* reduction */ TK_2OPI, TK_PIO2_1, TK_PIO2_2, TK_PIO2_3};
+#endif
+
 TK_HD double tk_sincos_core(double x, int shift) {
-    if (!(fabs(x) < 1073741824.0)) return x - x == 0.0 ? tk_u2d(0x7ff8000000000000ULL) : (x - x) / (x - x);
+#if defined(__CUDA_ARCH__)
+    const double* const T = tk_sc_tab;
+    const double t = __fma_rn(x, T[12], TK_RMAGIC);
+    const int n = __double2loint(t) + shift;
+    const double kd = __dsub_rn(t, TK_RMAGIC);
+    double r = __fma_rn(-kd, T[13], x);
+    r = __fma_rn(-kd, T[14], r);
+    r = __fma_rn(-kd, T[15], r);
+    const double z = __dmul_rn(r, r);
+    double ps = __fma_rn(z, T[5], T[4]);
+    double pc = __fma_rn(z, T[11], T[10]);
+    ps = __fma_rn(z, ps, T[3]);
+    pc = __fma_rn(z, pc, T[9]);
+    ps = __fma_rn(z, ps, T[2]);
+    pc = __fma_rn(z, pc, T[8]);
+    ps = __fma_rn(z, ps, T[1]);
+    pc = __fma_rn(z, pc, T[7]);
+    ps = __fma_rn(z, ps, T[0]);
+    pc = __fma_rn(z, pc, T[6]);
+    const double vs = __fma_rn(__dmul_rn(z, r), ps, r);
+    const double vc = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, -0.5, 1.0));
+    double v = (n & 1) ? vc : vs;
+    /* negate when n&2: flip the sign bit with integer logic */
+    v = __hiloint2double(__double2hiint(v) ^ ((n & 2) << 30), __double2loint(v));
+    return (fabs(x) < 1073741824.0) ? v : __longlong_as_double(0x7ff8000000000000LL);
+#else
+    if (!(fabs(x) < 1073741824.0)) return tk_u2d(0x7ff8000000000000ULL);
     const double t = TK_FMA(x, TK_2OPI, TK_RMAGIC);
     const int n = (int)(uint32_t)(tk_d2u(t) & 0xffffffffu) + shift;
     const double kd = TK_SUB(t, TK_RMAGIC);
@@ -81,24 +119,24 @@ TK_HD double tk_sincos_core(double x, int shift) {
     r = TK_FMA(-kd, TK_PIO2_2, r);
     r = TK_FMA(-kd, TK_PIO2_3, r);
     const double z = TK_MUL(r, r);
-    const int usecos = n & 1;
-    /* coefficient select keeps one straight-line path for both polynomials */
-    const double c6 = usecos ? -1.13596475577881948265e-11 : 1.58969099521155010221e-10;
-    const double c5 = usecos ? 2.08757232129817482790e-09 : -2.50507602534068634195e-08;
-    const double c4 = usecos ? -2.75573143513906633035e-07 : 2.75573137070700676789e-06;
-    const double c3 = usecos ? 2.48015872894767294178e-05 : -1.98412698298579493134e-04;
-    const double c2 = usecos ? -1.38888888888741095749e-03 : 8.33333333332248946124e-03;
-    const double c1 = usecos ? 4.16666666666666019037e-02 : -1.66666666666666324348e-01;
-    double p = TK_FMA(z, c6, c5);
-    p = TK_FMA(z, p, c4);
-    p = TK_FMA(z, p, c3);
-    p = TK_FMA(z, p, c2);
-    p = TK_FMA(z, p, c1);
-    /* sin: r + (z*r)*p      cos: (1 - z/2) + (z*z)*p */
-    const double a = usecos ? TK_MUL(z, z) : TK_MUL(z, r);
-    const double b = usecos ? TK_FMA(z, -0.5, 1.0) : r;
-    const double v = TK_FMA(a, p, b);
+    double v;
+    if (n & 1) {
+        double p = TK_FMA(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+        p = TK_FMA(z, p, -2.75573143513906633035e-07);
+        p = TK_FMA(z, p, 2.48015872894767294178e-05);
+        p = TK_FMA(z, p, -1.38888888888741095749e-03);
+        p = TK_FMA(z, p, 4.16666666666666019037e-02);
+        v = TK_FMA(TK_MUL(z, z), p, TK_FMA(z, -0.5, 1.0));
+    } else {
+        double p = TK_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+        p = TK_FMA(z, p, 2.75573137070700676789e-06);
+        p = TK_FMA(z, p, -1.98412698298579493134e-04);
+        p = TK_FMA(z, p, 8.33333333332248946124e-03);
+        p = TK_FMA(z, p, -1.66666666666666324348e-01);
+        v = TK_FMA(TK_MUL(z, r), p, r);
+    }
     return (n & 2) ? -v : v;
+#endif
 }
 
 TK_HD double tk_cos(double x) { return tk_sincos_core(x, 1); }

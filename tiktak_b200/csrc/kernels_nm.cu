@@ -241,6 +241,189 @@ __global__ void __launch_bounds__(128) nm_kernel(const TkTablesG T, const TkScal
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Lane-per-coordinate variant for nx <= 31 (one restart per warp, as above): lane j keeps psum_j and the
+ * four trial coordinates of the iteration in registers, lane i keeps y_i, so argmin/argmax are two
+ * warp REDUX + one ballot on the order-preserving integer image of y (first occurrence = lowest
+ * lane), the per-coordinate `term`s of all four trial points are evaluated by lane j back to back
+ * (4-way ILP on the cos chains) and only the in-order `fold` runs on one lane per trial point.
+ * Same arithmetic and the same decisions as nm_kernel; ~5x lower latency per simplex iteration.
+ * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ unsigned long long nm_order_key(double f) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(f);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ int warp_first_min_key(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return __ffs(__ballot_sync(0xffffffffu, hi == mh && lo == ml)) - 1;
+}
+
+template <class Obj>
+__global__ void __launch_bounds__(128) nm_lane_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+    extern __shared__ double smem[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int nx = sc.nx, np = nx + 1;
+    const int nt = Obj::nterms(nx);
+    double* sbl = smem;
+    double* sbu = sbl + nx;
+    double* saux = sbu + nx;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
+    __syncthreads();
+    const int r = blockIdx.x * wpb + warp;
+    if (r >= a.n_run) return;
+    const int slot = a.rank + r * a.world;
+    const int per_warp = np * nx + 4 * nx + 8 * nx;
+    double* p = smem + 3 * nx + (size_t)warp * per_warp; /* p[i*nx + j] */
+    double* cand = p + np * nx;                           /* cand[c*nx + j] */
+    double* ta = cand + 4 * nx;
+    double* tb = ta + 4 * nx;
+    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
+    const bool has_j = lane < nx, has_i = lane < np;
+    const int j = has_j ? lane : 0;
+    const double blj = sbl[j], buj = sbu[j];
+
+    /* runAmoeba :622-627 */
+    for (int e = lane; e < np * nx; e += 32) {
+        const int ia = e / nx, i = e - ia * nx;
+        const double wd = a.per_restart_width ? a.width[(size_t)i * a.n_k + slot] : a.width[i];
+        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wd), a.scale));
+        t = fmax(fmin(t, sbu[i]), sbl[i]);
+        p[e] = t;
+    }
+    __syncwarp();
+    double yl = 0.0; /* y(lane) */
+    if (has_i) yl = tk_objfun<Obj>(ctx, TkMemX{p + (size_t)lane * nx, 1});
+    double psum = 0.0; /* psum(lane) */
+    if (has_j)
+        for (int i = 0; i < np; i++) psum = TK_ADD(psum, p[i * nx + j]);
+
+    int iter = 0, ilo = 0;
+    for (;;) {
+        const unsigned long long key = nm_order_key(yl);
+        ilo = warp_first_min_key(has_i ? key : ~0ULL);
+        const int ihi = warp_first_min_key(has_i ? ~key : ~0ULL);
+        const double ylo = __shfl_sync(FULL, yl, ilo), yhi = __shfl_sync(FULL, yl, ihi);
+        const unsigned long long klo = nm_order_key(ylo);
+        const int inhi = warp_first_min_key(has_i ? ~(lane == ihi ? klo : key) : ~0ULL);
+        const double ynhi = __shfl_sync(FULL, yl, inhi);
+        /* rtol < ftol (:84-85); the division is only formed when the product test is within 2^-40 */
+        const double num = TK_MUL(2.0, fabs(TK_SUB(yhi, ylo)));
+        const double den = TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny);
+        const double thr = TK_MUL(a.ftol, den);
+        bool conv;
+        if (num < TK_MUL(thr, 0.99999999999909051)) conv = true;
+        else if (num > TK_MUL(thr, 1.00000000000090949)) conv = false;
+        else conv = TK_DIV(num, den) < a.ftol;
+        if (conv || iter >= a.itmax) break;
+
+        /* trial points (amotry :124-126, unfused) */
+        double ph = has_j ? p[ihi * nx + j] : 0.0;
+        const double R = TK_SUB(TK_MUL(psum, a.fac1r), TK_MUL(ph, a.fac2r));
+        const double ps1 = TK_ADD(TK_SUB(psum, ph), R);
+        const double E = TK_SUB(TK_MUL(ps1, a.fac1e), TK_MUL(R, a.fac2e));
+        const double Co = TK_SUB(TK_MUL(ps1, a.fac1c), TK_MUL(R, a.fac2c));
+        const double Ci = TK_SUB(TK_MUL(psum, a.fac1c), TK_MUL(ph, a.fac2c));
+        unsigned oob = 0;
+        oob |= __ballot_sync(FULL, has_j && (R < blj || R > buj)) ? 1u : 0u;
+        oob |= __ballot_sync(FULL, has_j && (E < blj || E > buj)) ? 2u : 0u;
+        oob |= __ballot_sync(FULL, has_j && (Co < blj || Co > buj)) ? 4u : 0u;
+        oob |= __ballot_sync(FULL, has_j && (Ci < blj || Ci > buj)) ? 8u : 0u;
+        if (has_j) { cand[j] = R; cand[nx + j] = E; cand[2 * nx + j] = Co; cand[3 * nx + j] = Ci; }
+        __syncwarp();
+        if (lane < nt) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if ((oob >> c) & 1u) continue;
+                double ta_, tb_;
+                Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, lane, ta_, tb_);
+                ta[c * nx + lane] = ta_;
+                tb[c * nx + lane] = tb_;
+            }
+        }
+        __syncwarp();
+        double yc = 0.0;
+        if (lane < 4) {
+            if ((oob >> lane) & 1u) {
+                yc = tk_objfun<Obj>(ctx, TkMemX{cand + (size_t)lane * nx, 1});
+            } else {
+                double s_, p_;
+                Obj::fold_init(ctx, s_, p_);
+                const double* qa = ta + lane * nx;
+                const double* qb = tb + lane * nx;
+                int i = 0;
+                for (; i + 4 <= nt; i += 4) { /* loads first, then the in-order chain */
+                    const double a0 = qa[i], a1 = qa[i + 1], a2 = qa[i + 2], a3 = qa[i + 3];
+                    const double b0 = qb[i], b1 = qb[i + 1], b2 = qb[i + 2], b3 = qb[i + 3];
+                    Obj::fold(s_, p_, a0, b0); Obj::fold(s_, p_, a1, b1);
+                    Obj::fold(s_, p_, a2, b2); Obj::fold(s_, p_, a3, b3);
+                }
+                for (; i < nt; i++) Obj::fold(s_, p_, qa[i], qb[i]);
+                yc = tk_objfun_finish(ctx, Obj::finish(ctx, s_, p_), 0.0);
+            }
+        }
+        const double yR = __shfl_sync(FULL, yc, 0);
+        const bool accR = yR < yhi; /* :128 */
+        if (accR) {
+            psum = ps1;
+            if (has_j) p[ihi * nx + j] = R;
+            ph = R;
+            if (lane == ihi) yl = yR;
+        }
+        iter++;
+        if (yR <= ylo) { /* :99 expansion */
+            double yE = __shfl_sync(FULL, yc, 1);
+            double Ev = E;
+            if (!accR) { /* unreachable unless all y are equal; evaluated from the live state */
+                Ev = TK_SUB(TK_MUL(psum, a.fac1e), TK_MUL(ph, a.fac2e));
+                if (has_j) cand[nx + j] = Ev;
+                __syncwarp();
+                double t_ = 0.0;
+                if (lane == 0) t_ = tk_objfun<Obj>(ctx, TkMemX{cand + nx, 1});
+                yE = __shfl_sync(FULL, t_, 0);
+            }
+            iter++;
+            const double ycur = accR ? yR : yhi;
+            if (yE < ycur) {
+                psum = TK_ADD(TK_SUB(psum, ph), Ev);
+                if (has_j) p[ihi * nx + j] = Ev;
+                if (lane == ihi) yl = yE;
+            }
+        } else if (yR >= ynhi) { /* :102 contraction */
+            const double ysave = accR ? yR : yhi;
+            const double yC = __shfl_sync(FULL, yc, accR ? 2 : 3);
+            const double Cv = accR ? Co : Ci;
+            iter++;
+            if (yC < ysave) {
+                psum = TK_ADD(TK_SUB(psum, ph), Cv);
+                if (has_j) p[ihi * nx + j] = Cv;
+                if (lane == ihi) yl = yC;
+            } else { /* :106-113 shrink */
+                __syncwarp();
+                if (has_j) {
+                    const double pl = p[ilo * nx + j];
+                    for (int i = 0; i < np; i++)
+                        if (i != ilo) p[i * nx + j] = TK_MUL(0.5, TK_ADD(p[i * nx + j], pl));
+                }
+                __syncwarp();
+                if (has_i && lane != ilo) yl = tk_objfun<Obj>(ctx, TkMemX{p + (size_t)lane * nx, 1});
+                iter += nx;
+                psum = 0.0;
+                if (has_j)
+                    for (int i = 0; i < np; i++) psum = TK_ADD(psum, p[i * nx + j]);
+            }
+        }
+        __syncwarp();
+    }
+    if (has_j) a.out_x[(size_t)j * a.n_k + slot] = p[ilo * nx + j];
+    if (lane == ilo) {
+        a.out_f[slot] = yl;
+        a.out_evals[slot] = np + iter + 1;
+    }
+}
+
 /* getSortedResults/getBestLine (:781-823) over the device-resident result rows.
  * res: rows 0..K, each [fval, x(nx)]; best: [0]=fval [1]=row [2]=#rows, [3..] = x */
 __global__ void best_kernel(const double* res, const int* valid, int nrows, int nx, double* best) {
@@ -331,7 +514,8 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     a.out_f = h->d_out_f;
     a.out_evals = h->d_out_evals;
     (void)first_k;
-    const size_t per_warp = (size_t)(np * nx + np + nx + 4 * nx + 4 + 8 * nx) * sizeof(double);
+    const bool lane_variant = nx <= 31;
+    const size_t per_warp = (size_t)(lane_variant ? (np * nx + 12 * nx) : (np * nx + np + nx + 4 * nx + 4 + 8 * nx)) * sizeof(double);
     const size_t per_block = (size_t)3 * nx * sizeof(double);
     int wpb = 4;
     while (wpb > 1 && per_warp * wpb + per_block > 200 * 1024) wpb >>= 1;
@@ -344,8 +528,14 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     const size_t shmem = per_warp * wpb + per_block;
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
-        TK_CUDA(cudaFuncSetAttribute(nm_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        nm_kernel<Obj><<<(a.n_run + wpb - 1) / wpb, wpb * 32, shmem, h->stream>>>(T, h->sc, a);
+        const unsigned grid = (unsigned)((a.n_run + wpb - 1) / wpb);
+        if (lane_variant) {
+            TK_CUDA(cudaFuncSetAttribute(nm_lane_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            nm_lane_kernel<Obj><<<grid, wpb * 32, shmem, h->stream>>>(T, h->sc, a);
+        } else {
+            TK_CUDA(cudaFuncSetAttribute(nm_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            nm_kernel<Obj><<<grid, wpb * 32, shmem, h->stream>>>(T, h->sc, a);
+        }
         h->launches++;
         TK_CUDA(cudaGetLastError());
         return TIKTAK_OK;

@@ -204,20 +204,24 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
         T.bu[d] = h->bound[NX + d];
         T.aux[d] = h->aux[d];
     }
-    /* points per thread: enough blocks to fill the machine for small N, long strides for big N */
-    const int64_t pts = owned_cbs * TIKTAK_SOBOL_BLOCK;
-    if (pts >= ((int64_t)1 << 24)) {
-        constexpr int BT = 128, P = 32;
-        const unsigned grid = (unsigned)(owned_cbs * (TIKTAK_SOBOL_BLOCK / (BT * P)));
-        sobol_eval_kernel<Obj, NX, BT, P><<<grid, BT, 0, h->stream>>>(T, h->sc, wv);
-    } else {
-        constexpr int BT = 128, P = 4;
-        const unsigned grid = (unsigned)(owned_cbs * (TIKTAK_SOBOL_BLOCK / (BT * P)));
-        sobol_eval_kernel<Obj, NX, BT, P><<<grid, BT, 0, h->stream>>>(T, h->sc, wv);
-    }
-    h->launches++;
-    TK_CUDA(cudaGetLastError());
-    return TIKTAK_OK;
+    /* points per thread P: the smallest P whose grid is resident in ONE wave (no tail wave, seeding
+     * amortised as little as necessary); a job too big for that takes the longest stride. */
+    constexpr int BT = 128;
+    auto try_launch = [&]<int P>(bool force) -> int {
+        const int64_t grid = owned_cbs * (TIKTAK_SOBOL_BLOCK / (BT * P));
+        int per_sm = 0;
+        TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sobol_eval_kernel<Obj, NX, BT, P>, BT, 0));
+        if (!force && grid > (int64_t)per_sm * h->sm_count) return 1;
+        sobol_eval_kernel<Obj, NX, BT, P><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+        return TIKTAK_OK;
+    };
+    int rc = try_launch.template operator()<4>(false);
+    if (rc == 1) rc = try_launch.template operator()<8>(false);
+    if (rc == 1) rc = try_launch.template operator()<16>(false);
+    if (rc == 1) rc = try_launch.template operator()<32>(true);
+    return rc;
 }
 
 TkTablesG tablesG(tiktak_handle* h) { return TkTablesG{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux}; }
