@@ -1,0 +1,89 @@
+"""CPU tests: the C ABI library loads and exports every declared symbol; struct layout; config parser."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tiktak_b200 import TikTakError, TikTakSearch, baseline_config, lib, parse_config
+from tiktak_b200._abi import TiktakConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "tiktak_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(tiktak_cuda_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_header_symbol(built):
+    L = C.CDLL(lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/tiktak_cuda.h but not exported"
+    assert sorted(lib.SIGNATURES) == names, "tiktak_b200/lib.py binds a different set than the header declares"
+
+
+def test_struct_layout_matches_c(built):
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "tiktak_cuda.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tiktak_config), offsetof(tiktak_config,fvalmax), offsetof(tiktak_config,range), offsetof(tiktak_config,objective_id), offsetof(tiktak_config,nm_ftol), offsetof(tiktak_config,user));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    exp = [C.sizeof(TiktakConfig), TiktakConfig.fvalmax.offset, TiktakConfig.range.offset, TiktakConfig.objective_id.offset,
+           TiktakConfig.nm_ftol.offset, TiktakConfig.user.offset]
+    assert [int(v) for v in out] == exp
+
+
+def test_no_cpu_fallback(built):
+    """without a GPU the product path must fail loudly (never route through the oracle)"""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(TikTakError) as e:
+        TikTakSearch(baseline_config("C1"))
+    assert e.value.code == -4
+    src = open(os.path.join(ROOT, "tiktak_b200", "search.py")).read() + open(os.path.join(ROOT, "tiktak_b200", "lib.py")).read()
+    assert "oracle" not in src.replace("the oracle", "")
+
+
+def test_config_defaults_entry_point(built):
+    L = lib.load()
+    me, nd, lg, mp, lp = (C.c_int32(v) for v in (-1, -1, -1, -1, -1))
+    fv = C.c_double(-1.0)
+    assert L.tiktak_cuda_config_defaults(4, C.byref(me), C.byref(nd), C.byref(lg), C.byref(fv), C.byref(mp), C.byref(lp)) == 0
+    assert (me.value, nd.value, lg.value, fv.value, mp.value, lp.value) == (200, 500, 10500, 1e8, 200, 200)
+    nd, mp = C.c_int32(10), C.c_int32(11)
+    assert L.tiktak_cuda_config_defaults(4, C.byref(me), C.byref(nd), C.byref(lg), C.byref(fv), C.byref(mp), C.byref(lp)) == -1
+    assert b"maxpoints" in L.tiktak_cuda_last_error()
+
+
+def test_parse_shipped_config():
+    cfg = parse_config(os.path.join(ROOT, "tests", "golden", "config_c1.txt"))
+    assert (cfg.nx, cfg.nm, cfg.maxeval, cfg.qr_ndraw, cfg.legitimate, cfg.fvalmax, cfg.maxpoints, cfg.search_type,
+            cfg.lottery_points) == (4, 8, 40 * 5, 20, 10, 50.0, 3, 0, 10)
+    assert cfg.p_maxpoints == 4 and cfg.p_ninterppt == 9
+    assert np.array_equal(cfg.range, [[-1, 1]] * 4) and np.array_equal(cfg.bound, [[-3, 3]] * 4)
+    assert np.array_equal(cfg.init, [0.811530031, -0.185093302, 0.299819619, 0.196328895])
+    ref = baseline_config("C1")
+    for k in ("nx", "nm", "maxeval", "qr_ndraw", "legitimate", "fvalmax", "maxpoints", "lottery_points"):
+        assert getattr(cfg, k) == getattr(ref, k)
+
+
+def test_parse_config_defaults_and_errors(tmp_path):
+    body = "! c\n3\n2\n-1\n-1\n-1\n-1.0\n-1\n0\n-1\n!\n0 1\n0,1\n0 1\n!\n0.5\n0.5\n0.5\n!\n0 1\n0 1\n0 1\n"
+    p = tmp_path / "c.txt"; p.write_text(body)
+    cfg = parse_config(str(p))
+    assert (cfg.maxeval, cfg.qr_ndraw, cfg.legitimate, cfg.fvalmax, cfg.maxpoints, cfg.lottery_points) == (160, 500, 10500, 1e8, 200, 200)
+    p.write_text(body.replace("\n-1\n0\n-1\n!", "\n600\n0\n-1\n!", 1))
+    with pytest.raises(ValueError):
+        parse_config(str(p))
+    p.write_text("3\n2\n")
+    with pytest.raises(ValueError):
+        parse_config(str(p))

@@ -1,0 +1,216 @@
+"""CPU tests: the oracle (oracle/tiktak_oracle.cpp) against known answers.
+
+The reference ships no tests or golden files, so the pins are
+ (1) the known-answer vectors derived from the reference's formulas, and
+ (2) tests/golden/golden_small.json, produced by an independent pure-Python restatement
+     (tests/golden/make_golden.py) that shares no code with the C++ oracle.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.oracle import MATH_LIBM, MATH_TK, Oracle
+from tiktak_b200 import OBJ_GRIEWANK, OBJ_RASTRIGIN, OBJ_ROSENBROCK, baseline_config, make_config
+from tiktak_b200._abi import c_double_p, c_int32_p, dptr
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_small.json")))
+
+
+@pytest.fixture(scope="module")
+def L(built):
+    return orc.load()
+
+
+def unit_points(L, nx, n, atmost=None, quirk=0):
+    out = np.zeros((n, nx))
+    assert L.orc_sobol_unit(nx, atmost or max(n, 1), n, dptr(out), quirk) == 0
+    return out
+
+
+def test_no_fma_contraction(L):
+    assert L.orc_unfused_selfcheck() == 0
+
+
+def test_sobol_first_points_survey(L):
+    exp = np.array([[.5, .5, .5, .5], [.75, .25, .75, .25], [.25, .75, .25, .75], [.375, .375, .625, .125],
+                    [.875, .875, .125, .625], [.625, .125, .375, .375], [.125, .625, .875, .875],
+                    [.1875, .3125, .3125, .6875]])
+    assert np.array_equal(unit_points(L, 4, 8, 20), exp)
+
+
+def test_sobol_matches_independent_python(L):
+    assert np.array_equal(unit_points(L, 4, 16), np.array(GOLD["sobol_unit_nx4_first16"]))
+    assert np.array_equal(unit_points(L, 10, 200), np.array(GOLD["sobol_unit_nx10_first200"]))
+    p50 = unit_points(L, 50, 40)
+    assert np.array_equal(p50[[0, 1, 7, 38, 39]], np.array(GOLD["sobol_unit_nx50_sample"]))
+
+
+def test_sobol_independent_of_atmost(L):
+    a = unit_points(L, 10, 500, atmost=500)
+    b = unit_points(L, 10, 500, atmost=(1 << 30) - 1)
+    assert np.array_equal(a, b)
+    assert L.orc_sobol_maxcol(4, 20) == 5  # C1: maxcol = 5
+
+
+def test_sobol_dims_1_2_match_scipy(L):
+    qmc = pytest.importorskip("scipy.stats.qmc")
+    ref = qmc.Sobol(d=2, scramble=False, bits=30).random(257)[1:]  # scipy starts at the zero vector, Gray order
+    # scipy >= 1.7 generates in Gray-code order as well; dims 1-2 share direction numbers with Bratley-Fox
+    ours = unit_points(L, 2, 256)
+    assert np.array_equal(np.sort(ours, axis=0), np.sort(ref, axis=0))
+    assert np.array_equal(ours, ref)
+
+
+def test_sobol_single_precision_quirk(L):
+    """utilities.f90:1090 `i = floor(real(i/2))`: identical to the integer rule up to Scount 33,554,434,
+    first mismatch at 33,554,435 (l_ref = 2, l_true = 3), then only columns 1..2 are ever used."""
+    for s in [0, 1, 2, 3, 7, 1023, 2**20 - 1, 2**24 + 1, 33554431, 33554433, 33554434]:
+        assert L.orc_sobol_l(s, 1) == L.orc_sobol_l(s, 0), s
+    assert (L.orc_sobol_l(33554435, 1), L.orc_sobol_l(33554435, 0)) == (2, 3)
+    rng = np.random.default_rng(0)
+    for s in rng.integers(33554435, 2**30 - 1, size=2000):
+        lt = L.orc_sobol_l(int(s), 0)
+        assert L.orc_sobol_l(int(s), 1) == min(lt, 2)
+
+
+def test_c1_pretest_and_choose(built):
+    cfg = baseline_config("C1")
+    o = Oracle(cfg, MATH_LIBM)
+    _, ne, nl = o.solveAtSobolPoints()
+    assert (ne, nl) == (10, 10)  # only the first 10 of 20 points are evaluated (legitimate = 10)
+    pts = o.setupSobol(1, 10)
+    assert np.array_equal(pts, np.array(GOLD["c1_points"]))
+    f = o.sobolFnVal()
+    assert np.array_equal(f, np.array(GOLD["c1_fvals"]))  # bit-exact vs the independent restatement
+    surv = [8.0, 12.306743316801496, 12.306743316801496, 10.133087507051615, 16.595497939018895, 11.19727818240388,
+            15.688444943098277, 12.562292117323677, 12.655206982365566, 18.96798569747271]
+    assert np.allclose(f, surv, rtol=3e-16, atol=0)  # SURVEY's figures used 8*v^2, the code sums v^2 eight times
+    assert f[1] == f[2]  # mirror points tie exactly
+    xs = o.chooseSobol(mode=0)
+    assert o.sobol_idx.tolist() == [0, 1, 4, 6] and not o.tie_straddle
+    assert xs[0, 0] == GOLD["c1_finit"] and abs(xs[0, 0] - 14.258672740927095) < 1e-14
+    assert o.objFun([3.5, 0, 0, 0])[0] == GOLD["c1_penalty_case"] == 4145.6790123456785
+
+
+def test_tk_math_vs_libm_objective(built):
+    for name in ("C1",):
+        cfg = baseline_config(name)
+        a, b = Oracle(cfg, MATH_LIBM), Oracle(cfg, MATH_TK)
+        a.solveAtSobolPoints(); b.solveAtSobolPoints()
+        assert np.max(np.abs(a.sobolFnVal() - b.sobolFnVal()) / a.sobolFnVal()) <= 1e-12
+    for oid, nx, lo, hi in ((OBJ_GRIEWANK, 10, -400, 600), (OBJ_RASTRIGIN, 20, -4.12, 5.12)):
+        cfg = make_config(nx, 1, 20000, 10, lo, hi, objective_id=oid)
+        a, b = Oracle(cfg, MATH_LIBM), Oracle(cfg, MATH_TK)
+        a.solveAtSobolPoints(); b.solveAtSobolPoints()
+        assert np.max(np.abs(a.sobolFnVal() - b.sobolFnVal()) / a.sobolFnVal()) <= 1e-12
+
+
+def test_blend_weights_single_precision(L):
+    assert [float(L.orc_w11(k, 4)) for k in range(1, 5)] == GOLD["w11_K4"] == [
+        0.5, 0.7071067690849304, 0.8660253882408142, 0.949999988079071]
+    assert [float(L.orc_w11(k, 1001)) for k in (1, 2, 10, 11, 500, 903, 904, 1001)] == GOLD["w11_K1001"]
+
+
+def test_simplex_coordinates2(L):
+    for n, key in ((4, "simplex4"), (10, "simplex10")):
+        x = np.zeros((n + 1, n))
+        L.orc_simplex_coordinates2(n, dptr(x))
+        g = np.array(GOLD[key])  # (n, n+1)
+        assert np.allclose(x.T, g, rtol=0, atol=2e-16)
+        assert np.allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-15)
+    x = np.zeros((5, 4)); L.orc_simplex_coordinates2(4, dptr(x))
+    assert abs(x[0, 0] - 0.9635254915624212) < 1e-15 and abs(x[0, 1] + 0.1545084971874737) < 1e-15
+    assert abs(x[4, 0] + 0.5000000000000001) < 1e-15
+
+
+def test_indexx_is_a_sort_and_insertion_part_is_stable(L):
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 14, 15, 16, 17, 100, 5000):
+        a = rng.standard_normal(n)
+        idx = np.zeros(n, dtype=np.int32)
+        assert L.orc_indexx(n, dptr(a), idx.ctypes.data_as(c_int32_p)) == 0
+        assert np.array_equal(idx - 1, np.argsort(a, kind="stable"))  # no ties: any correct sort agrees
+    a = np.array([3.0, 1.0, 3.0, 1.0, 2.0, 3.0])  # n < 15 -> pure insertion sort, stable (utilities.f90:1355 `<=`)
+    idx = np.zeros(6, dtype=np.int32)
+    L.orc_indexx(6, dptr(a), idx.ctypes.data_as(c_int32_p))
+    assert idx.tolist() == [2, 4, 5, 1, 3, 6]
+
+
+def test_text_roundtrip_matches_arithmetic_version(L):
+    """snprintf/strtod ('200f40.20' records) vs include/tiktak_math.h's closed form used on the GPU"""
+    src = r'''
+#include "tiktak_math.h"
+double f(double x) { return tk_f4020_roundtrip(x); }
+double c(double x) { return tk_cos(x); }
+double s(double x) { return tk_sin(x); }
+'''
+    import subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        so = os.path.join(d, "t.so")
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-I", os.path.join(root, "include"),
+                               os.path.join(d, "t.c"), "-o", so, "-lm"])
+        T = C.CDLL(so)
+        for fn in (T.f, T.c, T.s):
+            fn.restype = C.c_double; fn.argtypes = [C.c_double]
+        rng = np.random.default_rng(2)
+        xs = np.concatenate([rng.uniform(-1, 1, 4000) * 2.0 ** -rng.integers(0, 45, 4000),
+                             [(2 * k + 1) / 2.0 ** 21 for k in range(64)], [0.0, -0.0, 1e-30, 123.456, -7e-5, 6.103515625e-05]])
+        for x in xs:
+            assert T.f(float(x)) == L.orc_text4020(float(x)) or (x == 0 and T.f(float(x)) == 0)
+        # tk_cos / tk_sin against libm: <= 2 ulp on the ranges the objectives use
+        xs = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-40, 40, 20000), rng.uniform(-1e5, 1e5, 5000)])
+        for x in xs[:8000]:
+            for mine, ref in ((T.c(float(x)), np.cos(x)), (T.s(float(x)), np.sin(x))):
+                assert abs(mine - ref) <= 2.0 * np.spacing(abs(ref)) + 0.0
+
+
+def test_nelder_mead_reaches_known_minima(built):
+    """analytic minima: objFun = nm * (f + 1)^2 with f_min = 0 -> nm"""
+    cfg = make_config(10, 1, 4000, 20, -400.0, 600.0, init=[100.0] * 10, objective_id=OBJ_GRIEWANK, round_size=1)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(); o.LocalMinimizations(1)
+    assert o.evals.max() <= 5000 + 10 + 2
+    fb, xb, kb = o.getBestLine()
+    assert 1.0 <= fb < 1.5
+    cfg = make_config(4, 1, 2000, 10, -2.0, 2.0, init=[0.5] * 4, objective_id=OBJ_ROSENBROCK, round_size=1)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(); o.LocalMinimizations(1)
+    fb, xb, _ = o.getBestLine()
+    assert abs(fb - 1.0) < 1e-3 and np.allclose(xb, 1.0, atol=0.05)
+
+
+def test_round_schedule_and_counter_column(built):
+    cfg = baseline_config("C1")
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol()
+    o.LocalMinimizations(1, round_size=1)
+    seq = o.searchResults.copy(); st = o.searchStart.copy()
+    # restart 1 starts at p_init itself; restart 2 is blended toward the best row so far
+    assert np.array_equal(st[0], cfg.init)
+    assert not np.array_equal(st[1], o.x_starts[1, 1:])
+    assert list(seq[:, 1]) == [1, 2, 3, 4]
+    assert np.all(np.diff(seq[:, 2]) >= 0)  # the #improvements counter never decreases
+    o.LocalMinimizations(1, round_size=4)  # one round: nobody sees a finished search -> pure Sobol starts
+    assert np.array_equal(o.searchStart[1:], o.x_starts[1:, 1:])
+
+
+def test_legitimate_cut_prefix_semantics(built):
+    cfg = make_config(10, 1, 5000, 10, -400.0, 600.0, objective_id=OBJ_GRIEWANK)
+    o = Oracle(cfg, MATH_TK); o.solveAtSobolPoints()
+    f = o.sobolFnVal()
+    med = float(np.median(f))
+    cfg2 = make_config(10, 1, 5000, 10, -400.0, 600.0, objective_id=OBJ_GRIEWANK, fvalmax=med, legitimate=100)
+    o2 = Oracle(cfg2, MATH_TK)
+    _, ne, nl = o2.solveAtSobolPoints()
+    # NB fvalmax also sets the penalty constants, but all Sobol points are inside the bounds
+    valid = np.cumsum(f < med)
+    assert nl == 100 and ne == int(np.argmax(valid >= 100)) + 1
+    cfg3 = make_config(10, 1, 50, 10, -400.0, 600.0, objective_id=OBJ_GRIEWANK, fvalmax=1e-3, legitimate=5)
+    o3 = Oracle(cfg3, MATH_TK)
+    assert o3.solveAtSobolPoints() == (True, 50, 0)  # never reached: all points evaluated (soft goal)

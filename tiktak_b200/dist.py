@@ -53,9 +53,10 @@ def exchange_rows(pack_local, world, group=None, device="cpu"):
     """pack_local (ncol, n_k): this rank's columns are valid for slots s with s % world == rank."""
     torch, dist = _torch()
     mine = torch.as_tensor(np.ascontiguousarray(pack_local, dtype=np.float64)).to(device)
-    allr = torch.empty((world,) + tuple(mine.shape), dtype=torch.float64, device=device)
+    ncol, n_k = mine.shape
+    allr = torch.empty((world * ncol, n_k), dtype=torch.float64, device=device)  # rank-major concatenation
     dist.all_gather_into_tensor(allr, mine, group=group)
-    allh = allr.cpu().numpy()
+    allh = allr.cpu().numpy().reshape(world, ncol, n_k)
     merged = np.empty_like(allh[0])
     for s in range(merged.shape[1]):
         merged[:, s] = allh[s % world, :, s]
