@@ -129,3 +129,24 @@ def test_local_minimizations_nm(built, name, B):
     assert np.array_equal(ge, o.evals)
     ob = o.getBestLine()
     assert abs(gbest[0] - ob[0]) <= 1e-6 * abs(ob[0]) and gbest[2] == ob[2]
+
+
+@pytest.mark.parametrize("name,B,nm", [("template4", 1, 8), ("template4", 4, 8), ("griewank10", 5, 6), ("griewank7", 4, 3),
+                                       ("rastrigin20", 8, 2), ("rosenbrock33", 3, 4)])
+def test_local_minimizations_dfnls(built, name, B, nm):
+    """DFNLS (bobyqa_h family, minimize.f90:262-2563), one restart per block, vs the serial restatement"""
+    cfg = cfg_of(name, round_size=B, nm=nm, maxpoints=min(SMALL[name]["maxpoints"], 9))
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizations("b")
+        gs, gr, ge = s.searchStart, s.searchResults, s.evals
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizations(0)
+    assert np.array_equal(gs, o.searchStart)
+    rel = np.abs(gr[:, 3] - o.searchResults[:, 3]) / np.abs(o.searchResults[:, 3])
+    assert np.max(rel) <= 1e-8, rel  # BASELINE.json bar; bit-exact expected:
+    assert np.array_equal(ge, o.evals)
+    assert np.array_equal(gr, o.searchResults)

@@ -247,10 +247,12 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
                     h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
-                    h->d_out_f, h->d_width, h->d_out_evals};
+                    h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evw0) cudaEventDestroy(h->evw0);
+    if (h->evw1) cudaEventDestroy(h->evw1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -261,7 +263,13 @@ int64_t tiktak_cuda_launch_count(tiktak_handle* h) { return h ? h->launches : 0;
 int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms) {
     if (!h || !stage || !ms) return TIKTAK_ERR_ARG;
     if (!strcmp(stage, "pretest")) *ms = h->ms_pretest;
-    else if (!strcmp(stage, "pretest_eval")) *ms = h->ms_pretest_eval;
+    else if (!strcmp(stage, "pretest_eval")) {
+        if (h->wave_pending) {
+            TK_CUDA(cudaEventSynchronize(h->evw1));
+            float w = 0; cudaEventElapsedTime(&w, h->evw0, h->evw1); h->ms_pretest_eval += w; h->wave_pending = false;
+        }
+        *ms = h->ms_pretest_eval;
+    }
     else if (!strcmp(stage, "choose")) *ms = h->ms_choose;
     else if (!strcmp(stage, "local")) *ms = h->ms_local;
     else return TIKTAK_ERR_ARG;
@@ -341,7 +349,16 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     TkWave wv;
     wv.N = h->cfg.qr_ndraw; wv.cb0 = cb0; wv.ncb = ncb; wv.rank = h->cfg.rank; wv.world = h->cfg.world;
     wv.fval = h->d_fval; wv.counts = h->d_counts;
+    if (!h->evw0) { TK_CUDA(cudaEventCreate(&h->evw0)); TK_CUDA(cudaEventCreate(&h->evw1)); }
+    if (h->wave_pending) { /* fold the previous wave's duration in before the events are reused */
+        TK_CUDA(cudaEventSynchronize(h->evw1));
+        float ms = 0; cudaEventElapsedTime(&ms, h->evw0, h->evw1); h->ms_pretest_eval += ms; h->wave_pending = false;
+    }
+    if (cb0 == 0) h->ms_pretest_eval = 0;
+    TK_CUDA(cudaEventRecord(h->evw0, h->stream));
     int rc = tk_launch_sobol_wave(h, wv);
+    TK_CUDA(cudaEventRecord(h->evw1, h->stream));
+    h->wave_pending = true;
     if (rc) return rc;
     h->cblocks_done = std::max(h->cblocks_done, cb0 + ncb);
     return TIKTAK_OK;
@@ -395,19 +412,12 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     const bool can_cut = (L <= N) && h->cfg.world == 1;
     const int64_t wave = can_cut ? 64 : h->n_cblocks;
     int64_t cum = 0, kcut = -1, nleg = 0;
-    h->ms_pretest_eval = 0;
     for (int64_t cb0 = 0; cb0 < h->n_cblocks && kcut < 0; cb0 += wave) {
         const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
-        cudaEvent_t w0, w1;
-        TK_CUDA(cudaEventCreate(&w0)); TK_CUDA(cudaEventCreate(&w1));
-        TK_CUDA(cudaEventRecord(w0, h->stream));
         rc = tiktak_cuda_pretest_wave(h, cb0, ncb);
-        TK_CUDA(cudaEventRecord(w1, h->stream));
         if (rc) return rc;
         TK_CUDA(cudaMemcpyAsync(h->h_counts.data() + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
         TK_CUDA(cudaStreamSynchronize(h->stream));
-        float wms = 0; cudaEventElapsedTime(&wms, w0, w1); h->ms_pretest_eval += wms;
-        cudaEventDestroy(w0); cudaEventDestroy(w1);
         if (h->cfg.world > 1) continue;
         for (int64_t cb = cb0; cb < cb0 + ncb; cb++) {
             const int64_t c = (int64_t)h->h_counts[cb];
@@ -589,7 +599,7 @@ int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_
                       int32_t* evals) {
     if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
-    if (alg != TIKTAK_ALG_AMOEBA) { tk_set_error("local: algorithm %d not available in this build", alg); return TIKTAK_ERR_UNSUPPORTED; }
+    if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) { tk_set_error("local: algorithm %d not available in this build", alg); return TIKTAK_ERR_UNSUPPORTED; }
     if (n_k == 0) return TIKTAK_OK;
     const int nx = h->cfg.nx;
     TK_CUDA(cudaSetDevice(h->device));
@@ -602,7 +612,9 @@ int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_
     TK_CUDA(cudaMemsetAsync(h->d_out_x, 0, (size_t)n_k * nx * 8, h->stream));
     if ((rc = tk_launch_best(h))) return rc;
     if ((rc = tk_launch_blend(h, first_k, n_k))) return rc;
-    if ((rc = tk_launch_nm(h, first_k, n_k))) return rc;
+    if (alg == TIKTAK_ALG_AMOEBA) rc = tk_launch_nm(h, first_k, n_k);
+    else rc = tk_launch_dfnls(h, first_k, n_k);
+    if (rc) return rc;
     std::vector<double> hs((size_t)n_k * nx), hx((size_t)n_k * nx), hf(n_k);
     std::vector<int> he(n_k);
     TK_CUDA(cudaMemcpyAsync(hs.data(), h->d_starts, hs.size() * 8, cudaMemcpyDeviceToHost, h->stream));

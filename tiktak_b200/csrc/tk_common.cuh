@@ -64,7 +64,8 @@ struct tiktak_handle {
     double nm_scale = 1.0;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw0 = nullptr, evw1 = nullptr;
+    bool wave_pending = false;
     int sm_count = 148;
     int64_t launches = 0;
     TkScalars sc;
@@ -100,6 +101,11 @@ struct tiktak_handle {
     /* local stage scratch */
     double *d_starts = nullptr, *d_out_x = nullptr, *d_out_f = nullptr, *d_width = nullptr;
     int* d_out_evals = nullptr;
+    /* DFNLS */
+    double* d_dfnls_slab = nullptr;
+    size_t dfnls_slab_doubles = 0;
+    double* d_rho = nullptr;
+    int* d_out_status = nullptr;
     /* stage timings */
     double ms_pretest = 0, ms_choose = 0, ms_local = 0, ms_pretest_eval = 0;
 };
@@ -114,6 +120,7 @@ int tk_build_starts(tiktak_handle* h);
 int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k);
+int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
 int tk_fp64_peak(int device, double* flops, double* ms);
 
 /* objective dispatch: calls f.template operator()<Obj>() for the configured plugin */
