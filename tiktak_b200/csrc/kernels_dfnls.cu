@@ -1319,10 +1319,10 @@ int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
     const int threads = mv >= 256 ? 256 : (mv >= 128 ? 128 : 64);
     const size_t shd = (size_t)(3 * nx + nx + npt * nx + npt + nx + nx + nh + ndim * nx + npt * (nptm > 0 ? nptm : 1) + 5 * nx + ndim +
                                 (2 * ndim + 6 * nx + 2 * npt + 16) + nx + (ndim + npt + 8) + nx + threads) * sizeof(double);
-    if (shd > 227 * 1024) { tk_set_error("DFNLS small matrices do not fit in shared memory (nx=%d)", nx); return TIKTAK_ERR_UNSUPPORTED; }
+    if (shd > 226 * 1024) { tk_set_error("DFNLS small matrices do not fit in shared memory (nx=%d)", nx); return TIKTAK_ERR_UNSUPPORTED; }
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
-        TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shd));
         dfnls_kernel<Obj><<<a.n_run, threads, shd, h->stream>>>(T, h->sc, a);
         h->launches++;
         TK_CUDA(cudaGetLastError());
