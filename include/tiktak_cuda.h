@@ -52,6 +52,22 @@ enum {
     TIKTAK_OBJ_SMM = 4         /* synthetic simulated-method-of-moments panel, 1200 moments */
 };
 
+/* parameters of TIKTAK_OBJ_SMM (pass through tiktak_config.user): a synthetic simulated-method-of-
+ * moments problem of the size the reference's README quotes its scaling on (README.md:41-43: "1200+
+ * moments and 7 parameters").  Income process y_it = a_i + z_it + e_it, z_it = rho z_i,t-1 + eta_it,
+ * eta a two-component normal mixture; theta = (rho, sig_alpha, sig_eps, sig_eta1, sig_eta2, p_mix, mu_eta1).
+ * Panel of np persons x T ages simulated from common random numbers (Philox4x32-10, `seed`) on every
+ * evaluation; moments = for each age t and each of the 6 series {y_t, y_{t+k}-y_t, k=1,2,3,5,10} the 5 raw
+ * statistics E s, E s^2, E s^3, E s^4, E|s|  ->  nm = 30 T (1200 at T = 40); data moments simulated at
+ * theta_star with seed+1.  nx must be 7 and nm must be 30*T. */
+typedef struct tiktak_smm_params {
+    int32_t np;            /* persons, multiple of 256 */
+    int32_t T;             /* ages, <= 40 */
+    int32_t seed;          /* p_SEED = 314159265 in the reference (genericParams.f90:24) */
+    int32_t reserved;
+    double theta_star[7];
+} tiktak_smm_params;
+
 /* local-search algorithm ids = the reference's `alg` (genericParams.f90:12-13) */
 enum { TIKTAK_ALG_DFNLS = 0, TIKTAK_ALG_AMOEBA = 1, TIKTAK_ALG_DFPMIN = 2 };
 

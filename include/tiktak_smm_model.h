@@ -1,0 +1,42 @@
+/* tiktak_smm_model.h -- the arithmetic of the synthetic SMM objective (TIKTAK_OBJ_SMM), written once
+ * for host and device so that the CUDA kernels and any host-side user of the plugin agree bit for bit.
+ * (The CPU oracle restates the same model independently in oracle/smm_oracle.inc.)
+ * All operations are plain IEEE +,-,*,/ , comparisons and fabs -- no transcendental functions on the
+ * evaluation path; the common random numbers are drawn once on the host (Philox4x32-10 + Box-Muller).
+ */
+#ifndef TIKTAK_SMM_MODEL_H
+#define TIKTAK_SMM_MODEL_H
+#include "tiktak_math.h"
+
+#define TK_SMM_NSERIES 6
+#define TK_SMM_NSTAT 5
+#define TK_SMM_TMAX 40
+
+/* horizon of series h: 0 = level y_t, else y_{t+k} - y_t */
+TK_HD int tk_smm_horizon(int h) { return h == 0 ? 0 : (h == 1 ? 1 : (h == 2 ? 2 : (h == 3 ? 3 : (h == 4 ? 5 : 10)))); }
+
+/* one person's path: y[t], t = 0..T-1.  Shocks are read with stride `st` (SoA [t][person]). */
+TK_HD void tk_smm_simulate(const double* theta, int T, double alpha0, const double* eta0, const double* eps0, const double* u,
+                           long st, double* y) {
+    const double rho = theta[0], sa = theta[1], se = theta[2], s1 = theta[3], s2 = theta[4], p = theta[5], mu1 = theta[6];
+    const double mu2 = TK_DIV(-TK_MUL(p, mu1), TK_SUB(1.0, p)); /* zero-mean mixture */
+    const double a = TK_MUL(sa, alpha0);
+    double z = 0.0;
+    for (int t = 0; t < T; t++) {
+        const double e0 = eta0[(long)t * st];
+        const double eta = (u[(long)t * st] < p) ? TK_ADD(mu1, TK_MUL(s1, e0)) : TK_ADD(mu2, TK_MUL(s2, e0));
+        z = TK_ADD(TK_MUL(rho, z), eta);
+        y[t] = TK_ADD(TK_ADD(a, z), TK_MUL(se, eps0[(long)t * st]));
+    }
+}
+
+/* accumulate the 5 statistics of one observation s */
+TK_HD void tk_smm_accumulate(double s, double* acc) {
+    const double s2 = TK_MUL(s, s);
+    acc[0] = TK_ADD(acc[0], s);
+    acc[1] = TK_ADD(acc[1], s2);
+    acc[2] = TK_ADD(acc[2], TK_MUL(s2, s));
+    acc[3] = TK_ADD(acc[3], TK_MUL(s2, s2));
+    acc[4] = TK_ADD(acc[4], fabs(s));
+}
+#endif

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from tiktak_b200._abi import TiktakConfig, as_f64, c_double_p, c_int32_p, dptr
+from tiktak_b200._abi import TiktakConfig, as_f64, c_double_p, c_int32_p, dptr, smm_user
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtiktak_oracle.so")
@@ -72,13 +72,14 @@ class Oracle:
         self._range = as_f64(np.asarray(cfg.range).T.reshape(-1))
         self._init = as_f64(cfg.init)
         self._bound = as_f64(np.asarray(cfg.bound).T.reshape(-1))
+        self._user = smm_user(cfg)
         self._c = TiktakConfig(
             nx=cfg.nx, nm=cfg.nm, maxeval=cfg.maxeval, qr_ndraw=cfg.qr_ndraw, legitimate=cfg.legitimate,
             maxpoints_plus1=cfg.p_maxpoints, search_type=cfg.search_type, lottery_points=cfg.lottery_points,
             fvalmax=cfg.fvalmax, range=dptr(self._range), init=dptr(self._init), bound=dptr(self._bound),
             objective_id=cfg.objective_id, device=0, rank=0, world=1, nm_itmax=cfg.nm_itmax,
             nm_shrink_mode=cfg.nm_shrink_mode, sobol_quirk=cfg.sobol_quirk, text_roundtrip=cfg.text_roundtrip,
-            round_size=cfg.round_size, nm_ftol=cfg.nm_ftol, user=None)
+            round_size=cfg.round_size, nm_ftol=cfg.nm_ftol, user=C.cast(C.pointer(self._user), C.c_void_p) if self._user is not None else None)
         self.h = C.c_void_p(self.L.orc_create(C.byref(self._c), math_mode))
         assert self.h, "orc_create failed"
 

@@ -167,6 +167,8 @@ double text4020(double x) {
     return strtod(buf, nullptr);
 }
 
+#include "smm_oracle.inc"
+
 struct Row { /* one searchResults.dat record (TiktakGlobalSearch.f90:594) */
     int seq, k, imp;
     double fval;
@@ -193,6 +195,7 @@ struct Oracle {
     /* local stage */
     std::vector<Row> rows;
     long best_tie_events = 0;
+    SmmOracle smm;
 
     double COS(double a) const { return math_mode ? tk_cos(a) : cos(a); }
     const double* lo_r() const { return range.data(); }
@@ -259,6 +262,8 @@ struct Oracle {
         if (v_err > myeps) {
             double f = v_err / sqrt((double)c.nm);
             for (int m = 0; m < c.nm; m++) F[m] = f;
+        } else if (c.objective_id == TIKTAK_OBJ_SMM) {
+            smm.residuals(x, F);
         } else {
             double v = model_value(x);
             for (int m = 0; m < c.nm; m++) F[m] = v;
@@ -599,6 +604,11 @@ void* orc_create(const tiktak_config* cfg, int math_mode) {
     o->max_penalty = 1000.0 * o->penalty0;
     o->rsq.resize(nx);
     for (int i = 0; i < nx; i++) o->rsq[i] = 1.0 / sqrt((double)(i + 1));
+    if (cfg->objective_id == TIKTAK_OBJ_SMM) {
+        const tiktak_smm_params* sp = (const tiktak_smm_params*)cfg->user;
+        if (!sp || nx != 7 || cfg->nm != 30 * sp->T) { delete o; return nullptr; }
+        o->smm.init(sp);
+    }
     return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }

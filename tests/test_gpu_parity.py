@@ -9,7 +9,7 @@ import pytest
 
 from oracle.oracle import MATH_LIBM, MATH_TK, Oracle
 from tiktak_b200 import (OBJ_GRIEWANK, OBJ_RASTRIGIN, OBJ_ROSENBROCK, OBJ_TEMPLATE, TikTakSearch, baseline_config,
-                         make_config)
+                         make_config, smm_config)
 
 pytestmark = pytest.mark.gpu
 
@@ -150,3 +150,27 @@ def test_local_minimizations_dfnls(built, name, B, nm):
     assert np.max(rel) <= 1e-8, rel  # BASELINE.json bar; bit-exact expected:
     assert np.array_equal(ge, o.evals)
     assert np.array_equal(gr, o.searchResults)
+
+
+def test_smm_objective_pretest_and_dfnls(built):
+    """BASELINE config 5 at reduced panel size: synthetic SMM (30 T moments, 7 parameters, panel simulated per
+    evaluation), legitimate cut with a finite fvalmax, DFNLS local stage."""
+    cfg = smm_config(np_persons=1024, T=20, qr_ndraw=300, legitimate=40, maxpoints=5, fvalmax=20000.0, round_size=3)
+    o = Oracle(cfg, MATH_TK)
+    with TikTakSearch(cfg) as s:
+        pts = np.vstack([cfg.extra["smm"]["theta_star"], cfg.init, [0.999, 0.1, 0.1, 0.1, 0.1, 0.5, 0.0], [0.7, 2.0, 0.3, 0.3, 0.3, 0.5, 0.1]])
+        fg = s.objFun(pts)
+        assert np.array_equal(fg, o.objFun(pts))  # incl. one out-of-bounds point (penalty branch)
+        _, ne, nl = s.solveAtSobolPoints()
+        _, one, onl = o.solveAtSobolPoints()
+        assert (ne, nl) == (one, onl) and nl == 40 and ne < 300
+        assert np.array_equal(s.sobolFnVal(), o.sobolFnVal())
+        xs = s.chooseSobol()
+        assert np.array_equal(xs, o.chooseSobol(mode=1))
+        s.LocalMinimizations("b")
+        o.LocalMinimizations(0)
+        assert np.array_equal(s.searchStart, o.searchStart)
+        assert np.array_equal(s.evals, o.evals)
+        assert np.array_equal(s.searchResults, o.searchResults)
+        fb, xb, kb = s.getBestLine()
+    assert fb < 5.0 and abs(xb[0] - 0.9) < 0.1  # rho recovered near theta_star

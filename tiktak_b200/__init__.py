@@ -5,10 +5,10 @@ include/tiktak_cuda.h); this package is the host mirror of the reference's stage
 """
 from ._abi import (ALG_AMOEBA, ALG_DFNLS, OBJ_GRIEWANK, OBJ_RASTRIGIN, OBJ_ROSENBROCK, OBJ_SMM, OBJ_TEMPLATE,
                    SOBOL_BLOCK)
-from .config import TikTakConfig, baseline_config, make_config, parse_config
+from .config import TikTakConfig, baseline_config, make_config, parse_config, smm_config
 from .lib import TikTakError
 from .search import TikTakSearch
 
-__all__ = ["TikTakSearch", "TikTakConfig", "TikTakError", "parse_config", "make_config", "baseline_config",
+__all__ = ["TikTakSearch", "TikTakConfig", "TikTakError", "parse_config", "make_config", "baseline_config", "smm_config",
            "OBJ_TEMPLATE", "OBJ_GRIEWANK", "OBJ_RASTRIGIN", "OBJ_ROSENBROCK", "OBJ_SMM", "ALG_AMOEBA", "ALG_DFNLS",
            "SOBOL_BLOCK"]

@@ -48,3 +48,18 @@ def as_f64(a):
 
 def dptr(a):
     return a.ctypes.data_as(c_double_p)
+
+
+class TiktakSmmParams(C.Structure):
+    """struct tiktak_smm_params (include/tiktak_cuda.h)"""
+
+    _fields_ = [("np", C.c_int32), ("T", C.c_int32), ("seed", C.c_int32), ("reserved", C.c_int32), ("theta_star", C.c_double * 7)]
+
+
+def smm_user(cfg):
+    """ctypes object for tiktak_config.user from cfg.extra['smm'] (or None)"""
+    d = getattr(cfg, "extra", {}).get("smm") if getattr(cfg, "extra", None) else None
+    if not d:
+        return None
+    return TiktakSmmParams(np=int(d["np"]), T=int(d["T"]), seed=int(d.get("seed", 314159265)), reserved=0,
+                           theta_star=(C.c_double * 7)(*[float(v) for v in d["theta_star"]]))

@@ -150,4 +150,21 @@ def baseline_config(name, **kw):
         return make_config(20, 1, 100_000_000, 10_000, -4.12, 5.12, init=[1.0] * 20, objective_id=OBJ_RASTRIGIN, **kw)
     if name == "C4":
         return make_config(50, 1, 10_000_000, 20_000, -5.0, 10.0, init=[2.5] * 50, objective_id=OBJ_ROSENBROCK, **kw)
+    if name == "C5":
+        return smm_config(**kw)
     raise KeyError(name)
+
+
+#: true parameters and box of the synthetic SMM problem (theta = rho, sig_alpha, sig_eps, sig_eta1, sig_eta2, p_mix, mu_eta1)
+SMM_THETA_STAR = [0.90, 0.45, 0.30, 0.20, 0.60, 0.70, 0.05]
+SMM_BOUNDS = [[0.50, 0.99], [0.05, 1.50], [0.05, 1.50], [0.05, 1.50], [0.05, 1.50], [0.05, 0.95], [-0.50, 0.50]]
+
+
+def smm_config(np_persons=131072, T=40, qr_ndraw=200_000, legitimate=100_000, maxpoints=1000, fvalmax=50.0, **kw):
+    """BASELINE.json configs[4]: synthetic SMM least squares (30 T moments, 7 parameters), DFNLS local stage."""
+    from ._abi import OBJ_SMM
+
+    b = np.asarray(SMM_BOUNDS, dtype=np.float64)
+    extra = {"smm": {"np": np_persons, "T": T, "seed": 314159265, "theta_star": SMM_THETA_STAR}}
+    return make_config(7, 30 * T, qr_ndraw, maxpoints, b[:, 0], b[:, 1], init=0.5 * (b[:, 0] + b[:, 1]), legitimate=legitimate,
+                       fvalmax=fvalmax, objective_id=OBJ_SMM, extra=extra, **kw)

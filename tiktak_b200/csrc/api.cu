@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "tk_common.cuh"
+#include "smm.cuh"
 #include "../../tables/sobol_bf1111.inc"
 
 static thread_local char g_err[1024] = "";
@@ -184,7 +185,9 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     h->sc.sqrt_nm = sqrt((double)cfg->nm);
     h->sc.user = nullptr;
     h->aux.assign(nx, 0.0);
-    int rc = tk_dispatch_obj(cfg->objective_id, [&]<class Obj>() -> int { Obj::host_init(nx, h->aux.data()); return TIKTAK_OK; });
+    int rc = TIKTAK_OK;
+    if (cfg->objective_id != TIKTAK_OBJ_SMM)
+        rc = tk_dispatch_obj(cfg->objective_id, [&]<class Obj>() -> int { Obj::host_init(nx, h->aux.data()); return TIKTAK_OK; });
     if (rc) { delete h; return rc; }
     build_dirnums(nx, h->V);
     build_simplex(nx, h->simplex);
@@ -236,6 +239,10 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     TK_TRY(dalloc(&h->d_out_evals, (size_t)K));
 #undef TK_TRY
     TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (cfg->objective_id == TIKTAK_OBJ_SMM) {
+        rc = tk_smm_init(h);
+        if (rc) { tiktak_cuda_destroy(h); return rc; }
+    }
     *out = h;
     return TIKTAK_OK;
 }
@@ -244,6 +251,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    tk_smm_free(h);
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
                     h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
@@ -325,7 +333,8 @@ int tiktak_cuda_objfun(tiktak_handle* h, const double* x, int64_t n, double* fva
         TK_CUDA(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, h->stream));
     }
     if (!fdev) TK_CUDA(cudaMalloc(&df, fb));
-    rc = tk_launch_objfun(h, xdev ? x : dx, n, fdev ? fval : df);
+    rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_objfun(h, xdev ? x : dx, n, fdev ? fval : df)
+                                                  : tk_launch_objfun(h, xdev ? x : dx, n, fdev ? fval : df);
     if (!rc && !fdev) {
         cudaError_t e = cudaMemcpyAsync(fval, df, fb, cudaMemcpyDeviceToHost, h->stream);
         if (e != cudaSuccess) { tk_set_error("objfun copy: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
@@ -356,7 +365,7 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     }
     if (cb0 == 0) h->ms_pretest_eval = 0;
     TK_CUDA(cudaEventRecord(h->evw0, h->stream));
-    int rc = tk_launch_sobol_wave(h, wv);
+    int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
     TK_CUDA(cudaEventRecord(h->evw1, h->stream));
     h->wave_pending = true;
     if (rc) return rc;
@@ -601,6 +610,10 @@ int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
     if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) { tk_set_error("local: algorithm %d not available in this build", alg); return TIKTAK_ERR_UNSUPPORTED; }
     if (n_k == 0) return TIKTAK_OK;
+    if (alg == TIKTAK_ALG_AMOEBA && h->cfg.objective_id == TIKTAK_OBJ_SMM) {
+        tk_set_error("local: Nelder-Mead is not built for the vector-valued SMM objective; use DFNLS");
+        return TIKTAK_ERR_UNSUPPORTED;
+    }
     const int nx = h->cfg.nx;
     TK_CUDA(cudaSetDevice(h->device));
     int rc = begin_timer(h);

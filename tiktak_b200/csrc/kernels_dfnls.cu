@@ -23,6 +23,7 @@
  * cancellation in a denominator", :748-751) and reports status 1 so callers/tests can see it.
  */
 #include "tk_common.cuh"
+#include "smm.cuh"
 
 namespace {
 
@@ -59,7 +60,7 @@ struct Df {
     DfCtl* ctl;
     const tk_obj_ctx* ctx;
     /* shared small arrays (1-based through the macros below) */
-    double *XBASE, *XPT, *FVAL, *XOPT, *GOPT, *HQ, *BMAT, *ZMAT, *SL, *SU, *XNEW, *XALT, *D, *VLAG, *W, *HD1, *TK, *XC, *VBUF;
+    double *XBASE, *XPT, *FVAL, *XOPT, *GOPT, *HQ, *BMAT, *ZMAT, *SL, *SU, *XNEW, *XALT, *D, *VLAG, *W, *HD1, *TK, *XC, *VBUF, *VSH, *YSH;
     const double *XL, *XU;
     /* global per-moment arrays */
     double *GQV, *HQV, *PQV, *FVAL_V, *WV, *v_sumpq, *v_err, *v_beg, *v_temp, *v_diff, *v_vquad, *PQVold;
@@ -86,18 +87,34 @@ struct Df {
         const DfCtl& c = *ctl;
         switch (op) {
             case OP_DFOVEC: { /* dfovec (objective.f90:76-123) at XC */
-                if (tid == 0) {
-                    const TkMemX x{XC, 1};
-                    const double pen = tk_get_penalty(*ctx, x);
-                    double f;
-                    if (pen > TK_MYEPS) f = TK_DIV(pen, ctx->sqrt_nm);
-                    else f = tk_value_seq<Obj>(*ctx, x);
-                    ctl->d0 = f;
-                    ctl->d1 = pen; /* getPenalty(x), added to F by the caller (:823) */
+                if constexpr (Obj::kVector) {
+                    if (tid == 0) {
+                        const double pen = tk_get_penalty(*ctx, TkMemX{XC, 1});
+                        ctl->d1 = pen; /* getPenalty(x), added to F by the caller (:823) */
+                        ctl->d0 = (pen > TK_MYEPS) ? TK_DIV(pen, ctx->sqrt_nm) : 0.0;
+                    }
+                    bar();
+                    if (ctl->d1 > TK_MYEPS) {
+                        const double f = ctl->d0;
+                        FOR_M { VSH[m1 - 1] = f; V1(v_err, m1) = f; }
+                    } else {
+                        Obj::dfovec_block(ctx->user, XC, VSH, YSH); /* ends with a block barrier */
+                        FOR_M V1(v_err, m1) = VSH[m1 - 1];
+                    }
+                } else {
+                    if (tid == 0) {
+                        const TkMemX x{XC, 1};
+                        const double pen = tk_get_penalty(*ctx, x);
+                        double f;
+                        if (pen > TK_MYEPS) f = TK_DIV(pen, ctx->sqrt_nm);
+                        else f = tk_value_seq<Obj>(*ctx, x);
+                        ctl->d0 = f;
+                        ctl->d1 = pen; /* getPenalty(x), added to F by the caller (:823) */
+                    }
+                    bar();
+                    const double f = ctl->d0;
+                    FOR_M V1(v_err, m1) = f;
                 }
-                bar();
-                const double f = ctl->d0;
-                FOR_M V1(v_err, m1) = f;
                 break;
             }
             case OP_PRELIM_ZERO:
@@ -355,8 +372,12 @@ struct Df {
     __device__ double eval_at_XC() {
         par(OP_DFOVEC);
         double F = 0.0;
-        const double f = ctl->d0;
-        for (int m1 = 1; m1 <= mv; m1++) F = F + f * f; /* all moments equal for scalar plugins: same sum */
+        if constexpr (Obj::kVector) {
+            for (int m1 = 0; m1 < mv; m1++) F = F + VSH[m1] * VSH[m1];
+        } else {
+            const double f = ctl->d0;
+            for (int m1 = 1; m1 <= mv; m1++) F = F + f * f; /* all moments equal for scalar plugins: same sum */
+        }
         return F + ctl->d1;
     }
 
@@ -1236,6 +1257,8 @@ __global__ void __launch_bounds__(256) dfnls_kernel(const TkTablesG T, const TkS
     d.BMAT = take(NDIM * N); d.ZMAT = take(NPT * (d.NPTM > 0 ? d.NPTM : 1)); d.SL = take(N); d.SU = take(N); d.XNEW = take(N);
     d.XALT = take(N); d.D = take(N); d.VLAG = take(NDIM); d.W = take(2 * NDIM + 6 * N + 2 * NPT + 16); d.HD1 = take(N);
     d.TK = take(NDIM + NPT + 8); d.XC = take(N); d.VBUF = take(blockDim.x);
+    d.VSH = nullptr; d.YSH = nullptr;
+    if constexpr (Obj::kVector) { d.VSH = take(d.mv); d.YSH = take(Obj::smem_doubles(sc.user, 0)); }
     /* per-moment slab */
     double* g = a.slab + (size_t)r * a.slab_doubles;
     const size_t mv = (size_t)d.mv;
@@ -1316,11 +1339,20 @@ int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
     a.npt = npt; a.mv = mv;
     a.slab = h->d_dfnls_slab; a.slab_doubles = slab;
     a.out_x = h->d_out_x; a.out_f = h->d_out_f; a.out_evals = h->d_out_evals; a.out_status = h->d_out_status;
-    const int threads = mv >= 256 ? 256 : (mv >= 128 ? 128 : 64);
+    const int threads = (h->cfg.objective_id == TIKTAK_OBJ_SMM || mv >= 256) ? 256 : (mv >= 128 ? 128 : 64);
     const size_t shd = (size_t)(3 * nx + nx + npt * nx + npt + nx + nx + nh + ndim * nx + npt * (nptm > 0 ? nptm : 1) + 5 * nx + ndim +
                                 (2 * ndim + 6 * nx + 2 * npt + 16) + nx + (ndim + npt + 8) + nx + threads) * sizeof(double);
     if (shd > 226 * 1024) { tk_set_error("DFNLS small matrices do not fit in shared memory (nx=%d)", nx); return TIKTAK_ERR_UNSUPPORTED; }
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
+    if (h->cfg.objective_id == TIKTAK_OBJ_SMM) {
+        const size_t shv = shd + (size_t)(mv + TK_SMM_SMEM_DOUBLES(h->smm_T)) * sizeof(double);
+        if (shv > 226 * 1024) { tk_set_error("DFNLS+SMM shared memory"); return TIKTAK_ERR_UNSUPPORTED; }
+        TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<ObjSmm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shv));
+        dfnls_kernel<ObjSmm><<<a.n_run, 256, shv, h->stream>>>(T, h->sc, a);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+        return TIKTAK_OK;
+    }
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
         TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shd));
         dfnls_kernel<Obj><<<a.n_run, threads, shd, h->stream>>>(T, h->sc, a);

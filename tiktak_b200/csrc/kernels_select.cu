@@ -10,6 +10,7 @@
  * among equal keys is an artefact of its partitioning; DESIGN.md "ties").
  */
 #include "tk_common.cuh"
+#include "smm.cuh"
 
 namespace {
 
@@ -219,7 +220,8 @@ int tk_sort_candidates(tiktak_handle* h, const double* d_f, const unsigned int* 
 int tk_build_starts(tiktak_handle* h) {
     const int K = h->cfg.maxpoints_plus1, nx = h->cfg.nx;
     /* row 1: objFun(p_init) evaluated by the same plugin kernel */
-    int rc = tk_launch_objfun(h, h->d_init, 1, h->d_best); /* d_best[0] used as scratch */
+    int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_objfun(h, h->d_init, 1, h->d_best)
+                                                      : tk_launch_objfun(h, h->d_init, 1, h->d_best); /* d_best[0] used as scratch */
     if (rc) return rc;
     init_row_kernel<<<1, 64, 0, h->stream>>>(h->d_init, h->d_best, nx, K, h->d_xstarts);
     h->launches++;

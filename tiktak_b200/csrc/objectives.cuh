@@ -13,6 +13,7 @@
 
 struct ObjTemplate { /* val1 = sum x^2/200 ; val2 = cos(x1) * prod cos(x_i/sqrt(i)) ; v = val1 - val2 + 1 + 1 */
     static constexpr int kId = TIKTAK_OBJ_TEMPLATE;
+    static constexpr bool kVector = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = sqrt((double)(i + 1) + 0.0); /* sqrt(ii+0.0D0), :106 */
     }
@@ -35,6 +36,7 @@ struct ObjTemplate { /* val1 = sum x^2/200 ; val2 = cos(x1) * prod cos(x_i/sqrt(
 
 struct ObjGriewank { /* f = 1 + sum x^2/4000 - prod cos(x_i/sqrt(i)) */
     static constexpr int kId = TIKTAK_OBJ_GRIEWANK;
+    static constexpr bool kVector = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 1.0 / sqrt((double)(i + 1));
     }
@@ -57,6 +59,7 @@ struct ObjGriewank { /* f = 1 + sum x^2/4000 - prod cos(x_i/sqrt(i)) */
 
 struct ObjRastrigin { /* f = 10 n + sum (x^2 - 10 cos(2 pi x)) */
     static constexpr int kId = TIKTAK_OBJ_RASTRIGIN;
+    static constexpr bool kVector = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }
@@ -77,6 +80,7 @@ struct ObjRastrigin { /* f = 10 n + sum (x^2 - 10 cos(2 pi x)) */
 
 struct ObjRosenbrock { /* f = sum_{i<n} 100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2 */
     static constexpr int kId = TIKTAK_OBJ_ROSENBROCK;
+    static constexpr bool kVector = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }

@@ -106,6 +106,9 @@ struct tiktak_handle {
     size_t dfnls_slab_doubles = 0;
     double* d_rho = nullptr;
     int* d_out_status = nullptr;
+    /* TIKTAK_OBJ_SMM */
+    void* smm = nullptr;
+    int smm_T = 0;
     /* stage timings */
     double ms_pretest = 0, ms_choose = 0, ms_local = 0, ms_pretest_eval = 0;
 };

@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from ._abi import ALG_AMOEBA, ALG_DFNLS, SOBOL_BLOCK, TiktakConfig, as_f64, dptr
+from ._abi import ALG_AMOEBA, ALG_DFNLS, SOBOL_BLOCK, TiktakConfig, as_f64, dptr, smm_user
 from .config import TikTakConfig
 
 _ALG = {"a": ALG_AMOEBA, "b": ALG_DFNLS, "amoeba": ALG_AMOEBA, "dfnls": ALG_DFNLS, 0: ALG_DFNLS, 1: ALG_AMOEBA}
@@ -37,13 +37,14 @@ class TikTakSearch:
         self._range = as_f64(np.asarray(cfg.range).T.reshape(-1))  # column-major (nx,2): lo.., hi..
         self._init = as_f64(cfg.init)
         self._bound = as_f64(np.asarray(cfg.bound).T.reshape(-1))
+        self._user = smm_user(cfg)
         self._c = TiktakConfig(
             nx=cfg.nx, nm=cfg.nm, maxeval=cfg.maxeval, qr_ndraw=cfg.qr_ndraw, legitimate=cfg.legitimate,
             maxpoints_plus1=cfg.p_maxpoints, search_type=cfg.search_type, lottery_points=cfg.lottery_points,
             fvalmax=cfg.fvalmax, range=dptr(self._range), init=dptr(self._init), bound=dptr(self._bound),
             objective_id=cfg.objective_id, device=device, rank=rank, world=world, nm_itmax=cfg.nm_itmax,
             nm_shrink_mode=cfg.nm_shrink_mode, sobol_quirk=cfg.sobol_quirk, text_roundtrip=cfg.text_roundtrip,
-            round_size=cfg.round_size, nm_ftol=cfg.nm_ftol, user=None)
+            round_size=cfg.round_size, nm_ftol=cfg.nm_ftol, user=C.cast(C.pointer(self._user), C.c_void_p) if self._user is not None else None)
         self._h = C.c_void_p()
         _lib.check(self._L.tiktak_cuda_create(C.byref(self._h), C.byref(self._c)), "tiktak_cuda_create")
         self.n_evaluated = None
