@@ -33,7 +33,9 @@ import numpy as np  # noqa: E402
 
 # algorithmic FP64 flops per Sobol evaluation, SURVEY.md section 8(d) / BASELINE.md section 3
 F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905}
-ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 1024}
+ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 1024, "C5": 128}
+# C5 (synthetic SMM): HBM-bound, the panel is streamed once per evaluation: 8*(3*np*T + np) + 8*nm bytes
+C5_SIZES = dict(np_persons=131072, T=40, qr_ndraw=20000, legitimate=10000, maxpoints=127)
 
 
 def parse_args():
@@ -42,7 +44,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--round-size", type=int, default=0)
     ap.add_argument("--no-local", action="store_true", help="time only the Sobol stage + selection")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -51,13 +53,13 @@ def parse_args():
 
 
 def workload_config(name, world, round_size=0):
-    from tiktak_b200 import baseline_config
+    from tiktak_b200 import baseline_config, smm_config
 
-    cfg = baseline_config(name)
+    cfg = smm_config(**C5_SIZES) if name == "C5" else baseline_config(name)
     if world > 1:  # weak scaling: per-GPU work fixed
         cfg.qr_ndraw *= world
         cfg.maxpoints *= world
-        cfg.legitimate = cfg.qr_ndraw + 10000
+        cfg.legitimate = cfg.legitimate * world if name == "C5" else cfg.qr_ndraw + 10000
         cfg.lottery_points = cfg.maxpoints
     cfg.round_size = (round_size or ROUND_SIZE[name]) * world
     return cfg
@@ -122,6 +124,8 @@ def _cpu_worker(args):
     t0 = time.perf_counter()
     o.solveAtSobolPoints()
     t1 = time.perf_counter()
+    if name == "C5":  # one DFNLS restart costs 320 panel simulations (~1 min/core): not sampled, see `sample`
+        return t1 - t0, 0.0, npts, 0, 320.0
     o.chooseSobol(mode=0)
     t2 = time.perf_counter()
     o.LocalMinimizations(1, round_size=1)
@@ -140,9 +144,10 @@ def cpu_arm(name, world, budget_s, round_size):
     orc.load()
     cores = os.cpu_count() or 1
     # calibrate on a tiny sample, then size the bounded sample to the budget
-    t_s, t_l, n0, r0, _ = _cpu_worker((name, world, 2000, 2, round_size))
-    per_eval, per_restart = t_s / n0, t_l / r0
-    npts = int(max(2000, min(2_000_000, 0.5 * budget_s / per_eval)))
+    n_cal = 3 if name == "C5" else 2000
+    t_s, t_l, n0, r0, _ = _cpu_worker((name, world, n_cal, 2, round_size))
+    per_eval, per_restart = t_s / n0, (t_l / r0 if r0 else 1.0)
+    npts = int(max(n_cal, min(2_000_000, 0.5 * budget_s / per_eval)))
     nres = int(max(2, min(2000, 0.5 * budget_s / per_restart)))
     with mp.get_context("fork").Pool(cores) as pool:
         t0 = time.perf_counter()
@@ -151,7 +156,7 @@ def cpu_arm(name, world, budget_s, round_size):
     ts = max(o[0] for o in outs)
     tl = max(o[1] for o in outs)
     evals_s = cores * npts / ts
-    restarts_s = cores * (nres + 1) / tl
+    restarts_s = (cores * (nres + 1) / tl) if tl > 0 else evals_s / 320.0
     return {"value": evals_s, "unit": "evals/s", "cores": cores, "kind": "port",
             "sample": f"{cores} independent oracle instances x ({npts} Sobol points of {name} + {nres + 1} "
                       f"Nelder-Mead restarts), libm cos, compute-only; wall {wall:.1f}s",
@@ -241,7 +246,7 @@ def run_graft(args, rank, world, local_rank):
         starts = np.full((K, nx), np.nan); results = np.full((K, nx + 4), np.nan); evals = np.zeros(K, dtype=np.int32)
         for first_k, n_k in s.rounds():
             sb = np.empty((nx, n_k)); r = np.empty((nx + 4, n_k)); e = np.zeros(n_k, dtype=np.int32)
-            lib.check(L.tiktak_cuda_local(s._h, 1, first_k, n_k, sb.ctypes.data, r.ctypes.data, e.ctypes.data), "local")
+            lib.check(L.tiktak_cuda_local(s._h, 0 if name == "C5" else 1, first_k, n_k, sb.ctypes.data, r.ctypes.data, e.ctypes.data), "local")
             tot += s.stage_ms("local")
             if world > 1:
                 r, e = s._exchange_round(r, e, n_k)
@@ -285,7 +290,8 @@ def run_graft(args, rank, world, local_rank):
         timing = "wall clock between device synchronisations per stage (includes the NCCL exchanges), max over ranks"
     eval_ms = mx(np.mean([d["pretest_eval_ms"] for d in dev_steps]))
     step_ms = pre_ms + choose_ms + local_ms
-    value = npts / (pre_ms * 1e-3)
+    n_eval_total = s.n_evaluated if s.n_evaluated else npts  # the legitimate cut may stop early (C5)
+    value = n_eval_total / (pre_ms * 1e-3)
     restarts_s = (nrest / (local_ms * 1e-3)) if local_ms > 0 else None
     e2e_sobol_s = mx(np.mean([d["wall_pretest"] + d["wall_values"] for d in e2e_steps]))
     e2e_step_s = mx(np.mean([d["wall"] for d in e2e_steps]))
@@ -295,21 +301,34 @@ def run_graft(args, rank, world, local_rank):
         fl, ms = C.c_double(), C.c_double()
         lib.check(L.tiktak_cuda_fp64_peak(local_rank, C.byref(fl), C.byref(ms)), "fp64_peak")
         peak_tf = fl.value / 1e12
-        per_gpu_evals = npts / world
-        achieved_tf = per_gpu_evals * F_ALG[name] / (eval_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp64", "kernel": "sobol_eval_kernel", "achieved": achieved_tf, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
-                    "flops_per_eval": F_ALG[name], "evals_per_launch": per_gpu_evals, "kernel_ms": eval_ms,
-                    "peak_source": "measured: DFMA-chain microbenchmark (tiktak_cuda_fp64_peak) on this GPU; "
-                                   "MEASURED_PEAKS.json has no FP64 entry",
-                    "share_of_step": eval_ms / step_ms if step_ms > 0 else None}
+        per_gpu_evals = (s.n_evaluated if name == "C5" else npts) / world
+        if name == "C5":
+            sm = cfg.extra["smm"]
+            bpe = 8 * (3 * sm["np"] * sm["T"] + sm["np"]) + 8 * cfg.nm
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+            ach = per_gpu_evals * bpe / (eval_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "smm_wave_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": ach / peak_gbs, "traffic": None, "bytes_per_eval": bpe, "evals_per_launch": per_gpu_evals,
+                        "kernel_ms": eval_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                        "note": "algorithmic bytes = the panel streamed once per evaluation; concurrent blocks share the "
+                                "panel through the 126 MB L2, so DRAM traffic can be below this figure (frac may exceed 1)",
+                        "fp64_peak_tflops": peak_tf, "share_of_step": eval_ms / step_ms if step_ms > 0 else None}
+        else:
+            achieved_tf = per_gpu_evals * F_ALG[name] / (eval_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp64", "kernel": "sobol_eval_kernel", "achieved": achieved_tf, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                        "flops_per_eval": F_ALG[name], "evals_per_launch": per_gpu_evals, "kernel_ms": eval_ms,
+                        "peak_source": "measured: DFMA-chain microbenchmark (tiktak_cuda_fp64_peak) on this GPU; "
+                                       "MEASURED_PEAKS.json has no FP64 entry",
+                        "share_of_step": eval_ms / step_ms if step_ms > 0 else None}
         cpu = cpu_arm(name, world, args.cpu_seconds, args.round_size) if (world == 1 and not args.no_cpu) else None
         tables_bytes = 32 * 4 * cfg.nx + 5 * 8 * cfg.nx + 64
         line = {
             "metric": "sobol_objective_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name}: {['', '', 'Griewank', 'Rastrigin', 'Rosenbrock'][int(name[1])] if name != 'C1' else 'template'} "
+            "config": {"workload": f"{name}: {['', 'template', 'Griewank', 'Rastrigin', 'Rosenbrock', 'synthetic SMM'][int(name[1])]} "
                                    f"{cfg.nx}-D, qr_ndraw={npts}, maxpoints={cfg.maxpoints} (+1 = {nrest} Nelder-Mead restarts), "
                                    f"round_size={cfg.round_size}, nm_itmax={cfg.nm_itmax}, ftol={cfg.nm_ftol}",
                        "parallelism": f"sobol index blocks + restarts sharded over {world} GPU(s)",
@@ -319,8 +338,8 @@ def run_graft(args, rank, world, local_rank):
             "stage_ms": {"pretest": pre_ms, "pretest_eval_kernel": eval_ms, "choose": choose_ms, "local": local_ms},
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "e2e": {"value": npts / e2e_sobol_s, "unit": "evals/s",
-                    "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": int(npts / world * 8),
+            "e2e": {"value": n_eval_total / e2e_sobol_s, "unit": "evals/s",
+                    "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": int(n_eval_total * 8),
                     "step_s": e2e_step_s, "restarts_per_s": (nrest / wall_local) if wall_local > 0 else None,
                     "what": "solveAtSobolPoints + sobolFnVal (all fvals to host) through the public API, wall clock"},
             "gpu_launches": int(launches),

@@ -421,6 +421,41 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     const bool can_cut = (L <= N) && h->cfg.world == 1;
     const int64_t wave = can_cut ? 64 : h->n_cblocks;
     int64_t cum = 0, kcut = -1, nleg = 0;
+    if (h->cfg.objective_id == TIKTAK_OBJ_SMM && can_cut) {
+        /* one evaluation simulates a whole panel: stop as soon as the cut is reached, in sub-waves of a few
+         * points per SM instead of whole count blocks (same prefix semantics, :429) */
+        if ((rc = tiktak_cuda_pretest_wave(h, 0, 0))) return rc; /* reset state + counts */
+        const int64_t chunk = (int64_t)h->sm_count * 8;
+        std::vector<unsigned long long> cnt(h->n_cblocks);
+        for (int64_t n0 = 1; n0 <= N && kcut < 0; n0 += chunk) {
+            TkWave wv;
+            wv.N = N; wv.cb0 = 0; wv.ncb = h->n_cblocks; wv.rank = 0; wv.world = 1; wv.fval = h->d_fval; wv.counts = h->d_counts;
+            wv.n_lo = n0; wv.n_hi = std::min<int64_t>(N, n0 + chunk - 1);
+            if (!h->evw0) { TK_CUDA(cudaEventCreate(&h->evw0)); TK_CUDA(cudaEventCreate(&h->evw1)); }
+            TK_CUDA(cudaEventRecord(h->evw0, h->stream));
+            if ((rc = tk_launch_smm_wave(h, wv))) return rc;
+            TK_CUDA(cudaEventRecord(h->evw1, h->stream));
+            TK_CUDA(cudaMemcpyAsync(cnt.data(), h->d_counts, (size_t)h->n_cblocks * 8, cudaMemcpyDeviceToHost, h->stream));
+            TK_CUDA(cudaStreamSynchronize(h->stream));
+            float wms = 0; cudaEventElapsedTime(&wms, h->evw0, h->evw1); h->ms_pretest_eval += wms;
+            h->cblocks_done = h->n_cblocks;
+            cum = 0;
+            for (int64_t cb = 0; cb < h->n_cblocks; cb++) {
+                if (cum + (int64_t)cnt[cb] >= L) {
+                    int64_t n = 0;
+                    if ((rc = tiktak_cuda_pretest_find(h, cb, L - cum, &n))) return rc;
+                    kcut = n; nleg = L;
+                    break;
+                }
+                cum += (int64_t)cnt[cb];
+            }
+        }
+        if (kcut < 0) { kcut = N; nleg = cum; }
+        h->kcut = kcut; h->nlegit = nleg; h->pretest_done = true;
+        if (n_evaluated) *n_evaluated = kcut;
+        if (n_legit) *n_legit = nleg;
+        return end_timer(h, &h->ms_pretest);
+    }
     for (int64_t cb0 = 0; cb0 < h->n_cblocks && kcut < 0; cb0 += wave) {
         const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
         rc = tiktak_cuda_pretest_wave(h, cb0, ncb);

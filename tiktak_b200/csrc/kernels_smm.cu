@@ -187,8 +187,9 @@ int tk_launch_smm_wave(tiktak_handle* h, const TkWave& wv) {
     std::vector<int64_t> list;
     for (int64_t cb = wv.cb0; cb < wv.cb0 + wv.ncb; cb++) {
         if (cb % wv.world != wv.rank) continue;
-        const int64_t lo = std::max<int64_t>(1, cb * (int64_t)TIKTAK_SOBOL_BLOCK);
-        const int64_t hi = std::min<int64_t>(wv.N, (cb + 1) * (int64_t)TIKTAK_SOBOL_BLOCK - 1);
+        int64_t lo = std::max<int64_t>(1, cb * (int64_t)TIKTAK_SOBOL_BLOCK);
+        int64_t hi = std::min<int64_t>(wv.N, (cb + 1) * (int64_t)TIKTAK_SOBOL_BLOCK - 1);
+        if (wv.n_hi >= 0) { lo = std::max(lo, wv.n_lo); hi = std::min(hi, wv.n_hi); }
         for (int64_t n = lo; n <= hi; n++) list.push_back(n);
     }
     if (list.empty()) return TIKTAK_OK;

@@ -48,6 +48,7 @@ struct TkWave {
     int rank, world;
     double* fval;         /* local store, indexed by local n (see tk_local_index) */
     unsigned long long* counts; /* per GLOBAL count block */
+    int64_t n_lo = 1, n_hi = -1; /* optional sub-range of indices (expensive objectives: finer early-stop grain); n_hi < 0: all */
 };
 
 __host__ __device__ inline int64_t tk_local_index(int64_t n, int world) {
