@@ -200,6 +200,7 @@ def run_graft(args, rank, world, local_rank):
     L = lib.load()
     s = TikTakSearch(cfg, device=local_rank, rank=rank, world=world)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    pinned = torch.empty(cfg.qr_ndraw, dtype=torch.float64, pin_memory=True).numpy()  # host side of the e2e copy
 
     def barrier():
         torch.cuda.synchronize()
@@ -219,7 +220,7 @@ def run_graft(args, rank, world, local_rank):
         out["pretest_eval_ms"] = s.stage_ms("pretest_eval")
         t1 = time.perf_counter()
         if e2e:
-            fv = s.sobolFnVal()  # D2H of every evaluated fval: the rows of sobolFnVal.dat
+            fv = s.sobolFnVal(out=pinned)  # D2H of every evaluated fval (the rows of sobolFnVal.dat) into pinned memory
             out["d2h"] = fv.nbytes
         t2 = time.perf_counter()
         s.chooseSobol()

@@ -15,9 +15,9 @@
 /* horizon of series h: 0 = level y_t, else y_{t+k} - y_t */
 TK_HD int tk_smm_horizon(int h) { return h == 0 ? 0 : (h == 1 ? 1 : (h == 2 ? 2 : (h == 3 ? 3 : (h == 4 ? 5 : 10)))); }
 
-/* one person's path: y[t], t = 0..T-1.  Shocks are read with stride `st` (SoA [t][person]). */
+/* one person's path: y[t * ys], t = 0..T-1.  Shocks are read with stride `st` (SoA [t][person]). */
 TK_HD void tk_smm_simulate(const double* theta, int T, double alpha0, const double* eta0, const double* eps0, const double* u,
-                           long st, double* y) {
+                           long st, double* y, int ys) {
     const double rho = theta[0], sa = theta[1], se = theta[2], s1 = theta[3], s2 = theta[4], p = theta[5], mu1 = theta[6];
     const double mu2 = TK_DIV(-TK_MUL(p, mu1), TK_SUB(1.0, p)); /* zero-mean mixture */
     const double a = TK_MUL(sa, alpha0);
@@ -26,17 +26,18 @@ TK_HD void tk_smm_simulate(const double* theta, int T, double alpha0, const doub
         const double e0 = eta0[(long)t * st];
         const double eta = (u[(long)t * st] < p) ? TK_ADD(mu1, TK_MUL(s1, e0)) : TK_ADD(mu2, TK_MUL(s2, e0));
         z = TK_ADD(TK_MUL(rho, z), eta);
-        y[t] = TK_ADD(TK_ADD(a, z), TK_MUL(se, eps0[(long)t * st]));
+        y[(long)t * ys] = TK_ADD(TK_ADD(a, z), TK_MUL(se, eps0[(long)t * st]));
     }
 }
 
-/* accumulate the 5 statistics of one observation s */
+/* accumulate the 5 statistics of one observation s.  The power sums use explicit fused multiply-adds
+ * (one rounding each) -- part of the DEFINITION of this synthetic objective; the oracle uses fma() too. */
 TK_HD void tk_smm_accumulate(double s, double* acc) {
     const double s2 = TK_MUL(s, s);
     acc[0] = TK_ADD(acc[0], s);
-    acc[1] = TK_ADD(acc[1], s2);
-    acc[2] = TK_ADD(acc[2], TK_MUL(s2, s));
-    acc[3] = TK_ADD(acc[3], TK_MUL(s2, s2));
+    acc[1] = TK_FMA(s, s, acc[1]);
+    acc[2] = TK_FMA(s2, s, acc[2]);
+    acc[3] = TK_FMA(s2, s2, acc[3]);
     acc[4] = TK_ADD(acc[4], fabs(s));
 }
 #endif

@@ -353,6 +353,7 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     if (cb0 == 0) {
         TK_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
         h->cblocks_done = 0; h->kcut = -1; h->pretest_done = false; h->starts_ready = false;
+        h->ms_pretest_eval = 0; h->wave_pending = false;
     }
     if (ncb == 0) return TIKTAK_OK;
     TkWave wv;
@@ -363,7 +364,6 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
         TK_CUDA(cudaEventSynchronize(h->evw1));
         float ms = 0; cudaEventElapsedTime(&ms, h->evw0, h->evw1); h->ms_pretest_eval += ms; h->wave_pending = false;
     }
-    if (cb0 == 0) h->ms_pretest_eval = 0;
     TK_CUDA(cudaEventRecord(h->evw0, h->stream));
     int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
     TK_CUDA(cudaEventRecord(h->evw1, h->stream));
@@ -489,6 +489,10 @@ int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first, int64_t count, d
     if (!h->pretest_done) return TIKTAK_ERR_STATE;
     TK_CUDA(cudaSetDevice(h->device));
     TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->cfg.world == 1 && first + count - 1 <= h->kcut) { /* one shard, inside the evaluated prefix: one direct copy */
+        TK_CUDA(cudaMemcpy(fval, h->d_fval + first, (size_t)count * 8, cudaMemcpyDefault));
+        return TIKTAK_OK;
+    }
     std::vector<double> tmp((size_t)count, NAN);
     int64_t n = first;
     while (n < first + count) {

@@ -333,14 +333,18 @@ __global__ void __launch_bounds__(128) nm_lane_kernel(const TkTablesG T, const T
         oob |= __ballot_sync(FULL, has_j && (Ci < blj || Ci > buj)) ? 8u : 0u;
         if (has_j) { cand[j] = R; cand[nx + j] = E; cand[2 * nx + j] = Co; cand[3 * nx + j] = Ci; }
         __syncwarp();
-        if (lane < nt) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if ((oob >> c) & 1u) continue;
-                double ta_, tb_;
-                Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, lane, ta_, tb_);
-                ta[c * nx + lane] = ta_;
-                tb[c * nx + lane] = tb_;
+        {   /* the 4*nt independent terms, dealt over all 32 lanes (item e = c*nt + i) */
+            int c = 0, i = lane;
+            while (i >= nt) { i -= nt; c++; }
+            for (int e = lane; e < 4 * nt; e += 32) {
+                if (!((oob >> c) & 1u)) {
+                    double ta_, tb_;
+                    Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, i, ta_, tb_);
+                    ta[c * nx + i] = ta_;
+                    tb[c * nx + i] = tb_;
+                }
+                i += 32;
+                while (i >= nt) { i -= nt; c++; }
             }
         }
         __syncwarp();

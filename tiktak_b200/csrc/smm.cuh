@@ -40,9 +40,7 @@ __device__ inline void tk_smm_dfovec_block(const SmmDev& S, const double* theta,
         tk_smm_bar();
         if (tid < TK_SMM_CHUNK) {
             const long i = c0 + tid;
-            double y[TK_SMM_TMAX];
-            tk_smm_simulate(th, T, S.alpha0[i], S.eta0 + i, S.eps0 + i, S.u + i, (long)S.np, y);
-            for (int t = 0; t < T; t++) ysh[t * TK_SMM_ROW + tid] = y[t]; /* [t][p]: conflict-free */
+            tk_smm_simulate(th, T, S.alpha0[i], S.eta0 + i, S.eps0 + i, S.u + i, (long)S.np, ysh + tid, TK_SMM_ROW); /* [t][p] */
         }
         tk_smm_bar();
 #pragma unroll

@@ -149,10 +149,11 @@ class TikTakSearch:
         self.n_evaluated, self.n_legit = kcut, nleg
         return True, kcut, nleg
 
-    def sobolFnVal(self, first=1, count=None):
-        """fval column of sobolFnVal.dat rows first.. (:467); NaN for points of other shards / beyond the cut."""
+    def sobolFnVal(self, first=1, count=None, out=None):
+        """fval column of sobolFnVal.dat rows first.. (:467); NaN for points of other shards / beyond the cut.
+        `out`: optional preallocated float64 array (e.g. a view of pinned host memory)."""
         count = self.n_evaluated if count is None else count
-        f = np.empty(count, dtype=np.float64)
+        f = np.empty(count, dtype=np.float64) if out is None else out[:count]
         _lib.check(self._L.tiktak_cuda_pretest_values(self._h, first, count, f.ctypes.data), "sobolFnVal")
         return f
 
