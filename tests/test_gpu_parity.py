@@ -174,3 +174,19 @@ def test_smm_objective_pretest_and_dfnls(built):
         assert np.array_equal(s.searchResults, o.searchResults)
         fb, xb, kb = s.getBestLine()
     assert fb < 5.0 and abs(xb[0] - 0.9) < 0.1  # rho recovered near theta_star
+
+
+@pytest.mark.parametrize("name,B", [("griewank10", 5), ("rosenbrock50", 4)])
+def test_nm_shrink_mode(built, name, B):
+    """nm_shrink_mode = 1 (README.md:36 rule; SURVEY finding 3): later restarts scale their initial simplex by the
+    spread of the best minima so far.  Same rule in the oracle -> bit-exact; and it must change something."""
+    cfg = cfg_of(name, round_size=B, nm_shrink_mode=1)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations("a")
+        gr, ge = s.searchResults, s.evals
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(1)
+    assert np.array_equal(gr, o.searchResults) and np.array_equal(ge, o.evals)
+    o0 = Oracle(cfg_of(name, round_size=B, nm_shrink_mode=0), MATH_TK)
+    o0.solveAtSobolPoints(); o0.chooseSobol(mode=1); o0.LocalMinimizations(1)
+    assert not np.array_equal(o0.searchResults, o.searchResults)

@@ -255,7 +255,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
                     h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
-                    h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status};
+                    h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_width_round};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -664,6 +664,42 @@ int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_
     TK_CUDA(cudaMemsetAsync(h->d_out_x, 0, (size_t)n_k * nx * 8, h->stream));
     if ((rc = tk_launch_best(h))) return rc;
     if ((rc = tk_launch_blend(h, first_k, n_k))) return rc;
+    h->use_round_width = false;
+    if (alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1) {
+        /* README.md:36 ("the algorithm takes the min and max of the best local minima found so far and uses
+         * them as the bounds of the initial simplex"), not present in the reference code (SURVEY finding 3):
+         * for restarts in the second half (itratio > 0.5, like the DFNLS radius rule :565) the per-coordinate
+         * simplex width is max-min over the 10 best local minima known at the round's start. */
+        const int K = h->cfg.maxpoints_plus1;
+        std::vector<int> cand;
+        for (int k = 1; k <= K; k++) if (h->h_res_valid[k]) cand.push_back(k);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return h->h_res_f[a] < h->h_res_f[b]; });
+        std::vector<double> wshr(nx);
+        for (int d = 0; d < nx; d++) wshr[d] = h->range[nx + d] - h->range[d];
+        bool have = cand.size() >= 2;
+        if (have) {
+            const int T = (int)std::min<size_t>(cand.size(), 10);
+            std::vector<double> rows((size_t)T * (nx + 1));
+            for (int t = 0; t < T; t++)
+                TK_CUDA(cudaMemcpyAsync(&rows[(size_t)t * (nx + 1)], h->d_res + (size_t)cand[t] * (nx + 1), (size_t)(nx + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+            TK_CUDA(cudaStreamSynchronize(h->stream));
+            for (int d = 0; d < nx; d++) {
+                double mn = rows[1 + d], mx = mn;
+                for (int t = 1; t < T; t++) { const double v = rows[(size_t)t * (nx + 1) + 1 + d]; mn = std::min(mn, v); mx = std::max(mx, v); }
+                if (mx - mn > 0.0) wshr[d] = mx - mn;
+            }
+        }
+        std::vector<double> wr((size_t)n_k * nx);
+        for (int s = 0; s < n_k; s++) {
+            const float itratio = (float)(first_k + s) / (float)K;
+            const bool shrink = have && itratio > 0.5f;
+            for (int d = 0; d < nx; d++) wr[(size_t)d * n_k + s] = shrink ? wshr[d] : (h->range[nx + d] - h->range[d]);
+        }
+        if (!h->d_width_round) TK_CUDA(cudaMalloc(&h->d_width_round, (size_t)K * nx * 8));
+        TK_CUDA(cudaMemcpyAsync(h->d_width_round, wr.data(), wr.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        h->use_round_width = true;
+    }
     if (alg == TIKTAK_ALG_AMOEBA) rc = tk_launch_nm(h, first_k, n_k);
     else rc = tk_launch_dfnls(h, first_k, n_k);
     if (rc) return rc;

@@ -300,6 +300,13 @@ __global__ void __launch_bounds__(128) nm_lane_kernel(const TkTablesG T, const T
     if (has_j)
         for (int i = 0; i < np; i++) psum = TK_ADD(psum, p[i * nx + j]);
 
+    int item_c[4], item_i[4]; /* this lane's (trial point, term) items; c = 4 marks "none" */
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int e = lane + 32 * u;
+        item_c[u] = (e < 4 * nt) ? e / nt : 4;
+        item_i[u] = (e < 4 * nt) ? e - item_c[u] * nt : 0;
+    }
     int iter = 0, ilo = 0;
     for (;;) {
         const unsigned long long key = nm_order_key(yl);
@@ -333,18 +340,16 @@ __global__ void __launch_bounds__(128) nm_lane_kernel(const TkTablesG T, const T
         oob |= __ballot_sync(FULL, has_j && (Ci < blj || Ci > buj)) ? 8u : 0u;
         if (has_j) { cand[j] = R; cand[nx + j] = E; cand[2 * nx + j] = Co; cand[3 * nx + j] = Ci; }
         __syncwarp();
-        {   /* the 4*nt independent terms, dealt over all 32 lanes (item e = c*nt + i) */
-            int c = 0, i = lane;
-            while (i >= nt) { i -= nt; c++; }
-            for (int e = lane; e < 4 * nt; e += 32) {
-                if (!((oob >> c) & 1u)) {
-                    double ta_, tb_;
-                    Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, i, ta_, tb_);
-                    ta[c * nx + i] = ta_;
-                    tb[c * nx + i] = tb_;
-                }
-                i += 32;
-                while (i >= nt) { i -= nt; c++; }
+        /* the 4*nt independent terms, dealt over all 32 lanes (item e = lane + 32u = c*nt + i); the loop is
+         * unrolled so that the (latency-bound) term chains of one lane interleave */
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = item_c[u], i = item_i[u];
+            if (c < 4 && !((oob >> c) & 1u)) {
+                double ta_, tb_;
+                Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, i, ta_, tb_);
+                ta[c * nx + i] = ta_;
+                tb[c * nx + i] = tb_;
             }
         }
         __syncwarp();
@@ -503,8 +508,8 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     a.n_run = (n_k > a.rank) ? (n_k - a.rank + a.world - 1) / a.world : 0;
     if (a.n_run <= 0) return TIKTAK_OK;
     a.starts = h->d_starts;
-    a.width = h->d_width;
-    a.per_restart_width = 0;
+    a.width = h->use_round_width ? h->d_width_round : h->d_width;
+    a.per_restart_width = h->use_round_width ? 1 : 0;
     a.simplex = h->d_simplex;
     a.scale = h->nm_scale;
     a.ftol = h->cfg.nm_ftol;

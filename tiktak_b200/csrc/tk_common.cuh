@@ -102,6 +102,8 @@ struct tiktak_handle {
     /* local stage scratch */
     double *d_starts = nullptr, *d_out_x = nullptr, *d_out_f = nullptr, *d_width = nullptr;
     int* d_out_evals = nullptr;
+    double* d_width_round = nullptr; /* (n_k, nx) column-major per-restart simplex widths (nm_shrink_mode = 1) */
+    bool use_round_width = false;
     /* DFNLS */
     double* d_dfnls_slab = nullptr;
     size_t dfnls_slab_doubles = 0;
