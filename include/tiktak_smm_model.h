@@ -22,11 +22,29 @@ TK_HD void tk_smm_simulate(const double* theta, int T, double alpha0, const doub
     const double mu2 = TK_DIV(-TK_MUL(p, mu1), TK_SUB(1.0, p)); /* zero-mean mixture */
     const double a = TK_MUL(sa, alpha0);
     double z = 0.0;
-    for (int t = 0; t < T; t++) {
-        const double e0 = eta0[(long)t * st];
-        const double eta = (u[(long)t * st] < p) ? TK_ADD(mu1, TK_MUL(s1, e0)) : TK_ADD(mu2, TK_MUL(s2, e0));
-        z = TK_ADD(TK_MUL(rho, z), eta);
-        y[(long)t * ys] = TK_ADD(TK_ADD(a, z), TK_MUL(se, eps0[(long)t * st]));
+    /* ages in groups of 8: the 24 shock loads of a group are independent of the z recursion and are issued
+     * together (memory-level parallelism on the device); the arithmetic order is unchanged */
+    for (int t0 = 0; t0 < T; t0 += 8) {
+        double e0[8], uu[8], ep[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 8; j++) {
+            const int t = (t0 + j < T) ? t0 + j : T - 1;
+            e0[j] = eta0[(long)t * st];
+            uu[j] = u[(long)t * st];
+            ep[j] = eps0[(long)t * st];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 8; j++) {
+            if (t0 + j < T) {
+                const double eta = (uu[j] < p) ? TK_ADD(mu1, TK_MUL(s1, e0[j])) : TK_ADD(mu2, TK_MUL(s2, e0[j]));
+                z = TK_ADD(TK_MUL(rho, z), eta);
+                y[(long)(t0 + j) * ys] = TK_ADD(TK_ADD(a, z), TK_MUL(se, ep[j]));
+            }
+        }
     }
 }
 
