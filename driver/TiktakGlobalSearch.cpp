@@ -1,0 +1,204 @@
+/* TiktakGlobalSearch -- host driver with the reference's process surface, on top of libtiktak_cuda.
+ *
+ *     ./TiktakGlobalSearch <-1|0|1|2|3|4|5> configfile <a|b|d>        (README.md:50-70)
+ *
+ * Mirrors, for one instance on one GPU: parseCommandLine (TiktakGlobalSearch.f90:1150-1246), parseConfig
+ * (genericParams.f90:265-450), the state sequence 1->2->3->(4)->6->7->(8)->10 of a cold start (:217-401)
+ * and the output files with their record formats:
+ *   sobol.dat / x_starts.dat   mywrite2  '(1x,1000(3x,F30.15))'   (stateControl.f90:283)
+ *   sobolFnVal.dat             '(i8, 200f40.20)'                   (TiktakGlobalSearch.f90:467)
+ *   searchStart.dat            '(2i10, 200f40.20)'                 (:598)
+ *   searchResults.dat          '(3i10, 200f40.20)'                 (:597)
+ *   FinalStart.dat / FinalResults.dat '(2i10, 200f40.20)'          (:677)
+ *   state.dat, seqNo.dat, lastSobol.dat, legitSobol.dat, lastParam.dat  list-directed integers
+ * The reference's Fortran toolchain is not in the build image, so this driver is C++; the Fortran
+ * binding of the same ABI is in INTEGRATION.md.  Options 1/2/3/-1 coordinate several CPU processes through
+ * lock files in the reference; with device-resident state there is nothing to join, so they only report that.
+ * Knobs outside the reference surface come from the environment: TIKTAK_OBJECTIVE (0 template, 1 Griewank,
+ * 2 Rastrigin, 3 Rosenbrock), TIKTAK_ROUND_SIZE (default 1 = the sequential reference order), TIKTAK_DEVICE,
+ * TIKTAK_WRITE_SOBOL (1 = also dump sobol.dat like setupSobol does).
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../include/tiktak_cuda.h"
+
+static void usage() { /* myusage, :1235-1246 */
+    printf("Usage: TiktakGlobalSearch <-1|0|1|2|3|4|5> [configfile] [a|b|d]\n"
+           "  -1 exit state, 0 cold start, 1 warm start, 2 update sobol points, 3 update local searches,\n"
+           "   4 diagnostic (objective at the initial guess), 5 local minimization from the initial guess\n"
+           "  a = amoeba (Nelder-Mead), b = DFNLS (default), d = dfpmin (BFGS)\n");
+}
+static bool next_data_line(std::ifstream& f, std::string& line) {
+    while (std::getline(f, line)) { if (!line.empty() && line[0] == '!') continue; return true; }
+    return false;
+}
+static std::vector<double> nums(const std::string& line, size_t n) {
+    std::string s = line.substr(0, line.find('!'));
+    for (char& c : s) { if (c == ',') c = ' '; if (c == 'D' || c == 'd') c = 'e'; }
+    std::istringstream is(s);
+    std::vector<double> v; double x;
+    while (v.size() < n && (is >> x)) v.push_back(x);
+    return v;
+}
+struct Cfg { int nx, nm, maxeval, qr, legit, maxpoints, stype, lottery; double fvalmax; std::vector<double> range, init, bound; };
+static bool parse_config(const char* path, Cfg& c) { /* parseConfig, genericParams.f90:265-450 */
+    std::ifstream f(path);
+    if (!f) { printf("<genericParams.parseConfig()> Error: unable to open file:%s\n", path); return false; }
+    std::string line;
+    double sc[9];
+    if (!next_data_line(f, line) || nums(line, 1).empty()) goto bad;
+    sc[0] = nums(line, 1)[0];
+    for (int i = 1; i < 9; i++) { if (!std::getline(f, line) || nums(line, 1).empty()) goto bad; sc[i] = nums(line, 1)[0]; }
+    c.nx = (int)sc[0]; c.nm = (int)sc[1]; c.maxeval = (int)sc[2]; c.qr = (int)sc[3]; c.legit = (int)sc[4]; c.fvalmax = sc[5];
+    c.maxpoints = (int)sc[6]; c.stype = (int)sc[7]; c.lottery = (int)sc[8];
+    if (tiktak_cuda_config_defaults(c.nx, &c.maxeval, &c.qr, &c.legit, &c.fvalmax, &c.maxpoints, &c.lottery)) {
+        printf("<genericParams:parseConfig> Error in config file. maxpoints > # sobol points\n"); return false;
+    }
+    c.range.assign(2 * c.nx, 0); c.init.assign(c.nx, 0); c.bound.assign(2 * c.nx, 0);
+    for (int grp = 0; grp < 3; grp++) {
+        for (int i = 0; i < c.nx; i++) {
+            if (!(i == 0 ? next_data_line(f, line) : (bool)std::getline(f, line))) goto bad;
+            std::vector<double> v = nums(line, grp == 1 ? 1 : 2);
+            if (v.size() < (size_t)(grp == 1 ? 1 : 2)) goto bad;
+            if (grp == 0) { c.range[i] = v[0]; c.range[c.nx + i] = v[1]; }      /* column-major (nx,2) */
+            else if (grp == 1) c.init[i] = v[0];
+            else { c.bound[i] = v[0]; c.bound[c.nx + i] = v[1]; }
+        }
+    }
+    return true;
+bad:
+    printf("<genericParams:parseConfig> Error. %s Unable to read all parameters\n", path);
+    return false;
+}
+static void write_int(const char* file, long v) { FILE* f = fopen(file, "w"); if (f) { fprintf(f, " %11ld\n", v); fclose(f); } }
+static void logmsg(const std::string& m) { FILE* f = fopen("logFile.txt", "a"); if (f) { fprintf(f, " %s\n", m.c_str()); fclose(f); } printf(" %s\n", m.c_str()); }
+static void mywrite2(const char* file, const double* a, int rows, int cols) { /* a is column-major (rows, cols) */
+    FILE* f = fopen(file, "w");
+    if (!f) return;
+    for (int r = 0; r < rows; r++) { fputc(' ', f); for (int c = 0; c < cols; c++) fprintf(f, "   %30.15f", a[(size_t)c * rows + r]); fputc('\n', f); }
+    fclose(f);
+}
+#define CHECK(call) do { int rc_ = (call); if (rc_) { char b_[1200]; snprintf(b_, sizeof b_, "EXIT STATE: %s: %s; %s", #call, tiktak_cuda_strerror(rc_), tiktak_cuda_last_error()); \
+    logmsg(b_); write_int("state.dat", -1); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    if (argc < 2) { usage(); return 0; }
+    const int option = atoi(argv[1]);
+    int alg = 0; /* p_default_alg = 0 = DFNLS (genericParams.f90:12) */
+    const char* config = argc >= 3 ? argv[2] : "config.txt";
+    const char* algarg = option == 1 ? (argc >= 3 ? argv[2] : nullptr) : (argc >= 4 ? argv[3] : nullptr); /* warm start: alg is arg 2 */
+    if (algarg) { if (algarg[0] == 'a') alg = 1; else if (algarg[0] == 'b') alg = 0; else if (algarg[0] == 'd') alg = 2; else { usage(); return 0; } }
+    if (option < -1 || option > 5) { usage(); return 0; }
+    if (option == -1) { write_int("state.dat", -1); logmsg("exit state written; no other instance is attached to device-resident state"); return 0; }
+    if (option == 1 || option == 2 || option == 3) {
+        logmsg("options 1-3 join/extend a multi-process CPU run through the .dat lock files; the GPU library keeps that state "
+               "on the device and runs the whole job in one cold start (option 0). Nothing to do.");
+        return 0;
+    }
+    Cfg c;
+    if (!parse_config(config, c)) return 1;
+    auto envi = [](const char* k, int d) { const char* v = getenv(k); return v ? atoi(v) : d; };
+    tiktak_config tc;
+    memset(&tc, 0, sizeof tc);
+    tc.nx = c.nx; tc.nm = c.nm; tc.maxeval = c.maxeval; tc.qr_ndraw = c.qr; tc.legitimate = c.legit; tc.maxpoints_plus1 = c.maxpoints + 1;
+    tc.search_type = c.stype; tc.lottery_points = c.lottery; tc.fvalmax = c.fvalmax;
+    tc.range = c.range.data(); tc.init = c.init.data(); tc.bound = c.bound.data();
+    tc.objective_id = envi("TIKTAK_OBJECTIVE", 0); tc.device = envi("TIKTAK_DEVICE", 0); tc.rank = 0; tc.world = 1;
+    tc.nm_itmax = 5000; tc.nm_ftol = 1.0e-4; tc.text_roundtrip = 1; tc.round_size = envi("TIKTAK_ROUND_SIZE", 1);
+    tiktak_handle* h = nullptr;
+    const int K = tc.maxpoints_plus1, nx = c.nx, seqNo = 1;
+    write_int("state.dat", 0);
+    CHECK(tiktak_cuda_create(&h, &tc));
+    write_int("seqNo.dat", seqNo);
+    if (option == 4) { /* :138-149 */
+        double f;
+        printf(" Running diagnostics for the initial guess:\n");
+        CHECK(tiktak_cuda_objfun(h, c.init.data(), 1, &f));
+        printf("Objective value = %12.6f\n", f);
+        tiktak_cuda_destroy(h);
+        return 0;
+    }
+    if (alg == 2 && option != 5) { logmsg("<main:search> dfpmin as the stage-7 algorithm is not built; use a or b"); tiktak_cuda_destroy(h); return 1; }
+    for (const char* fn : {"sobolFnVal.dat", "searchStart.dat", "searchResults.dat", "FinalStart.dat", "FinalResults.dat", "logFile.txt"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); }
+    /* states 2-5 */
+    write_int("state.dat", 2);
+    if (envi("TIKTAK_WRITE_SOBOL", 0) && c.qr > 0) {
+        std::vector<double> pts((size_t)c.qr * nx);
+        CHECK(tiktak_cuda_sobol_points(h, 1, c.qr, pts.data()));
+        mywrite2("sobol.dat", pts.data(), c.qr, nx);
+    }
+    write_int("state.dat", 3);
+    int64_t ne = 0, nl = 0;
+    CHECK(tiktak_cuda_pretest(h, &ne, &nl));
+    {
+        FILE* f = fopen("sobolFnVal.dat", "a");
+        const int64_t chunk = 65536;
+        std::vector<double> fv(chunk), pts((size_t)chunk * nx);
+        for (int64_t first = 1; first <= ne; first += chunk) {
+            const int64_t cnt = std::min<int64_t>(chunk, ne - first + 1);
+            CHECK(tiktak_cuda_pretest_values(h, first, cnt, fv.data()));
+            CHECK(tiktak_cuda_sobol_points(h, first, cnt, pts.data()));
+            for (int64_t r = 0; r < cnt; r++) {
+                fprintf(f, "%8lld%40.20f", (long long)(first + r), fv[r]);
+                for (int d = 0; d < nx; d++) fprintf(f, "%40.20f", pts[(size_t)d * cnt + r]);
+                fputc('\n', f);
+            }
+        }
+        fclose(f);
+    }
+    write_int("lastSobol.dat", (long)ne + 1);
+    write_int("legitSobol.dat", (long)nl);
+    { char b[200]; snprintf(b, sizeof b, "%d has evaluated %lld sobol points, %lld legitimate", seqNo, (long long)ne, (long long)nl); logmsg(b); }
+    /* state 6 */
+    write_int("state.dat", 6);
+    std::vector<double> xs((size_t)K * (nx + 1));
+    std::vector<int32_t> idx(K);
+    CHECK(tiktak_cuda_choose(h, xs.data(), idx.data()));
+    mywrite2("x_starts.dat", xs.data(), K, nx + 1);
+    /* state 7 */
+    write_int("state.dat", 7);
+    {
+        FILE* fr = fopen("searchResults.dat", "a"); FILE* fs = fopen("searchStart.dat", "a");
+        fprintf(fr, "%10d%10d%10d", seqNo, 0, 0); for (int c2 = 0; c2 <= nx; c2++) fprintf(fr, "%40.20f", xs[(size_t)c2 * K]); fputc('\n', fr); /* :496-501 */
+        fprintf(fs, "%10d%10d", seqNo, 0); for (int c2 = 1; c2 <= nx; c2++) fprintf(fs, "%40.20f", xs[(size_t)c2 * K]); fputc('\n', fs);
+        const int B = tc.round_size < 1 ? 1 : tc.round_size;
+        int k0 = option == 5 ? 1 : 1, kend = option == 5 ? 1 : K; /* option 5: only the initial guess (:151-197) */
+        for (; k0 <= kend; k0 += B) {
+            const int nk = std::min(B, kend - k0 + 1);
+            std::vector<double> st((size_t)nk * nx), rs((size_t)nk * (nx + 4));
+            std::vector<int32_t> ev(nk);
+            CHECK(tiktak_cuda_local(h, alg, k0, nk, st.data(), rs.data(), ev.data()));
+            for (int s = 0; s < nk; s++) {
+                fprintf(fs, "%10d%10d", seqNo, k0 + s); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[(size_t)d * nk + s]); fputc('\n', fs);
+                fprintf(fr, "%10d%10d%10d", seqNo, k0 + s, (int)rs[(size_t)2 * nk + s]);
+                for (int d = 3; d < nx + 4; d++) fprintf(fr, "%40.20f", rs[(size_t)d * nk + s]);
+                fputc('\n', fr);
+            }
+        }
+        fclose(fr); fclose(fs);
+        write_int("lastParam.dat", (long)kend + 1);
+    }
+    /* state 10: lastSearch */
+    write_int("state.dat", 10);
+    {
+        double fb; std::vector<double> xb(nx); int32_t kb, it;
+        CHECK(tiktak_cuda_best(h, &fb, xb.data(), &kb));
+        FILE* f = fopen("FinalStart.dat", "a");
+        fprintf(f, "%10d%10d", seqNo, kb); for (int d = 0; d < nx; d++) fprintf(f, "%40.20f", xb[d]); fputc('\n', f); fclose(f);
+        double ff; std::vector<double> xf(nx);
+        CHECK(tiktak_cuda_last_search(h, &ff, xf.data(), &it));
+        f = fopen("FinalResults.dat", "a");
+        fprintf(f, "%10d%10d%40.20f", seqNo, kb, ff); for (int d = 0; d < nx; d++) fprintf(f, "%40.20f", xf[d]); fputc('\n', f); fclose(f);
+        char b[300]; snprintf(b, sizeof b, "The best final point is %.12f (restart %d), after the final search %.12f", fb, kb, ff); logmsg(b);
+    }
+    { char b[100]; snprintf(b, sizeof b, "%d has no more tasks.", seqNo); logmsg(b); }
+    tiktak_cuda_destroy(h);
+    return 0;
+}

@@ -156,6 +156,13 @@ class Oracle:
         assert self.L.orc_best(self.h, C.byref(f), dptr(x), C.byref(k)) == 0
         return f.value, x, k.value
 
+    def lastSearch(self):
+        f, it = C.c_double(), C.c_int32()
+        x = np.empty(self.cfg.nx)
+        self.L.orc_last_search.argtypes = [C.c_void_p, c_double_p, c_double_p, c_int32_p]
+        assert self.L.orc_last_search(self.h, C.byref(f), dptr(x), C.byref(it)) == 0
+        return f.value, x, it.value
+
     def run_amoeba(self, start):
         p = as_f64(start).copy()
         it = C.c_int32()

@@ -505,6 +505,103 @@ struct Oracle {
         rows.push_back(r);
     }
 
+    /* EST_dfpmin with dograd and lnsrch (minimize.f90:2572-2816): BFGS with central-difference gradients.
+     * Sums (DOT_PRODUCT, MATMUL) in index order.  Where lnsrch returns early on slope >= 0 (:2760-2763) the
+     * reference leaves x and f unset; here they stay at xold / fold. */
+    int dfpmin(std::vector<double>& p, double& fret, int itmax, double gtol) {
+        const int nn = c.nx;
+        const double stpmx = 100.0, eps = 2.220446049250313e-16, tolx = 4.0 * eps, xinc = 1.0e-5;
+        auto func = [&](const std::vector<double>& x) { return objFun(x.data()); };
+        auto dograd = [&](const std::vector<double>& x) {
+            std::vector<double> dh(nn), yy(nn), grad(nn);
+            const double tolera = 10.0 * xinc;
+            for (int i = 0; i < nn; i++) dh[i] = (fabs(x[i]) >= tolera) ? x[i] * xinc : xinc;
+            for (int i = 0; i < nn; i++) {
+                for (int j = 0; j < nn; j++) yy[j] = x[j] - (i == j ? dh[i] : 0.0);
+                double tempf1 = func(yy);
+                for (int j = 0; j < nn; j++) yy[j] = x[j] + (i == j ? dh[i] : 0.0);
+                double tempf2 = func(yy);
+                grad[i] = (tempf2 - tempf1) / (2.0 * dh[i]);
+            }
+            return grad;
+        };
+        auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double s = 0.0; for (int i = 0; i < nn; i++) s = s + a[i] * b[i]; return s; };
+        auto lnsrch = [&](const std::vector<double>& xold, double fold, const std::vector<double>& g, std::vector<double>& pdir,
+                          std::vector<double>& x, double& f, double stpmax) {
+            const double alf = 1.0e-4, tolx2 = eps;
+            double a, alam, alam2 = 0, alamin, b, disc, f2 = 0, pabs, rhs1, rhs2, slope, tmplam;
+            pabs = sqrt(dot(pdir, pdir));
+            if (pabs > stpmax) for (int i = 0; i < nn; i++) pdir[i] = pdir[i] * stpmax / pabs;
+            slope = dot(g, pdir);
+            x = xold; f = fold;
+            if (slope >= 0.0) return;
+            double mx = 0.0;
+            for (int i = 0; i < nn; i++) mx = std::max(mx, fabs(pdir[i]) / std::max(fabs(xold[i]), 1.0));
+            alamin = tolx2 / mx;
+            alam = 1.0;
+            for (;;) {
+                for (int i = 0; i < nn; i++) x[i] = xold[i] + alam * pdir[i];
+                f = func(x);
+                if (alam < alamin) { x = xold; return; }
+                else if (f <= fold + alf * alam * slope) return;
+                else {
+                    if (alam == 1.0) tmplam = -slope / (2.0 * (f - fold - slope));
+                    else {
+                        rhs1 = f - fold - alam * slope;
+                        rhs2 = f2 - fold - alam2 * slope;
+                        a = (rhs1 / (alam * alam) - rhs2 / (alam2 * alam2)) / (alam - alam2);
+                        b = (-alam2 * rhs1 / (alam * alam) + alam * rhs2 / (alam2 * alam2)) / (alam - alam2);
+                        if (a == 0.0) tmplam = -slope / (2.0 * b);
+                        else {
+                            disc = b * b - 3.0 * a * slope;
+                            if (disc < 0.0) tmplam = 0.5 * alam;
+                            else if (b <= 0.0) tmplam = (-b + sqrt(disc)) / (3.0 * a);
+                            else tmplam = -slope / (b + sqrt(disc));
+                        }
+                        if (tmplam > 0.5 * alam) tmplam = 0.5 * alam;
+                    }
+                }
+                alam2 = alam;
+                f2 = f;
+                alam = std::max(tmplam, 0.1 * alam);
+            }
+        };
+        double fp = func(p);
+        std::vector<double> g = dograd(p), dg(nn), hdg(nn), pnew(nn), xi(nn), hessin((size_t)nn * nn, 0.0);
+        for (int i = 0; i < nn; i++) hessin[(size_t)i * nn + i] = 1.0;
+        for (int i = 0; i < nn; i++) xi[i] = -g[i];
+        const double stpmax = stpmx * std::max(sqrt(dot(p, p)), (double)nn);
+        fret = fp;
+        for (int its = 1; its <= itmax; its++) {
+            lnsrch(p, fp, g, xi, pnew, fret, stpmax);
+            fp = fret;
+            for (int i = 0; i < nn; i++) xi[i] = pnew[i] - p[i];
+            p = pnew;
+            double t = 0.0;
+            for (int i = 0; i < nn; i++) t = std::max(t, fabs(xi[i]) / std::max(fabs(p[i]), 1.0));
+            if (t < tolx) return its;
+            dg = g;
+            g = dograd(p);
+            const double den = std::max(fret, 1.0);
+            t = 0.0;
+            for (int i = 0; i < nn; i++) t = std::max(t, fabs(g[i]) * std::max(fabs(p[i]), 1.0) / den);
+            if (t < gtol) return its;
+            for (int i = 0; i < nn; i++) dg[i] = g[i] - dg[i];
+            for (int i = 0; i < nn; i++) { double sm = 0.0; for (int j = 0; j < nn; j++) sm = sm + hessin[(size_t)i * nn + j] * dg[j]; hdg[i] = sm; }
+            double fac = dot(dg, xi), fae = dot(dg, hdg), sumdg = dot(dg, dg), sumxi = dot(xi, xi);
+            if (fac > sqrt(eps * sumdg * sumxi)) {
+                fac = 1.0 / fac;
+                const double fad = 1.0 / fae;
+                for (int i = 0; i < nn; i++) dg[i] = fac * xi[i] - fad * hdg[i];
+                for (int i = 0; i < nn; i++)
+                    for (int j = 0; j < nn; j++)
+                        hessin[(size_t)i * nn + j] = hessin[(size_t)i * nn + j] + fac * (xi[i] * xi[j]) - fad * (hdg[i] * hdg[j]) + fae * (dg[i] * dg[j]);
+            }
+            for (int i = 0; i < nn; i++) { double sm = 0.0; for (int j = 0; j < nn; j++) sm = sm + hessin[(size_t)i * nn + j] * g[j]; xi[i] = -sm; }
+        }
+        return itmax;
+    }
+
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out);
@@ -717,6 +814,19 @@ int orc_best(void* h, double* fbest, double* xbest, int32_t* k) {
     if (fbest) *fbest = o->rows[b].fval;
     if (xbest) for (int i = 0; i < o->c.nx; i++) xbest[i] = o->rows[b].x[i];
     if (k) *k = o->rows[b].k;
+    return 0;
+}
+/* lastSearch (TiktakGlobalSearch.f90:635-681): EST_dfpmin from the best row, itmax 1000, gtol 1e-6 */
+int orc_last_search(void* h, double* fval, double* x, int32_t* iters) {
+    Oracle* o = (Oracle*)h;
+    if (o->rows.empty()) return -1;
+    int b = o->best_row(o->rows, (int)o->rows.size());
+    std::vector<double> p = o->rows[b].x;
+    double fret = o->rows[b].fval;
+    int it = o->dfpmin(p, fret, 1000, 1.0e-6);
+    if (fval) *fval = fret;
+    if (x) for (int i = 0; i < o->c.nx; i++) x[i] = p[i];
+    if (iters) *iters = it;
     return 0;
 }
 long orc_nfev(void* h) { return ((Oracle*)h)->nfev; }

@@ -190,3 +190,48 @@ def test_nm_shrink_mode(built, name, B):
     o0 = Oracle(cfg_of(name, round_size=B, nm_shrink_mode=0), MATH_TK)
     o0.solveAtSobolPoints(); o0.chooseSobol(mode=1); o0.LocalMinimizations(1)
     assert not np.array_equal(o0.searchResults, o.searchResults)
+
+
+@pytest.mark.parametrize("name,alg", [("template4", "a"), ("griewank10", "a"), ("rosenbrock33", "a"), ("griewank7", "b")])
+def test_last_search_bfgs(built, name, alg):
+    """state 10: EST_dfpmin polish from the best row (minimize.f90:2572-2816); final global minimum <= 1e-6"""
+    cfg = cfg_of(name, round_size=4)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations(alg)
+        fb = s.getBestLine()[0]
+        f, x, it = s.lastSearch()
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(1 if alg == "a" else 0)
+    of, ox, oit = o.lastSearch()
+    assert abs(f - of) <= 1e-6 * abs(of)  # BASELINE.json bar
+    assert f == of and np.array_equal(x, ox) and it == oit  # and in fact bit-exact
+    assert f <= fb
+
+
+def test_cli_driver_writes_reference_files(built, tmp_path):
+    """driver/TiktakGlobalSearch 0 config a: same CLI, config.txt grammar and .dat record formats as the reference"""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "driver", "TiktakGlobalSearch")
+    cfgfile = os.path.join(root, "tests", "golden", "config_c1.txt")
+    r = subprocess.run([exe, "0", cfgfile, "a"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert int(open(tmp_path / "state.dat").read()) == 10
+    rows = np.loadtxt(tmp_path / "searchResults.dat")
+    fn = np.loadtxt(tmp_path / "sobolFnVal.dat")
+    xs = np.loadtxt(tmp_path / "x_starts.dat")
+    fin = np.loadtxt(tmp_path / "FinalResults.dat")
+    line = open(tmp_path / "searchResults.dat").readline().rstrip("\n")
+    assert len(line) == 3 * 10 + 5 * 40  # (3i10, 200f40.20) with nx = 4
+    assert len(open(tmp_path / "sobolFnVal.dat").readline().rstrip("\n")) == 8 + 5 * 40  # (i8, 200f40.20)
+    cfg = baseline_config("C1")
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); oxs = o.chooseSobol(mode=1); o.LocalMinimizations(1)
+    assert fn.shape == (10, 6) and np.array_equal(fn[:, 0], np.arange(1, 11))
+    assert np.allclose(fn[:, 1], o.sobolFnVal(), rtol=1e-15, atol=0)
+    assert np.allclose(xs, oxs, rtol=0, atol=1e-15)  # F30.15
+    assert rows.shape == (5, 8) and rows[0, 1] == 0  # the k = 0 record first (:496-501)
+    assert np.allclose(rows[1:], o.searchResults, rtol=1e-15, atol=1e-19)
+    of, ox, _ = o.lastSearch()
+    assert abs(fin[2] - of) <= 1e-6 * abs(of)
+    assert int(open(tmp_path / "lastSobol.dat").read()) == 11 and int(open(tmp_path / "legitSobol.dat").read()) == 10

@@ -754,10 +754,118 @@ int tiktak_cuda_best(tiktak_handle* h, double* fbest, double* xbest, int32_t* k)
     return TIKTAK_OK;
 }
 
+/* lastSearch (TiktakGlobalSearch.f90:635-681) = EST_dfpmin + dograd + lnsrch (minimize.f90:2572-2816) from the
+ * best row.  It runs once per job; the BFGS recurrences (O(nx^2) per iteration) are host arithmetic in the
+ * reference's order, every objective evaluation goes through the device plugin: the 2 nx points of a central-
+ * difference gradient as one batch, line-search trial points one by one. */
 int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* iters) {
-    (void)h; (void)fval; (void)x; (void)iters;
-    tk_set_error("last_search (EST_dfpmin polish) is not built yet");
-    return TIKTAK_ERR_UNSUPPORTED;
+    if (!h) return TIKTAK_ERR_ARG;
+    const int nn = h->cfg.nx, itmax = 1000;
+    const double gtol = 1.0e-6; /* itmax_DFPMIN, gtol_DFPMIN (genericParams.f90:27-28) */
+    double fbest = 0;
+    std::vector<double> p(nn);
+    int kb = 0;
+    int rc = tiktak_cuda_best(h, &fbest, p.data(), &kb);
+    if (rc) return rc;
+    const double stpmx = 100.0, eps = 2.220446049250313e-16, tolx = 4.0 * eps, xinc = 1.0e-5;
+    auto func = [&](const std::vector<double>& xx, double& out) -> int { return tiktak_cuda_objfun(h, xx.data(), 1, &out); };
+    auto dograd = [&](const std::vector<double>& xx, std::vector<double>& grad) -> int {
+        std::vector<double> dh(nn), pts((size_t)2 * nn * nn), f((size_t)2 * nn);
+        const double tolera = 10.0 * xinc;
+        for (int i = 0; i < nn; i++) dh[i] = (fabs(xx[i]) >= tolera) ? xx[i] * xinc : xinc;
+        const int n = 2 * nn; /* point 2i: x - dh e_i, point 2i+1: x + dh e_i ; column-major (n, nn) */
+        for (int i = 0; i < nn; i++)
+            for (int j = 0; j < nn; j++) {
+                pts[(size_t)j * n + 2 * i] = xx[j] - (i == j ? dh[i] : 0.0);
+                pts[(size_t)j * n + 2 * i + 1] = xx[j] + (i == j ? dh[i] : 0.0);
+            }
+        int r = tiktak_cuda_objfun(h, pts.data(), n, f.data());
+        if (r) return r;
+        grad.resize(nn);
+        for (int i = 0; i < nn; i++) grad[i] = (f[2 * i + 1] - f[2 * i]) / (2.0 * dh[i]);
+        return TIKTAK_OK;
+    };
+    auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double sm = 0.0; for (int i = 0; i < nn; i++) sm = sm + a[i] * b[i]; return sm; };
+    double fp = 0, fret = 0;
+    if ((rc = func(p, fp))) return rc;
+    std::vector<double> g, dg(nn), hdg(nn), pnew(nn), xi(nn), hessin((size_t)nn * nn, 0.0);
+    if ((rc = dograd(p, g))) return rc;
+    for (int i = 0; i < nn; i++) hessin[(size_t)i * nn + i] = 1.0;
+    for (int i = 0; i < nn; i++) xi[i] = -g[i];
+    const double stpmax = stpmx * std::max(sqrt(dot(p, p)), (double)nn);
+    fret = fp;
+    int its_done = itmax;
+    for (int its = 1; its <= itmax; its++) {
+        { /* lnsrch :2719-2814 */
+            const double alf = 1.0e-4;
+            double a, alam, alam2 = 0, alamin, b, disc, f2 = 0, pabs, rhs1, rhs2, slope, tmplam, f;
+            pabs = sqrt(dot(xi, xi));
+            if (pabs > stpmax) for (int i = 0; i < nn; i++) xi[i] = xi[i] * stpmax / pabs;
+            slope = dot(g, xi);
+            pnew = p; f = fp;
+            if (!(slope >= 0.0)) {
+                double mx = 0.0;
+                for (int i = 0; i < nn; i++) mx = std::max(mx, fabs(xi[i]) / std::max(fabs(p[i]), 1.0));
+                alamin = eps / mx;
+                alam = 1.0;
+                for (;;) {
+                    for (int i = 0; i < nn; i++) pnew[i] = p[i] + alam * xi[i];
+                    if ((rc = func(pnew, f))) return rc;
+                    if (alam < alamin) { pnew = p; break; }
+                    else if (f <= fp + alf * alam * slope) break;
+                    else {
+                        if (alam == 1.0) tmplam = -slope / (2.0 * (f - fp - slope));
+                        else {
+                            rhs1 = f - fp - alam * slope;
+                            rhs2 = f2 - fp - alam2 * slope;
+                            a = (rhs1 / (alam * alam) - rhs2 / (alam2 * alam2)) / (alam - alam2);
+                            b = (-alam2 * rhs1 / (alam * alam) + alam * rhs2 / (alam2 * alam2)) / (alam - alam2);
+                            if (a == 0.0) tmplam = -slope / (2.0 * b);
+                            else {
+                                disc = b * b - 3.0 * a * slope;
+                                if (disc < 0.0) tmplam = 0.5 * alam;
+                                else if (b <= 0.0) tmplam = (-b + sqrt(disc)) / (3.0 * a);
+                                else tmplam = -slope / (b + sqrt(disc));
+                            }
+                            if (tmplam > 0.5 * alam) tmplam = 0.5 * alam;
+                        }
+                    }
+                    alam2 = alam;
+                    f2 = f;
+                    alam = std::max(tmplam, 0.1 * alam);
+                }
+            }
+            fret = f;
+        }
+        fp = fret;
+        for (int i = 0; i < nn; i++) xi[i] = pnew[i] - p[i];
+        p = pnew;
+        double t = 0.0;
+        for (int i = 0; i < nn; i++) t = std::max(t, fabs(xi[i]) / std::max(fabs(p[i]), 1.0));
+        if (t < tolx) { its_done = its; break; }
+        dg = g;
+        if ((rc = dograd(p, g))) return rc;
+        const double den = std::max(fret, 1.0);
+        t = 0.0;
+        for (int i = 0; i < nn; i++) t = std::max(t, fabs(g[i]) * std::max(fabs(p[i]), 1.0) / den);
+        if (t < gtol) { its_done = its; break; }
+        for (int i = 0; i < nn; i++) dg[i] = g[i] - dg[i];
+        for (int i = 0; i < nn; i++) { double sm = 0.0; for (int j = 0; j < nn; j++) sm = sm + hessin[(size_t)i * nn + j] * dg[j]; hdg[i] = sm; }
+        double fac = dot(dg, xi), fae = dot(dg, hdg), sumdg = dot(dg, dg), sumxi = dot(xi, xi);
+        if (fac > sqrt(eps * sumdg * sumxi)) {
+            fac = 1.0 / fac;
+            const double fad = 1.0 / fae;
+            for (int i = 0; i < nn; i++) dg[i] = fac * xi[i] - fad * hdg[i];
+            for (int i = 0; i < nn; i++)
+                for (int j = 0; j < nn; j++)
+                    hessin[(size_t)i * nn + j] = hessin[(size_t)i * nn + j] + fac * (xi[i] * xi[j]) - fad * (hdg[i] * hdg[j]) + fae * (dg[i] * dg[j]);
+        }
+        for (int i = 0; i < nn; i++) { double sm = 0.0; for (int j = 0; j < nn; j++) sm = sm + hessin[(size_t)i * nn + j] * g[j]; xi[i] = -sm; }
+    }
+    if (fval) *fval = fret;
+    if (x) for (int i = 0; i < nn; i++) x[i] = p[i];
+    if (iters) *iters = its_done;
+    return TIKTAK_OK;
 }
 
 int tiktak_cuda_fp64_peak(int device, double* flops_per_s, double* ms) { return tk_fp64_peak(device, flops_per_s, ms); }

@@ -242,6 +242,13 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_best(self._h, C.byref(f), dptr(x), C.byref(k)), "getBestLine")
         return f.value, x, k.value
 
+    def lastSearch(self):
+        """state 10 (:635-681): BFGS polish (EST_dfpmin) from the best row; returns (fn_val, evalParam, iterations)."""
+        f, it = C.c_double(), C.c_int32()
+        x = np.empty(self.cfg.nx, dtype=np.float64)
+        _lib.check(self._L.tiktak_cuda_last_search(self._h, C.byref(f), dptr(x), C.byref(it)), "lastSearch")
+        return f.value, x, it.value
+
     # ------------------------------------------------------------------ the single-instance state machine
     def run(self, algor="a"):
         """Cold start, states 2..8 (TiktakGlobalSearch.f90:217-401) with nothing missing."""
