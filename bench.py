@@ -208,57 +208,44 @@ def run_graft(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ext = s.torch_stream()  # the library's stream: CUDA events recorded on it time the stages on the device
+    alg = "b" if name == "C5" else "a"
+
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(ext)
+        return e
+
     def one_step(e2e):
-        """returns dict of device stage times (ms) and wall times (s)"""
+        """returns dict of device stage times (ms, CUDA events on the library stream) and wall times (s)"""
         out = {}
         flush.zero_()  # evict L2 between steps (untimed)
         barrier()
         t0 = time.perf_counter()
+        e0 = mark()
         _, ne, nl = s.solveAtSobolPoints()
-        torch.cuda.synchronize()
-        out["pretest_ms"] = s.stage_ms("pretest")
-        out["pretest_eval_ms"] = s.stage_ms("pretest_eval")
+        e1 = mark()
+        if e2e:
+            ext.synchronize()
         t1 = time.perf_counter()
         if e2e:
             fv = s.sobolFnVal(out=pinned)  # D2H of every evaluated fval (the rows of sobolFnVal.dat) into pinned memory
             out["d2h"] = fv.nbytes
         t2 = time.perf_counter()
+        e2 = mark()
         s.chooseSobol()
-        torch.cuda.synchronize()
-        out["choose_ms"] = s.stage_ms("choose")
+        e3 = mark()
         t3 = time.perf_counter()
-        local_ms = 0.0
         if not args.no_local:
-            s.LocalMinimizations("a")
-            local_ms = s.local_ms_total
-        out["local_ms"] = local_ms
-        torch.cuda.synchronize()
+            s.LocalMinimizations(alg)
+        e4 = mark()
+        ext.synchronize()
         t4 = time.perf_counter()
-        out.update(wall_pretest=t1 - t0, wall_values=t2 - t1, wall_choose=t3 - t2, wall_local=t4 - t3, wall=t4 - t0,
+        out.update(pretest_ms=e0.elapsed_time(e1), choose_ms=e2.elapsed_time(e3),
+                   local_ms=0.0 if args.no_local else e3.elapsed_time(e4), pretest_eval_ms=s.stage_ms("pretest_eval"),
+                   wall_pretest=t1 - t0, wall_values=t2 - t1, wall_choose=t3 - t2, wall_local=t4 - t3, wall=t4 - t0,
                    ne=ne, nl=nl)
         return out
-
-    # LocalMinimizations: accumulate the per-round CUDA-event times
-    orig_local = s.LocalMinimizations
-
-    def timed_local(algor="a"):
-        tot = 0.0
-        K, nx = s.K, s.cfg.nx
-        starts = np.full((K, nx), np.nan); results = np.full((K, nx + 4), np.nan); evals = np.zeros(K, dtype=np.int32)
-        for first_k, n_k in s.rounds():
-            sb = np.empty((nx, n_k)); r = np.empty((nx + 4, n_k)); e = np.zeros(n_k, dtype=np.int32)
-            lib.check(L.tiktak_cuda_local(s._h, 0 if name == "C5" else 1, first_k, n_k, sb.ctypes.data, r.ctypes.data, e.ctypes.data), "local")
-            tot += s.stage_ms("local")
-            if world > 1:
-                r, e = s._exchange_round(r, e, n_k)
-            sl = slice(first_k - 1, first_k - 1 + n_k)
-            starts[sl] = sb.T; results[sl] = r.T; evals[sl] = e
-        s.searchStart, s.searchResults, s.evals = starts, results, evals
-        s.local_ms_total = tot
-        return True
-
-    s.LocalMinimizations = timed_local
-    _ = orig_local
 
     for _ in range(max(args.warmup, 3)):
         one_step(False)
@@ -279,16 +266,12 @@ def run_graft(args, rank, world, local_rank):
         return float(t.item())
 
     npts, nrest = cfg.qr_ndraw, cfg.p_maxpoints
-    if world == 1:  # CUDA events on the library's stream
-        pre_ms = mx(np.mean([d["pretest_ms"] for d in dev_steps]))
-        choose_ms = mx(np.mean([d["choose_ms"] for d in dev_steps]))
-        local_ms = mx(np.mean([d["local_ms"] for d in dev_steps]))
-        timing = "CUDA events on the library stream per stage"
-    else:  # stages include host-driven NCCL exchanges: wall clock between device synchronisations, max over ranks
-        pre_ms = mx(1e3 * np.mean([d["wall_pretest"] for d in dev_steps]))
-        choose_ms = mx(1e3 * np.mean([d["wall_choose"] for d in dev_steps]))
-        local_ms = mx(1e3 * np.mean([d["wall_local"] for d in dev_steps]))
-        timing = "wall clock between device synchronisations per stage (includes the NCCL exchanges), max over ranks"
+    # CUDA events on the library's stream (the NCCL exchanges of a sharded run are queued on the same stream),
+    # mean over the timed steps, max over ranks
+    pre_ms = mx(np.mean([d["pretest_ms"] for d in dev_steps]))
+    choose_ms = mx(np.mean([d["choose_ms"] for d in dev_steps]))
+    local_ms = mx(np.mean([d["local_ms"] for d in dev_steps]))
+    timing = "CUDA events on the library stream per stage, max over ranks"
     eval_ms = mx(np.mean([d["pretest_eval_ms"] for d in dev_steps]))
     step_ms = pre_ms + choose_ms + local_ms
     n_eval_total = s.n_evaluated if s.n_evaluated else npts  # the legitimate cut may stop early (C5)

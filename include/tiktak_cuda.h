@@ -141,24 +141,42 @@ int tiktak_cuda_pretest_set_cut(tiktak_handle* h, int64_t kcut, int64_t n_legit)
  * x_starts is (K, nx+1) column-major, sobol_idx[K] (0 for row 1).  With world > 1 this selects
  * the shard-local top K-1; merge with tiktak_cuda_choose_merge. */
 int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx);
-/* merge `world` shard-local candidate lists (each (K-1) rows of [fval, idx] pairs, fval first)
- * into the replicated x_starts; cand is (world*(K-1), 2) row-major doubles. */
+/* export this shard's candidates for the all-gather: (K, 2) row-major doubles = K-1 rows [fval, (double)idx]
+ * in ascending (fval, idx), NaN-padded, plus a trailer row [#valid points of the shard, #rows filled].
+ * A device pointer keeps the export on the handle's stream (no host round trip). */
+int tiktak_cuda_choose_candidates(tiktak_handle* h, double* cand);
+/* merge the `world` gathered lists (nrows = world*K rows as above, host or device memory) into the
+ * replicated x_starts: the position of a row in the union is its index in its own list plus the number of
+ * rows below it in every other list -- one kernel, identical result on every rank. */
 int tiktak_cuda_choose_merge(tiktak_handle* h, const double* cand, int64_t nrows, double* x_starts,
                              int32_t* sobol_idx);
-/* export this shard's candidates for the all-gather: (K-1, 2) row-major [fval, (double)idx]. */
-int tiktak_cuda_choose_candidates(tiktak_handle* h, double* cand);
 
 /* LocalMinimizations + completeSearch (TiktakGlobalSearch.f90:473-600) for restarts
  * first_k .. first_k+n_k-1 of ONE round: starts = getModifiedParam (:683-720) blended against
- * the best row known to the handle when the call begins; then runAmoeba (:602-633) /
- * bobyqa_h (:572); then the re-evaluation (:582).  stride = `world`-style dealing is the
- * caller's business: only restarts with (k - first_k) % world == rank are run, rows of the
- * others are left untouched (NaN-filled) for the all-gather.
+ * the best row known to the handle when the round begins; then runAmoeba (:602-633) /
+ * bobyqa_h (:572); then the re-evaluation (:582).  Blocking convenience form (world == 1 only) =
+ * local_enqueue + local_ingest + local_fetch of the same restarts.
  * starts  : (n_k, nx)   column-major, the searchStart.dat rows (:557)
  * results : (n_k, nx+4) column-major = seqNo, k, #improvements, fval, x -- searchResults.dat (:594)
  * evals   : objective evaluations spent per restart (may be NULL). */
 int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* starts,
                       double* results, int32_t* evals);
+
+/* The same round, device-resident and asynchronous: nothing below synchronises the host, so a whole
+ * LocalMinimizations stage is queued on the handle's stream back to back and read once at the end.
+ *   local_enqueue : best-so-far -> blend -> local searches of this rank's restarts of the round
+ *                   (slot s = k - first_k is run by rank s % world).  With world > 1 the outcomes are
+ *                   packed into `send` (DEVICE memory, ceil(n_k/world) rows of nx+2 doubles =
+ *                   fval, x, #evaluations) for ONE all-gather per round, issued by the caller on the
+ *                   handle's stream (tiktak_cuda_stream) -- e.g. torch.distributed/NCCL over NVLink.
+ *   local_ingest  : the round's rows (world > 1: `recv` = the gathered world x ceil(n_k/world) rows,
+ *                   device memory) become rows k of the device-resident searchResults table and update
+ *                   the best row, identically on every rank.  world == 1: send/recv are NULL.
+ *   local_fetch   : synchronise and copy out rows first_k.. (same layouts as tiktak_cuda_local). */
+int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* send);
+int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, const double* recv);
+int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, double* starts, double* results,
+                            int32_t* evals);
 /* make rows computed elsewhere (other ranks, or a resumed searchResults.dat) known to the handle;
  * rows is (n, nx+4) column-major.  Rows whose fval is NaN are ignored.  Also how the k=0 row
  * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */

@@ -9,12 +9,13 @@
  *     static constexpr int kId;                          // TIKTAK_OBJ_* id it registers under
  *     static void host_init(int nx, double* aux);        // obj_initialize/GetData: per-coordinate
  *                                                        // constants aux[nx], computed once on the host
- *     static __device__ int    nterms(int nx);           // how many per-coordinate terms
+ *     static __host__ __device__ int nterms(int nx);     // how many per-coordinate terms (<= nx)
  *     template <class X>
  *     static __device__ void   term(const tk_obj_ctx&, const X& x, int i, double& a, double& b);
  *     static __device__ void   fold_init(const tk_obj_ctx&, double& s, double& p);
  *     static __device__ void   fold(double& s, double& p, double a, double b);
  *     static __device__ double finish(const tk_obj_ctx&, double s, double p);
+ *     static constexpr bool kTermLocal;                  // true when term(.,i,.) reads x[i] only
  * Together they are the user part of dfovec (objective.f90:96-117), i.e. the scalar v_err that the
  * shipped template replicates over the nm moments:
  *     fold_init(s,p); for i = 0 .. nterms-1 { term(x,i,a,b); fold(s,p,a,b); }  v_err = finish(s,p)
@@ -107,8 +108,8 @@ __device__ __forceinline__ double tk_value_seq(const tk_obj_ctx& c, const X& x) 
  * DOT_PRODUCT over the nm identical moments in index order, then + getPenalty. */
 __device__ __forceinline__ double tk_objfun_finish(const tk_obj_ctx& c, double f, double pen) {
     const double ff = TK_MUL(f, f);
-    double dot = 0.0;
-    for (int m = 0; m < c.nm; m++) dot = TK_ADD(dot, ff);
+    double dot = ff; /* 0 + ff is exact, so the first term needs no addition */
+    for (int m = 1; m < c.nm; m++) dot = TK_ADD(dot, ff);
     return TK_ADD(dot, pen);
 }
 

@@ -49,23 +49,30 @@ def _worker(rank, world, port, q):
             mine = int(inblk[need - 1]) + 1
         kcut = D.agree_max(mine)
         assert kcut == kcut_true
-        # --- 2. candidates: local top-M of owned, evaluated points -> merge == global top-M
+        # --- 2. candidates: local top-M of owned, evaluated points (+ trailer row) -> merge == global top-M
+        import torch
+
         own = np.nonzero((blk % world == rank) & (np.arange(1, N + 1) <= kcut))[0]
         order = own[np.lexsort((own, f[own]))][:M]
-        cand = np.full((M, 2), np.nan); cand[: len(order), 0] = f[order]; cand[: len(order), 1] = order + 1
-        allc = D.gather_candidates(cand, world)
-        ok = ~np.isnan(allc[:, 0])
-        merged = allc[ok][np.lexsort((allc[ok][:, 1], allc[ok][:, 0]))][:M]
+        cand = np.full((M + 1, 2), np.nan); cand[: len(order), 0] = f[order]; cand[: len(order), 1] = order + 1
+        cand[M] = [int(valid[own].sum()), len(order)]  # trailer: [#valid points of the shard, #rows filled]
+        allc = D.gather_candidates(torch.as_tensor(cand), world).numpy().reshape(world, M + 1, 2)
+        rows = np.concatenate([allc[r, : int(allc[r, M, 1])] for r in range(world)])
+        merged = rows[np.lexsort((rows[:, 1], rows[:, 0]))][:M]
         ev = np.arange(kcut)
         glob = ev[np.lexsort((ev, f[:kcut]))][:M]
         assert np.array_equal(merged[:, 1].astype(int), glob + 1)
-        # --- 3. one round of result rows, slot s run by rank s % world
-        n_k, ncol = 7, 10 + 5
-        truth = np.arange(ncol * n_k, dtype=np.float64).reshape(ncol, n_k) + 0.25
-        pack = np.full((ncol, n_k), np.nan)
-        for s in range(rank, n_k, world):
-            pack[:, s] = truth[:, s]
-        assert np.array_equal(D.exchange_rows(pack, world), truth)
+        assert int(allc[:, M, 0].sum()) == int(valid[:kcut].sum())
+        # --- 3. restart rounds: slot s is run by rank s % world and travels as row s // world of that rank's pack
+        for n_k in (7, 8, 1):
+            ncol = 10 + 2
+            truth = np.arange(ncol * n_k, dtype=np.float64).reshape(n_k, ncol) + 0.25
+            mine = np.full((n_k, ncol), np.nan)
+            mine[rank::world] = truth[rank::world]  # this rank only knows its own slots
+            send = torch.as_tensor(D.pack_rows_ref(mine, rank, world))
+            recv = torch.empty((world * send.shape[0], ncol), dtype=torch.float64)
+            D.gather_rows(recv, send)
+            assert np.array_equal(D.unpack_rows_ref(recv.numpy(), n_k, world), truth)
         fmin, kmin = D.best_allreduce(3.0 - rank, 10 + rank)
         assert (fmin, kmin) == (3.0 - (world - 1), 10 + world - 1)
         q.put((rank, "ok"))

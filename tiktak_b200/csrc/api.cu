@@ -26,8 +26,8 @@ void tk_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int tk_sort_candidates(tiktak_handle* h, const double* d_f, const unsigned int* d_i, int64_t n, double* d_sf,
-                       unsigned int* d_si);
+int tk_export_candidates(tiktak_handle* h, double* d_cand);
+int tk_merge_candidates(tiktak_handle* h, const double* d_cand);
 
 namespace {
 
@@ -237,6 +237,14 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     TK_TRY(dalloc(&h->d_out_x, (size_t)K * nx));
     TK_TRY(dalloc(&h->d_out_f, (size_t)K));
     TK_TRY(dalloc(&h->d_out_evals, (size_t)K));
+    TK_TRY(dalloc(&h->d_arch_starts, (size_t)K * nx));
+    TK_TRY(dalloc(&h->d_arch_evals, (size_t)K + 1));
+    TK_TRY(dalloc(&h->d_wshr, (size_t)nx));
+    TK_TRY(dalloc(&h->d_shr_have, 1));
+    TK_CUDA(cudaMemsetAsync(h->d_shr_have, 0, sizeof(int), h->stream));
+    TK_CUDA(cudaMemsetAsync(h->d_arch_evals, 0, (size_t)(K + 1) * sizeof(int), h->stream));
+    TK_CUDA(cudaEventCreate(&h->evl0));
+    TK_CUDA(cudaEventCreate(&h->evl1));
 #undef TK_TRY
     TK_CUDA(cudaStreamSynchronize(h->stream));
     if (cfg->objective_id == TIKTAK_OBJ_SMM) {
@@ -255,12 +263,15 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
                     h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
-                    h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_width_round};
+                    h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
+                    h->d_shr_have, h->d_arch_starts, h->d_arch_evals};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evw0) cudaEventDestroy(h->evw0);
     if (h->evw1) cudaEventDestroy(h->evw1);
+    if (h->evl0) cudaEventDestroy(h->evl0);
+    if (h->evl1) cudaEventDestroy(h->evl1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -279,7 +290,13 @@ int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms) {
         *ms = h->ms_pretest_eval;
     }
     else if (!strcmp(stage, "choose")) *ms = h->ms_choose;
-    else if (!strcmp(stage, "local")) *ms = h->ms_local;
+    else if (!strcmp(stage, "local")) {
+        if (h->local_timing_open) { /* close the interval opened by the first local_enqueue since the last query */
+            TK_CUDA(cudaEventSynchronize(h->evl1));
+            float w = 0; cudaEventElapsedTime(&w, h->evl0, h->evl1); h->ms_local = w; h->local_timing_open = false;
+        }
+        *ms = h->ms_local;
+    }
     else return TIKTAK_ERR_ARG;
     return TIKTAK_OK;
 }
@@ -560,39 +577,47 @@ int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
 int tiktak_cuda_choose_candidates(tiktak_handle* h, double* cand) {
     if (!h || !cand) return TIKTAK_ERR_ARG;
     if (!h->starts_ready) return TIKTAK_ERR_STATE;
-    const int M = h->cfg.maxpoints_plus1 - 1;
-    std::vector<double> f(std::max(M, 1)); std::vector<unsigned int> si(std::max(M, 1));
-    if (h->n_cand > 0) {
-        TK_CUDA(cudaMemcpyAsync(f.data(), h->d_sorted_f, (size_t)h->n_cand * 8, cudaMemcpyDeviceToHost, h->stream));
-        TK_CUDA(cudaMemcpyAsync(si.data(), h->d_sorted_i, (size_t)h->n_cand * 4, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)2 * h->cfg.maxpoints_plus1 * 8; /* (M+1) rows of 2 doubles */
+    if (is_device_ptr(cand)) return tk_export_candidates(h, cand); /* stays on the stream: no host round trip */
+    double* d = nullptr;
+    TK_CUDA(cudaMalloc(&d, bytes));
+    int rc = tk_export_candidates(h, d);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(cand, d, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { tk_set_error("choose_candidates copy: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
     }
-    TK_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<double> out((size_t)2 * std::max(M, 1), NAN);
-    for (int r = 0; r < M; r++)
-        if (r < h->n_cand) { out[2 * r] = f[r]; out[2 * r + 1] = (double)si[r]; }
-    TK_CUDA(cudaMemcpy(cand, out.data(), (size_t)2 * M * 8, cudaMemcpyDefault));
-    return TIKTAK_OK;
+    cudaFree(d);
+    return rc;
 }
 
 int tiktak_cuda_choose_merge(tiktak_handle* h, const double* cand, int64_t nrows, double* x_starts, int32_t* sobol_idx) {
-    if (!h || !cand || nrows < 0) return TIKTAK_ERR_ARG;
+    if (!h || !cand) return TIKTAK_ERR_ARG;
     const int M = h->cfg.maxpoints_plus1 - 1;
-    if (nrows > (int64_t)M * h->cfg.world) return TIKTAK_ERR_ARG;
+    if (nrows != (int64_t)(M + 1) * h->cfg.world) { tk_set_error("choose_merge: expected world*(K) rows"); return TIKTAK_ERR_ARG; }
     TK_CUDA(cudaSetDevice(h->device));
-    std::vector<double> host((size_t)2 * std::max<int64_t>(nrows, 1));
-    TK_CUDA(cudaMemcpy(host.data(), cand, (size_t)2 * nrows * 8, cudaMemcpyDefault));
-    std::vector<double> f; std::vector<unsigned int> si;
-    for (int64_t r = 0; r < nrows; r++)
-        if (host[2 * r] == host[2 * r] && host[2 * r + 1] >= 1) { f.push_back(host[2 * r]); si.push_back((unsigned int)host[2 * r + 1]); }
-    const int64_t n = (int64_t)f.size();
-    if (n > 0) {
-        TK_CUDA(cudaMemcpyAsync(h->d_cand_f, f.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-        TK_CUDA(cudaMemcpyAsync(h->d_cand_i, si.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-        int rc = tk_sort_candidates(h, h->d_cand_f, h->d_cand_i, n, h->d_sorted_f, h->d_sorted_i);
-        if (rc) return rc;
+    int rc = TIKTAK_OK;
+    double* d = nullptr;
+    const double* src = cand;
+    if (!is_device_ptr(cand)) {
+        TK_CUDA(cudaMalloc(&d, (size_t)nrows * 16));
+        TK_CUDA(cudaMemcpyAsync(d, cand, (size_t)nrows * 16, cudaMemcpyHostToDevice, h->stream));
+        src = d;
     }
-    h->n_cand = std::min<int64_t>(n, M);
-    int rc = tk_build_starts(h);
+    unsigned int tot = 0;
+    if (M > 0) {
+        rc = tk_merge_candidates(h, src);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(&tot, h->d_cand_n, sizeof tot, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { tk_set_error("choose_merge: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
+        }
+    }
+    if (d) cudaFree(d);
+    if (rc) return rc;
+    h->n_cand = tot;
+    rc = tk_build_starts(h);
     if (rc) return rc;
     h->starts_ready = true;
     rc = push_init_row(h);
@@ -606,6 +631,7 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
     TK_CUDA(cudaSetDevice(h->device));
     std::vector<double> host((size_t)n * (nx + 4));
     if (n == 0) return TIKTAK_OK;
+    h->best_dirty = true;
     TK_CUDA(cudaMemcpy(host.data(), rows, host.size() * 8, cudaMemcpyDefault));
     /* running best, for the #improvements column (completeSearch :585-589) */
     double best_f = 1.0e7; /* pos_miss, getBestLine :791-796 */
@@ -643,8 +669,7 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
     return flush();
 }
 
-int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* starts, double* results,
-                      int32_t* evals) {
+int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* send) {
     if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
     if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) { tk_set_error("local: algorithm %d not available in this build", alg); return TIKTAK_ERR_UNSUPPORTED; }
@@ -653,84 +678,90 @@ int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_
         tk_set_error("local: Nelder-Mead is not built for the vector-valued SMM objective; use DFNLS");
         return TIKTAK_ERR_UNSUPPORTED;
     }
-    const int nx = h->cfg.nx;
+    if (h->cfg.world > 1 && !send) { tk_set_error("local: world > 1 needs the send buffer of the round's all-gather"); return TIKTAK_ERR_ARG; }
     TK_CUDA(cudaSetDevice(h->device));
-    int rc = begin_timer(h);
-    if (rc) return rc;
-    /* rows of restarts this rank does not run stay NaN */
-    std::vector<double> nanf(n_k, NAN);
-    TK_CUDA(cudaMemcpyAsync(h->d_out_f, nanf.data(), (size_t)n_k * 8, cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemsetAsync(h->d_out_evals, 0, (size_t)n_k * sizeof(int), h->stream));
-    TK_CUDA(cudaMemsetAsync(h->d_out_x, 0, (size_t)n_k * nx * 8, h->stream));
-    if ((rc = tk_launch_best(h))) return rc;
+    int rc;
+    if (!h->local_timing_open) {
+        TK_CUDA(cudaEventRecord(h->evl0, h->stream));
+        h->local_timing_open = true;
+    }
+    if (h->best_dirty) { /* rows were pushed from the host: recompute the best row once */
+        if ((rc = tk_launch_best(h))) return rc;
+        h->best_dirty = false;
+    }
     if ((rc = tk_launch_blend(h, first_k, n_k))) return rc;
-    h->use_round_width = false;
-    if (alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1) {
-        /* README.md:36 ("the algorithm takes the min and max of the best local minima found so far and uses
-         * them as the bounds of the initial simplex"), not present in the reference code (SURVEY finding 3):
-         * for restarts in the second half (itratio > 0.5, like the DFNLS radius rule :565) the per-coordinate
-         * simplex width is max-min over the 10 best local minima known at the round's start. */
-        const int K = h->cfg.maxpoints_plus1;
-        std::vector<int> cand;
-        for (int k = 1; k <= K; k++) if (h->h_res_valid[k]) cand.push_back(k);
-        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return h->h_res_f[a] < h->h_res_f[b]; });
-        std::vector<double> wshr(nx);
-        for (int d = 0; d < nx; d++) wshr[d] = h->range[nx + d] - h->range[d];
-        bool have = cand.size() >= 2;
-        if (have) {
-            const int T = (int)std::min<size_t>(cand.size(), 10);
-            std::vector<double> rows((size_t)T * (nx + 1));
-            for (int t = 0; t < T; t++)
-                TK_CUDA(cudaMemcpyAsync(&rows[(size_t)t * (nx + 1)], h->d_res + (size_t)cand[t] * (nx + 1), (size_t)(nx + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
-            TK_CUDA(cudaStreamSynchronize(h->stream));
-            for (int d = 0; d < nx; d++) {
-                double mn = rows[1 + d], mx = mn;
-                for (int t = 1; t < T; t++) { const double v = rows[(size_t)t * (nx + 1) + 1 + d]; mn = std::min(mn, v); mx = std::max(mx, v); }
-                if (mx - mn > 0.0) wshr[d] = mx - mn;
-            }
-        }
-        std::vector<double> wr((size_t)n_k * nx);
-        for (int s = 0; s < n_k; s++) {
-            const float itratio = (float)(first_k + s) / (float)K;
-            const bool shrink = have && itratio > 0.5f;
-            for (int d = 0; d < nx; d++) wr[(size_t)d * n_k + s] = shrink ? wshr[d] : (h->range[nx + d] - h->range[d]);
-        }
-        if (!h->d_width_round) TK_CUDA(cudaMalloc(&h->d_width_round, (size_t)K * nx * 8));
-        TK_CUDA(cudaMemcpyAsync(h->d_width_round, wr.data(), wr.size() * 8, cudaMemcpyHostToDevice, h->stream));
-        TK_CUDA(cudaStreamSynchronize(h->stream));
-        h->use_round_width = true;
-    }
-    if (alg == TIKTAK_ALG_AMOEBA) rc = tk_launch_nm(h, first_k, n_k);
-    else rc = tk_launch_dfnls(h, first_k, n_k);
+    if (alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1 && (rc = tk_launch_shrink_width(h))) return rc;
+    rc = (alg == TIKTAK_ALG_AMOEBA) ? tk_launch_nm(h, first_k, n_k) : tk_launch_dfnls(h, first_k, n_k);
     if (rc) return rc;
-    std::vector<double> hs((size_t)n_k * nx), hx((size_t)n_k * nx), hf(n_k);
-    std::vector<int> he(n_k);
-    TK_CUDA(cudaMemcpyAsync(hs.data(), h->d_starts, hs.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaMemcpyAsync(hx.data(), h->d_out_x, hx.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaMemcpyAsync(hf.data(), h->d_out_f, hf.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaMemcpyAsync(he.data(), h->d_out_evals, he.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = end_timer(h, &h->ms_local))) return rc; /* synchronises the stream */
-    /* searchResults.dat records (:594): seqNo, k, #improvements, fval, x -- as re-read from the file */
-    std::vector<double> rows((size_t)n_k * (nx + 4));
-    const bool rt = h->cfg.text_roundtrip != 0;
-    for (int s = 0; s < n_k; s++) {
-        rows[(size_t)0 * n_k + s] = 1.0;
-        rows[(size_t)1 * n_k + s] = (double)(first_k + s);
-        rows[(size_t)2 * n_k + s] = 0.0;
-        rows[(size_t)3 * n_k + s] = rt ? tk_f4020_roundtrip(hf[s]) : hf[s];
-        for (int d = 0; d < nx; d++) {
-            const double xv = hx[(size_t)d * n_k + s];
-            rows[(size_t)(4 + d) * n_k + s] = (hf[s] == hf[s]) ? (rt ? tk_f4020_roundtrip(xv) : xv) : NAN;
-        }
-    }
-    if (h->cfg.world == 1) {
-        if ((rc = tiktak_cuda_push_results(h, rows.data(), n_k))) return rc;
-        for (int s = 0; s < n_k; s++) rows[(size_t)2 * n_k + s] = (double)h->h_res_imp[first_k + s];
-    }
-    if (starts) TK_CUDA(cudaMemcpy(starts, hs.data(), hs.size() * 8, cudaMemcpyDefault));
-    if (results) TK_CUDA(cudaMemcpy(results, rows.data(), rows.size() * 8, cudaMemcpyDefault));
-    if (evals) TK_CUDA(cudaMemcpy(evals, he.data(), he.size() * sizeof(int), cudaMemcpyDefault));
+    if (h->cfg.world > 1 && (rc = tk_launch_pack(h, n_k, send))) return rc;
+    TK_CUDA(cudaEventRecord(h->evl1, h->stream));
     return TIKTAK_OK;
+}
+
+int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, const double* recv) {
+    if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (h->cfg.world > 1 && !recv) { tk_set_error("local_ingest: world > 1 needs the gathered rows"); return TIKTAK_ERR_ARG; }
+    if (n_k == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc = tk_launch_ingest(h, first_k, n_k, h->cfg.world > 1 ? recv : nullptr);
+    if (rc) return rc;
+    TK_CUDA(cudaEventRecord(h->evl1, h->stream));
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, double* starts, double* results, int32_t* evals) {
+    if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (n_k == 0) return TIKTAK_OK;
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1, last = first_k + n_k - 1;
+    TK_CUDA(cudaSetDevice(h->device));
+    std::vector<double> hres((size_t)(last + 1) * (nx + 1)), hst((size_t)K * nx);
+    std::vector<int> hval(last + 1), hev(last + 1);
+    TK_CUDA(cudaMemcpyAsync(hres.data(), h->d_res, hres.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hval.data(), h->d_res_valid, hval.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hev.data(), h->d_arch_evals, hev.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (starts) TK_CUDA(cudaMemcpyAsync(hst.data(), h->d_arch_starts, hst.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    /* the #improvements column (completeSearch :585-589): previous best row's counter, +1 when strictly lower;
+     * rows are taken in restart order k = 0, 1, 2, ... (ties: the earlier row stays the best) */
+    double best_f = 1.0e7; /* pos_miss, getBestLine :791-796 */
+    int best_imp = 0;
+    bool any = false;
+    std::vector<double> rows((size_t)n_k * (nx + 4)), st((size_t)n_k * nx);
+    for (int k = 0; k <= last; k++) {
+        const bool valid = hval[k] != 0;
+        const double fv = hres[(size_t)k * (nx + 1)];
+        int imp = best_imp;
+        if (valid) {
+            if (k > 0 && fv < best_f) imp = best_imp + 1;
+            if (!any || fv < best_f) { best_f = fv; best_imp = imp; any = true; }
+            h->h_res_f[k] = fv; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
+        }
+        if (k < first_k) continue;
+        const int s = k - first_k;
+        rows[(size_t)0 * n_k + s] = 1.0; /* seqNo */
+        rows[(size_t)1 * n_k + s] = (double)k;
+        rows[(size_t)2 * n_k + s] = valid ? (double)imp : 0.0;
+        rows[(size_t)3 * n_k + s] = valid ? fv : NAN;
+        for (int d = 0; d < nx; d++) rows[(size_t)(4 + d) * n_k + s] = valid ? hres[(size_t)k * (nx + 1) + 1 + d] : NAN;
+        if (starts) for (int d = 0; d < nx; d++) st[(size_t)d * n_k + s] = hst[(size_t)d * K + (k - 1)];
+    }
+    if (starts) TK_CUDA(cudaMemcpy(starts, st.data(), st.size() * 8, cudaMemcpyDefault));
+    if (results) TK_CUDA(cudaMemcpy(results, rows.data(), rows.size() * 8, cudaMemcpyDefault));
+    if (evals) TK_CUDA(cudaMemcpy(evals, hev.data() + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDefault));
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* starts, double* results,
+                      int32_t* evals) {
+    if (!h) return TIKTAK_ERR_ARG;
+    if (h->cfg.world > 1) {
+        tk_set_error("local: with world > 1 drive the rounds with local_enqueue / all-gather / local_ingest");
+        return TIKTAK_ERR_UNSUPPORTED;
+    }
+    int rc = tiktak_cuda_local_enqueue(h, alg, first_k, n_k, nullptr);
+    if (rc) return rc;
+    if ((rc = tiktak_cuda_local_ingest(h, first_k, n_k, nullptr))) return rc;
+    return tiktak_cuda_local_fetch(h, first_k, n_k, starts, results, evals);
 }
 
 int tiktak_cuda_best(tiktak_handle* h, double* fbest, double* xbest, int32_t* k) {

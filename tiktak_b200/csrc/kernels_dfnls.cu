@@ -1309,14 +1309,22 @@ int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
     a.n_run = (n_k > a.rank) ? (n_k - a.rank + a.world - 1) / a.world : 0;
     if (a.n_run <= 0) return TIKTAK_OK;
     if (nx > 50) { tk_set_error("DFNLS on the device supports nx <= 50"); return TIKTAK_ERR_UNSUPPORTED; }
-    /* rhobeg / rhoend per restart (completeSearch :564-571): itratio is a single-precision quotient */
-    std::vector<double> rb(n_k), re(n_k);
-    double mn = h->bound[nx] - h->bound[0];
-    for (int i = 1; i < nx; i++) mn = std::min(mn, h->bound[nx + i] - h->bound[i]);
-    for (int s = 0; s < n_k; s++) {
-        const double itratio = (double)((float)(first_k + s) / (float)h->cfg.maxpoints_plus1);
-        if (itratio > 0.5) { rb[s] = (mn / 2.5) / (4 * itratio); re[s] = 1.0e-3 / (4 * itratio); }
-        else { rb[s] = mn / 2.50; re[s] = 1.0e-3; }
+    /* rhobeg / rhoend per restart k (completeSearch :564-571): itratio is a single-precision quotient.
+     * Computed once for all K restarts and kept on the device (d_rho[k-1], d_rho[K + k-1]). */
+    const int K = h->cfg.maxpoints_plus1;
+    if (!h->rho_ready) {
+        std::vector<double> rho((size_t)2 * K);
+        double mn = h->bound[nx] - h->bound[0];
+        for (int i = 1; i < nx; i++) mn = std::min(mn, h->bound[nx + i] - h->bound[i]);
+        for (int k = 1; k <= K; k++) {
+            const double itratio = (double)((float)k / (float)K);
+            if (itratio > 0.5) { rho[k - 1] = (mn / 2.5) / (4 * itratio); rho[K + k - 1] = 1.0e-3 / (4 * itratio); }
+            else { rho[k - 1] = mn / 2.50; rho[K + k - 1] = 1.0e-3; }
+        }
+        if (!h->d_rho) TK_CUDA(cudaMalloc(&h->d_rho, (size_t)2 * K * sizeof(double)));
+        TK_CUDA(cudaMemcpyAsync(h->d_rho, rho.data(), rho.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream)); /* rho is stack-local */
+        h->rho_ready = true;
     }
     const size_t slab = (size_t)mv * (nx + nh + npt + npt + nx + 8) + 8;
     const size_t need = slab * (size_t)a.n_run;
@@ -1326,15 +1334,11 @@ int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
         TK_CUDA(cudaMalloc(&h->d_dfnls_slab, need * sizeof(double)));
         h->dfnls_slab_doubles = need;
     }
-    if (!h->d_rho) TK_CUDA(cudaMalloc(&h->d_rho, (size_t)2 * h->cfg.maxpoints_plus1 * sizeof(double)));
-    if (!h->d_out_status) TK_CUDA(cudaMalloc(&h->d_out_status, (size_t)h->cfg.maxpoints_plus1 * sizeof(int)));
-    TK_CUDA(cudaMemcpyAsync(h->d_rho, rb.data(), (size_t)n_k * 8, cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemcpyAsync(h->d_rho + h->cfg.maxpoints_plus1, re.data(), (size_t)n_k * 8, cudaMemcpyHostToDevice, h->stream));
+    if (!h->d_out_status) TK_CUDA(cudaMalloc(&h->d_out_status, (size_t)K * sizeof(int)));
     TK_CUDA(cudaMemsetAsync(h->d_out_status, 0, (size_t)n_k * sizeof(int), h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream)); /* rb/re are stack-local */
     a.starts = h->d_starts;
-    a.rhobeg = h->d_rho;
-    a.rhoend = h->d_rho + h->cfg.maxpoints_plus1;
+    a.rhobeg = h->d_rho + (first_k - 1);
+    a.rhoend = h->d_rho + K + (first_k - 1);
     a.maxfun = h->cfg.maxeval;
     a.npt = npt; a.mv = mv;
     a.slab = h->d_dfnls_slab; a.slab_doubles = slab;

@@ -25,9 +25,11 @@ struct NmArgs {
     int n_run;            /* restarts this launch runs */
     int n_k;              /* restarts of the round (column length of starts/out_x) */
     int rank, world;      /* restart slot = rank + r*world */
+    int first_k, K;       /* restart number of slot 0; p_maxpoints */
     const double* starts; /* (n_k, nx) column-major */
-    const double* width;  /* nx: p_range(:,2)-p_range(:,1), or (n_k, nx) column-major if per_restart_width */
-    int per_restart_width;
+    const double* width;  /* nx: p_range(:,2)-p_range(:,1) */
+    const double* wshr;   /* nx: simplex width from the best minima so far (nm_shrink_mode = 1), else NULL */
+    const int* shr_have;  /* device flag: wshr is defined (>= 2 finished restarts), else NULL */
     const double* simplex; /* (nx, nx+1) column-major unit simplex */
     double scale;          /* DBLE(p_maxpoints)**(1/nx) */
     double ftol;
@@ -95,10 +97,11 @@ __global__ void __launch_bounds__(128) nm_kernel(const TkTablesG T, const TkScal
     const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
 
     /* runAmoeba :622-627 -- initial simplex around the blended start */
+    const bool shr = a.shr_have && a.shr_have[0] && ((float)(a.first_k + slot) / (float)a.K > 0.5f);
+    const double* wsrc = shr ? a.wshr : a.width;
     for (int e = lane; e < np * nx; e += 32) {
         const int ia = e / nx, i = e - ia * nx;
-        const double wd = a.per_restart_width ? a.width[(size_t)i * a.n_k + slot] : a.width[i];
-        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wd), a.scale));
+        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
         t = fmax(fmin(t, T.bu[i]), T.bl[i]);
         p[e] = t;
     }
@@ -242,174 +245,239 @@ __global__ void __launch_bounds__(128) nm_kernel(const TkTablesG T, const TkScal
 }
 
 /* ---------------------------------------------------------------------------------------------
- * Lane-per-coordinate variant for nx <= 31 (one restart per warp, as above): lane j keeps psum_j and the
- * four trial coordinates of the iteration in registers, lane i keeps y_i, so argmin/argmax are two
- * warp REDUX + one ballot on the order-preserving integer image of y (first occurrence = lowest
- * lane), the per-coordinate `term`s of all four trial points are evaluated by lane j back to back
- * (4-way ILP on the cos chains) and only the in-order `fold` runs on one lane per trial point.
- * Same arithmetic and the same decisions as nm_kernel; ~5x lower latency per simplex iteration.
+ * Variant for nx <= 31 and nterms <= nx: ONE RESTART PER BLOCK OF FOUR WARPS.
+ *
+ * amoeba's iteration is a chain of dependent steps (worst vertex -> reflection -> objFun -> expansion OR
+ * contraction -> objFun -> ...), so a restart is latency-bound; the kernel shortens the chain instead of
+ * widening it:
+ *   - the four trial points an iteration can need (reflection R, expansion from R, contraction after an
+ *     accepted R, contraction after a rejected R) are evaluated AT ONCE, one per warp (one warp per SM
+ *     sub-partition): lane j computes `term` j, lane 0 folds the terms in index order -- the roundings of a
+ *     single-thread evaluation (tiktak_obj.cuh) -- and the four values meet in shared memory behind the one
+ *     block barrier of the iteration.  Which of them count, and the `iter` bookkeeping, follow
+ *     minimize.f90:97-114 exactly, so the trajectory is the sequential one.
+ *   - every warp carries the full simplex state redundantly (own copy of p in shared memory, psum_j in lane
+ *     j), so nothing else is exchanged and all four warps take the same decisions.
+ *   - the vertices are kept SORTED by (y ascending, vertex index descending) across lanes 0..nx: yhi and
+ *     ihi = MAXLOC's first occurrence are lane nx, ynhi (y(inhi) after the y(ihi)=y(ilo) substitution,
+ *     :80-83) is lane nx-1, ylo is lane 0 -- no reductions; replacing the worst vertex is one ballot +
+ *     shuffle-up insertion.  MINLOC's first occurrence (lowest vertex index among equal minima) is only
+ *     needed by the shrink and at the end and is resolved there.
+ *   - out-of-bounds trial points (rare) take the literal getPenalty/dfovec path on one lane.
+ * NXC > 0 compiles nx in (unrolled folds, constant index arithmetic); NXC = 0 reads nx at run time.
  * --------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ unsigned long long nm_order_key(double f) {
-    const unsigned long long u = (unsigned long long)__double_as_longlong(f);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
-}
-__device__ __forceinline__ int warp_first_min_key(unsigned long long key) {
-    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-    return __ffs(__ballot_sync(0xffffffffu, hi == mh && lo == ml)) - 1;
+struct TkLaneX { /* accessor for plugins whose term i reads x[i] only: the lane's own coordinate */
+    double v;
+    __device__ __forceinline__ double operator[](int) const { return v; }
+};
+/* (ya, ra) sorts before (yb, rb): y ascending, vertex index descending among equal y */
+__device__ __forceinline__ bool nm_before(double ya, int ra, double yb, int rb) { return ya < yb || (ya == yb && ra > rb); }
+
+/* sort the np (y, vertex) pairs held one per lane; every lane returns the pair of its sorted position */
+__device__ __forceinline__ void nm_full_sort(double& y, int& row, int np, int lane, double* scr_y, int* scr_r) {
+    int rank = 0;
+    for (int k = 0; k < np; k++) {
+        const double yk = __shfl_sync(0xffffffffu, y, k);
+        const int rk = __shfl_sync(0xffffffffu, row, k);
+        rank += (k != lane && nm_before(yk, rk, y, row)) ? 1 : 0;
+    }
+    __syncwarp();
+    if (lane < np) { scr_y[rank] = y; scr_r[rank] = row; }
+    __syncwarp();
+    if (lane < np) { y = scr_y[lane]; row = scr_r[lane]; }
+    __syncwarp();
 }
 
-template <class Obj>
-__global__ void __launch_bounds__(128) nm_lane_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+/* per-warp scratch of the warp-cooperative objFun */
+struct NmScratch {
+    double* ta;   /* [ts] per-term partials a_i */
+    double* tb;   /* [ts] per-term partials b_i */
+    double* pn;   /* [ts] per-coordinate penalty terms (out-of-bounds points only) */
+    double* cand; /* [ts] the point, for plugins whose terms read neighbouring coordinates */
+};
+
+/* objFun (objective.f90:125-142) at the point whose coordinate j sits in lane j (xj), by one warp; the value
+ * is returned on lane 0.  Lane i evaluates `term` i, lane 0 folds them in index order: the roundings of a
+ * single-thread evaluation.  A point outside the bounds takes the literal getPenalty sum (:51-74: per-
+ * coordinate terms in parallel, summed in index order on lane 0) and dfovec's penalty branch (:92-95). */
+template <class Obj, int NXC>
+__device__ __forceinline__ double nm_eval_warp(const tk_obj_ctx& ctx, const NmScratch& sc, double xj, double blj, double buj,
+                                               int lane, int nx, int nt) {
+    const bool has_j = lane < nx, has_t = lane < nt;
+    const bool oob = __any_sync(0xffffffffu, has_j && (xj < blj || xj > buj));
+    double ta_ = 0.0, tb_ = 0.0;
+    if (Obj::kTermLocal) {
+        if (has_t) Obj::term(ctx, TkLaneX{xj}, lane, ta_, tb_);
+    } else {
+        __syncwarp();
+        if (has_j) sc.cand[lane] = xj;
+        __syncwarp();
+        if (has_t) Obj::term(ctx, TkMemX{sc.cand, 1}, lane, ta_, tb_);
+    }
+    if (has_t) { sc.ta[lane] = ta_; sc.tb[lane] = tb_; }
+    if (oob && has_j) { /* getPenalty :57-66, coordinate `lane` */
+        const double a = TK_DIV(fmax(0.0, TK_SUB(blj, xj)), fmax(0.1, fabs(blj)));
+        const double b = TK_DIV(fmax(0.0, TK_SUB(xj, buj)), fmax(0.1, fabs(buj)));
+        sc.pn[lane] = TK_ADD(TK_MUL(ctx.penaltyc, TK_MUL(a, a)), TK_MUL(ctx.penaltyc, TK_MUL(b, b)));
+    }
+    __syncwarp();
+    double yc = 0.0;
+    if (lane == 0) {
+        double pen = 0.0;
+        if (oob) {
+            double penalty = 0.0;
+            for (int i = 0; i < nx; i++) penalty = TK_ADD(penalty, sc.pn[i]);
+            if (penalty > TK_MYEPS) pen = fmin(ctx.max_penalty, TK_ADD(ctx.penalty0, penalty));
+        }
+        double f;
+        if (pen > TK_MYEPS) {
+            f = TK_DIV(pen, ctx.sqrt_nm); /* objective.f90:93-94 */
+        } else {
+            double s_, p_;
+            Obj::fold_init(ctx, s_, p_);
+            const double2* qa = reinterpret_cast<const double2*>(sc.ta);
+            const double2* qb = reinterpret_cast<const double2*>(sc.tb);
+            if (NXC) {
+                double2 va[(NXC + 1) / 2 + 1], vb[(NXC + 1) / 2 + 1];
+#pragma unroll
+                for (int i = 0; i < (NXC + 1) / 2; i++) { va[i] = qa[i]; vb[i] = qb[i]; }
+#pragma unroll
+                for (int i = 0; i < (NXC + 1) / 2; i++) {
+                    if (2 * i < nt) Obj::fold(s_, p_, va[i].x, vb[i].x);
+                    if (2 * i + 1 < nt) Obj::fold(s_, p_, va[i].y, vb[i].y);
+                }
+            } else {
+                int i = 0;
+                for (; i + 2 <= nt; i += 2) {
+                    const double2 va = qa[i >> 1], vb = qb[i >> 1];
+                    Obj::fold(s_, p_, va.x, vb.x);
+                    Obj::fold(s_, p_, va.y, vb.y);
+                }
+                if (i < nt) Obj::fold(s_, p_, sc.ta[i], sc.tb[i]);
+            }
+            f = Obj::finish(ctx, s_, p_);
+        }
+        yc = tk_objfun_finish(ctx, f, pen);
+    }
+    __syncwarp();
+    return yc;
+}
+
+template <class Obj, int NXC>
+__global__ void __launch_bounds__(128) nm_quad_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
     extern __shared__ double smem[];
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int nx = sc.nx, np = nx + 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nx = NXC ? NXC : sc.nx, np = nx + 1;
     const int nt = Obj::nterms(nx);
+    const int ts = (nx + 2) & ~1; /* even stride >= np */
+    /* block-shared */
     double* sbl = smem;
-    double* sbu = sbl + nx;
-    double* saux = sbu + nx;
+    double* sbu = sbl + ts;
+    double* saux = sbu + ts;
+    double* yv = saux + ts;                     /* yv[vertex]: values of re-evaluated vertices (start, shrink) */
+    double* yx = yv + ts;                       /* yx[parity*4 + c]: the four trial values of an iteration */
+    /* per warp */
+    double* mine = yx + 8 + (size_t)w * (5 * ts + (size_t)np * nx);
+    NmScratch scr;
+    scr.ta = mine;
+    scr.tb = mine + ts;
+    scr.pn = mine + 2 * ts;
+    scr.cand = mine + 3 * ts;
+    int* scr_r = reinterpret_cast<int*>(mine + 4 * ts); /* sort scratch (with scr.cand) */
+    double* p = mine + 5 * ts;                  /* p[i*nx + j]: this warp's copy of the simplex */
     for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
     __syncthreads();
-    const int r = blockIdx.x * wpb + warp;
-    if (r >= a.n_run) return;
-    const int slot = a.rank + r * a.world;
-    const int per_warp = np * nx + 4 * nx + 8 * nx;
-    double* p = smem + 3 * nx + (size_t)warp * per_warp; /* p[i*nx + j] */
-    double* cand = p + np * nx;                           /* cand[c*nx + j] */
-    double* ta = cand + 4 * nx;
-    double* tb = ta + 4 * nx;
+    const int slot = a.rank + (int)blockIdx.x * a.world;
     const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
     const bool has_j = lane < nx, has_i = lane < np;
     const int j = has_j ? lane : 0;
     const double blj = sbl[j], buj = sbu[j];
 
-    /* runAmoeba :622-627 */
+    /* runAmoeba :622-627 -- initial simplex around the blended start */
+    const bool shr = a.shr_have && a.shr_have[0] && ((float)(a.first_k + slot) / (float)a.K > 0.5f);
+    const double* wsrc = shr ? a.wshr : a.width;
     for (int e = lane; e < np * nx; e += 32) {
         const int ia = e / nx, i = e - ia * nx;
-        const double wd = a.per_restart_width ? a.width[(size_t)i * a.n_k + slot] : a.width[i];
-        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wd), a.scale));
+        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
         t = fmax(fmin(t, sbu[i]), sbl[i]);
         p[e] = t;
     }
     __syncwarp();
-    double yl = 0.0; /* y(lane) */
-    if (has_i) yl = tk_objfun<Obj>(ctx, TkMemX{p + (size_t)lane * nx, 1});
-    double psum = 0.0; /* psum(lane) */
+    /* objFun at the vertices: dealt over the four warps, collected through yv */
+    for (int v = w; v < np; v += 4) {
+        const double yc = nm_eval_warp<Obj, NXC>(ctx, scr, p[v * nx + j], blj, buj, lane, nx, nt);
+        if (lane == 0) yv[v] = yc;
+    }
+    __syncthreads();
+    double ys = has_i ? yv[lane] : 0.0; /* y of the vertex at sorted position `lane` */
+    int row = lane;                     /* ... and which vertex (row of p) that is */
+    nm_full_sort(ys, row, np, lane, scr.cand, scr_r);
+    double psum = 0.0; /* psum(lane), amoeba :49 in index order */
     if (has_j)
         for (int i = 0; i < np; i++) psum = TK_ADD(psum, p[i * nx + j]);
 
-    int item_c[4], item_i[4]; /* this lane's (trial point, term) items; c = 4 marks "none" */
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const int e = lane + 32 * u;
-        item_c[u] = (e < 4 * nt) ? e / nt : 4;
-        item_i[u] = (e < 4 * nt) ? e - item_c[u] * nt : 0;
-    }
-    int iter = 0, ilo = 0;
+    int iter = 0;
+    unsigned par = 0;
+    double ylo;
     for (;;) {
-        const unsigned long long key = nm_order_key(yl);
-        ilo = warp_first_min_key(has_i ? key : ~0ULL);
-        const int ihi = warp_first_min_key(has_i ? ~key : ~0ULL);
-        const double ylo = __shfl_sync(FULL, yl, ilo), yhi = __shfl_sync(FULL, yl, ihi);
-        const unsigned long long klo = nm_order_key(ylo);
-        const int inhi = warp_first_min_key(has_i ? ~(lane == ihi ? klo : key) : ~0ULL);
-        const double ynhi = __shfl_sync(FULL, yl, inhi);
+        ylo = __shfl_sync(FULL, ys, 0);
+        const double yhi = __shfl_sync(FULL, ys, nx);
+        const double ynhi = __shfl_sync(FULL, ys, nx - 1);
+        const int ihi = __shfl_sync(FULL, row, nx);
+        /* the four possible trial points (amotry :124-126, unfused); this warp evaluates number w */
+        const double ph = p[ihi * nx + j];
+        const double R = TK_SUB(TK_MUL(psum, a.fac1r), TK_MUL(ph, a.fac2r));
+        const double ps1 = TK_ADD(TK_SUB(psum, ph), R); /* psum after R is accepted (:130) */
+        const double E = TK_SUB(TK_MUL(ps1, a.fac1e), TK_MUL(R, a.fac2e));
+        const double Co = TK_SUB(TK_MUL(ps1, a.fac1c), TK_MUL(R, a.fac2c));
+        const double Ci = TK_SUB(TK_MUL(psum, a.fac1c), TK_MUL(ph, a.fac2c));
         /* rtol < ftol (:84-85); the division is only formed when the product test is within 2^-40 */
         const double num = TK_MUL(2.0, fabs(TK_SUB(yhi, ylo)));
         const double den = TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny);
         const double thr = TK_MUL(a.ftol, den);
-        bool conv;
-        if (num < TK_MUL(thr, 0.99999999999909051)) conv = true;
-        else if (num > TK_MUL(thr, 1.00000000000090949)) conv = false;
-        else conv = TK_DIV(num, den) < a.ftol;
+        bool conv = num < TK_MUL(thr, 0.99999999999909051);
+        if (!conv && !(num > TK_MUL(thr, 1.00000000000090949))) conv = TK_DIV(num, den) < a.ftol;
         if (conv || iter >= a.itmax) break;
 
-        /* trial points (amotry :124-126, unfused) */
-        double ph = has_j ? p[ihi * nx + j] : 0.0;
-        const double R = TK_SUB(TK_MUL(psum, a.fac1r), TK_MUL(ph, a.fac2r));
-        const double ps1 = TK_ADD(TK_SUB(psum, ph), R);
-        const double E = TK_SUB(TK_MUL(ps1, a.fac1e), TK_MUL(R, a.fac2e));
-        const double Co = TK_SUB(TK_MUL(ps1, a.fac1c), TK_MUL(R, a.fac2c));
-        const double Ci = TK_SUB(TK_MUL(psum, a.fac1c), TK_MUL(ph, a.fac2c));
-        unsigned oob = 0;
-        oob |= __ballot_sync(FULL, has_j && (R < blj || R > buj)) ? 1u : 0u;
-        oob |= __ballot_sync(FULL, has_j && (E < blj || E > buj)) ? 2u : 0u;
-        oob |= __ballot_sync(FULL, has_j && (Co < blj || Co > buj)) ? 4u : 0u;
-        oob |= __ballot_sync(FULL, has_j && (Ci < blj || Ci > buj)) ? 8u : 0u;
-        if (has_j) { cand[j] = R; cand[nx + j] = E; cand[2 * nx + j] = Co; cand[3 * nx + j] = Ci; }
-        __syncwarp();
-        /* the 4*nt independent terms, dealt over all 32 lanes (item e = lane + 32u = c*nt + i); the loop is
-         * unrolled so that the (latency-bound) term chains of one lane interleave */
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int c = item_c[u], i = item_i[u];
-            if (c < 4 && !((oob >> c) & 1u)) {
-                double ta_, tb_;
-                Obj::term(ctx, TkMemX{cand + (size_t)c * nx, 1}, i, ta_, tb_);
-                ta[c * nx + i] = ta_;
-                tb[c * nx + i] = tb_;
-            }
-        }
-        __syncwarp();
-        double yc = 0.0;
-        if (lane < 4) {
-            if ((oob >> lane) & 1u) {
-                yc = tk_objfun<Obj>(ctx, TkMemX{cand + (size_t)lane * nx, 1});
-            } else {
-                double s_, p_;
-                Obj::fold_init(ctx, s_, p_);
-                const double* qa = ta + lane * nx;
-                const double* qb = tb + lane * nx;
-                int i = 0;
-                for (; i + 4 <= nt; i += 4) { /* loads first, then the in-order chain */
-                    const double a0 = qa[i], a1 = qa[i + 1], a2 = qa[i + 2], a3 = qa[i + 3];
-                    const double b0 = qb[i], b1 = qb[i + 1], b2 = qb[i + 2], b3 = qb[i + 3];
-                    Obj::fold(s_, p_, a0, b0); Obj::fold(s_, p_, a1, b1);
-                    Obj::fold(s_, p_, a2, b2); Obj::fold(s_, p_, a3, b3);
-                }
-                for (; i < nt; i++) Obj::fold(s_, p_, qa[i], qb[i]);
-                yc = tk_objfun_finish(ctx, Obj::finish(ctx, s_, p_), 0.0);
-            }
-        }
-        const double yR = __shfl_sync(FULL, yc, 0);
+        const double xc = (w == 0) ? R : (w == 1) ? E : (w == 2) ? Co : Ci;
+        const double yc = nm_eval_warp<Obj, NXC>(ctx, scr, xc, blj, buj, lane, nx, nt);
+        if (lane == 0) yx[par * 4 + w] = yc;
+        __syncthreads(); /* the one block barrier of the iteration; yx is double-buffered by parity */
+        const double2 y01 = reinterpret_cast<const double2*>(yx + par * 4)[0];
+        const double2 y23 = reinterpret_cast<const double2*>(yx + par * 4)[1];
+        par ^= 1u;
+        const double yR = y01.x;
         const bool accR = yR < yhi; /* :128 */
-        if (accR) {
-            psum = ps1;
-            if (has_j) p[ihi * nx + j] = R;
-            ph = R;
-            if (lane == ihi) yl = yR;
-        }
+        double pnew = ph, ynew = yhi;
+        bool moved = accR;
+        if (accR) { psum = ps1; pnew = R; ynew = yR; }
         iter++;
         if (yR <= ylo) { /* :99 expansion */
-            double yE = __shfl_sync(FULL, yc, 1);
+            double yE = y01.y;
             double Ev = E;
-            if (!accR) { /* unreachable unless all y are equal; evaluated from the live state */
+            if (!accR) { /* only when every y is equal; not speculated -- evaluated from the live state */
                 Ev = TK_SUB(TK_MUL(psum, a.fac1e), TK_MUL(ph, a.fac2e));
-                if (has_j) cand[nx + j] = Ev;
-                __syncwarp();
-                double t_ = 0.0;
-                if (lane == 0) t_ = tk_objfun<Obj>(ctx, TkMemX{cand + nx, 1});
-                yE = __shfl_sync(FULL, t_, 0);
+                yE = __shfl_sync(FULL, nm_eval_warp<Obj, NXC>(ctx, scr, Ev, blj, buj, lane, nx, nt), 0);
             }
             iter++;
-            const double ycur = accR ? yR : yhi;
-            if (yE < ycur) {
-                psum = TK_ADD(TK_SUB(psum, ph), Ev);
-                if (has_j) p[ihi * nx + j] = Ev;
-                if (lane == ihi) yl = yE;
+            if (yE < ynew) {
+                psum = TK_ADD(TK_SUB(psum, pnew), Ev);
+                pnew = Ev; ynew = yE; moved = true;
             }
         } else if (yR >= ynhi) { /* :102 contraction */
-            const double ysave = accR ? yR : yhi;
-            const double yC = __shfl_sync(FULL, yc, accR ? 2 : 3);
+            const double yC = accR ? y23.x : y23.y;
             const double Cv = accR ? Co : Ci;
             iter++;
-            if (yC < ysave) {
-                psum = TK_ADD(TK_SUB(psum, ph), Cv);
-                if (has_j) p[ihi * nx + j] = Cv;
-                if (lane == ihi) yl = yC;
-            } else { /* :106-113 shrink */
+            if (yC < ynew) {
+                psum = TK_ADD(TK_SUB(psum, pnew), Cv);
+                pnew = Cv; ynew = yC; moved = true;
+            } else { /* :106-113 shrink toward the best vertex, re-evaluate, re-sum */
+                if (moved && has_j) p[ihi * nx + j] = pnew;
+                if (lane == nx) ys = ynew;
+                moved = false;
+                /* MINLOC: the lowest vertex index among the minima.  ynew > ylo here, so lane nx is not one. */
+                const int ilo = (int)__reduce_min_sync(FULL, (has_i && ys == ylo) ? (unsigned)row : 0xffffffffu);
                 __syncwarp();
                 if (has_j) {
                     const double pl = p[ilo * nx + j];
@@ -417,19 +485,40 @@ __global__ void __launch_bounds__(128) nm_lane_kernel(const TkTablesG T, const T
                         if (i != ilo) p[i * nx + j] = TK_MUL(0.5, TK_ADD(p[i * nx + j], pl));
                 }
                 __syncwarp();
-                if (has_i && lane != ilo) yl = tk_objfun<Obj>(ctx, TkMemX{p + (size_t)lane * nx, 1});
+                for (int v = w; v < np; v += 4) {
+                    if (v == ilo) continue;
+                    const double yc2 = nm_eval_warp<Obj, NXC>(ctx, scr, p[v * nx + j], blj, buj, lane, nx, nt);
+                    if (lane == 0) yv[v] = yc2;
+                }
+                __syncthreads();
+                if (has_i && row != ilo) ys = yv[row];
                 iter += nx;
+                nm_full_sort(ys, row, np, lane, scr.cand, scr_r);
                 psum = 0.0;
                 if (has_j)
                     for (int i = 0; i < np; i++) psum = TK_ADD(psum, p[i * nx + j]);
+                __syncthreads(); /* yv may be rewritten by the next shrink only after every warp has read it */
             }
+        }
+        if (moved) { /* vertex ihi takes (pnew, ynew): remove lane nx, insert at its sorted position */
+            if (has_j) p[ihi * nx + j] = pnew;
+            const int pos = __popc(__ballot_sync(FULL, lane < nx && nm_before(ys, row, ynew, ihi)));
+            const double yu = __shfl_up_sync(FULL, ys, 1);
+            const int ru = __shfl_up_sync(FULL, row, 1);
+            if (lane > pos && lane <= nx) { ys = yu; row = ru; }
+            if (lane == pos) { ys = ynew; row = ihi; }
         }
         __syncwarp();
     }
-    if (has_j) a.out_x[(size_t)j * a.n_k + slot] = p[ilo * nx + j];
-    if (lane == ilo) {
-        a.out_f[slot] = yl;
-        a.out_evals[slot] = np + iter + 1;
+    /* runAmoeba :631-632 returns the first minimal vertex; completeSearch :582 re-evaluates objFun there:
+     * same point, same value. */
+    if (w == 0) {
+        const int ilo = (int)__reduce_min_sync(FULL, (has_i && ys == ylo) ? (unsigned)row : 0xffffffffu);
+        if (has_j) a.out_x[(size_t)j * a.n_k + slot] = p[ilo * nx + j];
+        if (lane == 0) {
+            a.out_f[slot] = ylo;
+            a.out_evals[slot] = np + iter + 1;
+        }
     }
 }
 
@@ -468,7 +557,7 @@ __global__ void best_kernel(const double* res, const int* valid, int nrows, int 
 /* getModifiedParam (:683-720): start = w11*best + (1-w11)*x_starts(k), unfused; w11 is the
  * single-precision weight widened to double (computed on the host, h->w11). */
 __global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11,
-                             const double* best, double* starts) {
+                             const double* best, double* starts, double* arch_starts) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_k * nx) return;
     const int d = e / n_k, s = e - d * n_k, k = first_k + s; /* k is 1-based */
@@ -479,6 +568,138 @@ __global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n
         out = TK_ADD(TK_MUL(w, best[3 + d]), TK_MUL(TK_SUB(1.0, w), ev));
     }
     starts[(size_t)d * n_k + s] = out;
+    arch_starts[(size_t)d * K + (k - 1)] = out; /* the searchStart.dat row of restart k (:557) */
+}
+
+/* One round's outcomes -> the device-resident searchResults table (completeSearch :582-597 without the
+ * file): row k = [fval, x] through the f40.20 record when text_roundtrip is on, the evaluation count, and
+ * the running best row (getBestLine :781-802: lowest fval, first row among equals) -- so the next round's
+ * blend needs no re-read and no re-sort.  Source: this GPU's slot-indexed outputs (world == 1), or the
+ * all-gathered packed rows [rank][n_max][nx+2] = f, x, evals (slot s was run by rank s % world). */
+struct IngestArgs {
+    int first_k, n_k, nx, world, n_max, roundtrip;
+    const double* pack;
+    const double* out_f;
+    const double* out_x;
+    const int* out_evals;
+    double* res;
+    int* valid;
+    int* arch_evals;
+    double* best;
+};
+__global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs g) {
+    __shared__ double sv[256];
+    __shared__ int sk[256];
+    __shared__ int sc[256];
+    __shared__ int take;
+    const int nx = g.nx;
+    double v = DBL_MAX; int bk = 0x7fffffff, cnt = 0;
+    for (int s = threadIdx.x; s < g.n_k; s += blockDim.x) {
+        const double* row = g.pack ? g.pack + ((size_t)(s % g.world) * g.n_max + s / g.world) * (nx + 2) : nullptr;
+        const double f = row ? row[0] : g.out_f[s];
+        if (!(f == f)) continue;
+        const int k = g.first_k + s;
+        const double frt = g.roundtrip ? tk_f4020_roundtrip(f) : f;
+        double* dst = g.res + (size_t)k * (nx + 1);
+        dst[0] = frt;
+        for (int d = 0; d < nx; d++) {
+            const double xv = row ? row[1 + d] : g.out_x[(size_t)d * g.n_k + s];
+            dst[1 + d] = g.roundtrip ? tk_f4020_roundtrip(xv) : xv;
+        }
+        g.valid[k] = 1;
+        g.arch_evals[k] = row ? (int)row[nx + 1] : g.out_evals[s];
+        cnt++;
+        if (bk == 0x7fffffff || frt < v) { v = frt; bk = k; }
+    }
+    sv[threadIdx.x] = v; sk[threadIdx.x] = bk; sc[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double v2 = sv[threadIdx.x + o]; const int k2 = sk[threadIdx.x + o];
+            if (k2 != 0x7fffffff && (sk[threadIdx.x] == 0x7fffffff || v2 < sv[threadIdx.x] ||
+                                     (v2 == sv[threadIdx.x] && k2 < sk[threadIdx.x]))) {
+                sv[threadIdx.x] = v2; sk[threadIdx.x] = k2;
+            }
+            sc[threadIdx.x] += sc[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const bool none = g.best[1] < 0.0;
+        take = (sk[0] != 0x7fffffff) && (none || sv[0] < g.best[0]);
+        g.best[2] = (none ? 0.0 : g.best[2]) + (double)sc[0];
+        if (take) { g.best[0] = sv[0]; g.best[1] = (double)sk[0]; }
+    }
+    __syncthreads();
+    if (take)
+        for (int d = threadIdx.x; d < nx; d += blockDim.x) g.best[3 + d] = g.res[(size_t)sk[0] * (nx + 1) + 1 + d];
+}
+
+/* this rank's slots of the round, packed for the all-gather: row q = slot rank + q*world = [f, x, evals] */
+__global__ void pack_kernel(int n_k, int nx, int rank, int world, const double* out_f, const double* out_x,
+                            const int* out_evals, double* pack) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = rank + q * world;
+    if (s >= n_k) return;
+    double* row = pack + (size_t)q * (nx + 2);
+    row[0] = out_f[s];
+    for (int d = 0; d < nx; d++) row[1 + d] = out_x[(size_t)d * n_k + s];
+    row[nx + 1] = (double)out_evals[s];
+}
+
+/* nm_shrink_mode = 1 (README.md:36, SURVEY finding 3): per-coordinate spread of the (up to) 10 best local
+ * minima known so far, ordered by (fval, k); wshr = max - min where positive, else the Sobol range width;
+ * have = at least two finished restarts.  One block; 10 argmin passes over the result rows. */
+__global__ void __launch_bounds__(256) shrink_width_kernel(const double* res, const int* valid, int K, int nx,
+                                                           const double* width, double* wshr, int* have) {
+    __shared__ double sv[256];
+    __shared__ int sk[256];
+    __shared__ int topk[10];
+    __shared__ int T;
+    double pf = 0.0; int pk = -1;
+    if (threadIdx.x == 0) T = 0;
+    for (int t = 0; t < 10; t++) {
+        double v = DBL_MAX; int bk = 0x7fffffff;
+        for (int k = 1 + threadIdx.x; k <= K; k += blockDim.x) {
+            if (!valid[k]) continue;
+            const double f = res[(size_t)k * (nx + 1)];
+            if (pk >= 0 && !(f > pf || (f == pf && k > pk))) continue;
+            if (bk == 0x7fffffff || f < v) { v = f; bk = k; }
+        }
+        sv[threadIdx.x] = v; sk[threadIdx.x] = bk;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                const double v2 = sv[threadIdx.x + o]; const int k2 = sk[threadIdx.x + o];
+                if (k2 != 0x7fffffff && (sk[threadIdx.x] == 0x7fffffff || v2 < sv[threadIdx.x] ||
+                                         (v2 == sv[threadIdx.x] && k2 < sk[threadIdx.x]))) {
+                    sv[threadIdx.x] = v2; sk[threadIdx.x] = k2;
+                }
+            }
+            __syncthreads();
+        }
+        const int fk = sk[0];
+        const double ff = sv[0];
+        __syncthreads();
+        if (fk == 0x7fffffff) break;
+        if (threadIdx.x == 0) { topk[t] = fk; T = t + 1; }
+        pf = ff; pk = fk;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) have[0] = (T >= 2) ? 1 : 0;
+    for (int d = threadIdx.x; d < nx; d += blockDim.x) {
+        double w = width[d];
+        if (T >= 2) {
+            double mn = res[(size_t)topk[0] * (nx + 1) + 1 + d], mx = mn;
+            for (int t = 1; t < T; t++) {
+                const double x = res[(size_t)topk[t] * (nx + 1) + 1 + d];
+                mn = fmin(mn, x); mx = fmax(mx, x);
+            }
+            const double ww = TK_SUB(mx, mn);
+            if (ww > 0.0) w = ww;
+        }
+        wshr[d] = w;
+    }
 }
 
 } /* namespace */
@@ -493,9 +714,46 @@ int tk_launch_best(tiktak_handle* h) {
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k) {
     const int tot = n_k * h->cfg.nx;
     blend_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, h->cfg.maxpoints_plus1, h->cfg.nx, first_k, n_k,
-                                                            h->d_w11, h->d_best, h->d_starts);
+                                                            h->d_w11, h->d_best, h->d_starts, h->d_arch_starts);
     h->launches++;
     TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, const double* pack) {
+    IngestArgs g;
+    g.first_k = first_k; g.n_k = n_k; g.nx = h->cfg.nx; g.world = h->cfg.world;
+    g.n_max = (n_k + h->cfg.world - 1) / h->cfg.world;
+    g.roundtrip = h->cfg.text_roundtrip;
+    g.pack = pack; g.out_f = h->d_out_f; g.out_x = h->d_out_x; g.out_evals = h->d_out_evals;
+    g.res = h->d_res; g.valid = h->d_res_valid; g.arch_evals = h->d_arch_evals; g.best = h->d_best;
+    ingest_kernel<<<1, 256, 0, h->stream>>>(g);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_launch_pack(tiktak_handle* h, int n_k, double* pack) {
+    const int n_max = (n_k + h->cfg.world - 1) / h->cfg.world;
+    pack_kernel<<<(n_max + 127) / 128, 128, 0, h->stream>>>(n_k, h->cfg.nx, h->cfg.rank, h->cfg.world, h->d_out_f, h->d_out_x,
+                                                            h->d_out_evals, pack);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_launch_shrink_width(tiktak_handle* h) {
+    shrink_width_kernel<<<1, 256, 0, h->stream>>>(h->d_res, h->d_res_valid, h->cfg.maxpoints_plus1, h->cfg.nx, h->d_width,
+                                                  h->d_wshr, h->d_shr_have);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+template <class Obj, int NXC>
+static int nm_launch_warp(tiktak_handle* h, const TkTablesG& T, const NmArgs& a, size_t shmem) {
+    TK_CUDA(cudaFuncSetAttribute(nm_quad_kernel<Obj, NXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    nm_quad_kernel<Obj, NXC><<<(unsigned)a.n_run, 128, shmem, h->stream>>>(T, h->sc, a);
     return TIKTAK_OK;
 }
 
@@ -507,9 +765,12 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     a.world = h->cfg.world;
     a.n_run = (n_k > a.rank) ? (n_k - a.rank + a.world - 1) / a.world : 0;
     if (a.n_run <= 0) return TIKTAK_OK;
+    a.first_k = first_k;
+    a.K = h->cfg.maxpoints_plus1;
     a.starts = h->d_starts;
-    a.width = h->use_round_width ? h->d_width_round : h->d_width;
-    a.per_restart_width = h->use_round_width ? 1 : 0;
+    a.width = h->d_width;
+    a.wshr = h->cfg.nm_shrink_mode == 1 ? h->d_wshr : nullptr;
+    a.shr_have = h->cfg.nm_shrink_mode == 1 ? h->d_shr_have : nullptr;
     a.simplex = h->d_simplex;
     a.scale = h->nm_scale;
     a.ftol = h->cfg.nm_ftol;
@@ -522,29 +783,34 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     a.out_x = h->d_out_x;
     a.out_f = h->d_out_f;
     a.out_evals = h->d_out_evals;
-    (void)first_k;
-    const bool lane_variant = nx <= 31;
-    const size_t per_warp = (size_t)(lane_variant ? (np * nx + 12 * nx) : (np * nx + np + nx + 4 * nx + 4 + 8 * nx)) * sizeof(double);
-    const size_t per_block = (size_t)3 * nx * sizeof(double);
-    int wpb = 4;
-    while (wpb > 1 && per_warp * wpb + per_block > 200 * 1024) wpb >>= 1;
-    if (per_warp * wpb + per_block > 227 * 1024) {
-        tk_set_error("nx=%d: Nelder-Mead simplex does not fit in shared memory", nx);
-        return TIKTAK_ERR_UNSUPPORTED;
-    }
-    /* spread the restarts over the SMs before stacking warps in a block */
-    while (wpb > 1 && (a.n_run + wpb - 1) / wpb < h->sm_count) wpb >>= 1;
-    const size_t shmem = per_warp * wpb + per_block;
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
-        const unsigned grid = (unsigned)((a.n_run + wpb - 1) / wpb);
-        if (lane_variant) {
-            TK_CUDA(cudaFuncSetAttribute(nm_lane_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            nm_lane_kernel<Obj><<<grid, wpb * 32, shmem, h->stream>>>(T, h->sc, a);
+        int rc = TIKTAK_OK;
+        if (nx <= 31 && Obj::nterms(nx) <= nx) { /* one restart per block of four warps */
+            const int ts = (nx + 2) & ~1;
+            const size_t shmem = (size_t)(4 * ts + 8 + 4 * (5 * ts + np * nx)) * sizeof(double);
+            switch (nx) {
+                case 4: rc = nm_launch_warp<Obj, 4>(h, T, a, shmem); break;
+                case 10: rc = nm_launch_warp<Obj, 10>(h, T, a, shmem); break;
+                case 20: rc = nm_launch_warp<Obj, 20>(h, T, a, shmem); break;
+                default: rc = nm_launch_warp<Obj, 0>(h, T, a, shmem); break;
+            }
         } else {
+            const size_t per_warp = (size_t)(np * nx + np + nx + 4 * nx + 4 + 8 * nx) * sizeof(double);
+            const size_t per_block = (size_t)3 * nx * sizeof(double);
+            int wpb = 4;
+            while (wpb > 1 && per_warp * wpb + per_block > 200 * 1024) wpb >>= 1;
+            if (per_warp * wpb + per_block > 227 * 1024) {
+                tk_set_error("nx=%d: Nelder-Mead simplex does not fit in shared memory", nx);
+                return TIKTAK_ERR_UNSUPPORTED;
+            }
+            /* spread the restarts over the SMs before stacking warps in a block */
+            while (wpb > 1 && (a.n_run + wpb - 1) / wpb < h->sm_count) wpb >>= 1;
+            const unsigned grid = (unsigned)((a.n_run + wpb - 1) / wpb);
             TK_CUDA(cudaFuncSetAttribute(nm_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            nm_kernel<Obj><<<grid, wpb * 32, shmem, h->stream>>>(T, h->sc, a);
+            nm_kernel<Obj><<<grid, wpb * 32, per_warp * wpb + per_block, h->stream>>>(T, h->sc, a);
         }
+        if (rc) return rc;
         h->launches++;
         TK_CUDA(cudaGetLastError());
         return TIKTAK_OK;

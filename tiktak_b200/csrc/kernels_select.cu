@@ -9,6 +9,8 @@
  * rank-by-counting pass.  Order among exactly equal fvals is ascending Sobol index (indexx's order
  * among equal keys is an artefact of its partitioning; DESIGN.md "ties").
  */
+#include <utility>
+
 #include "tk_common.cuh"
 #include "smm.cuh"
 
@@ -102,28 +104,117 @@ select_collect_kernel(const SelView v, const unsigned long long* state, double* 
     }
 }
 
-/* order m candidates by (key, n): rank = number of strictly smaller composites (all distinct) */
+/* Ordering the winners by (key, n) -- all composites are distinct because every n occurs once.
+ * Runs of SORT_CHUNK candidates are sorted in shared memory (bitonic network), then merged pairwise by
+ * rank: an element's position in the merged run is its own index plus the number of partner-run elements
+ * below it (binary search), so every pass is one fully parallel kernel and the whole sort is
+ * O(m log^2 m) work at any m (the multi-GPU merge of world x (K-1) candidates included). */
+#define SORT_CHUNK 1024
+struct Comp { unsigned long long key; unsigned int n; };
+__device__ __forceinline__ bool comp_less(unsigned long long ka, unsigned int na, unsigned long long kb, unsigned int nb) {
+    return ka < kb || (ka == kb && na < nb);
+}
 __global__ void __launch_bounds__(256)
-rank_sort_kernel(const double* cf, const unsigned int* ci, unsigned int m, double* sf, unsigned int* si) {
-    __shared__ unsigned long long tk[256];
-    __shared__ unsigned int tn[256];
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long mykey = 0;
-    unsigned int myn = 0;
-    double myf = 0;
-    if (i < m) { myf = cf[i]; mykey = tk_order_key(myf); myn = ci[i]; }
-    unsigned int rank = 0;
-    for (unsigned int base = 0; base < m; base += 256) {
-        const unsigned int j = base + threadIdx.x;
-        if (j < m) { tk[threadIdx.x] = tk_order_key(cf[j]); tn[threadIdx.x] = ci[j]; }
-        __syncthreads();
-        const unsigned int lim = min(256u, m - base);
-        if (i < m)
-            for (unsigned int u = 0; u < lim; u++)
-                rank += (tk[u] < mykey || (tk[u] == mykey && tn[u] < myn)) ? 1u : 0u;
-        __syncthreads();
+chunk_sort_kernel(const double* cf, const unsigned int* ci, unsigned int m, double* sf, unsigned int* si) {
+    __shared__ unsigned long long k[SORT_CHUNK];
+    __shared__ unsigned int n[SORT_CHUNK];
+    const unsigned int base = blockIdx.x * SORT_CHUNK;
+    for (unsigned int t = threadIdx.x; t < SORT_CHUNK; t += blockDim.x) {
+        const unsigned int e = base + t;
+        /* padding sorts last: NaN never reaches here, so the all-ones key is free */
+        k[t] = (e < m) ? tk_order_key(cf[e]) : ~0ULL;
+        n[t] = (e < m) ? ci[e] : 0xffffffffu;
     }
-    if (i < m) { sf[rank] = myf; si[rank] = myn; }
+    __syncthreads();
+    for (unsigned int size = 2; size <= SORT_CHUNK; size <<= 1)
+        for (unsigned int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned int t = threadIdx.x; t < SORT_CHUNK / 2; t += blockDim.x) {
+                const unsigned int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long ka = k[lo], kb = k[hi];
+                const unsigned int na = n[lo], nb = n[hi];
+                if (comp_less(kb, nb, ka, na) == up) { k[lo] = kb; k[hi] = ka; n[lo] = nb; n[hi] = na; }
+            }
+            __syncthreads();
+        }
+    for (unsigned int t = threadIdx.x; t < SORT_CHUNK; t += blockDim.x) {
+        const unsigned int e = base + t;
+        if (e < m) {
+            const unsigned long long u = k[t];
+            sf[e] = __longlong_as_double((long long)((u >> 63) ? (u ^ 0x8000000000000000ULL) : ~u));
+            si[e] = n[t];
+        }
+    }
+}
+/* merge neighbouring sorted runs of length `run` (the last one may be short) */
+__global__ void __launch_bounds__(256)
+merge_pass_kernel(const double* inf, const unsigned int* ini, unsigned int m, unsigned int run, double* outf,
+                  unsigned int* outi) {
+    const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const unsigned int pair = e / (2 * run), base = pair * 2 * run;
+    const bool inA = (e - base) < run;
+    const unsigned int ob = inA ? base + run : base;               /* partner run */
+    const unsigned int oe = inA ? min(base + 2 * run, m) : base + run;
+    const double f = inf[e];
+    const unsigned long long key = tk_order_key(f);
+    const unsigned int n = ini[e];
+    unsigned int lo = ob, hi = (ob < oe) ? oe : ob; /* count partner elements below (key, n) */
+    while (lo < hi) {
+        const unsigned int mid = (lo + hi) >> 1;
+        if (comp_less(tk_order_key(inf[mid]), ini[mid], key, n)) lo = mid + 1; else hi = mid;
+    }
+    const unsigned int below = lo - ob;
+    const unsigned int pos = base + (inA ? (e - base) : (e - base - run)) + below;
+    outf[pos] = f;
+    outi[pos] = n;
+}
+
+/* multi-GPU merge: `world` candidate lists, each (M+1) rows of [fval, (double)n]: rows 0..cnt-1 sorted by
+ * (fval, n), NaN padding, and a trailer row [#valid points of the shard, cnt].  Position of an element in
+ * the union = its index in its own list + the number of elements below it in every other list. */
+__global__ void __launch_bounds__(256)
+merge_lists_kernel(const double* cand, int world, unsigned int M, double* outf, unsigned int* outi, unsigned int* total) {
+    const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) {
+        unsigned int t = 0;
+        for (int r = 0; r < world; r++) t += (unsigned int)cand[((size_t)r * (M + 1) + M) * 2 + 1];
+        *total = t < M ? t : M;
+    }
+    if (e >= (unsigned int)world * M) return;
+    const int r = e / M;
+    const unsigned int i = e - r * M;
+    const double* mine = cand + (size_t)r * (M + 1) * 2;
+    if (i >= (unsigned int)mine[(size_t)M * 2 + 1]) return;
+    const double f = mine[2 * i];
+    const unsigned long long key = tk_order_key(f);
+    const unsigned int n = (unsigned int)mine[2 * i + 1];
+    unsigned int pos = i;
+    for (int q = 0; q < world; q++) {
+        if (q == r) continue;
+        const double* oth = cand + (size_t)q * (M + 1) * 2;
+        unsigned int lo = 0, hi = (unsigned int)oth[(size_t)M * 2 + 1];
+        while (lo < hi) {
+            const unsigned int mid = (lo + hi) >> 1;
+            if (comp_less(tk_order_key(oth[2 * mid]), (unsigned int)oth[2 * mid + 1], key, n)) lo = mid + 1; else hi = mid;
+        }
+        pos += lo;
+    }
+    if (pos < M) { outf[pos] = f; outi[pos] = n; }
+}
+/* this shard's list in that format */
+__global__ void export_candidates_kernel(const double* sf, const unsigned int* si, unsigned int cnt, unsigned int M,
+                                         const unsigned long long* counts, int64_t ncb, double* cand) {
+    const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < M) {
+        cand[2 * e] = (e < cnt) ? sf[e] : __longlong_as_double(0x7ff8000000000000LL);
+        cand[2 * e + 1] = (e < cnt) ? (double)si[e] : 0.0;
+    } else if (e == M) {
+        unsigned long long v = 0;
+        for (int64_t b = 0; b < ncb; b++) v += counts[b];
+        cand[2 * e] = (double)v;
+        cand[2 * e + 1] = (double)cnt;
+    }
 }
 
 /* x_starts rows 2..: [fval, Sobol point n], through the f40.20 record when text_roundtrip is on
@@ -156,6 +247,8 @@ __global__ void init_row_kernel(const double* init, const double* finit, int nx,
 }
 
 } /* namespace */
+
+int tk_sort_candidates(tiktak_handle* h, double* d_f, unsigned int* d_i, int64_t n, double* d_sf, unsigned int* d_si);
 
 /* select the M smallest evaluated points of this shard into d_sorted_f / d_sorted_i (n_cand of them) */
 int tk_select_top(tiktak_handle* h, int64_t M) {
@@ -200,18 +293,47 @@ int tk_select_top(tiktak_handle* h, int64_t M) {
     }
     select_collect_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n,
                                                        (unsigned int)m);
-    rank_sort_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cand_f, h->d_cand_i, (unsigned int)m,
-                                                                          h->d_sorted_f, h->d_sorted_i);
-    h->launches += 2;
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return tk_sort_candidates(h, h->d_cand_f, h->d_cand_i, m, h->d_sorted_f, h->d_sorted_i);
+}
+
+/* order n candidates by (fval, n): d_f/d_i are clobbered (ping-pong), the result lands in d_sf/d_si */
+int tk_sort_candidates(tiktak_handle* h, double* d_f, unsigned int* d_i, int64_t n, double* d_sf, unsigned int* d_si) {
+    if (n <= 0) return TIKTAK_OK;
+    const unsigned int m = (unsigned int)n;
+    int passes = 0;
+    for (unsigned int run = SORT_CHUNK; run < m; run <<= 1) passes++;
+    /* an even number of merge passes must end in (d_sf, d_si): start there when `passes` is even */
+    double* af = (passes % 2 == 0) ? d_sf : d_f;
+    unsigned int* ai = (passes % 2 == 0) ? d_si : d_i;
+    double* bf = (passes % 2 == 0) ? d_f : d_sf;
+    unsigned int* bi = (passes % 2 == 0) ? d_i : d_si;
+    /* chunk sort reads the input; when it writes in place that is safe (each block loads its chunk first) */
+    chunk_sort_kernel<<<(m + SORT_CHUNK - 1) / SORT_CHUNK, 256, 0, h->stream>>>(d_f, d_i, m, af, ai);
+    h->launches++;
+    for (unsigned int run = SORT_CHUNK; run < m; run <<= 1) {
+        merge_pass_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(af, ai, m, run, bf, bi);
+        h->launches++;
+        std::swap(af, bf); std::swap(ai, bi);
+    }
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;
 }
 
-/* order an externally supplied candidate list (multi-GPU merge) and keep the best M */
-int tk_sort_candidates(tiktak_handle* h, const double* d_f, const unsigned int* d_i, int64_t n, double* d_sf,
-                       unsigned int* d_si) {
-    if (n <= 0) return TIKTAK_OK;
-    rank_sort_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_f, d_i, (unsigned int)n, d_sf, d_si);
+int tk_export_candidates(tiktak_handle* h, double* d_cand) {
+    const unsigned int M = (unsigned int)(h->cfg.maxpoints_plus1 - 1);
+    export_candidates_kernel<<<(M + 1 + 127) / 128, 128, 0, h->stream>>>(h->d_sorted_f, h->d_sorted_i, (unsigned int)h->n_cand, M,
+                                                                         h->d_counts, h->n_cblocks, d_cand);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_merge_candidates(tiktak_handle* h, const double* d_cand) {
+    const unsigned int M = (unsigned int)(h->cfg.maxpoints_plus1 - 1);
+    const unsigned int tot = M * (unsigned int)h->cfg.world;
+    merge_lists_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(d_cand, h->cfg.world, M, h->d_sorted_f, h->d_sorted_i, h->d_cand_n);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;

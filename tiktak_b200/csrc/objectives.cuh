@@ -14,10 +14,11 @@
 struct ObjTemplate { /* val1 = sum x^2/200 ; val2 = cos(x1) * prod cos(x_i/sqrt(i)) ; v = val1 - val2 + 1 + 1 */
     static constexpr int kId = TIKTAK_OBJ_TEMPLATE;
     static constexpr bool kVector = false;
+    static constexpr bool kTermLocal = true;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = sqrt((double)(i + 1) + 0.0); /* sqrt(ii+0.0D0), :106 */
     }
-    static __device__ __forceinline__ int nterms(int nx) { return nx; }
+    static __host__ __device__ __forceinline__ int nterms(int nx) { return nx; }
     template <class X>
     static __device__ __forceinline__ void term(const tk_obj_ctx& c, const X& x, int i, double& a, double& b) {
         const double xi = x[i];
@@ -37,10 +38,11 @@ struct ObjTemplate { /* val1 = sum x^2/200 ; val2 = cos(x1) * prod cos(x_i/sqrt(
 struct ObjGriewank { /* f = 1 + sum x^2/4000 - prod cos(x_i/sqrt(i)) */
     static constexpr int kId = TIKTAK_OBJ_GRIEWANK;
     static constexpr bool kVector = false;
+    static constexpr bool kTermLocal = true;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 1.0 / sqrt((double)(i + 1));
     }
-    static __device__ __forceinline__ int nterms(int nx) { return nx; }
+    static __host__ __device__ __forceinline__ int nterms(int nx) { return nx; }
     template <class X>
     static __device__ __forceinline__ void term(const tk_obj_ctx& c, const X& x, int i, double& a, double& b) {
         const double xi = x[i];
@@ -60,10 +62,11 @@ struct ObjGriewank { /* f = 1 + sum x^2/4000 - prod cos(x_i/sqrt(i)) */
 struct ObjRastrigin { /* f = 10 n + sum (x^2 - 10 cos(2 pi x)) */
     static constexpr int kId = TIKTAK_OBJ_RASTRIGIN;
     static constexpr bool kVector = false;
+    static constexpr bool kTermLocal = true;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }
-    static __device__ __forceinline__ int nterms(int nx) { return nx; }
+    static __host__ __device__ __forceinline__ int nterms(int nx) { return nx; }
     template <class X>
     static __device__ __forceinline__ void term(const tk_obj_ctx&, const X& x, int i, double& a, double& b) {
         const double xi = x[i];
@@ -81,10 +84,11 @@ struct ObjRastrigin { /* f = 10 n + sum (x^2 - 10 cos(2 pi x)) */
 struct ObjRosenbrock { /* f = sum_{i<n} 100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2 */
     static constexpr int kId = TIKTAK_OBJ_ROSENBROCK;
     static constexpr bool kVector = false;
+    static constexpr bool kTermLocal = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }
-    static __device__ __forceinline__ int nterms(int nx) { return nx - 1; }
+    static __host__ __device__ __forceinline__ int nterms(int nx) { return nx - 1; }
     template <class X>
     static __device__ __forceinline__ void term(const tk_obj_ctx&, const X& x, int i, double& a, double& b) {
         const double x0 = x[i];

@@ -102,8 +102,14 @@ struct tiktak_handle {
     /* local stage scratch */
     double *d_starts = nullptr, *d_out_x = nullptr, *d_out_f = nullptr, *d_width = nullptr;
     int* d_out_evals = nullptr;
-    double* d_width_round = nullptr; /* (n_k, nx) column-major per-restart simplex widths (nm_shrink_mode = 1) */
-    bool use_round_width = false;
+    double* d_wshr = nullptr;        /* nx: simplex widths from the best minima so far (nm_shrink_mode = 1) */
+    int* d_shr_have = nullptr;
+    double* d_arch_starts = nullptr; /* (K, nx) column-major: the searchStart.dat rows of every restart */
+    int* d_arch_evals = nullptr;     /* [K+1]: objective evaluations of restart k */
+    bool best_dirty = true;          /* d_best must be recomputed from the rows (after push_results) */
+    cudaEvent_t evl0 = nullptr, evl1 = nullptr;
+    bool local_timing_open = false;
+    bool rho_ready = false;
     /* DFNLS */
     double* d_dfnls_slab = nullptr;
     size_t dfnls_slab_doubles = 0;
@@ -127,6 +133,9 @@ int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
+int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, const double* pack);
+int tk_launch_pack(tiktak_handle* h, int n_k, double* pack);
+int tk_launch_shrink_width(tiktak_handle* h);
 int tk_fp64_peak(int device, double* flops, double* ms);
 
 /* objective dispatch: calls f.template operator()<Obj>() for the configured plugin */

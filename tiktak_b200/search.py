@@ -86,10 +86,18 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_stage_ms(self._h, stage.encode(), C.byref(ms)), "stage_ms")
         return ms.value
 
-    def _dist(self):
-        import torch.distributed as dist
+    def stream_ptr(self):
+        """the cudaStream_t every kernel of this handle is queued on"""
+        return int(self._L.tiktak_cuda_stream(self._h) or 0)
 
-        return dist
+    def torch_stream(self):
+        """that stream as a torch stream: collectives issued under `with torch.cuda.stream(...)` are ordered with
+        the library's kernels on the device, without host synchronisation"""
+        import torch
+
+        if getattr(self, "_ext_stream", None) is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.stream_ptr(), device=torch.device("cuda", self.device))
+        return self._ext_stream
 
     # ------------------------------------------------------------------ stage 2
     def setupSobol(self, first=1, count=None):
@@ -118,26 +126,38 @@ class TikTakSearch:
         return self._solve_sharded()
 
     def _solve_sharded(self):
+        """world > 1: count blocks are dealt block-cyclically.  When the `legitimate` cut cannot fire
+        (legitimate > qr_ndraw, the default) every rank just evaluates its blocks -- no exchange at all; the
+        global valid count rides along with the candidate all-gather of chooseSobol.  Otherwise blocks are
+        evaluated in waves with one all-reduce of the per-block valid counts per wave."""
+        import torch
+
         from . import dist as D
 
         N, Lg = self.cfg.qr_ndraw, self.cfg.legitimate
         nblocks = N // SOBOL_BLOCK + 1
-        can_cut = Lg <= N
-        wave = 64 * self.world if can_cut else nblocks
-        dev = f"cuda:{self.device}"
-        cum, kcut, nleg = 0, -1, 0
-        cb0 = 0
         if N == 0 or Lg <= 0:
             _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, 0, 0), "pretest_wave")
-            kcut, nleg, cb0 = 0, 0, nblocks
+            _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, 0, 0), "pretest_set_cut")
+            self.n_evaluated, self.n_legit = 0, 0
+            return True, 0, 0
+        if Lg > N:
+            _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, 0, nblocks), "pretest_wave")
+            _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, N, -1), "pretest_set_cut")
+            self.n_evaluated, self.n_legit = N, None  # n_legit is known after chooseSobol
+            return True, N, None
+        dev = torch.device("cuda", self.device)
+        wave = 64 * self.world
+        counts = torch.zeros(nblocks, dtype=torch.int64, device=dev)
+        cum, kcut, nleg, cb0 = 0, -1, 0, 0
         while cb0 < nblocks and kcut < 0:
             ncb = min(wave, nblocks - cb0)
             _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, cb0, ncb), "pretest_wave")
-            counts = np.zeros(nblocks, dtype=np.int64)
-            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.ctypes.data, nblocks), "pretest_counts")
-            counts[cb0 + ncb:] = 0
-            # one exchange per wave: all-reduce of the per-block valid counts
-            _, b, need, cum = D.global_cut(counts, cb0, Lg if can_cut else 2**62, cum, self.group, dev)
+            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), nblocks), "pretest_counts")
+            with torch.cuda.stream(self.torch_stream()):
+                D.reduce_counts(counts, self.group)
+                cg = counts.cpu().numpy()
+            b, need, cum = D.find_cut(cg[: cb0 + ncb], cb0, Lg, cum)
             if b >= 0:
                 n = C.c_int64()
                 _lib.check(self._L.tiktak_cuda_pretest_find(self._h, b, need, C.byref(n)), "pretest_find")
@@ -162,16 +182,23 @@ class TikTakSearch:
         K, nx = self.K, self.cfg.nx
         xs = np.empty((nx + 1, K), dtype=np.float64)
         idx = np.zeros(K, dtype=np.int32)
-        _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
-        if self.world > 1 and K > 1:
+        if self.world == 1:
+            _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
+        else:
+            import torch
+
             from . import dist as D
 
-            M = K - 1
-            cand = np.empty((M, 2), dtype=np.float64)
-            _lib.check(self._L.tiktak_cuda_choose_candidates(self._h, cand.ctypes.data), "choose_candidates")
-            allh = D.gather_candidates(cand, self.world, self.group, f"cuda:{self.device}")
-            _lib.check(self._L.tiktak_cuda_choose_merge(self._h, allh.ctypes.data, allh.shape[0], xs.ctypes.data,
-                                                        idx.ctypes.data), "choose_merge")
+            # shard-local top-(K-1), exported on the device, one all-gather, merged on the device
+            _lib.check(self._L.tiktak_cuda_choose(self._h, None, None), "chooseSobol")
+            cand = torch.empty((K, 2), dtype=torch.float64, device=torch.device("cuda", self.device))
+            with torch.cuda.stream(self.torch_stream()):
+                _lib.check(self._L.tiktak_cuda_choose_candidates(self._h, cand.data_ptr()), "choose_candidates")
+                allc = D.gather_candidates(cand, self.world, self.group)
+                _lib.check(self._L.tiktak_cuda_choose_merge(self._h, allc.data_ptr(), allc.shape[0], xs.ctypes.data,
+                                                            idx.ctypes.data), "choose_merge")
+                if self.n_legit is None:  # no-cut run: the global valid count travelled in the trailer rows
+                    self.n_legit = int(allc.view(self.world, K, 2)[:, K - 1, 0].sum().item())
         self.x_starts = xs.T.copy()  # (K, nx+1) = [fval, x]
         self.sobol_idx = idx
         return self.x_starts
@@ -186,54 +213,38 @@ class TikTakSearch:
             k += n
 
     def LocalMinimizations(self, algor="a"):
-        """Runs every restart; returns `complete` (:536).  Rows land in searchStart / searchResults."""
+        """Runs every restart; returns `complete` (:536).  Rows land in searchStart / searchResults.
+
+        All rounds are queued on the handle's stream back to back (blend -> local searches -> [one all-gather
+        of the round's rows over NCCL, world > 1] -> ingest + best-so-far); the host reads the rows once at the end."""
         alg = _ALG[algor]
-        K, nx = self.K, self.cfg.nx
-        starts = np.full((K, nx), np.nan)
-        results = np.full((K, nx + 4), np.nan)
-        evals = np.zeros(K, dtype=np.int32)
+        K, nx, W = self.K, self.cfg.nx, self.world
+        send = recv = None
+        if W > 1:
+            import torch
+
+            from . import dist as D
+
+            cap = D.n_max(max(1, int(self.cfg.round_size)), W) * (nx + 2)
+            dev = torch.device("cuda", self.device)
+            send = torch.empty(cap, dtype=torch.float64, device=dev)
+            recv = torch.empty(W * cap, dtype=torch.float64, device=dev)
         for first_k, n_k in self.rounds():
-            s = np.empty((nx, n_k), dtype=np.float64)
-            r = np.empty((nx + 4, n_k), dtype=np.float64)
-            e = np.zeros(n_k, dtype=np.int32)
-            _lib.check(self._L.tiktak_cuda_local(self._h, alg, first_k, n_k, s.ctypes.data, r.ctypes.data, e.ctypes.data),
+            _lib.check(self._L.tiktak_cuda_local_enqueue(self._h, alg, first_k, n_k, send.data_ptr() if W > 1 else None),
                        "LocalMinimizations")
-            if self.world > 1:
-                r, e = self._exchange_round(r, e, n_k)
-            sl = slice(first_k - 1, first_k - 1 + n_k)
-            starts[sl] = s.T
-            results[sl] = r.T
-            evals[sl] = e
-        self.searchStart, self.searchResults, self.evals = starts, results, evals
+            if W > 1:
+                cnt = D.n_max(n_k, W) * (nx + 2)
+                with torch.cuda.stream(self.torch_stream()):
+                    D.gather_rows(recv[: W * cnt], send[:cnt], self.group)
+            _lib.check(self._L.tiktak_cuda_local_ingest(self._h, first_k, n_k, recv.data_ptr() if W > 1 else None),
+                       "LocalMinimizations")
+        s = np.empty((nx, K), dtype=np.float64)
+        r = np.empty((nx + 4, K), dtype=np.float64)
+        e = np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_fetch(self._h, 1, K, s.ctypes.data, r.ctypes.data, e.ctypes.data),
+                   "LocalMinimizations")
+        self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
         return True
-
-    def _exchange_round(self, r, e, n_k):
-        """one all-gather of this round's rows over NVLink; every rank then ingests all of them."""
-        from . import dist as D
-
-        nx = self.cfg.nx
-        pack = np.concatenate([r, e[None, :].astype(np.float64)], axis=0)  # (nx+5, n_k)
-        merged = D.exchange_rows(pack, self.world, self.group, f"cuda:{self.device}")
-        rows = np.ascontiguousarray(merged[: nx + 4])
-        _lib.check(self._L.tiktak_cuda_push_results(self._h, rows.ctypes.data, n_k), "push_results")
-        # the #improvements column is assigned at ingestion (identically on every rank)
-        out = rows.copy()
-        out[2] = self._improvements(rows)
-        return out, merged[nx + 4].astype(np.int32)
-
-    def _improvements(self, rows):
-        if not hasattr(self, "_bestf"):
-            self._bestf, self._bestimp = None, 0
-        imp = np.zeros(rows.shape[1])
-        for s in range(rows.shape[1]):
-            f = rows[3, s]
-            if self._bestf is None:
-                self._bestf = self.x_starts[0, 0]
-            if f < self._bestf:
-                self._bestimp += 1
-                self._bestf = f
-            imp[s] = self._bestimp
-        return imp
 
     # ------------------------------------------------------------------ queries
     def getBestLine(self):

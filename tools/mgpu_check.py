@@ -22,8 +22,9 @@ for name, kw in {
 }.items():
     cfg = make_config(**kw)
     with TikTakSearch(cfg, device=lr, rank=rank, world=world) as s:
-        _, ne, nl = s.solveAtSobolPoints()
+        _, ne, _ = s.solveAtSobolPoints()
         xs = s.chooseSobol()
+        nl = s.n_legit  # without a possible cut the global valid count arrives with the candidate all-gather
         s.LocalMinimizations("a")
         res, st, ev, best = s.searchResults, s.searchStart, s.evals, s.getBestLine()
     if rank == 0:
