@@ -200,7 +200,9 @@ def run_graft(args, rank, world, local_rank):
     L = lib.load()
     s = TikTakSearch(cfg, device=local_rank, rank=rank, world=world)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    pinned = torch.empty(cfg.qr_ndraw, dtype=torch.float64, pin_memory=True).numpy()  # host side of the e2e copy
+    from tiktak_b200 import SOBOL_BLOCK
+    n_host = cfg.qr_ndraw + 1 if world == 1 else ((cfg.qr_ndraw // SOBOL_BLOCK + world) // world) * SOBOL_BLOCK
+    pinned = torch.empty(n_host, dtype=torch.float64, pin_memory=True).numpy()  # host side of the e2e copy
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,13 +225,15 @@ def run_graft(args, rank, world, local_rank):
         barrier()
         t0 = time.perf_counter()
         e0 = mark()
-        _, ne, nl = s.solveAtSobolPoints()
+        _, ne, nl = s.solveAtSobolPoints(wait=False)
         e1 = mark()
         if e2e:
             ext.synchronize()
         t1 = time.perf_counter()
         if e2e:
-            fv = s.sobolFnVal(out=pinned)  # D2H of every evaluated fval (the rows of sobolFnVal.dat) into pinned memory
+            # D2H of every evaluated fval (the fval column of sobolFnVal.dat) into pinned host memory; a shard of a
+            # multi-GPU run copies the values it owns
+            fv = s.sobolFnVal(out=pinned) if world == 1 else s.sobolFnValShard(out=pinned)
             out["d2h"] = fv.nbytes
         t2 = time.perf_counter()
         e2 = mark()
@@ -244,7 +248,7 @@ def run_graft(args, rank, world, local_rank):
         out.update(pretest_ms=e0.elapsed_time(e1), choose_ms=e2.elapsed_time(e3),
                    local_ms=0.0 if args.no_local else e3.elapsed_time(e4), pretest_eval_ms=s.stage_ms("pretest_eval"),
                    wall_pretest=t1 - t0, wall_values=t2 - t1, wall_choose=t3 - t2, wall_local=t4 - t3, wall=t4 - t0,
-                   ne=ne, nl=nl)
+                   ne=ne, nl=s.n_legit, d2h=out.get("d2h", 0))
         return out
 
     for _ in range(max(args.warmup, 3)):
@@ -280,6 +284,7 @@ def run_graft(args, rank, world, local_rank):
     e2e_sobol_s = mx(np.mean([d["wall_pretest"] + d["wall_values"] for d in e2e_steps]))
     e2e_step_s = mx(np.mean([d["wall"] for d in e2e_steps]))
     wall_local = mx(np.mean([d["wall_local"] for d in e2e_steps]))
+    d2h_total = int(mx(e2e_steps[-1]["d2h"]) * world)
 
     if rank == 0:
         fl, ms = C.c_double(), C.c_double()
@@ -323,7 +328,7 @@ def run_graft(args, rank, world, local_rank):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": n_eval_total / e2e_sobol_s, "unit": "evals/s",
-                    "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": int(n_eval_total * 8),
+                    "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": d2h_total,
                     "step_s": e2e_step_s, "restarts_per_s": (nrest / wall_local) if wall_local > 0 else None,
                     "what": "solveAtSobolPoints + sobolFnVal (all fvals to host) through the public API, wall clock"},
             "gpu_launches": int(launches),

@@ -124,6 +124,13 @@ int tiktak_cuda_objfun(tiktak_handle* h, const double* x, int64_t n, double* fva
  * with tiktak_cuda_pretest_set_cut; with world == 1 the cut is final on return.
  * n_evaluated = Kcut (the evaluated prefix 1..Kcut), n_legit = #(fval < fvalmax) within it. */
 int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit);
+/* When legitimate > qr_ndraw (the default, genericParams.f90:317-319) the cut cannot fire: called with
+ * n_legit == NULL, tiktak_cuda_pretest then only QUEUES the evaluation of all qr_ndraw points and returns;
+ * the valid count (the final legitSobol.dat value) is read back when first asked for, here or by choose. */
+int tiktak_cuda_pretest_result(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit);
+/* the shard's own fval store in one copy: count blocks rank, rank+world, ... (65536 values each, point n of
+ * block b at [(b/world)*65536 + n%65536]) up to the block holding the cut; n_local = values copied. */
+int tiktak_cuda_pretest_values_shard(tiktak_handle* h, double* fval_local, int64_t capacity, int64_t* n_local);
 /* fval of points first..first+count-1 (the rows of sobolFnVal.dat, :467); points this shard
  * does not own or beyond the cut come back as NaN. */
 int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first_1based, int64_t count, double* fval);

@@ -281,7 +281,13 @@ int64_t tiktak_cuda_launch_count(tiktak_handle* h) { return h ? h->launches : 0;
 
 int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms) {
     if (!h || !stage || !ms) return TIKTAK_ERR_ARG;
-    if (!strcmp(stage, "pretest")) *ms = h->ms_pretest;
+    if (!strcmp(stage, "pretest")) {
+        if (h->pretest_timing_open) {
+            TK_CUDA(cudaEventSynchronize(h->ev1));
+            float w = 0; cudaEventElapsedTime(&w, h->ev0, h->ev1); h->ms_pretest = w; h->pretest_timing_open = false;
+        }
+        *ms = h->ms_pretest;
+    }
     else if (!strcmp(stage, "pretest_eval")) {
         if (h->wave_pending) {
             TK_CUDA(cudaEventSynchronize(h->evw1));
@@ -438,6 +444,17 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     const bool can_cut = (L <= N) && h->cfg.world == 1;
     const int64_t wave = can_cut ? 64 : h->n_cblocks;
     int64_t cum = 0, kcut = -1, nleg = 0;
+    if (!can_cut && h->cfg.world == 1 && !n_legit) {
+        /* legitimate > qr_ndraw: the cut cannot fire, every point is evaluated and nobody waits for the valid
+         * count -- queue the evaluation and return; the count is read when it is first asked for */
+        rc = tiktak_cuda_pretest_wave(h, 0, h->n_cblocks);
+        if (rc) return rc;
+        h->kcut = N; h->nlegit = -1; h->pretest_done = true;
+        if (n_evaluated) *n_evaluated = N;
+        TK_CUDA(cudaEventRecord(h->ev1, h->stream));
+        h->pretest_timing_open = true;
+        return TIKTAK_OK;
+    }
     if (h->cfg.objective_id == TIKTAK_OBJ_SMM && can_cut) {
         /* one evaluation simulates a whole panel: stop as soon as the cut is reached, in sub-waves of a few
          * points per SM instead of whole count blocks (same prefix semantics, :429) */
@@ -501,6 +518,46 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     return end_timer(h, &h->ms_pretest);
 }
 
+/* valid count of the evaluated prefix when it was not needed to place the cut (sum of the per-block counts) */
+static int resolve_legit(tiktak_handle* h) {
+    if (h->nlegit >= 0 || !h->pretest_done) return TIKTAK_OK;
+    if (h->pretest_timing_open) { /* close the stage timer before other work reuses the events */
+        TK_CUDA(cudaEventSynchronize(h->ev1));
+        float w = 0; cudaEventElapsedTime(&w, h->ev0, h->ev1); h->ms_pretest = w; h->pretest_timing_open = false;
+    }
+    TK_CUDA(cudaMemcpyAsync(h->h_counts.data(), h->d_counts, (size_t)h->n_cblocks * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    int64_t tot = 0;
+    for (int64_t cb = 0; cb < h->n_cblocks; cb++) tot += (int64_t)h->h_counts[cb];
+    if (h->cfg.world == 1) h->nlegit = tot; /* a shard only knows its own count; the host sums the shards */
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_pretest_result(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit) {
+    if (!h) return TIKTAK_ERR_ARG;
+    if (!h->pretest_done) return TIKTAK_ERR_STATE;
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc = resolve_legit(h);
+    if (rc) return rc;
+    if (n_evaluated) *n_evaluated = h->kcut;
+    if (n_legit) *n_legit = h->nlegit;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_pretest_values_shard(tiktak_handle* h, double* fval_local, int64_t capacity, int64_t* n_local) {
+    if (!h || !fval_local) return TIKTAK_ERR_ARG;
+    if (!h->pretest_done) return TIKTAK_ERR_STATE;
+    const int64_t lastcb = h->kcut / TIKTAK_SOBOL_BLOCK;
+    const int64_t nl = (lastcb >= h->cfg.rank) ? ((lastcb - h->cfg.rank) / h->cfg.world + 1) : 0; /* owned blocks touching 0..kcut */
+    const int64_t n = nl * (int64_t)TIKTAK_SOBOL_BLOCK;
+    if (n_local) *n_local = n;
+    if (capacity < n) { tk_set_error("pretest_values_shard: capacity %lld < %lld", (long long)capacity, (long long)n); return TIKTAK_ERR_ARG; }
+    TK_CUDA(cudaSetDevice(h->device));
+    if (n > 0) TK_CUDA(cudaMemcpyAsync(fval_local, h->d_fval, (size_t)n * 8, cudaMemcpyDefault, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return TIKTAK_OK;
+}
+
 int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first, int64_t count, double* fval) {
     if (!h || !fval || first < 1 || count < 0) return TIKTAK_ERR_ARG;
     if (!h->pretest_done) return TIKTAK_ERR_STATE;
@@ -560,7 +617,9 @@ int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
     if (!h) return TIKTAK_ERR_ARG;
     if (!h->pretest_done) { tk_set_error("choose: pretest has not completed"); return TIKTAK_ERR_STATE; }
     TK_CUDA(cudaSetDevice(h->device));
-    int rc = begin_timer(h);
+    int rc = resolve_legit(h);
+    if (rc) return rc;
+    rc = begin_timer(h);
     if (rc) return rc;
     rc = tk_select_top(h, h->cfg.maxpoints_plus1 - 1);
     if (rc) return rc;

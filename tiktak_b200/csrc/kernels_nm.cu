@@ -522,6 +522,313 @@ __global__ void __launch_bounds__(128) nm_quad_kernel(const TkTablesG T, const T
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * The same four-warp scheme for 32 <= nx <= 127 (CJ = ceil((nx+1)/32) coordinates / vertices per lane):
+ * lane l owns coordinates j = l + 32c, the sorted (y, vertex) list lives in the warp's shared memory
+ * (insertion = CJ ballots + a shift by one), the simplex p is ONE shared copy per block (every warp stores
+ * the same values), and the in-order fold of the nt terms on lane 0 is the longest dependent chain of the
+ * iteration (nt DADDs -- the price of the reference's index-order sum).
+ * --------------------------------------------------------------------------------------------- */
+template <class Obj, int CJ>
+__device__ __forceinline__ double nm_eval_warp_wide(const tk_obj_ctx& ctx, const NmScratch& sc, const double (&xj)[CJ],
+                                                    const double (&blj)[CJ], const double (&buj)[CJ], int lane, int nx, int nt) {
+    bool ob = false;
+#pragma unroll
+    for (int c = 0; c < CJ; c++) ob = ob || ((lane + 32 * c < nx) && (xj[c] < blj[c] || xj[c] > buj[c]));
+    const bool oob = __any_sync(0xffffffffu, ob);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CJ; c++)
+        if (lane + 32 * c < nx) sc.cand[lane + 32 * c] = xj[c];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CJ; c++) {
+        const int i = lane + 32 * c;
+        if (i < nt) {
+            double ta_, tb_;
+            Obj::term(ctx, TkMemX{sc.cand, 1}, i, ta_, tb_);
+            sc.ta[i] = ta_; sc.tb[i] = tb_;
+        }
+        if (oob && i < nx) { /* getPenalty :57-66, coordinate i */
+            const double a = TK_DIV(fmax(0.0, TK_SUB(blj[c], xj[c])), fmax(0.1, fabs(blj[c])));
+            const double b = TK_DIV(fmax(0.0, TK_SUB(xj[c], buj[c])), fmax(0.1, fabs(buj[c])));
+            sc.pn[i] = TK_ADD(TK_MUL(ctx.penaltyc, TK_MUL(a, a)), TK_MUL(ctx.penaltyc, TK_MUL(b, b)));
+        }
+    }
+    __syncwarp();
+    double yc = 0.0;
+    if (lane == 0) {
+        double pen = 0.0;
+        if (oob) {
+            double penalty = 0.0;
+            for (int i = 0; i < nx; i++) penalty = TK_ADD(penalty, sc.pn[i]);
+            if (penalty > TK_MYEPS) pen = fmin(ctx.max_penalty, TK_ADD(ctx.penalty0, penalty));
+        }
+        double f;
+        if (pen > TK_MYEPS) {
+            f = TK_DIV(pen, ctx.sqrt_nm); /* objective.f90:93-94 */
+        } else {
+            double s_, p_;
+            Obj::fold_init(ctx, s_, p_);
+            const double2* qa = reinterpret_cast<const double2*>(sc.ta);
+            const double2* qb = reinterpret_cast<const double2*>(sc.tb);
+            int i = 0;
+            for (; i + 8 <= nt; i += 8) { /* loads first, then the in-order chain */
+                const double2 a0 = qa[(i >> 1)], a1 = qa[(i >> 1) + 1], a2 = qa[(i >> 1) + 2], a3 = qa[(i >> 1) + 3];
+                const double2 b0 = qb[(i >> 1)], b1 = qb[(i >> 1) + 1], b2 = qb[(i >> 1) + 2], b3 = qb[(i >> 1) + 3];
+                Obj::fold(s_, p_, a0.x, b0.x); Obj::fold(s_, p_, a0.y, b0.y);
+                Obj::fold(s_, p_, a1.x, b1.x); Obj::fold(s_, p_, a1.y, b1.y);
+                Obj::fold(s_, p_, a2.x, b2.x); Obj::fold(s_, p_, a2.y, b2.y);
+                Obj::fold(s_, p_, a3.x, b3.x); Obj::fold(s_, p_, a3.y, b3.y);
+            }
+            for (; i < nt; i++) Obj::fold(s_, p_, sc.ta[i], sc.tb[i]);
+            f = Obj::finish(ctx, s_, p_);
+        }
+        yc = tk_objfun_finish(ctx, f, pen);
+    }
+    __syncwarp();
+    return yc;
+}
+
+/* sort the np (y, vertex) pairs of the warp's list in shared memory (rank by counting, then scatter) */
+template <int CJ>
+__device__ __forceinline__ void nm_full_sort_wide(double* ys, int* rows, int np, int lane, double* scr_y, int* scr_r) {
+    __syncwarp();
+    double my[CJ]; int mr[CJ], rk[CJ];
+#pragma unroll
+    for (int c = 0; c < CJ; c++) {
+        const int e = lane + 32 * c;
+        my[c] = (e < np) ? ys[e] : 0.0; mr[c] = (e < np) ? rows[e] : 0; rk[c] = 0;
+    }
+    for (int k = 0; k < np; k++) {
+        const double yk = ys[k]; const int rkk = rows[k];
+#pragma unroll
+        for (int c = 0; c < CJ; c++) rk[c] += (k != lane + 32 * c && nm_before(yk, rkk, my[c], mr[c])) ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CJ; c++)
+        if (lane + 32 * c < np) { scr_y[rk[c]] = my[c]; scr_r[rk[c]] = mr[c]; }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CJ; c++) {
+        const int e = lane + 32 * c;
+        if (e < np) { ys[e] = scr_y[e]; rows[e] = scr_r[e]; }
+    }
+    __syncwarp();
+}
+
+template <class Obj, int CJ>
+__global__ void __launch_bounds__(128) nm_quad_wide_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+    extern __shared__ double smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nx = sc.nx, np = nx + 1;
+    const int nt = Obj::nterms(nx);
+    const int ts = (nx + 2) & ~1; /* even stride >= np */
+    /* block-shared */
+    double* sbl = smem;
+    double* sbu = sbl + ts;
+    double* saux = sbu + ts;
+    double* yv = saux + ts;      /* yv[vertex]: values of re-evaluated vertices (start, shrink) */
+    double* yx = yv + ts;        /* yx[parity*4 + c]: the four trial values of an iteration */
+    double* p = yx + 8;          /* p[i*nx + j]: the simplex, one copy (all warps store identical values) */
+    /* per warp */
+    double* mine = p + (size_t)np * nx + (size_t)w * (8 * ts);
+    NmScratch scr;
+    scr.ta = mine;
+    scr.tb = mine + ts;
+    scr.pn = mine + 2 * ts;
+    scr.cand = mine + 3 * ts;
+    double* ys = mine + 4 * ts;                          /* sorted y */
+    int* rows = reinterpret_cast<int*>(mine + 5 * ts);   /* vertex at each sorted position */
+    double* scr_y = mine + 6 * ts;
+    int* scr_r = reinterpret_cast<int*>(mine + 7 * ts);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
+    const int slot = a.rank + (int)blockIdx.x * a.world;
+    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
+    /* runAmoeba :622-627 -- initial simplex around the blended start */
+    const bool shr = a.shr_have && a.shr_have[0] && ((float)(a.first_k + slot) / (float)a.K > 0.5f);
+    const double* wsrc = shr ? a.wshr : a.width;
+    for (int e = threadIdx.x; e < np * nx; e += blockDim.x) {
+        const int ia = e / nx, i = e - ia * nx;
+        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
+        t = fmax(fmin(t, T.bu[i]), T.bl[i]);
+        p[e] = t;
+    }
+    __syncthreads();
+    double blj[CJ], buj[CJ], psum[CJ];
+    int jj[CJ];
+#pragma unroll
+    for (int c = 0; c < CJ; c++) {
+        jj[c] = (lane + 32 * c < nx) ? lane + 32 * c : 0;
+        blj[c] = sbl[jj[c]]; buj[c] = sbu[jj[c]];
+    }
+    /* objFun at the vertices: dealt over the four warps, collected through yv */
+    for (int v = w; v < np; v += 4) {
+        double xv[CJ];
+#pragma unroll
+        for (int c = 0; c < CJ; c++) xv[c] = p[v * nx + jj[c]];
+        const double yc = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xv, blj, buj, lane, nx, nt);
+        if (lane == 0) yv[v] = yc;
+    }
+    __syncthreads();
+    for (int e = lane; e < np; e += 32) { ys[e] = yv[e]; rows[e] = e; }
+    nm_full_sort_wide<CJ>(ys, rows, np, lane, scr_y, scr_r);
+#pragma unroll
+    for (int c = 0; c < CJ; c++) { /* psum, amoeba :49 in index order */
+        double s_ = 0.0;
+        for (int i = 0; i < np; i++) s_ = TK_ADD(s_, p[i * nx + jj[c]]);
+        psum[c] = s_;
+    }
+    __syncthreads(); /* every warp has read the start simplex before anyone replaces a vertex */
+
+    int iter = 0;
+    unsigned par = 0;
+    double ylo;
+    for (;;) {
+        ylo = ys[0];
+        const double yhi = ys[nx], ynhi = ys[nx - 1];
+        const int ihi = rows[nx];
+        /* the four possible trial points (amotry :124-126, unfused); this warp evaluates number w */
+        double ph[CJ], R[CJ], ps1[CJ], E[CJ], Co[CJ], Ci[CJ], xc[CJ];
+#pragma unroll
+        for (int c = 0; c < CJ; c++) {
+            ph[c] = p[ihi * nx + jj[c]];
+            R[c] = TK_SUB(TK_MUL(psum[c], a.fac1r), TK_MUL(ph[c], a.fac2r));
+            ps1[c] = TK_ADD(TK_SUB(psum[c], ph[c]), R[c]); /* psum after R is accepted (:130) */
+            E[c] = TK_SUB(TK_MUL(ps1[c], a.fac1e), TK_MUL(R[c], a.fac2e));
+            Co[c] = TK_SUB(TK_MUL(ps1[c], a.fac1c), TK_MUL(R[c], a.fac2c));
+            Ci[c] = TK_SUB(TK_MUL(psum[c], a.fac1c), TK_MUL(ph[c], a.fac2c));
+            xc[c] = (w == 0) ? R[c] : (w == 1) ? E[c] : (w == 2) ? Co[c] : Ci[c];
+        }
+        /* rtol < ftol (:84-85); the division is only formed when the product test is within 2^-40 */
+        const double num = TK_MUL(2.0, fabs(TK_SUB(yhi, ylo)));
+        const double den = TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny);
+        const double thr = TK_MUL(a.ftol, den);
+        bool conv = num < TK_MUL(thr, 0.99999999999909051);
+        if (!conv && !(num > TK_MUL(thr, 1.00000000000090949))) conv = TK_DIV(num, den) < a.ftol;
+        if (conv || iter >= a.itmax) break;
+
+        const double yc = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xc, blj, buj, lane, nx, nt);
+        if (lane == 0) yx[par * 4 + w] = yc;
+        __syncthreads(); /* the one block barrier of the iteration; yx is double-buffered by parity */
+        const double2 y01 = reinterpret_cast<const double2*>(yx + par * 4)[0];
+        const double2 y23 = reinterpret_cast<const double2*>(yx + par * 4)[1];
+        par ^= 1u;
+        const double yR = y01.x;
+        const bool accR = yR < yhi; /* :128 */
+        double pnew[CJ], ynew = yhi;
+        bool moved = accR;
+#pragma unroll
+        for (int c = 0; c < CJ; c++) { pnew[c] = accR ? R[c] : ph[c]; if (accR) psum[c] = ps1[c]; }
+        if (accR) ynew = yR;
+        iter++;
+        if (yR <= ylo) { /* :99 expansion */
+            double yE = y01.y;
+            if (!accR) { /* only when every y is equal; not speculated -- evaluated from the live state */
+#pragma unroll
+                for (int c = 0; c < CJ; c++) E[c] = TK_SUB(TK_MUL(psum[c], a.fac1e), TK_MUL(ph[c], a.fac2e));
+                yE = __shfl_sync(FULL, nm_eval_warp_wide<Obj, CJ>(ctx, scr, E, blj, buj, lane, nx, nt), 0);
+            }
+            iter++;
+            if (yE < ynew) {
+#pragma unroll
+                for (int c = 0; c < CJ; c++) { psum[c] = TK_ADD(TK_SUB(psum[c], pnew[c]), E[c]); pnew[c] = E[c]; }
+                ynew = yE; moved = true;
+            }
+        } else if (yR >= ynhi) { /* :102 contraction */
+            const double yC = accR ? y23.x : y23.y;
+            iter++;
+            if (yC < ynew) {
+#pragma unroll
+                for (int c = 0; c < CJ; c++) {
+                    const double Cv = accR ? Co[c] : Ci[c];
+                    psum[c] = TK_ADD(TK_SUB(psum[c], pnew[c]), Cv); pnew[c] = Cv;
+                }
+                ynew = yC; moved = true;
+            } else { /* :106-113 shrink toward the best vertex, re-evaluate, re-sum */
+                if (moved) {
+#pragma unroll
+                    for (int c = 0; c < CJ; c++)
+                        if (lane + 32 * c < nx) p[ihi * nx + jj[c]] = pnew[c];
+                }
+                if (lane == 0) ys[nx] = ynew;
+                moved = false;
+                __syncwarp();
+                /* MINLOC: the lowest vertex index among the minima */
+                unsigned cand_lo = 0xffffffffu;
+                for (int e = lane; e < np; e += 32)
+                    if (ys[e] == ylo) cand_lo = min(cand_lo, (unsigned)rows[e]);
+                const int ilo = (int)__reduce_min_sync(FULL, cand_lo);
+                __syncthreads(); /* all warps have stored vertex ihi and chosen ilo */
+                if (w == 0) { /* one warp halves the simplex (:107); the others wait */
+#pragma unroll
+                    for (int c = 0; c < CJ; c++) {
+                        if (lane + 32 * c >= nx) continue;
+                        const double pl = p[ilo * nx + jj[c]];
+                        for (int i = 0; i < np; i++)
+                            if (i != ilo) p[i * nx + jj[c]] = TK_MUL(0.5, TK_ADD(p[i * nx + jj[c]], pl));
+                    }
+                }
+                __syncthreads();
+                for (int v = w; v < np; v += 4) {
+                    if (v == ilo) continue;
+                    double xv[CJ];
+#pragma unroll
+                    for (int c = 0; c < CJ; c++) xv[c] = p[v * nx + jj[c]];
+                    const double yc2 = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xv, blj, buj, lane, nx, nt);
+                    if (lane == 0) yv[v] = yc2;
+                }
+                __syncthreads();
+                for (int e = lane; e < np; e += 32)
+                    if (rows[e] != ilo) ys[e] = yv[rows[e]];
+                iter += nx;
+                nm_full_sort_wide<CJ>(ys, rows, np, lane, scr_y, scr_r);
+#pragma unroll
+                for (int c = 0; c < CJ; c++) {
+                    double s_ = 0.0;
+                    for (int i = 0; i < np; i++) s_ = TK_ADD(s_, p[i * nx + jj[c]]);
+                    psum[c] = s_;
+                }
+                __syncthreads(); /* yv / p may change again only after every warp is done with them */
+            }
+        }
+        if (moved) { /* vertex ihi takes (pnew, ynew): drop position nx, insert at its sorted position */
+            int pos = 0;
+            double ye[CJ]; int re[CJ];
+#pragma unroll
+            for (int c = 0; c < CJ; c++) {
+                const int e = lane + 32 * c;
+                if (e < nx) p[ihi * nx + e] = pnew[c];
+                ye[c] = (e < nx) ? ys[e] : 0.0; re[c] = (e < nx) ? rows[e] : 0;
+                pos += __popc(__ballot_sync(FULL, e < nx && nm_before(ye[c], re[c], ynew, ihi)));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < CJ; c++) {
+                const int e = lane + 32 * c;
+                if (e < nx && e >= pos) { ys[e + 1] = ye[c]; rows[e + 1] = re[c]; }
+            }
+            if (lane == 0) { ys[pos] = ynew; rows[pos] = ihi; }
+        }
+        __syncwarp();
+    }
+    /* runAmoeba :631-632 returns the first minimal vertex; completeSearch :582 re-evaluates objFun there:
+     * same point, same value. */
+    if (w == 0) {
+        unsigned cand_lo = 0xffffffffu;
+        for (int e = lane; e < np; e += 32)
+            if (ys[e] == ylo) cand_lo = min(cand_lo, (unsigned)rows[e]);
+        const int ilo = (int)__reduce_min_sync(FULL, cand_lo);
+        for (int jx = lane; jx < nx; jx += 32) a.out_x[(size_t)jx * a.n_k + slot] = p[ilo * nx + jx];
+        if (lane == 0) {
+            a.out_f[slot] = ylo;
+            a.out_evals[slot] = np + iter + 1;
+        }
+    }
+}
+
 /* getSortedResults/getBestLine (:781-823) over the device-resident result rows.
  * res: rows 0..K, each [fval, x(nx)]; best: [0]=fval [1]=row [2]=#rows, [3..] = x */
 __global__ void best_kernel(const double* res, const int* valid, int nrows, int nx, double* best) {
@@ -795,6 +1102,17 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
                 case 20: rc = nm_launch_warp<Obj, 20>(h, T, a, shmem); break;
                 default: rc = nm_launch_warp<Obj, 0>(h, T, a, shmem); break;
             }
+        } else if (nx <= 127 && Obj::nterms(nx) <= nx) { /* four warps per restart, CJ coordinates per lane */
+            const int ts = (nx + 2) & ~1;
+            const size_t shmem = (size_t)(4 * ts + 8 + np * nx + 4 * 8 * ts) * sizeof(double);
+            const int cj = (np + 31) / 32;
+            auto go = [&]<int CJ>() -> int {
+                TK_CUDA(cudaFuncSetAttribute(nm_quad_wide_kernel<Obj, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                TK_CUDA(cudaFuncSetAttribute(nm_quad_wide_kernel<Obj, CJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                nm_quad_wide_kernel<Obj, CJ><<<(unsigned)a.n_run, 128, shmem, h->stream>>>(T, h->sc, a);
+                return TIKTAK_OK;
+            };
+            rc = cj == 2 ? go.template operator()<2>() : cj == 3 ? go.template operator()<3>() : go.template operator()<4>();
         } else {
             const size_t per_warp = (size_t)(np * nx + np + nx + 4 * nx + 4 + 8 * nx) * sizeof(double);
             const size_t per_block = (size_t)3 * nx * sizeof(double);

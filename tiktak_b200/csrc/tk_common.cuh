@@ -108,7 +108,7 @@ struct tiktak_handle {
     int* d_arch_evals = nullptr;     /* [K+1]: objective evaluations of restart k */
     bool best_dirty = true;          /* d_best must be recomputed from the rows (after push_results) */
     cudaEvent_t evl0 = nullptr, evl1 = nullptr;
-    bool local_timing_open = false;
+    bool local_timing_open = false, pretest_timing_open = false;
     bool rho_ready = false;
     /* DFNLS */
     double* d_dfnls_slab = nullptr;

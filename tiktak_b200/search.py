@@ -116,10 +116,39 @@ class TikTakSearch:
         return f
 
     # ------------------------------------------------------------------ stages 3-5
-    def solveAtSobolPoints(self):
-        """Returns (complete, n_evaluated, n_legit) -- `complete` as in :465."""
+    def solveAtSobolPoints(self, wait=True):
+        """Returns (complete, n_evaluated, n_legit) -- `complete` as in :465.
+
+        wait=False: when the `legitimate` cut cannot fire (legitimate > qr_ndraw) the evaluation is only queued on
+        the device and n_legit comes back as None; it is filled in (self.n_legit) by chooseSobol."""
+        out = self._solve(wait)
+        if wait and self.n_legit is None:
+            self._resolve_legit()
+            out = (out[0], out[1], self.n_legit)
+        return out
+
+    def _resolve_legit(self):
+        nl = C.c_int64()
+        _lib.check(self._L.tiktak_cuda_pretest_result(self._h, None, C.byref(nl)), "pretest_result")
+        if self.world == 1:
+            self.n_legit = nl.value
+        else:  # a shard knows its own count only
+            import torch
+
+            from . import dist as D
+
+            counts = torch.zeros(self.cfg.qr_ndraw // SOBOL_BLOCK + 1, dtype=torch.int64, device=torch.device("cuda", self.device))
+            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), counts.numel()), "pretest_counts")
+            self.n_legit = int(D.reduce_counts(counts.sum().reshape(1), self.group).item())
+
+    def _solve(self, wait):
         ne, nl = C.c_int64(), C.c_int64()
         if self.world == 1:
+            if not wait and self.cfg.legitimate > self.cfg.qr_ndraw > 0:
+                # the cut cannot fire: the evaluation is only queued; n_legit is read back by chooseSobol
+                _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), None), "solveAtSobolPoints")
+                self.n_evaluated, self.n_legit = ne.value, None
+                return True, ne.value, None
             _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), C.byref(nl)), "solveAtSobolPoints")
             self.n_evaluated, self.n_legit = ne.value, nl.value
             return True, ne.value, nl.value
@@ -177,6 +206,14 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_pretest_values(self._h, first, count, f.ctypes.data), "sobolFnVal")
         return f
 
+    def sobolFnValShard(self, out=None):
+        """this shard's fval store in one copy (world > 1): count blocks rank, rank+world, ... of 65536 values"""
+        cap = (self.cfg.qr_ndraw // SOBOL_BLOCK + 1 + self.world - 1) // self.world * SOBOL_BLOCK
+        f = np.empty(cap, dtype=np.float64) if out is None else out
+        n = C.c_int64()
+        _lib.check(self._L.tiktak_cuda_pretest_values_shard(self._h, f.ctypes.data, f.size, C.byref(n)), "sobolFnValShard")
+        return f[: n.value]
+
     # ------------------------------------------------------------------ stage 6
     def chooseSobol(self):
         K, nx = self.K, self.cfg.nx
@@ -184,6 +221,10 @@ class TikTakSearch:
         idx = np.zeros(K, dtype=np.int32)
         if self.world == 1:
             _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
+            if self.n_legit is None:
+                nl = C.c_int64()
+                _lib.check(self._L.tiktak_cuda_pretest_result(self._h, None, C.byref(nl)), "pretest_result")
+                self.n_legit = nl.value
         else:
             import torch
 
