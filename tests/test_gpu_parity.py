@@ -235,3 +235,118 @@ def test_cli_driver_writes_reference_files(built, tmp_path):
     of, ox, _ = o.lastSearch()
     assert abs(fin[2] - of) <= 1e-6 * abs(of)
     assert int(open(tmp_path / "lastSobol.dat").read()) == 11 and int(open(tmp_path / "legitSobol.dat").read()) == 10
+
+
+def test_start_selection_large_m(built):
+    """more winners than one sort chunk (1024): chunk sort + merge-by-rank passes, odd and even pass counts"""
+    for maxpoints, nd in ((1500, 4000), (3000, 20000), (5000, 6000)):
+        cfg = cfg_of("griewank10", qr_ndraw=nd, maxpoints=maxpoints)
+        with TikTakSearch(cfg) as s:
+            s.solveAtSobolPoints(wait=False)
+            assert s.n_legit is None  # queued only; resolved by chooseSobol
+            xs = s.chooseSobol()
+            idx = s.sobol_idx.copy()
+            nl = s.n_legit
+        o = Oracle(cfg, MATH_TK)
+        _, _, onl = o.solveAtSobolPoints()
+        oxs = o.chooseSobol(mode=1)
+        assert nl == onl
+        assert np.array_equal(idx, o.sobol_idx)
+        assert np.array_equal(xs, oxs)
+
+
+def test_blocking_round_api_matches_queued_rounds(built):
+    """tiktak_cuda_local (one blocking call per round) and the queued enqueue/ingest/fetch form give the same rows"""
+    import ctypes as C
+    from tiktak_b200 import lib
+    cfg = cfg_of("griewank10", round_size=7)
+    L = lib.load()
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations("a")
+        qs, qr, qe = s.searchStart.copy(), s.searchResults.copy(), s.evals.copy()
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol()
+        K, nx = s.K, cfg.nx
+        bs, br, be = np.empty((K, nx)), np.empty((K, nx + 4)), np.zeros(K, dtype=np.int32)
+        for first_k, n_k in s.rounds():
+            st = np.empty((nx, n_k)); r = np.empty((nx + 4, n_k)); e = np.zeros(n_k, dtype=np.int32)
+            lib.check(L.tiktak_cuda_local(s._h, 1, first_k, n_k, st.ctypes.data, r.ctypes.data, e.ctypes.data), "local")
+            sl = slice(first_k - 1, first_k - 1 + n_k)
+            bs[sl], br[sl], be[sl] = st.T, r.T, e
+        assert s.stage_ms("local") > 0.0
+    assert np.array_equal(qs, bs) and np.array_equal(qr, br) and np.array_equal(qe, be)
+
+
+@pytest.mark.parametrize("name,alg,world", [("griewank10", "a", 2), ("rastrigin20", "a", 3), ("griewank7", "b", 2)])
+def test_sharded_protocol_on_one_gpu(built, name, alg, world):
+    """The whole N>1 protocol without NCCL: `world` handles (rank r of world) on the same GPU; the all-gathers are
+    replaced by concatenating the ranks' device buffers.  Exercises the block-cyclic Sobol shards, the device-side
+    candidate export/merge, pack -> gather -> ingest of every restart round, and the shard fval copy."""
+    import ctypes as C
+    import torch
+    from tiktak_b200 import SOBOL_BLOCK, lib
+    from tiktak_b200 import dist as D
+    kw = dict(qr_ndraw=3 * SOBOL_BLOCK + 4321, maxpoints=24, round_size=5)
+    if alg == "b":
+        kw.update(nm=3, maxpoints=8, round_size=3)
+    cfg = cfg_of(name, **kw)
+    L = lib.load()
+    K, nx, N = cfg.p_maxpoints, cfg.nx, cfg.qr_ndraw
+    nblocks = N // SOBOL_BLOCK + 1
+    dev = torch.device("cuda", 0)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); oxs = o.chooseSobol(mode=1); o.LocalMinimizations(1 if alg == "a" else 0)
+    hs = [TikTakSearch(cfg, device=0, rank=r, world=world) for r in range(world)]
+    try:
+        # --- Sobol stage: every shard evaluates its own count blocks, no exchange (legitimate > qr_ndraw)
+        for s in hs:
+            lib.check(L.tiktak_cuda_pretest_wave(s._h, 0, nblocks), "wave")
+            lib.check(L.tiktak_cuda_pretest_set_cut(s._h, N, -1), "set_cut")
+            s.n_evaluated = N
+        fo = o.sobolFnVal()
+        for r, s in enumerate(hs):
+            loc = s.sobolFnValShard()
+            for q in range(len(loc) // SOBOL_BLOCK):
+                b = r + q * world
+                lo, hi = max(b * SOBOL_BLOCK, 1), min((b + 1) * SOBOL_BLOCK - 1, N)
+                assert np.array_equal(loc[q * SOBOL_BLOCK + lo % SOBOL_BLOCK: q * SOBOL_BLOCK + hi % SOBOL_BLOCK + 1], fo[lo - 1: hi])
+        # --- start selection: local top-(K-1) -> exported on the device -> "all-gather" -> device merge
+        cands = []
+        for s in hs:
+            lib.check(L.tiktak_cuda_choose(s._h, None, None), "choose")
+            c = torch.empty((K, 2), dtype=torch.float64, device=dev)
+            lib.check(L.tiktak_cuda_choose_candidates(s._h, c.data_ptr()), "cand")
+            cands.append(c)
+        torch.cuda.synchronize()
+        allc = torch.cat(cands).contiguous()
+        assert int(allc.view(world, K, 2)[:, K - 1, 0].sum().item()) == o.n_legit  # trailer rows carry the valid counts
+        for s in hs:
+            xs = np.empty((nx + 1, K)); idx = np.zeros(K, dtype=np.int32)
+            lib.check(L.tiktak_cuda_choose_merge(s._h, allc.data_ptr(), allc.shape[0], xs.ctypes.data, idx.ctypes.data), "merge")
+            assert np.array_equal(xs.T, oxs) and np.array_equal(idx, o.sobol_idx)
+        # --- restart rounds
+        algid = 1 if alg == "a" else 0
+        cap = D.n_max(cfg.round_size, world) * (nx + 2)
+        sends = [torch.zeros(cap, dtype=torch.float64, device=dev) for _ in hs]
+        for first_k, n_k in hs[0].rounds():
+            cnt = D.n_max(n_k, world) * (nx + 2)
+            for s, snd in zip(hs, sends):
+                lib.check(L.tiktak_cuda_local_enqueue(s._h, algid, first_k, n_k, snd.data_ptr()), "enqueue")
+            torch.cuda.synchronize()
+            recv = torch.cat([snd[:cnt] for snd in sends]).contiguous()
+            # the numpy restatement of the layout agrees with what the device packed
+            got = D.unpack_rows_ref(recv.cpu().numpy().reshape(world * D.n_max(n_k, world), nx + 2), n_k, world)
+            assert np.array_equal(got[:, 0], o.searchResults[first_k - 1: first_k - 1 + n_k, 3])  # values >= 2^-14: f40.20 exact
+            for s in hs:
+                lib.check(L.tiktak_cuda_local_ingest(s._h, first_k, n_k, recv.data_ptr()), "ingest")
+            torch.cuda.synchronize()
+        for s in hs:
+            st = np.empty((nx, K)); r = np.empty((nx + 4, K)); e = np.zeros(K, dtype=np.int32)
+            lib.check(L.tiktak_cuda_local_fetch(s._h, 1, K, st.ctypes.data, r.ctypes.data, e.ctypes.data), "fetch")
+            assert np.array_equal(st.T, o.searchStart)
+            assert np.array_equal(r.T, o.searchResults)
+            assert np.array_equal(e, o.evals)
+            assert s.getBestLine()[0] == o.getBestLine()[0]
+    finally:
+        for s in hs:
+            s.close()
