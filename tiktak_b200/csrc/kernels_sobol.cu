@@ -209,8 +209,8 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
     constexpr int BT = 128;
     auto try_launch = [&]<int P>(bool force) -> int {
         const int64_t grid = owned_cbs * (TIKTAK_SOBOL_BLOCK / (BT * P));
-        int per_sm = 0;
-        TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sobol_eval_kernel<Obj, NX, BT, P>, BT, 0));
+        static int per_sm = 0; /* per instantiation: the occupancy query is host work in front of every launch */
+        if (per_sm == 0) TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sobol_eval_kernel<Obj, NX, BT, P>, BT, 0));
         if (!force && grid > (int64_t)per_sm * h->sm_count) return 1;
         sobol_eval_kernel<Obj, NX, BT, P><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
         h->launches++;
