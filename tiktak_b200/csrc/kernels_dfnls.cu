@@ -1234,7 +1234,7 @@ struct Df {
 };
 
 template <class Obj>
-__global__ void __launch_bounds__(256) dfnls_kernel(const TkTablesG T, const TkScalars sc, const DfArgs a) {
+__global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const TkTablesG T, const TkScalars sc, const DfArgs a) {
     extern __shared__ double sm[];
     __shared__ DfCtl ctl;
     __shared__ tk_obj_ctx sctx;
@@ -1343,16 +1343,17 @@ int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
     a.npt = npt; a.mv = mv;
     a.slab = h->d_dfnls_slab; a.slab_doubles = slab;
     a.out_x = h->d_out_x; a.out_f = h->d_out_f; a.out_evals = h->d_out_evals; a.out_status = h->d_out_status;
-    const int threads = (h->cfg.objective_id == TIKTAK_OBJ_SMM || mv >= 256) ? 256 : (mv >= 128 ? 128 : 64);
+    /* the SMM objective runs its panel simulation warp-specialised: 256 producer + 256 consumer threads (smm.cuh) */
+    const int threads = h->cfg.objective_id == TIKTAK_OBJ_SMM ? 512 : (mv >= 256 ? 256 : (mv >= 128 ? 128 : 64));
     const size_t shd = (size_t)(3 * nx + nx + npt * nx + npt + nx + nx + nh + ndim * nx + npt * (nptm > 0 ? nptm : 1) + 5 * nx + ndim +
                                 (2 * ndim + 6 * nx + 2 * npt + 16) + nx + (ndim + npt + 8) + nx + threads) * sizeof(double);
     if (shd > 226 * 1024) { tk_set_error("DFNLS small matrices do not fit in shared memory (nx=%d)", nx); return TIKTAK_ERR_UNSUPPORTED; }
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     if (h->cfg.objective_id == TIKTAK_OBJ_SMM) {
-        const size_t shv = shd + (size_t)(mv + TK_SMM_SMEM_DOUBLES(h->smm_T)) * sizeof(double);
+        const size_t shv = shd + (size_t)(mv + 2 * TK_SMM_SMEM_DOUBLES(h->smm_T)) * sizeof(double);
         if (shv > 226 * 1024) { tk_set_error("DFNLS+SMM shared memory"); return TIKTAK_ERR_UNSUPPORTED; }
         TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<ObjSmm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shv));
-        dfnls_kernel<ObjSmm><<<a.n_run, 256, shv, h->stream>>>(T, h->sc, a);
+        dfnls_kernel<ObjSmm><<<a.n_run, threads, shv, h->stream>>>(T, h->sc, a);
         h->launches++;
         TK_CUDA(cudaGetLastError());
         return TIKTAK_OK;

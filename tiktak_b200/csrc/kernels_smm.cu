@@ -73,7 +73,8 @@ __device__ double smm_objfun_block(const SmmDev& S, const tk_obj_ctx& ctx, const
         __syncthreads();
         return s_val;
     }
-    tk_smm_dfovec_block(S, theta, fsh, ysh);
+    if (blockDim.x >= 512) tk_smm_dfovec_block_ws(S, theta, fsh, ysh);
+    else tk_smm_dfovec_block(S, theta, fsh, ysh);
     if (threadIdx.x == 0) {
         double dot = 0.0;
         for (int m = 0; m < nm; m++) dot = TK_ADD(dot, TK_MUL(fsh[m], fsh[m]));
@@ -83,13 +84,13 @@ __device__ double smm_objfun_block(const SmmDev& S, const tk_obj_ctx& ctx, const
     return s_val;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 smm_wave_kernel(const SmmDev* Sp, const TkTablesG T, const TkScalars sc, const TkWave wv, const int64_t* list, int64_t nlist) {
     extern __shared__ double sh[];
     __shared__ double theta[8];
     const SmmDev S = *Sp;
     double* ysh = sh;
-    double* fsh = sh + TK_SMM_SMEM_DOUBLES(S.T);
+    double* fsh = sh + 2 * TK_SMM_SMEM_DOUBLES(S.T);
     const tk_obj_ctx ctx = tk_make_ctx(sc, sc.nx, T.bl, T.bu, T.aux);
     for (int64_t w = blockIdx.x; w < nlist; w += gridDim.x) {
         const int64_t n = list[w];
@@ -110,13 +111,13 @@ smm_wave_kernel(const SmmDev* Sp, const TkTablesG T, const TkScalars sc, const T
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 smm_objfun_kernel(const SmmDev* Sp, const TkTablesG T, const TkScalars sc, const double* x, int64_t n, double* f) {
     extern __shared__ double sh[];
     __shared__ double theta[8];
     const SmmDev S = *Sp;
     double* ysh = sh;
-    double* fsh = sh + TK_SMM_SMEM_DOUBLES(S.T);
+    double* fsh = sh + 2 * TK_SMM_SMEM_DOUBLES(S.T);
     const tk_obj_ctx ctx = tk_make_ctx(sc, sc.nx, T.bl, T.bu, T.aux);
     for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
         __syncthreads();
@@ -127,7 +128,8 @@ smm_objfun_kernel(const SmmDev* Sp, const TkTablesG T, const TkScalars sc, const
     }
 }
 
-size_t smm_shmem(int T, int nm) { return (size_t)(TK_SMM_SMEM_DOUBLES(T) + nm + 8) * sizeof(double); }
+size_t smm_shmem(int T, int nm) { return (size_t)(TK_SMM_SMEM_DOUBLES(T) + nm + 8) * sizeof(double); }       /* 256-thread blocks */
+size_t smm_shmem_ws(int T, int nm) { return (size_t)(2 * TK_SMM_SMEM_DOUBLES(T) + nm + 8) * sizeof(double); } /* 512-thread blocks */
 
 } /* namespace */
 
@@ -196,11 +198,11 @@ int tk_launch_smm_wave(tiktak_handle* h, const TkWave& wv) {
     int64_t* d_list = nullptr;
     TK_CUDA(cudaMalloc(&d_list, list.size() * 8));
     TK_CUDA(cudaMemcpyAsync(d_list, list.data(), list.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    const size_t shm = smm_shmem(h->smm_T, h->cfg.nm);
+    const size_t shm = smm_shmem_ws(h->smm_T, h->cfg.nm);
     TK_CUDA(cudaFuncSetAttribute(smm_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)list.size(), (int64_t)h->sm_count * 2);
+    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)list.size(), (int64_t)h->sm_count); /* one 512-thread block per SM */
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
-    smm_wave_kernel<<<grid, 256, shm, h->stream>>>((const SmmDev*)h->sc.user, T, h->sc, wv, d_list, (int64_t)list.size());
+    smm_wave_kernel<<<grid, 512, shm, h->stream>>>((const SmmDev*)h->sc.user, T, h->sc, wv, d_list, (int64_t)list.size());
     h->launches++;
     TK_CUDA(cudaGetLastError());
     TK_CUDA(cudaStreamSynchronize(h->stream));
@@ -209,11 +211,11 @@ int tk_launch_smm_wave(tiktak_handle* h, const TkWave& wv) {
 }
 
 int tk_launch_smm_objfun(tiktak_handle* h, const double* d_x, int64_t n, double* d_f) {
-    const size_t shm = smm_shmem(h->smm_T, h->cfg.nm);
+    const size_t shm = smm_shmem_ws(h->smm_T, h->cfg.nm);
     TK_CUDA(cudaFuncSetAttribute(smm_objfun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)h->sm_count * 2);
+    const unsigned grid = (unsigned)std::min<int64_t>(n, (int64_t)h->sm_count);
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
-    smm_objfun_kernel<<<grid, 256, shm, h->stream>>>((const SmmDev*)h->sc.user, T, h->sc, d_x, n, d_f);
+    smm_objfun_kernel<<<grid, 512, shm, h->stream>>>((const SmmDev*)h->sc.user, T, h->sc, d_x, n, d_f);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;
