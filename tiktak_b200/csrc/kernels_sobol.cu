@@ -14,6 +14,9 @@
  * n -> n+BT flips exactly two Gray-code bits, S-1 and S+ctz(~(n>>S)) -- the same two for the whole
  * block (block-uniform constant-bank reads).
  */
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tk_common.cuh"
 
 namespace {
@@ -26,7 +29,10 @@ __device__ __forceinline__ uint32_t tk_gray_point_coord(const uint32_t* Vd, uint
     return q;
 }
 
-template <class Obj, int NX, int BT, int P>
+/* INB: the host has verified that the whole Sobol box lies inside the bounds (lo >= bl and fl(lo + w) <= bu; every
+ * point is <= fl(lo + w) because q < 1 and rounding is monotonic), so getPenalty is identically 0 and the per-point
+ * bounds test (2 DSETP per coordinate on the FP64 pipe) is compiled out -- same values. */
+template <class Obj, int NX, int BT, int P, bool INB>
 __global__ void __launch_bounds__(BT)
 sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, const TkWave wv) {
     constexpr int S = (BT == 64) ? 6 : (BT == 128) ? 7 : 8;
@@ -78,7 +84,7 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
         TkRegX<NX> x;
 #pragma unroll
         for (int d = 0; d < NX; d++) x.v[d] = __dadd_rn(T.lo[d], __dmul_rn(tk_q2unit(q[d]), T.w[d]));
-        const double f = tk_objfun<Obj>(ctx, x);
+        const double f = INB ? tk_objfun_finish(ctx, tk_value_seq<Obj>(ctx, x), 0.0) : tk_objfun<Obj>(ctx, x);
         if (n >= 1 && n <= wv.N) {
             wv.fval[lbase + (int64_t)j * BT + t] = f;
             cnt += (f < sc.fvalmax) ? 1u : 0u;
@@ -206,21 +212,36 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
     }
     /* points per thread P: the smallest P whose grid is resident in ONE wave (no tail wave, seeding
      * amortised as little as necessary); a job too big for that takes the longest stride. */
-    constexpr int BT = 128;
-    auto try_launch = [&]<int P>(bool force) -> int {
+    bool inb = true; /* Sobol box inside the bounds? */
+    for (int d = 0; d < NX; d++) inb = inb && (T.lo[d] >= T.bl[d]) && (T.lo[d] + T.w[d] <= T.bu[d]);
+    auto try_launch = [&]<int BT, int P>(bool force) -> int {
         const int64_t grid = owned_cbs * (TIKTAK_SOBOL_BLOCK / (BT * P));
-        static int per_sm = 0; /* per instantiation: the occupancy query is host work in front of every launch */
-        if (per_sm == 0) TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sobol_eval_kernel<Obj, NX, BT, P>, BT, 0));
-        if (!force && grid > (int64_t)per_sm * h->sm_count) return 1;
-        sobol_eval_kernel<Obj, NX, BT, P><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
+        static int per_sm[2] = {0, 0}; /* per instantiation: the occupancy query is host work in front of every launch */
+        if (per_sm[inb] == 0) {
+            if (inb) TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sobol_eval_kernel<Obj, NX, BT, P, true>, BT, 0));
+            else TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sobol_eval_kernel<Obj, NX, BT, P, false>, BT, 0));
+        }
+        if (!force && grid > (int64_t)per_sm[inb] * h->sm_count) return 1;
+        if (inb) sobol_eval_kernel<Obj, NX, BT, P, true><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
+        else sobol_eval_kernel<Obj, NX, BT, P, false><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
         h->launches++;
         TK_CUDA(cudaGetLastError());
         return TIKTAK_OK;
     };
-    int rc = try_launch.template operator()<4>(false);
-    if (rc == 1) rc = try_launch.template operator()<8>(false);
-    if (rc == 1) rc = try_launch.template operator()<16>(false);
-    if (rc == 1) rc = try_launch.template operator()<32>(true);
+    /* experiment hook: TIKTAK_SOBOL_SHAPE=<BT>x<P> forces one shape */
+    static const char* shape = getenv("TIKTAK_SOBOL_SHAPE");
+    if (shape) {
+        int bt = 0, pp = 0;
+        if (sscanf(shape, "%dx%d", &bt, &pp) == 2) {
+            if (bt == 128 && pp == 4) return try_launch.template operator()<128, 4>(true);
+            if (bt == 128 && pp == 8) return try_launch.template operator()<128, 8>(true);
+            if (bt == 128 && pp == 16) return try_launch.template operator()<128, 16>(true);
+        }
+    }
+    int rc = try_launch.template operator()<128, 4>(false);
+    if (rc == 1) rc = try_launch.template operator()<128, 8>(false);
+    if (rc == 1) rc = try_launch.template operator()<128, 16>(false);
+    if (rc == 1) rc = try_launch.template operator()<128, 32>(true);
     return rc;
 }
 
