@@ -56,6 +56,10 @@ def load():
         L.orc_dfnls.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, c_int32_p, c_int32_p]
         L.orc_simplex_coordinates2.argtypes = [C.c_int, c_double_p]
         L.orc_indexx.argtypes = [C.c_int, c_double_p, c_int32_p]
+        L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32]
+        L.orc_philox4x32_10.restype = None
+        L.orc_uniform01.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+        L.orc_uniform01.restype = C.c_double
         _lib = L
     return _lib
 

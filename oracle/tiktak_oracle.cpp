@@ -34,6 +34,7 @@
 
 #include "../include/tiktak_cuda.h" /* tiktak_config layout only */
 #include "../include/tiktak_math.h" /* tk_cos for math_mode 1, tk_* bit casts */
+#include "../include/tiktak_rng.h"  /* the documented substitute for RANDOM_NUMBER (lottery) */
 #include "../tables/sobol_bf1111.inc"
 
 namespace {
@@ -602,6 +603,33 @@ struct Oracle {
         return itmax;
     }
 
+    /* getLotteryPoint (TiktakGlobalSearch.f90:722-766): among the best min(count, lotteryPoints) result rows, pick
+     * rank i with probability proportional to 1/i.  Deviations from the literal code, all documented in DESIGN.md:
+     * rows are ordered by (fval, k) instead of indexx's unstable order; RANDOM_NUMBER is replaced by
+     * tk_uniform01(seed 123456, restart k); `y = sortedPoints(i,4:)` (a size mismatch) is read as
+     * (i,5:), the parameters; if rounding leaves u >= the last cumulative probability the last row is taken. */
+    int lottery_row(const std::vector<Row>& snap, int count, int k) {
+        std::vector<int> ord(count);
+        for (int i = 0; i < count; i++) ord[i] = i;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+            if (snap[a].fval != snap[b].fval) return snap[a].fval < snap[b].fval;
+            return snap[a].k < snap[b].k; });
+        const int numPoints = std::min(count, (int)c.lottery_points);
+        const long long sumVal = ((long long)numPoints * (numPoints + 1)) / 2;
+        std::vector<double> prob(numPoints);
+        for (int i = 1; i <= numPoints; i++) prob[i - 1] = (double)sumVal / (double)i;
+        double sum2 = 0.0;
+        for (int i = 0; i < numPoints; i++) sum2 = sum2 + prob[i]; /* the remaining entries of probOfPoint are 0 */
+        for (int i = 0; i < numPoints; i++) prob[i] = prob[i] / sum2;
+        for (int i = 1; i < numPoints; i++) prob[i] = prob[i - 1] + prob[i];
+        const double u = tk_uniform01(TK_LOTTERY_SEED, TK_LOTTERY_STREAM, (uint64_t)k);
+        int sel = numPoints - 1;
+        for (int i = 0; i < numPoints; i++) if (u < prob[i]) { sel = i; break; }
+        lottery_pick.push_back(snap[ord[sel]].k);
+        return ord[sel];
+    }
+    std::vector<int> lottery_pick; /* lotPoint of every blended restart, for tests */
+
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out);
@@ -613,6 +641,7 @@ int Oracle::local(int alg, int round_size, double* starts_out, double* results_o
     if ((int)x_starts.size() != K * (nx + 1)) return -1;
     if (round_size < 1) round_size = 1;
     rows.clear();
+    lottery_pick.clear();
     best_tie_events = 0;
     const int seqNo = 1;
     write_row(seqNo, 0, 0, x_starts[0], &x_starts[1]); /* :496-501, whichPoint == 1 */
@@ -627,7 +656,7 @@ int Oracle::local(int alg, int round_size, double* starts_out, double* results_o
             if (count <= 1) { /* :701-705 */
                 for (int i = 0; i < nx; i++) evalParam[i] = evalPoint[i];
             } else {
-                const std::vector<double>& base = snapshot[bsnap].x;
+                const std::vector<double>& base = (c.search_type == 1) ? snapshot[lottery_row(snapshot, count, k)].x : snapshot[bsnap].x;
                 float wf = sqrtf((float)k / (float)K); /* :718, single precision */
                 wf = std::min(std::max(0.10f, wf), 0.95f);
                 double w11 = (double)wf;
@@ -856,6 +885,10 @@ int orc_indexx(int n, const double* arr, int32_t* index) {
     return rc;
 }
 double orc_text4020(double x) { return text4020(x); }
+
+/* the lottery's random numbers (include/tiktak_rng.h) */
+void orc_philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) { tk_philox4x32_10(c, k0, k1); }
+double orc_uniform01(uint32_t seed, uint32_t stream, uint64_t counter) { return tk_uniform01(seed, stream, counter); }
 float orc_w11(int k, int K) { float wf = sqrtf((float)k / (float)K); return std::min(std::max(0.10f, wf), 0.95f); }
 /* one DFNLS run (bobyqa_h) from x with explicit radii */
 int orc_dfnls(void* h, double* x, double rhobeg, double rhoend, int maxfun, int32_t* nf, int32_t* nrescue) {

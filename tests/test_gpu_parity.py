@@ -350,3 +350,23 @@ def test_sharded_protocol_on_one_gpu(built, name, alg, world):
     finally:
         for s in hs:
             s.close()
+
+
+@pytest.mark.parametrize("name,alg,B,lp", [("griewank10", "a", 1, 3), ("griewank10", "a", 6, 10), ("rastrigin20", "a", 4, 2),
+                                          ("griewank7", "b", 3, 4)])
+def test_lottery_start_selection(built, name, alg, B, lp):
+    """selectType = 1: getLotteryPoint (:722-766) with the counter-based random numbers of include/tiktak_rng.h"""
+    kw = dict(round_size=B, search_type=1, lottery_points=lp)
+    if alg == "b":
+        kw.update(nm=3, maxpoints=9)
+    cfg = cfg_of(name, **kw)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations(alg)
+        gs, gr, ge = s.searchStart, s.searchResults, s.evals
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(1 if alg == "a" else 0)
+    assert np.array_equal(gs, o.searchStart), "lottery-blended start points differ"
+    assert np.array_equal(gr, o.searchResults) and np.array_equal(ge, o.evals)
+    o0 = Oracle(cfg_of(name, **dict(kw, search_type=0)), MATH_TK)
+    o0.solveAtSobolPoints(); o0.chooseSobol(mode=1); o0.LocalMinimizations(1 if alg == "a" else 0)
+    assert not np.array_equal(o0.searchStart, o.searchStart)  # and it is not the best-point rule

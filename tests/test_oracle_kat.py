@@ -214,3 +214,60 @@ def test_legitimate_cut_prefix_semantics(built):
     cfg3 = make_config(10, 1, 50, 10, -400.0, 600.0, objective_id=OBJ_GRIEWANK, fvalmax=1e-3, legitimate=5)
     o3 = Oracle(cfg3, MATH_TK)
     assert o3.solveAtSobolPoints() == (True, 50, 0)  # never reached: all points evaluated (soft goal)
+
+
+def _philox_py(c, k0, k1):
+    """independent restatement of Philox4x32-10 (Salmon et al., SC'11)"""
+    c = list(c)
+    M = 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & M, p1 & M, ((p0 >> 32) ^ c[3] ^ k1) & M, p0 & M]
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return c
+
+
+def test_lottery_random_numbers(L):
+    """include/tiktak_rng.h: Philox4x32-10 known answers (Random123 kat_vectors) and the [0,1) mapping"""
+    import ctypes as C
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        c = (C.c_uint32 * 4)(*ctr)
+        L.orc_philox4x32_10(c, key[0], key[1])
+        assert tuple(c) == want == tuple(_philox_py(ctr, *key))
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        seed, stream, ctr = int(rng.integers(0, 2**32)), int(rng.integers(0, 2**32)), int(rng.integers(0, 2**63))
+        out = _philox_py((ctr & 0xFFFFFFFF, ctr >> 32, stream, 0), seed, 0)
+        u = ((out[0] << 32 | out[1]) >> 11) * 2.0 ** -53
+        assert L.orc_uniform01(seed, stream, ctr) == u and 0.0 <= u < 1.0
+
+
+def test_lottery_selection_oracle(built):
+    """selectType = 1 (getLotteryPoint :722-766): restarts blend toward a rank-weighted random earlier result, not only
+    the best one; rank probabilities 6/11, 3/11, 2/11 at three points"""
+    from tiktak_b200 import OBJ_GRIEWANK
+    cfg = make_config(nx=10, nm=1, qr_ndraw=3000, maxpoints=40, lo=-400.0, hi=600.0, init=[100.0] * 10, objective_id=OBJ_GRIEWANK,
+                      search_type=1, lottery_points=3, round_size=1)
+    o = Oracle(cfg, MATH_TK); o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(1)
+    cfg0 = make_config(nx=10, nm=1, qr_ndraw=3000, maxpoints=40, lo=-400.0, hi=600.0, init=[100.0] * 10, objective_id=OBJ_GRIEWANK,
+                       round_size=1)
+    o0 = Oracle(cfg0, MATH_TK); o0.solveAtSobolPoints(); o0.chooseSobol(mode=1); o0.LocalMinimizations(1)
+    assert np.array_equal(o.searchStart[0], o0.searchStart[0])  # k = 1: only the k = 0 record exists, no blend (:701)
+    assert not np.array_equal(o.searchStart, o0.searchStart)
+    # reconstruct the blend of every restart from the rows known at its start: the base point must be one of the 3 best rows
+    K, nx = cfg.p_maxpoints, cfg.nx
+    rows = [(o.x_starts[0, 0], 0, o.x_starts[0, 1:])]
+    hits = {1: 0, 2: 0, 3: 0}
+    for k in range(1, K + 1):
+        if len(rows) > 1:
+            order = sorted(rows, key=lambda r: (r[0], r[1]))[:3]
+            w = np.float64(min(max(np.float32(0.10), np.sqrt(np.float32(k) / np.float32(K))), np.float32(0.95)))
+            cands = [w * r[2] + (1.0 - w) * o.x_starts[k - 1, 1:] for r in order]
+            match = [i for i, c in enumerate(cands) if np.array_equal(c, o.searchStart[k - 1])]
+            assert match, k
+            hits[match[0] + 1] += 1
+        rows.append((o.searchResults[k - 1, 3], k, o.searchResults[k - 1, 4:]))
+    assert hits[1] > hits[3] and hits[2] > 0  # rank 1 is drawn most often, lower ranks do occur

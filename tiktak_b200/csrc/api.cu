@@ -149,7 +149,11 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
         return TIKTAK_ERR_ARG;
     }
     if (cfg->maxpoints_plus1 - 1 > cfg->qr_ndraw) { tk_set_error("create: maxpoints > qr_ndraw"); return TIKTAK_ERR_ARG; }
-    if (cfg->search_type != 0) { tk_set_error("create: only selectType 0 (best point) is implemented"); return TIKTAK_ERR_UNSUPPORTED; }
+    if (cfg->search_type != 0 && cfg->search_type != 1) { /* getModifiedParam :709-715 `stop 0` */
+        tk_set_error("create: unknown selectionMethod %d", cfg->search_type);
+        return TIKTAK_ERR_ARG;
+    }
+    if (cfg->search_type == 1 && cfg->lottery_points < 1) { tk_set_error("create: lotteryPoints must be >= 1"); return TIKTAK_ERR_ARG; }
     if (cfg->nx > TK_NX_GENERIC_MAX) { tk_set_error("create: nx > %d not supported by this build", TK_NX_GENERIC_MAX); return TIKTAK_ERR_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -264,7 +268,8 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
-                    h->d_shr_have, h->d_arch_starts, h->d_arch_evals};
+                    h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
+                    h->d_lot_k, h->d_lot_sk, h->d_lot_point};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -594,6 +599,7 @@ static int push_init_row(tiktak_handle* h) {
     rows[3] = h->cfg.text_roundtrip ? tk_f4020_roundtrip(row0[0]) : row0[0];
     for (int d = 0; d < nx; d++) rows[4 + d] = h->cfg.text_roundtrip ? tk_f4020_roundtrip(row0[1 + d]) : row0[1 + d];
     std::fill(h->h_res_valid.begin(), h->h_res_valid.end(), 0);
+    h->n_rows = 0;
     TK_CUDA(cudaMemsetAsync(h->d_res_valid, 0, (size_t)(K + 1) * sizeof(int), h->stream));
     return tiktak_cuda_push_results(h, rows.data(), 1);
 }
@@ -718,6 +724,7 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
         int imp = best_imp;
         if (k > 0 && fv < best_f) imp = best_imp + 1;
         if (!any || fv < best_f) { best_f = fv; best_imp = imp; any = true; }
+        if (!h->h_res_valid[k]) h->n_rows++;
         h->h_res_f[k] = fv; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
         if (run_len > 0 && k != run_k0 + run_len) { int rc = flush(); if (rc) return rc; }
         if (run_len == 0) run_k0 = k;
@@ -748,7 +755,7 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
         if ((rc = tk_launch_best(h))) return rc;
         h->best_dirty = false;
     }
-    if ((rc = tk_launch_blend(h, first_k, n_k))) return rc;
+    if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows) : tk_launch_blend(h, first_k, n_k))) return rc;
     if (alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1 && (rc = tk_launch_shrink_width(h))) return rc;
     rc = (alg == TIKTAK_ALG_AMOEBA) ? tk_launch_nm(h, first_k, n_k) : tk_launch_dfnls(h, first_k, n_k);
     if (rc) return rc;
@@ -764,6 +771,7 @@ int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, con
     TK_CUDA(cudaSetDevice(h->device));
     int rc = tk_launch_ingest(h, first_k, n_k, h->cfg.world > 1 ? recv : nullptr);
     if (rc) return rc;
+    h->n_rows += n_k;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
     return TIKTAK_OK;
 }

@@ -17,7 +17,10 @@
  */
 #include <float.h>
 
+#include <algorithm>
+
 #include "tk_common.cuh"
+#include "../../include/tiktak_rng.h"
 
 namespace {
 
@@ -878,6 +881,43 @@ __global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n
     arch_starts[(size_t)d * K + (k - 1)] = out; /* the searchStart.dat row of restart k (:557) */
 }
 
+/* getLotteryPoint (TiktakGlobalSearch.f90:722-766), selectType = 1: the base point of restart k is the result row of
+ * rank i (rows ordered by (fval, k)) with probability proportional to 1/i among the best numPoints rows.
+ * cum = the reference's cumulative probOfPoint (computed on the host in its arithmetic), u = tk_uniform01(seed
+ * 123456, k) in place of RANDOM_NUMBER; the first i with u < cum(i) wins (the last row if rounding leaves none). */
+__global__ void lottery_collect_kernel(const double* res, const int* valid, int nrows, int nx, double* f, unsigned int* kk,
+                                       unsigned int* n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows || !valid[r]) return;
+    const unsigned int pos = atomicAdd(n, 1u);
+    f[pos] = res[(size_t)r * (nx + 1)];
+    kk[pos] = (unsigned int)r;
+}
+__global__ void blend_lottery_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11, int count,
+                                     int num_points, const double* cum, const unsigned int* sorted_k, const double* res,
+                                     double* starts, double* arch_starts, int* lot_point) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_k * nx) return;
+    const int d = e / n_k, s = e - d * n_k, k = first_k + s;
+    const double ev = xs[(size_t)(d + 1) * K + (k - 1)];
+    double out = ev;
+    int lot = 0;
+    if (count > 1) { /* :701 */
+        const double u = tk_uniform01(TK_LOTTERY_SEED, TK_LOTTERY_STREAM, (uint64_t)k);
+        int lo = 0, hi = num_points - 1; /* first i with u < cum[i]; cum is non-decreasing */
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (u < cum[mid]) hi = mid; else lo = mid + 1;
+        }
+        lot = (int)sorted_k[lo];
+        const double w = w11[k];
+        out = TK_ADD(TK_MUL(w, res[(size_t)lot * (nx + 1) + 1 + d]), TK_MUL(TK_SUB(1.0, w), ev));
+    }
+    starts[(size_t)d * n_k + s] = out;
+    arch_starts[(size_t)d * K + (k - 1)] = out;
+    if (d == 0) lot_point[k] = lot;
+}
+
 /* One round's outcomes -> the device-resident searchResults table (completeSearch :582-597 without the
  * file): row k = [fval, x] through the f40.20 record when text_roundtrip is on, the evaluation count, and
  * the running best row (getBestLine :781-802: lowest fval, first row among equals) -- so the next round's
@@ -1022,6 +1062,47 @@ int tk_launch_blend(tiktak_handle* h, int first_k, int n_k) {
     const int tot = n_k * h->cfg.nx;
     blend_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, h->cfg.maxpoints_plus1, h->cfg.nx, first_k, n_k,
                                                             h->d_w11, h->d_best, h->d_starts, h->d_arch_starts);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+
+int tk_sort_candidates(tiktak_handle* h, double* d_f, unsigned int* d_i, int64_t n, double* d_sf, unsigned int* d_si);
+
+/* the blend of a round under selectType = 1 (lottery); `count` = result rows known to the handle */
+int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count) {
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
+    if (!h->d_lot_f) {
+        TK_CUDA(cudaMalloc(&h->d_lot_f, (size_t)(K + 1) * 8)); TK_CUDA(cudaMalloc(&h->d_lot_sf, (size_t)(K + 1) * 8));
+        TK_CUDA(cudaMalloc(&h->d_lot_k, (size_t)(K + 1) * 4)); TK_CUDA(cudaMalloc(&h->d_lot_sk, (size_t)(K + 1) * 4));
+        TK_CUDA(cudaMalloc(&h->d_lot_cum, (size_t)(K + 1) * 8)); TK_CUDA(cudaMalloc(&h->d_lot_point, (size_t)(K + 1) * 4));
+        TK_CUDA(cudaMemsetAsync(h->d_lot_point, 0, (size_t)(K + 1) * 4, h->stream));
+    }
+    const int num_points = std::max(1, std::min(count, (int)h->cfg.lottery_points));
+    if (count > 1) {
+        TK_CUDA(cudaMemsetAsync(h->d_cand_n, 0, sizeof(unsigned int), h->stream));
+        lottery_collect_kernel<<<(K + 1 + 255) / 256, 256, 0, h->stream>>>(h->d_res, h->d_res_valid, K + 1, nx, h->d_lot_f, h->d_lot_k, h->d_cand_n);
+        h->launches++;
+        int rc = tk_sort_candidates(h, h->d_lot_f, h->d_lot_k, count, h->d_lot_sf, h->d_lot_sk);
+        if (rc) return rc;
+        if (num_points != h->lot_cum_n) { /* probOfPoint, :742-754, in the reference's arithmetic */
+            std::vector<double>& prob = h->lot_cum;
+            prob.assign(num_points, 0.0);
+            const long long sumVal = ((long long)num_points * (num_points + 1)) / 2;
+            for (int i = 1; i <= num_points; i++) prob[i - 1] = (double)sumVal / (double)i;
+            double sum2 = 0.0;
+            for (int i = 0; i < num_points; i++) sum2 = sum2 + prob[i];
+            for (int i = 0; i < num_points; i++) prob[i] = prob[i] / sum2;
+            for (int i = 1; i < num_points; i++) prob[i] = prob[i - 1] + prob[i];
+            TK_CUDA(cudaStreamSynchronize(h->stream)); /* an earlier round may still be reading d_lot_cum / lot_cum */
+            TK_CUDA(cudaMemcpyAsync(h->d_lot_cum, prob.data(), (size_t)num_points * 8, cudaMemcpyHostToDevice, h->stream));
+            h->lot_cum_n = num_points;
+        }
+    }
+    const int tot = n_k * nx;
+    blend_lottery_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, K, nx, first_k, n_k, h->d_w11, count, num_points,
+                                                                    h->d_lot_cum, h->d_lot_sk, h->d_res, h->d_starts,
+                                                                    h->d_arch_starts, h->d_lot_point);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;

@@ -110,6 +110,13 @@ struct tiktak_handle {
     cudaEvent_t evl0 = nullptr, evl1 = nullptr;
     bool local_timing_open = false, pretest_timing_open = false;
     bool rho_ready = false;
+    /* selectType = 1 (lottery) */
+    double *d_lot_f = nullptr, *d_lot_sf = nullptr, *d_lot_cum = nullptr;
+    unsigned int *d_lot_k = nullptr, *d_lot_sk = nullptr;
+    int* d_lot_point = nullptr;       /* [K+1]: lotPoint of restart k (the row it was blended toward) */
+    std::vector<double> lot_cum;
+    int lot_cum_n = 0;
+    int n_rows = 0;                   /* result rows known to the handle (k = 0 record included) */
     /* DFNLS */
     double* d_dfnls_slab = nullptr;
     size_t dfnls_slab_doubles = 0;
@@ -131,6 +138,7 @@ int tk_select_top(tiktak_handle* h, int64_t M);
 int tk_build_starts(tiktak_handle* h);
 int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
+int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, const double* pack);
