@@ -12,8 +12,16 @@
  *   FinalStart.dat / FinalResults.dat '(2i10, 200f40.20)'          (:677)
  *   state.dat, seqNo.dat, lastSobol.dat, legitSobol.dat, lastParam.dat  list-directed integers
  * The reference's Fortran toolchain is not in the build image, so this driver is C++; the Fortran
- * binding of the same ABI is in INTEGRATION.md.  Options 1/2/3/-1 coordinate several CPU processes through
- * lock files in the reference; with device-resident state there is nothing to join, so they only report that.
+ * binding of the same ABI is in INTEGRATION.md.  Options 1/-1 coordinate several CPU processes through lock files in
+ * the reference; with device-resident state there is nothing to join, so they only report that.
+ * Options 2 and 3 (genericParams.f90:118-251) resume from the files of an earlier run:
+ *   2  more Sobol points / a higher `legitimate`: the same consistency checks against internalConfig.dat,
+ *      sobolFnVal.dat and legitSobol.dat, then the Sobol stage for the new config (the rows already in sobolFnVal.dat
+ *      are re-derived bit for bit -- evaluating them again costs microseconds, parsing them would not be faster) and
+ *      everything downstream from scratch, as the reference does (it resets searchResults.dat etc., :118-131).
+ *   3  more local searches: same Sobol config required; the finished rows of searchResults.dat are loaded back into
+ *      the device-resident results table (tiktak_cuda_push_results) and the restarts continue at lastParam + 1,
+ *      appending to searchStart.dat / searchResults.dat.
  * Knobs outside the reference surface come from the environment: TIKTAK_OBJECTIVE (0 template, 1 Griewank,
  * 2 Rastrigin, 3 Rosenbrock), TIKTAK_ROUND_SIZE (default 1 = the sequential reference order), TIKTAK_DEVICE,
  * TIKTAK_WRITE_SOBOL (1 = also dump sobol.dat like setupSobol does).
@@ -85,8 +93,25 @@ static void mywrite2(const char* file, const double* a, int rows, int cols) { /*
     for (int r = 0; r < rows; r++) { fputc(' ', f); for (int c = 0; c < cols; c++) fprintf(f, "   %30.15f", a[(size_t)c * rows + r]); fputc('\n', f); }
     fclose(f);
 }
+static int exit_state(const std::string& m) { /* exitState, stateControl.f90:203-216 */
+    logmsg("EXIT STATE: " + m);
+    write_int("state.dat", -1);
+    return 1;
+}
+struct Cfg;
+static void write_internal_config(const Cfg& c);
 #define CHECK(call) do { int rc_ = (call); if (rc_) { char b_[1200]; snprintf(b_, sizeof b_, "EXIT STATE: %s: %s; %s", #call, tiktak_cuda_strerror(rc_), tiktak_cuda_last_error()); \
     logmsg(b_); write_int("state.dat", -1); return 1; } } while (0)
+
+static void write_internal_config(const Cfg& c) { /* genericParams.f90:154-174; parse_config reads it back (maxpoints is stored raw) */
+    FILE* f = fopen("internalConfig.dat", "w");
+    if (!f) return;
+    fprintf(f, " %11d\n %11d\n %11d\n %11d\n %11d\n %24.16E\n %11d\n %11d\n %11d\n", c.nx, c.nm, c.maxeval, c.qr, c.legit, c.fvalmax, c.maxpoints, c.stype, c.lottery);
+    for (int i = 0; i < c.nx; i++) fprintf(f, " %24.16E %24.16E\n", c.range[i], c.range[c.nx + i]);
+    for (int i = 0; i < c.nx; i++) fprintf(f, " %24.16E\n", c.init[i]);
+    for (int i = 0; i < c.nx; i++) fprintf(f, " %24.16E %24.16E\n", c.bound[i], c.bound[c.nx + i]);
+    fclose(f);
+}
 
 int main(int argc, char** argv) {
     if (argc < 2) { usage(); return 0; }
@@ -97,13 +122,48 @@ int main(int argc, char** argv) {
     if (algarg) { if (algarg[0] == 'a') alg = 1; else if (algarg[0] == 'b') alg = 0; else if (algarg[0] == 'd') alg = 2; else { usage(); return 0; } }
     if (option < -1 || option > 5) { usage(); return 0; }
     if (option == -1) { write_int("state.dat", -1); logmsg("exit state written; no other instance is attached to device-resident state"); return 0; }
-    if (option == 1 || option == 2 || option == 3) {
-        logmsg("options 1-3 join/extend a multi-process CPU run through the .dat lock files; the GPU library keeps that state "
-               "on the device and runs the whole job in one cold start (option 0). Nothing to do.");
+    if (option == 1) {
+        logmsg("option 1 joins a multi-process CPU run through the .dat lock files; the GPU library keeps that state "
+               "on the device and runs the whole job in one process (options 0, 2, 3). Nothing to do.");
         return 0;
     }
     Cfg c;
     if (!parse_config(config, c)) return 1;
+    /* ---- options 2 / 3: consistency checks of initialize (genericParams.f90:118-251) ---- */
+    std::vector<std::vector<double>> old_rows; /* searchResults.dat rows with k >= 1 (option 3) */
+    int resume_k = 0;
+    if (option == 2 || option == 3) {
+        Cfg oldc;
+        if (!parse_config("internalConfig.dat", oldc)) return exit_state("update: internalConfig.dat of the earlier run cannot be read");
+        long numsolved = -1, legit = 0;
+        { std::ifstream f("sobolFnVal.dat"); std::string line; while (std::getline(f, line)) { std::vector<double> v = nums(line, 1); if (!v.empty()) numsolved = std::max(numsolved, (long)v[0]); } }
+        { std::ifstream f("legitSobol.dat"); f >> legit; }
+        char b[600];
+        if (option == 2 && numsolved >= 0) {
+            if (numsolved >= c.qr || legit >= c.legit) { /* :189-195 */
+                snprintf(b, sizeof b, "Update sobol: numsolved > p_qr_ndraw or legitSobol > p_legitimate %d %d %ld %d Change p_qr_ndraw to %ld or p_legitimate to %ld",
+                         oldc.qr, c.qr, legit, c.legit, std::max<long>(numsolved + 1, c.qr), std::max<long>(legit + 1, c.legit));
+                return exit_state(b);
+            }
+        }
+        if (option == 3) {
+            if (oldc.qr != c.qr) return exit_state("Update LocalMinimizations: old_p_qr_ndraw .NE. p_qr_ndraws. Run with option=2, update sobol points first"); /* :205-211 */
+            if (numsolved < 0) return exit_state("Update LocalMinimizations:  sobolFnVal.dat cannot be found!");                                               /* :224-227 */
+            if (numsolved < c.maxpoints + 1) return exit_state("Update LocalMinimizations: numsolved < p_maxpoints. Run with option=2, update sobol points first!"); /* :219-223 */
+            std::ifstream f("searchResults.dat"); std::string line;
+            while (std::getline(f, line)) {
+                std::vector<double> v = nums(line, (size_t)c.nx + 4);
+                if (v.size() < (size_t)c.nx + 4) continue;
+                if ((int)v[1] >= 1) { old_rows.push_back(v); resume_k = std::max(resume_k, (int)v[1]); }
+            }
+            if (resume_k > c.maxpoints + 1) { /* :238-243 */
+                snprintf(b, sizeof b, "Update LocalMinimizations: numsolved > p_maxpoints %d %d Change p_maxpoints to > %d", oldc.maxpoints + 1, c.maxpoints + 1, resume_k + 1);
+                return exit_state(b);
+            }
+            if ((int)old_rows.size() != resume_k) return exit_state("Update LocalMinimizations: searchResults.dat has gaps; the missing-work sweep of the reference is not built");
+        }
+    }
+    write_internal_config(c);
     auto envi = [](const char* k, int d) { const char* v = getenv(k); return v ? atoi(v) : d; };
     tiktak_config tc;
     memset(&tc, 0, sizeof tc);
@@ -126,7 +186,8 @@ int main(int argc, char** argv) {
         return 0;
     }
     if (alg == 2 && option != 5) { logmsg("<main:search> dfpmin as the stage-7 algorithm is not built; use a or b"); tiktak_cuda_destroy(h); return 1; }
-    for (const char* fn : {"sobolFnVal.dat", "searchStart.dat", "searchResults.dat", "FinalStart.dat", "FinalResults.dat", "logFile.txt"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); }
+    if (option == 3) { for (const char* fn : {"sobolFnVal.dat", "FinalStart.dat", "FinalResults.dat"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); } }
+    else for (const char* fn : {"sobolFnVal.dat", "searchStart.dat", "searchResults.dat", "FinalStart.dat", "FinalResults.dat", "logFile.txt"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); }
     /* states 2-5 */
     write_int("state.dat", 2);
     if (envi("TIKTAK_WRITE_SOBOL", 0) && c.qr > 0) {
@@ -166,10 +227,18 @@ int main(int argc, char** argv) {
     write_int("state.dat", 7);
     {
         FILE* fr = fopen("searchResults.dat", "a"); FILE* fs = fopen("searchStart.dat", "a");
-        fprintf(fr, "%10d%10d%10d", seqNo, 0, 0); for (int c2 = 0; c2 <= nx; c2++) fprintf(fr, "%40.20f", xs[(size_t)c2 * K]); fputc('\n', fr); /* :496-501 */
-        fprintf(fs, "%10d%10d", seqNo, 0); for (int c2 = 1; c2 <= nx; c2++) fprintf(fs, "%40.20f", xs[(size_t)c2 * K]); fputc('\n', fs);
+        if (resume_k == 0) { /* whichPoint == 1: the raw p_init record (:496-501) */
+            fprintf(fr, "%10d%10d%10d", seqNo, 0, 0); for (int c2 = 0; c2 <= nx; c2++) fprintf(fr, "%40.20f", xs[(size_t)c2 * K]); fputc('\n', fr);
+            fprintf(fs, "%10d%10d", seqNo, 0); for (int c2 = 1; c2 <= nx; c2++) fprintf(fs, "%40.20f", xs[(size_t)c2 * K]); fputc('\n', fs);
+        } else { /* option 3: the finished restarts go back into the device-resident results table, in file order */
+            const int n = (int)old_rows.size();
+            std::vector<double> rows((size_t)n * (nx + 4));
+            for (int r = 0; r < n; r++) for (int cc = 0; cc < nx + 4; cc++) rows[(size_t)cc * n + r] = old_rows[r][cc];
+            CHECK(tiktak_cuda_push_results(h, rows.data(), n));
+            char b[200]; snprintf(b, sizeof b, "%d resumes the local searches after restart %d (%d rows of searchResults.dat loaded)", seqNo, resume_k, n); logmsg(b);
+        }
         const int B = tc.round_size < 1 ? 1 : tc.round_size;
-        int k0 = option == 5 ? 1 : 1, kend = option == 5 ? 1 : K; /* option 5: only the initial guess (:151-197) */
+        int k0 = resume_k + 1, kend = option == 5 ? 1 : K; /* option 5: only the initial guess (:151-197) */
         for (; k0 <= kend; k0 += B) {
             const int nk = std::min(B, kend - k0 + 1);
             std::vector<double> st((size_t)nk * nx), rs((size_t)nk * (nx + 4));

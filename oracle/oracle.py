@@ -154,6 +154,18 @@ class Oracle:
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
         return True
 
+    def LocalMinimizationsResume(self, algor, rows, round_size=None):
+        """option 3: `rows` (n, nx+4) = the finished restarts 1..n as re-read from searchResults.dat; runs n+1..K"""
+        K, nx = self.K, self.cfg.nx
+        B = self.cfg.round_size if round_size is None else round_size
+        rin = np.ascontiguousarray(np.asarray(rows, dtype=np.float64).T)
+        s = np.full((nx, K), np.nan); r = np.empty((nx + 4, K)); e = np.zeros(K, dtype=np.int32)
+        self.L.orc_local_resume.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, c_int32_p]
+        rc = self.L.orc_local_resume(self.h, algor, B, dptr(rin), len(rows), dptr(s), dptr(r), e.ctypes.data_as(c_int32_p))
+        assert rc == 0, rc
+        self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
+        return True
+
     def getBestLine(self):
         f, k = C.c_double(), C.c_int32()
         x = np.empty(self.cfg.nx)

@@ -632,20 +632,25 @@ struct Oracle {
 
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
-    int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out);
+    int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first = 1);
     int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
 };
 
-int Oracle::local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out) {
+/* k_first > 1: continue an earlier run (option 3, genericParams.f90:133-251): `rows` already holds the k = 0 record and
+ * the finished restarts 1..k_first-1 (orc_set_rows), as re-read from searchResults.dat */
+int Oracle::local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first) {
     const int K = c.maxpoints_plus1, nx = c.nx;
     if ((int)x_starts.size() != K * (nx + 1)) return -1;
     if (round_size < 1) round_size = 1;
-    rows.clear();
+    const int seqNo = 1;
     lottery_pick.clear();
     best_tie_events = 0;
-    const int seqNo = 1;
-    write_row(seqNo, 0, 0, x_starts[0], &x_starts[1]); /* :496-501, whichPoint == 1 */
-    for (int k0 = 1; k0 <= K; k0 += round_size) {
+    if (k_first <= 1) {
+        k_first = 1;
+        rows.clear();
+        write_row(seqNo, 0, 0, x_starts[0], &x_starts[1]); /* :496-501, whichPoint == 1 */
+    } else if ((int)rows.size() != k_first) return -3;
+    for (int k0 = k_first; k0 <= K; k0 += round_size) {
         const int k1 = std::min(K, k0 + round_size - 1);
         const int count = (int)rows.size(); /* rows visible to this round */
         const std::vector<Row> snapshot(rows.begin(), rows.end());
@@ -835,6 +840,24 @@ int orc_set_starts(void* h, const double* x_starts) {
 /* starts (K, nx), results (K, nx+4) column-major, evals[K] */
 int orc_local(void* h, int alg, int round_size, double* starts, double* results, int32_t* evals) {
     return ((Oracle*)h)->local(alg, round_size, starts, results, evals);
+}
+/* resume: rows_in = the n finished restarts k = 1..n, (n, nx+4) column-major = seq, k, #improvements, fval, x as
+ * re-read from searchResults.dat; the k = 0 record is rebuilt from x_starts; then restarts n+1..K are run */
+int orc_local_resume(void* h, int alg, int round_size, const double* rows_in, int n, double* starts, double* results, int32_t* evals) {
+    Oracle* o = (Oracle*)h;
+    const int nx = o->c.nx;
+    o->rows.clear();
+    o->write_row(1, 0, 0, o->x_starts[0], &o->x_starts[1]);
+    for (int r = 0; r < n; r++) {
+        Row q;
+        q.seq = (int)rows_in[(size_t)0 * n + r]; q.k = (int)rows_in[(size_t)1 * n + r]; q.imp = (int)rows_in[(size_t)2 * n + r];
+        q.fval = rows_in[(size_t)3 * n + r];
+        q.x.resize(nx);
+        for (int i = 0; i < nx; i++) q.x[i] = rows_in[(size_t)(4 + i) * n + r];
+        if (q.k != r + 1) return -4;
+        o->rows.push_back(q);
+    }
+    return o->local(alg, round_size, starts, results, evals, n + 1);
 }
 int orc_best(void* h, double* fbest, double* xbest, int32_t* k) {
     Oracle* o = (Oracle*)h;

@@ -370,3 +370,64 @@ def test_lottery_start_selection(built, name, alg, B, lp):
     o0 = Oracle(cfg_of(name, **dict(kw, search_type=0)), MATH_TK)
     o0.solveAtSobolPoints(); o0.chooseSobol(mode=1); o0.LocalMinimizations(1 if alg == "a" else 0)
     assert not np.array_equal(o0.searchStart, o.searchStart)  # and it is not the best-point rule
+
+
+def _edit_config(src, dst, repl):
+    """rewrite scalar lines of a config.txt fixture: keys are the 1-based scalar positions (genericParams.f90:274-305)"""
+    out, pos = [], 0
+    for line in open(src):
+        if not line.startswith("!") and pos < 9:
+            pos += 1
+            if pos in repl:
+                line = f"{repl[pos]}   ! edited\n"
+        out.append(line)
+    open(dst, "w").writelines(out)
+
+
+def test_cli_update_options_2_and_3(built, tmp_path):
+    """driver options 2 (more Sobol points) and 3 (more local searches) resume from the .dat files of an earlier run
+    (genericParams.f90:118-251)"""
+    import os, shutil, subprocess
+    from tiktak_b200 import parse_config
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "driver", "TiktakGlobalSearch")
+    base = os.path.join(root, "tests", "golden", "config_c1.txt")
+    run = lambda cwd, *a: subprocess.run([exe, *a], cwd=cwd, capture_output=True, text=True, timeout=300)
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    # ---- option 2: 20 -> 48 draws, legitimate 10 -> 30.  Same files as a cold start with the new config.
+    cfg2 = str(tmp_path / "cfg2.txt")
+    _edit_config(base, cfg2, {4: 48, 5: 30})
+    assert run(a, "0", base, "a").returncode == 0
+    r = run(a, "2", cfg2, "a")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert run(b, "0", cfg2, "a").returncode == 0
+    for fn in ("sobolFnVal.dat", "x_starts.dat", "searchResults.dat", "searchStart.dat", "FinalResults.dat", "lastSobol.dat", "legitSobol.dat"):
+        assert open(a / fn).read() == open(b / fn).read(), fn
+    # an update that asks for fewer points than are solved is refused like the reference does (:189-195)
+    r = run(a, "2", base, "a")
+    assert r.returncode != 0 and int(open(a / "state.dat").read()) == -1
+    # ---- option 3: 3 -> 6 local searches on top of run b's files
+    cfg3 = str(tmp_path / "cfg3.txt")
+    _edit_config(base, cfg3, {4: 48, 5: 30, 7: 6})
+    before = open(b / "searchResults.dat").read().splitlines()
+    r = run(b, "3", cfg3, "a")
+    assert r.returncode == 0, r.stdout + r.stderr
+    after = open(b / "searchResults.dat").read().splitlines()
+    assert after[: len(before)] == before and len(after) == 1 + 7  # k = 0 record + restarts 1..7 (maxpoints + 1)
+    rows = np.loadtxt(b / "searchResults.dat")
+    cfg = parse_config(cfg3, objective_id=OBJ_TEMPLATE, round_size=1)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1)
+    o.LocalMinimizationsResume(1, rows[1:5], round_size=1)
+    assert np.allclose(np.loadtxt(b / "x_starts.dat"), o.x_starts, rtol=0, atol=1e-15)
+    assert np.array_equal(rows[1:, 1:3], o.searchResults[:, 1:3])  # k and the #improvements column continue
+    assert np.allclose(rows[1:], o.searchResults, rtol=1e-15, atol=1e-19)
+    starts = np.loadtxt(b / "searchStart.dat")
+    assert np.allclose(starts[5:, 2:], o.searchStart[4:], rtol=1e-15, atol=1e-19)
+    of, ox, _ = o.lastSearch()
+    fin = np.loadtxt(b / "FinalResults.dat")
+    assert abs(fin[2] - of) <= 1e-6 * abs(of)
+    # option 3 with a different number of Sobol points is refused (:205-211)
+    r = run(b, "3", base, "a")
+    assert r.returncode != 0 and int(open(b / "state.dat").read()) == -1
