@@ -128,15 +128,15 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
  * n_legit == NULL, tiktak_cuda_pretest then only QUEUES the evaluation of all qr_ndraw points and returns;
  * the valid count (the final legitSobol.dat value) is read back when first asked for, here or by choose. */
 int tiktak_cuda_pretest_result(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit);
-/* the shard's own fval store in one copy: count blocks rank, rank+world, ... (65536 values each, point n of
- * block b at [(b/world)*65536 + n%65536]) up to the block holding the cut; n_local = values copied. */
+/* the shard's own fval store in one copy: count blocks rank, rank+world, ... (TIKTAK_SOBOL_BLOCK values each, point n of
+ * block b at [(b/world)*TIKTAK_SOBOL_BLOCK + n%TIKTAK_SOBOL_BLOCK]) up to the block holding the cut; n_local = values copied. */
 int tiktak_cuda_pretest_values_shard(tiktak_handle* h, double* fval_local, int64_t capacity, int64_t* n_local);
 /* fval of points first..first+count-1 (the rows of sobolFnVal.dat, :467); points this shard
  * does not own or beyond the cut come back as NaN. */
 int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first_1based, int64_t count, double* fval);
 /* multi-GPU helpers: valid counts per TIKTAK_SOBOL_BLOCK-point block of the GLOBAL index range
  * (zeros for blocks of other ranks; summing over ranks gives the global histogram). */
-#define TIKTAK_SOBOL_BLOCK 65536
+#define TIKTAK_SOBOL_BLOCK 16384
 int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t first_block, int64_t n_blocks); /* evaluate owned blocks */
 int tiktak_cuda_pretest_counts(tiktak_handle* h, int64_t* counts, int64_t nblocks);
 /* exact Sobol index of the `need`-th valid point inside count block `block` (0 unless this rank owns it) */

@@ -27,7 +27,8 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        N, M, Lg = 3 * SOBOL_BLOCK + 1234, 25, 70000
+        N, M = 3 * SOBOL_BLOCK + 1234, 25
+        Lg = int(0.35 * N)  # about 70 % of the valid points (valid = below the median)
         cfg = make_config(10, 1, N, M, -400.0, 600.0, objective_id=OBJ_GRIEWANK)
         full = Oracle(cfg, MATH_TK); full.solveAtSobolPoints()
         f = full.sobolFnVal()  # index n-1

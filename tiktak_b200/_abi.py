@@ -5,7 +5,7 @@ import numpy as np
 
 OBJ_TEMPLATE, OBJ_GRIEWANK, OBJ_RASTRIGIN, OBJ_ROSENBROCK, OBJ_SMM = 0, 1, 2, 3, 4
 ALG_DFNLS, ALG_AMOEBA, ALG_DFPMIN = 0, 1, 2
-SOBOL_BLOCK = 65536
+SOBOL_BLOCK = 16384
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

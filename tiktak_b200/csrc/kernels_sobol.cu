@@ -7,7 +7,7 @@
  * point n = XOR of the direction numbers selected by the bits of n ^ (n>>1)), then strides through the
  * sequence with ONE 3-input XOR per coordinate per point, maps it to the search box with the
  * reference's unfused lo + q*(hi-lo) (:834) and evaluates the objective plugin in registers.
- * Output: 8 bytes per point (fval) + one valid-count per 65536-point count block.
+ * Output: 8 bytes per point (fval) + one valid-count per TIKTAK_SOBOL_BLOCK-point count block.
  *
  * Work decomposition: a CUDA block of BT = 2^S threads owns BT*P consecutive Sobol indices; thread t
  * handles n = base + j*BT + t, j = 0..P-1, so the fval stores of a warp are contiguous and the step

@@ -207,7 +207,7 @@ class TikTakSearch:
         return f
 
     def sobolFnValShard(self, out=None):
-        """this shard's fval store in one copy (world > 1): count blocks rank, rank+world, ... of 65536 values"""
+        """this shard's fval store in one copy (world > 1): count blocks rank, rank+world, ... of SOBOL_BLOCK values"""
         cap = (self.cfg.qr_ndraw // SOBOL_BLOCK + 1 + self.world - 1) // self.world * SOBOL_BLOCK
         f = np.empty(cap, dtype=np.float64) if out is None else out
         n = C.c_int64()

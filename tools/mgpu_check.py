@@ -18,7 +18,7 @@ for name, kw in {
     "griewank10_nocut": dict(nx=10, nm=1, qr_ndraw=5 * SOBOL_BLOCK + 777, maxpoints=63, lo=-400.0, hi=600.0, init=[100.0] * 10,
                              objective_id=OBJ_GRIEWANK, round_size=16),
     "rastrigin20_cut": dict(nx=20, nm=1, qr_ndraw=9 * SOBOL_BLOCK + 5, maxpoints=40, lo=-4.12, hi=5.12, init=[1.0] * 20,
-                            objective_id=OBJ_RASTRIGIN, round_size=7, fvalmax=140000.0, legitimate=200000),
+                            objective_id=OBJ_RASTRIGIN, round_size=7, fvalmax=140000.0, legitimate=int(0.34 * (9 * SOBOL_BLOCK + 5))),
 }.items():
     cfg = make_config(**kw)
     with TikTakSearch(cfg, device=lr, rank=rank, world=world) as s:
