@@ -227,6 +227,7 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     TK_TRY(dalloc(&h->d_cand_f, ncand));
     TK_TRY(dalloc(&h->d_cand_i, ncand));
     TK_TRY(dalloc(&h->d_cand_n, 1));
+    TK_TRY(dalloc(&h->d_ticket, 1));
     TK_TRY(dalloc(&h->d_sorted_f, ncand));
     TK_TRY(dalloc(&h->d_sorted_i, ncand));
     TK_TRY(dalloc(&h->d_xstarts, (size_t)K * (nx + 1)));
@@ -269,7 +270,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
-                    h->d_lot_k, h->d_lot_sk, h->d_lot_point};
+                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -4,9 +4,9 @@
  * from sobolFnVal.dat, index-sorts ALL of them with indexx (utilities.f90:1334-1424) and keeps the
  * first K-1.  Only the K-1 smallest are ever used, so the device does an exact radix SELECT on the
  * order-preserving 64-bit image of fval (8 histogram passes of 8 bits over the fval array, most
- * significant digit first), resolves a tie at the threshold by Sobol index (4 more passes, skipped
- * when there is none), compacts the <= K-1 winners and orders them by (fval, index) with a
- * rank-by-counting pass.  Order among exactly equal fvals is ascending Sobol index (indexx's order
+ * significant digit first; the last block of a pass scans the bins), resolves a tie at the threshold by
+ * Sobol index (4 more passes, skipped when there is none), compacts the <= K-1 winners and orders them by
+ * (fval, index) with a chunk sort + merge-by-rank passes.  Order among exactly equal fvals is ascending Sobol index (indexx's order
  * among equal keys is an artefact of its partitioning; DESIGN.md "ties").
  */
 #include <utility>
@@ -33,10 +33,14 @@ __device__ __forceinline__ int64_t tk_global_n(const SelView& v, int64_t li) {
     return ((li / TIKTAK_SOBOL_BLOCK) * v.world + v.rank) * (int64_t)TIKTAK_SOBOL_BLOCK + (li % TIKTAK_SOBOL_BLOCK);
 }
 
-/* phase 0: digits of the key; phase 1: digits of n among keys == threshold */
+/* One radix pass = one kernel: every block adds its shared-memory histogram to the global one and takes a ticket;
+ * the block that draws the last ticket scans the 256 bins, fixes the next digit of the threshold in `state`, and
+ * clears histogram and ticket for the next pass (no separate scan launch, no host round trip).
+ * phase 0: digits of the key; phase 1: digits of n among keys == threshold */
 __global__ void __launch_bounds__(256)
-select_hist_kernel(const SelView v, const unsigned long long* state, unsigned long long* hist, int phase, int shift) {
+select_hist_kernel(const SelView v, unsigned long long* state, unsigned long long* hist, unsigned int* ticket, int phase, int shift) {
     __shared__ unsigned int sh[256];
+    __shared__ bool last;
     if (phase == 1 && state[3] == 0) return;
     sh[threadIdx.x] = 0;
     __syncthreads();
@@ -58,33 +62,41 @@ select_hist_kernel(const SelView v, const unsigned long long* state, unsigned lo
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
-}
-
-__global__ void select_scan_kernel(unsigned long long* state, unsigned long long* hist, int phase, int shift) {
-    if (threadIdx.x != 0) return;
-    if (phase == 1 && state[3] == 0) return;
-    unsigned long long rem = state[1], cum = 0;
-    int b = 0;
-    for (; b < 256; b++) {
-        if (cum + hist[b] >= rem) break;
-        cum += hist[b];
-    }
-    if (b == 256) b = 255; /* fewer elements than requested: everything qualifies */
-    const unsigned long long inbin = hist[b];
-    rem -= cum;
-    if (phase == 0) {
-        state[0] |= ((unsigned long long)b) << shift;
-        state[1] = rem;
-        if (shift == 0) { /* threshold key fixed: ties iff more keys equal it than still needed */
-            state[4] = inbin;
-            state[3] = (inbin > rem) ? 1 : 0;
-            state[2] = (inbin > rem) ? 0 : 0xffffffffULL;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    __shared__ unsigned long long vh[256];
+    vh[threadIdx.x] = __ldcg(&hist[threadIdx.x]); /* all bins in one parallel read from L2 */
+    __syncthreads();
+    if (threadIdx.x == 0) { /* 256 bins, one thread, shared memory */
+        unsigned long long rem = state[1], cum = 0;
+        int b = 0;
+        for (; b < 256; b++) {
+            if (cum + vh[b] >= rem) break;
+            cum += vh[b];
         }
-    } else {
-        state[2] |= ((unsigned long long)b) << shift;
-        state[1] = rem;
+        if (b == 256) b = 255; /* fewer elements than requested: everything qualifies */
+        const unsigned long long inbin = vh[b];
+        rem -= cum;
+        if (phase == 0) {
+            state[0] |= ((unsigned long long)b) << shift;
+            state[1] = rem;
+            if (shift == 0) { /* threshold key fixed: ties iff more keys equal it than still needed */
+                state[4] = inbin;
+                state[3] = (inbin > rem) ? 1 : 0;
+                state[2] = (inbin > rem) ? 0 : 0xffffffffULL;
+            }
+        } else {
+            state[2] |= ((unsigned long long)b) << shift;
+            state[1] = rem;
+        }
+        *ticket = 0;
     }
-    for (int i = 0; i < 256; i++) hist[i] = 0;
+    __syncthreads();
+    hist[threadIdx.x] = 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -280,15 +292,15 @@ int tk_select_top(tiktak_handle* h, int64_t M) {
     TK_CUDA(cudaMemcpyAsync(h->d_selstate, st, sizeof st, cudaMemcpyHostToDevice, h->stream));
     TK_CUDA(cudaMemsetAsync(h->d_hist, 0, 256 * sizeof(unsigned long long), h->stream));
     TK_CUDA(cudaMemsetAsync(h->d_cand_n, 0, sizeof(unsigned int), h->stream));
+    TK_CUDA(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
     int64_t want = (v.nlocal + 255) / 256;
     const int64_t cap = (int64_t)h->sm_count * 16;
     const unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
     for (int phase = 0; phase < 2; phase++) {
         const int top = phase == 0 ? 56 : 24;
         for (int shift = top; shift >= 0; shift -= 8) {
-            select_hist_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate, h->d_hist, phase, shift);
-            select_scan_kernel<<<1, 32, 0, h->stream>>>(h->d_selstate, h->d_hist, phase, shift);
-            h->launches += 2;
+            select_hist_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate, h->d_hist, h->d_ticket, phase, shift);
+            h->launches++;
         }
     }
     select_collect_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n,

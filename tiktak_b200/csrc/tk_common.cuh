@@ -88,6 +88,7 @@ struct tiktak_handle {
     double* d_cand_f = nullptr;           /* K-1 candidates */
     unsigned int* d_cand_i = nullptr;
     unsigned int* d_cand_n = nullptr;
+    unsigned int* d_ticket = nullptr;   /* last-block ticket of the radix-select passes */
     double* d_sorted_f = nullptr;
     unsigned int* d_sorted_i = nullptr;
     int64_t n_cand = 0;
