@@ -33,7 +33,9 @@ import numpy as np  # noqa: E402
 
 # algorithmic FP64 flops per Sobol evaluation, SURVEY.md section 8(d) / BASELINE.md section 3
 F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905}
-ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 1024, "C5": 128}
+# restarts per round (all blended against the best row of the round's start).  C4: every restart runs into the
+# 5000-evaluation cap, so a round costs whole waves of blocks: 1184 = 148 SMs x 4 resident blocks x 2 waves
+ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 1184, "C5": 128}
 # C5 (synthetic SMM): HBM-bound, the panel is streamed once per evaluation: 8*(3*np*T + np) + 8*nm bytes
 C5_SIZES = dict(np_persons=131072, T=40, qr_ndraw=20000, legitimate=10000, maxpoints=127)
 
