@@ -316,6 +316,17 @@ def run_graft(args, rank, world, local_rank):
                         "peak_source": "measured: DFMA-chain microbenchmark (tiktak_cuda_fp64_peak) on this GPU; "
                                        "MEASURED_PEAKS.json has no FP64 entry",
                         "share_of_step": eval_ms / step_ms if step_ms > 0 else None}
+        # the local stage's kernel dominates the STEP (profiles/: ~95 % of the kernel time at C2) but is a chain of
+        # dependent simplex iterations, not a throughput kernel: reported for completeness against the same FP64 peak
+        roofline_local = None
+        if s.evals is not None and local_ms > 0 and name != "C5":
+            evals_total = float(np.sum(s.evals))
+            ach = evals_total * F_ALG[name] / (local_ms * 1e-3) / 1e12
+            roofline_local = {"bound": "latency", "kernel": "nm_quad_kernel" if cfg.nx <= 31 else "nm_quad_wide_kernel",
+                              "achieved": ach, "peak": peak_tf * world, "unit": "TFLOP/s", "frac": ach / (peak_tf * world),
+                              "objective_evals_per_step": evals_total, "share_of_step": local_ms / step_ms,
+                              "note": "one restart per 4-warp block; a round lasts as long as its longest restart; each "
+                                      "simplex iteration is ~930 dependent cycles (DESIGN.md section 3)"}
         cpu = cpu_arm(name, world, args.cpu_seconds, args.round_size) if (world == 1 and not args.no_cpu) else None
         tables_bytes = 32 * 4 * cfg.nx + 5 * 8 * cfg.nx + 64
         line = {
@@ -331,6 +342,7 @@ def run_graft(args, rank, world, local_rank):
             "mean_evals_per_restart": float(np.mean(s.evals)) if s.evals is not None else None,
             "stage_ms": {"pretest": pre_ms, "pretest_eval_kernel": eval_ms, "choose": choose_ms, "local": local_ms},
             "roofline": roofline,
+            "roofline_local": roofline_local,
             "cpu_baseline": cpu,
             "e2e": {"value": n_eval_total / e2e_sobol_s, "unit": "evals/s",
                     "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": d2h_total,
