@@ -184,6 +184,18 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
 int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, const double* recv);
 int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, double* starts, double* results,
                             int32_t* evals);
+/* Rounds started early.  A round depends on the earlier ones only through the best row, which changes in few
+ * rounds (the #improvements column).  local_enqueue may therefore be given SEVERAL consecutive rounds at once
+ * (n_k = a multiple of round_size, or up to the last restart): all of them start from the best row known now.
+ * local_ingest_rounds then ingests them round by round for as long as that row stayed the best one, stops after the
+ * first round that changes it (or that brings the row count above 1, which switches the blend on), and returns
+ * `accepted` = restarts ingested; the caller queues the rest again.  The accepted sequence is bit for bit the one
+ * of strictly sequential rounds; the idle SMs of a small round do the speculative work.  Synchronises the host.
+ * local_capacity: how many restarts fit on the machine at once (one resident wave x world) -- the natural size of
+ * such a launch; 0 when the mode (lottery, nm_shrink_mode) makes the start depend on more than the best row. */
+int tiktak_cuda_local_ingest_rounds(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t round_size, const double* recv,
+                                    int32_t* accepted);
+int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts);
 /* make rows computed elsewhere (other ranks, or a resumed searchResults.dat) known to the handle;
  * rows is (n, nx+4) column-major.  Rows whose fval is NaN are ignored.  Also how the k=0 row
  * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */

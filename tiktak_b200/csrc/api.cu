@@ -270,7 +270,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
-                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket};
+                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -770,10 +770,39 @@ int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, con
     if (h->cfg.world > 1 && !recv) { tk_set_error("local_ingest: world > 1 needs the gathered rows"); return TIKTAK_ERR_ARG; }
     if (n_k == 0) return TIKTAK_OK;
     TK_CUDA(cudaSetDevice(h->device));
-    int rc = tk_launch_ingest(h, first_k, n_k, h->cfg.world > 1 ? recv : nullptr);
+    int rc = tk_launch_ingest(h, first_k, n_k, n_k, h->cfg.world > 1 ? recv : nullptr, nullptr);
     if (rc) return rc;
     h->n_rows += n_k;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local_ingest_rounds(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t round_size, const double* recv,
+                                    int32_t* accepted) {
+    if (!h || !accepted || first_k < 1 || n_k < 0 || round_size < 1 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (h->cfg.world > 1 && !recv) { tk_set_error("local_ingest_rounds: world > 1 needs the gathered rows"); return TIKTAK_ERR_ARG; }
+    *accepted = 0;
+    if (n_k == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    if (!h->d_accepted) TK_CUDA(cudaMalloc(&h->d_accepted, sizeof(int)));
+    int rc = tk_launch_ingest(h, first_k, n_k, round_size, h->cfg.world > 1 ? recv : nullptr, h->d_accepted);
+    if (rc) return rc;
+    TK_CUDA(cudaEventRecord(h->evl1, h->stream));
+    int acc = 0;
+    TK_CUDA(cudaMemcpyAsync(&acc, h->d_accepted, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_rows += acc;
+    *accepted = acc;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts) {
+    if (!h || !restarts) return TIKTAK_ERR_ARG;
+    TK_CUDA(cudaSetDevice(h->device));
+    /* later rounds only depend on earlier ones through the best row, so they can be started early when the search
+     * mode makes the start a function of that row alone (not of the 10 best rows / the rank lottery) */
+    const bool speculate = h->cfg.search_type == 0 && !(alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1);
+    *restarts = speculate ? tk_nm_wave_capacity(h) * h->cfg.world : 0;
     return TIKTAK_OK;
 }
 

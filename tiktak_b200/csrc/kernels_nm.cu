@@ -925,6 +925,8 @@ __global__ void blend_lottery_kernel(const double* xs, int K, int nx, int first_
  * all-gathered packed rows [rank][n_max][nx+2] = f, x, evals (slot s was run by rank s % world). */
 struct IngestArgs {
     int first_k, n_k, nx, world, n_max, roundtrip;
+    int round_size; /* restarts per round inside the launch (== n_k: one round) */
+    int* accepted;  /* out: restarts ingested (may be NULL) */
     const double* pack;
     const double* out_f;
     const double* out_x;
@@ -934,52 +936,67 @@ struct IngestArgs {
     int* arch_evals;
     double* best;
 };
+/* The launch may hold SEVERAL rounds (g.n_k restarts, rounds of g.round_size): rounds after the first were started
+ * speculatively against the best row known when the launch was queued.  They are ingested in order for as long as
+ * that assumption held, i.e. until a round changes the best row (or brings the row count above 1, which switches
+ * the blend on, :701); `accepted` = restarts ingested.  The rest of the launch is discarded by the caller and run
+ * again against the new best row -- the accepted sequence is exactly the one of strictly sequential rounds. */
 __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs g) {
     __shared__ double sv[256];
     __shared__ int sk[256];
     __shared__ int sc[256];
-    __shared__ int take;
+    __shared__ int take, stop;
     const int nx = g.nx;
-    double v = DBL_MAX; int bk = 0x7fffffff, cnt = 0;
-    for (int s = threadIdx.x; s < g.n_k; s += blockDim.x) {
-        const double* row = g.pack ? g.pack + ((size_t)(s % g.world) * g.n_max + s / g.world) * (nx + 2) : nullptr;
-        const double f = row ? row[0] : g.out_f[s];
-        if (!(f == f)) continue;
-        const int k = g.first_k + s;
-        const double frt = g.roundtrip ? tk_f4020_roundtrip(f) : f;
-        double* dst = g.res + (size_t)k * (nx + 1);
-        dst[0] = frt;
-        for (int d = 0; d < nx; d++) {
-            const double xv = row ? row[1 + d] : g.out_x[(size_t)d * g.n_k + s];
-            dst[1 + d] = g.roundtrip ? tk_f4020_roundtrip(xv) : xv;
-        }
-        g.valid[k] = 1;
-        g.arch_evals[k] = row ? (int)row[nx + 1] : g.out_evals[s];
-        cnt++;
-        if (bk == 0x7fffffff || frt < v) { v = frt; bk = k; }
-    }
-    sv[threadIdx.x] = v; sk[threadIdx.x] = bk; sc[threadIdx.x] = cnt;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            const double v2 = sv[threadIdx.x + o]; const int k2 = sk[threadIdx.x + o];
-            if (k2 != 0x7fffffff && (sk[threadIdx.x] == 0x7fffffff || v2 < sv[threadIdx.x] ||
-                                     (v2 == sv[threadIdx.x] && k2 < sk[threadIdx.x]))) {
-                sv[threadIdx.x] = v2; sk[threadIdx.x] = k2;
+    int r0 = 0;
+    for (; r0 < g.n_k; r0 += g.round_size) {
+        const int r1 = min(g.n_k, r0 + g.round_size);
+        double v = DBL_MAX; int bk = 0x7fffffff, cnt = 0;
+        for (int s = r0 + threadIdx.x; s < r1; s += blockDim.x) {
+            const double* row = g.pack ? g.pack + ((size_t)(s % g.world) * g.n_max + s / g.world) * (nx + 2) : nullptr;
+            const double f = row ? row[0] : g.out_f[s];
+            if (!(f == f)) continue;
+            const int k = g.first_k + s;
+            const double frt = g.roundtrip ? tk_f4020_roundtrip(f) : f;
+            double* dst = g.res + (size_t)k * (nx + 1);
+            dst[0] = frt;
+            for (int d = 0; d < nx; d++) {
+                const double xv = row ? row[1 + d] : g.out_x[(size_t)d * g.n_k + s];
+                dst[1 + d] = g.roundtrip ? tk_f4020_roundtrip(xv) : xv;
             }
-            sc[threadIdx.x] += sc[threadIdx.x + o];
+            g.valid[k] = 1;
+            g.arch_evals[k] = row ? (int)row[nx + 1] : g.out_evals[s];
+            cnt++;
+            if (bk == 0x7fffffff || frt < v) { v = frt; bk = k; }
+        }
+        sv[threadIdx.x] = v; sk[threadIdx.x] = bk; sc[threadIdx.x] = cnt;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                const double v2 = sv[threadIdx.x + o]; const int k2 = sk[threadIdx.x + o];
+                if (k2 != 0x7fffffff && (sk[threadIdx.x] == 0x7fffffff || v2 < sv[threadIdx.x] ||
+                                         (v2 == sv[threadIdx.x] && k2 < sk[threadIdx.x]))) {
+                    sv[threadIdx.x] = v2; sk[threadIdx.x] = k2;
+                }
+                sc[threadIdx.x] += sc[threadIdx.x + o];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const bool none = g.best[1] < 0.0;
+            const double rows_before = none ? 0.0 : g.best[2];
+            take = (sk[0] != 0x7fffffff) && (none || sv[0] < g.best[0]);
+            g.best[2] = rows_before + (double)sc[0];
+            if (take) { g.best[0] = sv[0]; g.best[1] = (double)sk[0]; }
+            stop = take || (rows_before <= 1.0 && sc[0] > 0);
         }
         __syncthreads();
+        if (take)
+            for (int d = threadIdx.x; d < nx; d += blockDim.x) g.best[3 + d] = g.res[(size_t)sk[0] * (nx + 1) + 1 + d];
+        const int stop_now = stop;
+        __syncthreads();
+        if (stop_now) { r0 = r1; break; }
     }
-    if (threadIdx.x == 0) {
-        const bool none = g.best[1] < 0.0;
-        take = (sk[0] != 0x7fffffff) && (none || sv[0] < g.best[0]);
-        g.best[2] = (none ? 0.0 : g.best[2]) + (double)sc[0];
-        if (take) { g.best[0] = sv[0]; g.best[1] = (double)sk[0]; }
-    }
-    __syncthreads();
-    if (take)
-        for (int d = threadIdx.x; d < nx; d += blockDim.x) g.best[3 + d] = g.res[(size_t)sk[0] * (nx + 1) + 1 + d];
+    if (threadIdx.x == 0 && g.accepted) g.accepted[0] = min(r0, g.n_k);
 }
 
 /* this rank's slots of the round, packed for the all-gather: row q = slot rank + q*world = [f, x, evals] */
@@ -1108,17 +1125,40 @@ int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count) {
     return TIKTAK_OK;
 }
 
-int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, const double* pack) {
+int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, const double* pack, int* d_accepted) {
     IngestArgs g;
     g.first_k = first_k; g.n_k = n_k; g.nx = h->cfg.nx; g.world = h->cfg.world;
     g.n_max = (n_k + h->cfg.world - 1) / h->cfg.world;
     g.roundtrip = h->cfg.text_roundtrip;
+    g.round_size = round_size < 1 ? n_k : round_size;
+    g.accepted = d_accepted;
     g.pack = pack; g.out_f = h->d_out_f; g.out_x = h->d_out_x; g.out_evals = h->d_out_evals;
     g.res = h->d_res; g.valid = h->d_res_valid; g.arch_evals = h->d_arch_evals; g.best = h->d_best;
     ingest_kernel<<<1, 256, 0, h->stream>>>(g);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;
+}
+
+/* how many restarts of the local-search kernel are resident at once on this GPU (one wave) */
+int tk_nm_wave_capacity(tiktak_handle* h) {
+    const int nx = h->cfg.nx;
+    int per_sm = 1;
+    if (h->cfg.objective_id == TIKTAK_OBJ_SMM) return h->sm_count;
+    tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
+        if (nx <= 31 && Obj::nterms(nx) <= nx) {
+            const int ts = (nx + 2) & ~1;
+            const size_t shmem = (size_t)(4 * ts + 8 + 4 * (5 * ts + (nx + 1) * nx)) * sizeof(double);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_quad_kernel<Obj, 0>, 128, shmem);
+        } else if (nx <= 127 && Obj::nterms(nx) <= nx) {
+            const int ts = (nx + 2) & ~1;
+            const size_t shmem = (size_t)(4 * ts + 8 + (nx + 1) * nx + 4 * 8 * ts) * sizeof(double);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_quad_wide_kernel<Obj, 2>, 128, shmem);
+        }
+        return TIKTAK_OK;
+    });
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * h->sm_count;
 }
 
 int tk_launch_pack(tiktak_handle* h, int n_k, double* pack) {

@@ -118,6 +118,7 @@ struct tiktak_handle {
     std::vector<double> lot_cum;
     int lot_cum_n = 0;
     int n_rows = 0;                   /* result rows known to the handle (k = 0 record included) */
+    int* d_accepted = nullptr;        /* restarts ingested by the last multi-round ingest */
     /* DFNLS */
     double* d_dfnls_slab = nullptr;
     size_t dfnls_slab_doubles = 0;
@@ -142,7 +143,8 @@ int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
-int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, const double* pack);
+int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, const double* pack, int* d_accepted);
+int tk_nm_wave_capacity(tiktak_handle* h);
 int tk_launch_pack(tiktak_handle* h, int n_k, double* pack);
 int tk_launch_shrink_width(tiktak_handle* h);
 int tk_fp64_peak(int device, double* flops, double* ms);

@@ -253,32 +253,49 @@ class TikTakSearch:
             yield k, n
             k += n
 
-    def LocalMinimizations(self, algor="a"):
+    def LocalMinimizations(self, algor="a", window=None):
         """Runs every restart; returns `complete` (:536).  Rows land in searchStart / searchResults.
 
-        All rounds are queued on the handle's stream back to back (blend -> local searches -> [one all-gather
-        of the round's rows over NCCL, world > 1] -> ingest + best-so-far); the host reads the rows once at the end."""
+        Rounds of cfg.round_size restarts are blended against the best row at the round's start (DESIGN.md "round
+        schedule").  A launch holds `window` restarts = several rounds: the later ones are started early against the
+        same best row and kept only while that row stays the best (tiktak_cuda_local_ingest_rounds), so the accepted
+        sequence is exactly that of one round after the other while the idle SMs of a small round do useful work.
+        window=None: one resident wave of the local-search kernel (tiktak_cuda_local_capacity); window=0: no
+        early starts.  Per launch: blend -> local searches -> [one all-gather of the rows over NCCL, world > 1] ->
+        ingest; the host reads one integer per launch and all rows once at the end."""
         alg = _ALG[algor]
         K, nx, W = self.K, self.cfg.nx, self.world
+        B = max(1, int(self.cfg.round_size))
+        if window is None:
+            cap = C.c_int32()
+            _lib.check(self._L.tiktak_cuda_local_capacity(self._h, alg, C.byref(cap)), "local_capacity")
+            window = cap.value
+        per_launch = max(B, (int(window) // B) * B)  # whole rounds
         send = recv = None
         if W > 1:
             import torch
 
             from . import dist as D
 
-            cap = D.n_max(max(1, int(self.cfg.round_size)), W) * (nx + 2)
+            cap = D.n_max(min(per_launch, K), W) * (nx + 2)
             dev = torch.device("cuda", self.device)
             send = torch.empty(cap, dtype=torch.float64, device=dev)
             recv = torch.empty(W * cap, dtype=torch.float64, device=dev)
-        for first_k, n_k in self.rounds():
-            _lib.check(self._L.tiktak_cuda_local_enqueue(self._h, alg, first_k, n_k, send.data_ptr() if W > 1 else None),
+        k, acc = 1, C.c_int32()
+        self.local_launches = 0
+        while k <= K:
+            n = min(per_launch, K - k + 1)
+            _lib.check(self._L.tiktak_cuda_local_enqueue(self._h, alg, k, n, send.data_ptr() if W > 1 else None),
                        "LocalMinimizations")
             if W > 1:
-                cnt = D.n_max(n_k, W) * (nx + 2)
+                cnt = D.n_max(n, W) * (nx + 2)
                 with torch.cuda.stream(self.torch_stream()):
                     D.gather_rows(recv[: W * cnt], send[:cnt], self.group)
-            _lib.check(self._L.tiktak_cuda_local_ingest(self._h, first_k, n_k, recv.data_ptr() if W > 1 else None),
-                       "LocalMinimizations")
+            _lib.check(self._L.tiktak_cuda_local_ingest_rounds(self._h, k, n, B, recv.data_ptr() if W > 1 else None,
+                                                               C.byref(acc)), "LocalMinimizations")
+            assert 0 < acc.value <= n
+            k += acc.value
+            self.local_launches += 1
         s = np.empty((nx, K), dtype=np.float64)
         r = np.empty((nx + 4, K), dtype=np.float64)
         e = np.zeros(K, dtype=np.int32)
