@@ -431,3 +431,25 @@ def test_cli_update_options_2_and_3(built, tmp_path):
     # option 3 with a different number of Sobol points is refused (:205-211)
     r = run(b, "3", base, "a")
     assert r.returncode != 0 and int(open(b / "state.dat").read()) == -1
+
+
+@pytest.mark.parametrize("name,alg,B", [("griewank10", "a", 4), ("rastrigin20", "a", 3), ("griewank7", "b", 2)])
+def test_early_started_rounds_equal_sequential_rounds(built, name, alg, B):
+    """rounds started early against the current best row (tiktak_cuda_local_ingest_rounds) are accepted only while that
+    row stays the best: any launch size gives the rows of strictly sequential rounds, and needs fewer launches"""
+    kw = dict(round_size=B)
+    if alg == "b":
+        kw.update(nm=3, maxpoints=9)
+    cfg = cfg_of(name, **kw)
+    runs = {}
+    for window in (0, 2 * B, 5 * B + 1, None):
+        with TikTakSearch(cfg) as s:
+            s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations(alg, window=window)
+            runs[window] = (s.searchStart.copy(), s.searchResults.copy(), s.evals.copy(), s.local_launches, s.getBestLine()[0])
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(1 if alg == "a" else 0)
+    for window, (st, rs, ev, nl, fb) in runs.items():
+        assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals), window
+        assert fb == o.getBestLine()[0]
+    n_rounds = -(-cfg.p_maxpoints // B)
+    assert runs[0][3] == n_rounds and runs[None][3] < n_rounds
