@@ -247,7 +247,9 @@ def run_graft(args, rank, world, local_rank):
         e4 = mark()
         ext.synchronize()
         t4 = time.perf_counter()
-        out.update(pretest_ms=e0.elapsed_time(e1), choose_ms=e2.elapsed_time(e3),
+        # the pre-test stage is timed by the library's own events (first device operation of the stage -> last; the
+        # NCCL count reductions of a sharded run with a possible cut are queued on the same stream in between)
+        out.update(pretest_ms=s.stage_ms("pretest"), pretest_bracket_ms=e0.elapsed_time(e1), choose_ms=e2.elapsed_time(e3),
                    local_ms=0.0 if args.no_local else e3.elapsed_time(e4), pretest_eval_ms=s.stage_ms("pretest_eval"),
                    wall_pretest=t1 - t0, wall_values=t2 - t1, wall_choose=t3 - t2, wall_local=t4 - t3, wall=t4 - t0,
                    ne=ne, nl=s.n_legit, d2h=out.get("d2h", 0))
@@ -277,7 +279,8 @@ def run_graft(args, rank, world, local_rank):
     pre_ms = mx(np.mean([d["pretest_ms"] for d in dev_steps]))
     choose_ms = mx(np.mean([d["choose_ms"] for d in dev_steps]))
     local_ms = mx(np.mean([d["local_ms"] for d in dev_steps]))
-    timing = "CUDA events on the library stream per stage, max over ranks"
+    timing = ("CUDA events on the library stream per stage, max over ranks (pretest: the library's events around the "
+              "stage's own device work; choose/local: events bracketing the host calls)")
     eval_ms = mx(np.mean([d["pretest_eval_ms"] for d in dev_steps]))
     step_ms = pre_ms + choose_ms + local_ms
     n_eval_total = s.n_evaluated if s.n_evaluated else npts  # the legitimate cut may stop early (C5)

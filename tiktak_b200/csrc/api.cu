@@ -220,6 +220,9 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     h->n_local_cblocks = (h->n_cblocks > cfg->rank) ? (h->n_cblocks - cfg->rank + cfg->world - 1) / cfg->world : 0;
     TK_TRY(dalloc(&h->d_fval, (size_t)h->n_local_cblocks * TIKTAK_SOBOL_BLOCK));
     TK_TRY(dalloc(&h->d_counts, (size_t)h->n_cblocks + 1));
+    TK_TRY(dalloc(&h->d_counts_spare, (size_t)h->n_cblocks + 1));
+    TK_CUDA(cudaMemsetAsync(h->d_counts, 0, ((size_t)h->n_cblocks + 1) * sizeof(unsigned long long), h->stream));
+    TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, ((size_t)h->n_cblocks + 1) * sizeof(unsigned long long), h->stream));
     h->h_counts.assign(h->n_cblocks, 0ULL);
     TK_TRY(dalloc(&h->d_hist, 256));
     TK_TRY(dalloc(&h->d_selstate, 8));
@@ -250,6 +253,8 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     TK_CUDA(cudaMemsetAsync(h->d_arch_evals, 0, (size_t)(K + 1) * sizeof(int), h->stream));
     TK_CUDA(cudaEventCreate(&h->evl0));
     TK_CUDA(cudaEventCreate(&h->evl1));
+    TK_CUDA(cudaEventCreate(&h->evp0));
+    TK_CUDA(cudaEventCreate(&h->evp1));
 #undef TK_TRY
     TK_CUDA(cudaStreamSynchronize(h->stream));
     if (cfg->objective_id == TIKTAK_OBJ_SMM) {
@@ -270,12 +275,14 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
-                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted};
+                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_counts_spare};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evw0) cudaEventDestroy(h->evw0);
     if (h->evw1) cudaEventDestroy(h->evw1);
+    if (h->evp0) cudaEventDestroy(h->evp0);
+    if (h->evp1) cudaEventDestroy(h->evp1);
     if (h->evl0) cudaEventDestroy(h->evl0);
     if (h->evl1) cudaEventDestroy(h->evl1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -289,8 +296,8 @@ int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms) {
     if (!h || !stage || !ms) return TIKTAK_ERR_ARG;
     if (!strcmp(stage, "pretest")) {
         if (h->pretest_timing_open) {
-            TK_CUDA(cudaEventSynchronize(h->ev1));
-            float w = 0; cudaEventElapsedTime(&w, h->ev0, h->ev1); h->ms_pretest = w; h->pretest_timing_open = false;
+            TK_CUDA(cudaEventSynchronize(h->evp1));
+            float w = 0; cudaEventElapsedTime(&w, h->evp0, h->evp1); h->ms_pretest = w; h->pretest_timing_open = false;
         }
         *ms = h->ms_pretest;
     }
@@ -379,12 +386,19 @@ int tiktak_cuda_objfun(tiktak_handle* h, const double* x, int64_t n, double* fva
 int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     if (!h || cb0 < 0 || ncb < 0 || cb0 + ncb > h->n_cblocks) return TIKTAK_ERR_ARG;
     TK_CUDA(cudaSetDevice(h->device));
-    if (cb0 == 0) {
-        TK_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
+    const bool first_wave = (cb0 == 0);
+    if (first_wave) { /* the stage starts here: its device time runs from evp0 to the evp1 of the last wave */
+        TK_CUDA(cudaEventRecord(h->evp0, h->stream));
+        std::swap(h->d_counts, h->d_counts_spare); /* a buffer zeroed behind the previous job's kernel: no memset in front */
+        TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+        h->pretest_timing_open = true;
         h->cblocks_done = 0; h->kcut = -1; h->pretest_done = false; h->starts_ready = false;
         h->ms_pretest_eval = 0; h->wave_pending = false;
     }
-    if (ncb == 0) return TIKTAK_OK;
+    if (ncb == 0) {
+        if (first_wave) TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
+        return TIKTAK_OK;
+    }
     TkWave wv;
     wv.N = h->cfg.qr_ndraw; wv.cb0 = cb0; wv.ncb = ncb; wv.rank = h->cfg.rank; wv.world = h->cfg.world;
     wv.fval = h->d_fval; wv.counts = h->d_counts;
@@ -396,6 +410,9 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     TK_CUDA(cudaEventRecord(h->evw0, h->stream));
     int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
     TK_CUDA(cudaEventRecord(h->evw1, h->stream));
+    TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+    if (first_wave) /* clear the other counts buffer for the next job, behind this wave */
+        TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
     h->wave_pending = true;
     if (rc) return rc;
     h->cblocks_done = std::max(h->cblocks_done, cb0 + ncb);
@@ -438,14 +455,18 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     if (!h) return TIKTAK_ERR_ARG;
     TK_CUDA(cudaSetDevice(h->device));
     const int64_t N = h->cfg.qr_ndraw, L = h->cfg.legitimate;
-    int rc = begin_timer(h);
-    if (rc) return rc;
+    int rc = TIKTAK_OK;
+    auto end_stage = [&]() -> int { /* the find_cut / count reads after the last wave belong to the stage */
+        TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+        h->pretest_timing_open = true;
+        return TIKTAK_OK;
+    };
     if (N == 0 || L <= 0) { /* :429: nothing is evaluated */
         tiktak_cuda_pretest_wave(h, 0, 0);
         h->kcut = 0; h->nlegit = 0; h->pretest_done = true;
         if (n_evaluated) *n_evaluated = 0;
         if (n_legit) *n_legit = 0;
-        return end_timer(h, &h->ms_pretest);
+        return end_stage();
     }
     const bool can_cut = (L <= N) && h->cfg.world == 1;
     const int64_t wave = can_cut ? 64 : h->n_cblocks;
@@ -457,8 +478,6 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
         if (rc) return rc;
         h->kcut = N; h->nlegit = -1; h->pretest_done = true;
         if (n_evaluated) *n_evaluated = N;
-        TK_CUDA(cudaEventRecord(h->ev1, h->stream));
-        h->pretest_timing_open = true;
         return TIKTAK_OK;
     }
     if (h->cfg.objective_id == TIKTAK_OBJ_SMM && can_cut) {
@@ -494,7 +513,7 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
         h->kcut = kcut; h->nlegit = nleg; h->pretest_done = true;
         if (n_evaluated) *n_evaluated = kcut;
         if (n_legit) *n_legit = nleg;
-        return end_timer(h, &h->ms_pretest);
+        return end_stage();
     }
     for (int64_t cb0 = 0; cb0 < h->n_cblocks && kcut < 0; cb0 += wave) {
         const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
@@ -521,16 +540,12 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     }
     if (n_evaluated) *n_evaluated = h->cfg.world == 1 ? kcut : -1;
     if (n_legit) *n_legit = h->cfg.world == 1 ? nleg : -1;
-    return end_timer(h, &h->ms_pretest);
+    return end_stage();
 }
 
 /* valid count of the evaluated prefix when it was not needed to place the cut (sum of the per-block counts) */
 static int resolve_legit(tiktak_handle* h) {
     if (h->nlegit >= 0 || !h->pretest_done) return TIKTAK_OK;
-    if (h->pretest_timing_open) { /* close the stage timer before other work reuses the events */
-        TK_CUDA(cudaEventSynchronize(h->ev1));
-        float w = 0; cudaEventElapsedTime(&w, h->ev0, h->ev1); h->ms_pretest = w; h->pretest_timing_open = false;
-    }
     TK_CUDA(cudaMemcpyAsync(h->h_counts.data(), h->d_counts, (size_t)h->n_cblocks * 8, cudaMemcpyDeviceToHost, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     int64_t tot = 0;

@@ -78,6 +78,7 @@ struct tiktak_handle {
     int64_t n_cblocks = 0, n_local_cblocks = 0;
     double* d_fval = nullptr;             /* local fvals */
     unsigned long long* d_counts = nullptr; /* [n_cblocks] */
+    unsigned long long* d_counts_spare = nullptr; /* zeroed twin: the next job swaps to it */
     std::vector<unsigned long long> h_counts;
     int64_t cblocks_done = 0;
     int64_t kcut = -1, nlegit = 0;
@@ -108,7 +109,7 @@ struct tiktak_handle {
     double* d_arch_starts = nullptr; /* (K, nx) column-major: the searchStart.dat rows of every restart */
     int* d_arch_evals = nullptr;     /* [K+1]: objective evaluations of restart k */
     bool best_dirty = true;          /* d_best must be recomputed from the rows (after push_results) */
-    cudaEvent_t evl0 = nullptr, evl1 = nullptr;
+    cudaEvent_t evl0 = nullptr, evl1 = nullptr, evp0 = nullptr, evp1 = nullptr;
     bool local_timing_open = false, pretest_timing_open = false;
     bool rho_ready = false;
     /* selectType = 1 (lottery) */
