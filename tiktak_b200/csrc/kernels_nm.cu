@@ -525,6 +525,16 @@ __global__ void __launch_bounds__(128) nm_quad_kernel(const TkTablesG T, const T
     }
 }
 
+/* amoeba's stopping test rtol < ftol (:84-85); the division is only formed when the product test is within 2^-40 */
+__device__ __forceinline__ bool nm_converged(const NmArgs& a, double ylo, double yhi) {
+    const double num = TK_MUL(2.0, fabs(TK_SUB(yhi, ylo)));
+    const double den = TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny);
+    const double thr = TK_MUL(a.ftol, den);
+    bool conv = num < TK_MUL(thr, 0.99999999999909051);
+    if (!conv && !(num > TK_MUL(thr, 1.00000000000090949))) conv = TK_DIV(num, den) < a.ftol;
+    return conv;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * The same four-warp scheme for 32 <= nx <= 127 (CJ = ceil((nx+1)/32) coordinates / vertices per lane):
  * lane l owns coordinates j = l + 32c, the sorted (y, vertex) list lives in the warp's shared memory
@@ -621,11 +631,18 @@ __device__ __forceinline__ void nm_full_sort_wide(double* ys, int* rows, int np,
     __syncwarp();
 }
 
+/* Roles: warp 0 is the restart's "master" (sorted list, psum, trial points, decisions, simplex updates); all four
+ * warps evaluate.  Per iteration the master writes the four trial points to shared memory, barrier A, every warp
+ * evaluates one of them, barrier B, the master decides.  With several blocks per SM the kernel is issue-bound, and
+ * three of four warps now run only the evaluation (no redundant bookkeeping): ~2.4x fewer instructions per iteration
+ * than carrying the state in every warp. */
+enum { NMW_EVAL4 = 0, NMW_VERTS = 1, NMW_STOP = 2 };
 template <class Obj, int CJ>
 __global__ void __launch_bounds__(128) nm_quad_wide_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
     extern __shared__ double smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool master = w == (int)(blockIdx.x & 3u); /* rotate the master over the SM's four sub-partitions */
     const int nx = sc.nx, np = nx + 1;
     const int nt = Obj::nterms(nx);
     const int ts = (nx + 2) & ~1; /* even stride >= np */
@@ -634,19 +651,22 @@ __global__ void __launch_bounds__(128) nm_quad_wide_kernel(const TkTablesG T, co
     double* sbu = sbl + ts;
     double* saux = sbu + ts;
     double* yv = saux + ts;      /* yv[vertex]: values of re-evaluated vertices (start, shrink) */
-    double* yx = yv + ts;        /* yx[parity*4 + c]: the four trial values of an iteration */
-    double* p = yx + 8;          /* p[i*nx + j]: the simplex, one copy (all warps store identical values) */
-    /* per warp */
-    double* mine = p + (size_t)np * nx + (size_t)w * (8 * ts);
+    double* xcand = yv + ts;     /* xcand[c*ts + j]: the four trial points of the iteration */
+    double* yx = xcand + 4 * ts; /* yx[c]: their values */
+    int* ctl = reinterpret_cast<int*>(yx + 4); /* ctl[0] = mode, ctl[1] = vertex skipped by NMW_VERTS */
+    double* p = yx + 6;          /* p[i*nx + j]: the simplex (written by the master only) */
+    /* master's sorted list + sort scratch */
+    double* ys = p + (size_t)np * nx;
+    int* rows = reinterpret_cast<int*>(ys + ts);
+    double* scr_y = ys + 2 * ts;
+    int* scr_r = reinterpret_cast<int*>(ys + 3 * ts);
+    /* per warp evaluation scratch */
+    double* mine = ys + 4 * ts + (size_t)w * (4 * ts);
     NmScratch scr;
     scr.ta = mine;
     scr.tb = mine + ts;
     scr.pn = mine + 2 * ts;
     scr.cand = mine + 3 * ts;
-    double* ys = mine + 4 * ts;                          /* sorted y */
-    int* rows = reinterpret_cast<int*>(mine + 5 * ts);   /* vertex at each sorted position */
-    double* scr_y = mine + 6 * ts;
-    int* scr_r = reinterpret_cast<int*>(mine + 7 * ts);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
     const int slot = a.rank + (int)blockIdx.x * a.world;
     const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
@@ -659,42 +679,155 @@ __global__ void __launch_bounds__(128) nm_quad_wide_kernel(const TkTablesG T, co
         t = fmax(fmin(t, T.bu[i]), T.bl[i]);
         p[e] = t;
     }
+    if (threadIdx.x == 0) { ctl[0] = NMW_VERTS; ctl[1] = -1; } /* first pass: objFun at every vertex */
     __syncthreads();
     double blj[CJ], buj[CJ], psum[CJ];
     int jj[CJ];
 #pragma unroll
     for (int c = 0; c < CJ; c++) {
         jj[c] = (lane + 32 * c < nx) ? lane + 32 * c : 0;
-        blj[c] = sbl[jj[c]]; buj[c] = sbu[jj[c]];
+        blj[c] = sbl[jj[c]]; buj[c] = sbu[jj[c]]; psum[c] = 0.0;
     }
-    /* objFun at the vertices: dealt over the four warps, collected through yv */
-    for (int v = w; v < np; v += 4) {
-        double xv[CJ];
+    /* master state that lives across iterations */
+    int iter = 0, ihi = 0, ilo_keep = -1;
+    bool first = true, after_shrink = false;
+    double ylo = 0.0, yhi = 0.0, ynhi = 0.0;
+    double ph[CJ], R[CJ], ps1[CJ], E[CJ], Co[CJ], Ci[CJ];
 #pragma unroll
-        for (int c = 0; c < CJ; c++) xv[c] = p[v * nx + jj[c]];
-        const double yc = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xv, blj, buj, lane, nx, nt);
-        if (lane == 0) yv[v] = yc;
-    }
-    __syncthreads();
-    for (int e = lane; e < np; e += 32) { ys[e] = yv[e]; rows[e] = e; }
-    nm_full_sort_wide<CJ>(ys, rows, np, lane, scr_y, scr_r);
-#pragma unroll
-    for (int c = 0; c < CJ; c++) { /* psum, amoeba :49 in index order */
-        double s_ = 0.0;
-        for (int i = 0; i < np; i++) s_ = TK_ADD(s_, p[i * nx + jj[c]]);
-        psum[c] = s_;
-    }
-    __syncthreads(); /* every warp has read the start simplex before anyone replaces a vertex */
+    for (int c = 0; c < CJ; c++) { ph[c] = R[c] = ps1[c] = E[c] = Co[c] = Ci[c] = 0.0; }
 
-    int iter = 0;
-    unsigned par = 0;
-    double ylo;
     for (;;) {
-        ylo = ys[0];
-        const double yhi = ys[nx], ynhi = ys[nx - 1];
-        const int ihi = rows[nx];
-        /* the four possible trial points (amotry :124-126, unfused); this warp evaluates number w */
-        double ph[CJ], R[CJ], ps1[CJ], E[CJ], Co[CJ], Ci[CJ], xc[CJ];
+        /* ---- barrier A was prepared by the master (or by the prologue above) ---- */
+        __syncthreads();
+        const int mode = ctl[0];
+        if (mode == NMW_STOP) break;
+        if (mode == NMW_EVAL4) {
+            double xc[CJ];
+#pragma unroll
+            for (int c = 0; c < CJ; c++) xc[c] = xcand[w * ts + jj[c]];
+            const double yc = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xc, blj, buj, lane, nx, nt);
+            if (lane == 0) yx[w] = yc;
+        } else { /* NMW_VERTS: the vertices dealt over the warps */
+            const int skip = ctl[1];
+            for (int v = w; v < np; v += 4) {
+                if (v == skip) continue;
+                double xv[CJ];
+#pragma unroll
+                for (int c = 0; c < CJ; c++) xv[c] = p[v * nx + jj[c]];
+                const double yc = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xv, blj, buj, lane, nx, nt);
+                if (lane == 0) yv[v] = yc;
+            }
+        }
+        __syncthreads(); /* ---- barrier B: values ready ---- */
+        if (!master) continue;
+
+        /* ================= master ================= */
+        if (mode == NMW_VERTS) {
+            if (first) {
+                for (int e = lane; e < np; e += 32) { ys[e] = yv[e]; rows[e] = e; }
+                first = false;
+            } else { /* after a shrink: every vertex but ilo was re-evaluated */
+                for (int e = lane; e < np; e += 32)
+                    if (rows[e] != ilo_keep) ys[e] = yv[rows[e]];
+                iter += nx;
+            }
+            nm_full_sort_wide<CJ>(ys, rows, np, lane, scr_y, scr_r);
+#pragma unroll
+            for (int c = 0; c < CJ; c++) { /* psum, amoeba :49 / :112 in index order */
+                double s_ = 0.0;
+                for (int i = 0; i < np; i++) s_ = TK_ADD(s_, p[i * nx + jj[c]]);
+                psum[c] = s_;
+            }
+            after_shrink = false;
+        } else {
+            /* decisions of the iteration (minimize.f90:97-114) */
+            const double yR = yx[0];
+            const bool accR = yR < yhi; /* :128 */
+            double pnew[CJ], ynew = yhi;
+            bool moved = accR;
+#pragma unroll
+            for (int c = 0; c < CJ; c++) { pnew[c] = accR ? R[c] : ph[c]; if (accR) psum[c] = ps1[c]; }
+            if (accR) ynew = yR;
+            iter++;
+            if (yR <= ylo) { /* :99 expansion */
+                double yE = yx[1];
+                if (!accR) { /* only when every y is equal; not speculated -- evaluated from the live state */
+#pragma unroll
+                    for (int c = 0; c < CJ; c++) E[c] = TK_SUB(TK_MUL(psum[c], a.fac1e), TK_MUL(ph[c], a.fac2e));
+                    yE = __shfl_sync(FULL, nm_eval_warp_wide<Obj, CJ>(ctx, scr, E, blj, buj, lane, nx, nt), 0);
+                }
+                iter++;
+                if (yE < ynew) {
+#pragma unroll
+                    for (int c = 0; c < CJ; c++) { psum[c] = TK_ADD(TK_SUB(psum[c], pnew[c]), E[c]); pnew[c] = E[c]; }
+                    ynew = yE; moved = true;
+                }
+            } else if (yR >= ynhi) { /* :102 contraction */
+                const double yC = accR ? yx[2] : yx[3];
+                iter++;
+                if (yC < ynew) {
+#pragma unroll
+                    for (int c = 0; c < CJ; c++) {
+                        const double Cv = accR ? Co[c] : Ci[c];
+                        psum[c] = TK_ADD(TK_SUB(psum[c], pnew[c]), Cv); pnew[c] = Cv;
+                    }
+                    ynew = yC; moved = true;
+                } else { /* :106-113 shrink toward the best vertex; the re-evaluation is the next pass */
+                    if (moved) {
+#pragma unroll
+                        for (int c = 0; c < CJ; c++)
+                            if (lane + 32 * c < nx) p[ihi * nx + jj[c]] = pnew[c];
+                    }
+                    if (lane == 0) ys[nx] = ynew;
+                    moved = false;
+                    __syncwarp();
+                    unsigned cand_lo = 0xffffffffu; /* MINLOC: the lowest vertex index among the minima */
+                    for (int e = lane; e < np; e += 32)
+                        if (ys[e] == ylo) cand_lo = min(cand_lo, (unsigned)rows[e]);
+                    const int ilo = (int)__reduce_min_sync(FULL, cand_lo);
+#pragma unroll
+                    for (int c = 0; c < CJ; c++) {
+                        if (lane + 32 * c >= nx) continue;
+                        const double pl = p[ilo * nx + jj[c]];
+                        for (int i = 0; i < np; i++)
+                            if (i != ilo) p[i * nx + jj[c]] = TK_MUL(0.5, TK_ADD(p[i * nx + jj[c]], pl));
+                    }
+                    ilo_keep = ilo;
+                    after_shrink = true;
+                }
+            }
+            if (moved) { /* vertex ihi takes (pnew, ynew): drop position nx, insert at its sorted position */
+                int pos = 0;
+                double ye[CJ]; int re[CJ];
+#pragma unroll
+                for (int c = 0; c < CJ; c++) {
+                    const int e = lane + 32 * c;
+                    if (e < nx) p[ihi * nx + e] = pnew[c];
+                    ye[c] = (e < nx) ? ys[e] : 0.0; re[c] = (e < nx) ? rows[e] : 0;
+                    pos += __popc(__ballot_sync(FULL, e < nx && nm_before(ye[c], re[c], ynew, ihi)));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < CJ; c++) {
+                    const int e = lane + 32 * c;
+                    if (e < nx && e >= pos) { ys[e + 1] = ye[c]; rows[e + 1] = re[c]; }
+                }
+                if (lane == 0) { ys[pos] = ynew; rows[pos] = ihi; }
+            }
+        }
+        __syncwarp();
+        /* ---- prepare the next pass ---- */
+        if (after_shrink) {
+            if (lane == 0) { ctl[0] = NMW_VERTS; ctl[1] = ilo_keep; }
+            continue;
+        }
+        ylo = ys[0]; yhi = ys[nx]; ynhi = ys[nx - 1];
+        ihi = rows[nx];
+        if (nm_converged(a, ylo, yhi) || iter >= a.itmax) {
+            if (lane == 0) ctl[0] = NMW_STOP;
+            continue;
+        }
+        /* the four possible trial points (amotry :124-126, unfused) */
 #pragma unroll
         for (int c = 0; c < CJ; c++) {
             ph[c] = p[ihi * nx + jj[c]];
@@ -703,123 +836,15 @@ __global__ void __launch_bounds__(128) nm_quad_wide_kernel(const TkTablesG T, co
             E[c] = TK_SUB(TK_MUL(ps1[c], a.fac1e), TK_MUL(R[c], a.fac2e));
             Co[c] = TK_SUB(TK_MUL(ps1[c], a.fac1c), TK_MUL(R[c], a.fac2c));
             Ci[c] = TK_SUB(TK_MUL(psum[c], a.fac1c), TK_MUL(ph[c], a.fac2c));
-            xc[c] = (w == 0) ? R[c] : (w == 1) ? E[c] : (w == 2) ? Co[c] : Ci[c];
-        }
-        /* rtol < ftol (:84-85); the division is only formed when the product test is within 2^-40 */
-        const double num = TK_MUL(2.0, fabs(TK_SUB(yhi, ylo)));
-        const double den = TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny);
-        const double thr = TK_MUL(a.ftol, den);
-        bool conv = num < TK_MUL(thr, 0.99999999999909051);
-        if (!conv && !(num > TK_MUL(thr, 1.00000000000090949))) conv = TK_DIV(num, den) < a.ftol;
-        if (conv || iter >= a.itmax) break;
-
-        const double yc = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xc, blj, buj, lane, nx, nt);
-        if (lane == 0) yx[par * 4 + w] = yc;
-        __syncthreads(); /* the one block barrier of the iteration; yx is double-buffered by parity */
-        const double2 y01 = reinterpret_cast<const double2*>(yx + par * 4)[0];
-        const double2 y23 = reinterpret_cast<const double2*>(yx + par * 4)[1];
-        par ^= 1u;
-        const double yR = y01.x;
-        const bool accR = yR < yhi; /* :128 */
-        double pnew[CJ], ynew = yhi;
-        bool moved = accR;
-#pragma unroll
-        for (int c = 0; c < CJ; c++) { pnew[c] = accR ? R[c] : ph[c]; if (accR) psum[c] = ps1[c]; }
-        if (accR) ynew = yR;
-        iter++;
-        if (yR <= ylo) { /* :99 expansion */
-            double yE = y01.y;
-            if (!accR) { /* only when every y is equal; not speculated -- evaluated from the live state */
-#pragma unroll
-                for (int c = 0; c < CJ; c++) E[c] = TK_SUB(TK_MUL(psum[c], a.fac1e), TK_MUL(ph[c], a.fac2e));
-                yE = __shfl_sync(FULL, nm_eval_warp_wide<Obj, CJ>(ctx, scr, E, blj, buj, lane, nx, nt), 0);
-            }
-            iter++;
-            if (yE < ynew) {
-#pragma unroll
-                for (int c = 0; c < CJ; c++) { psum[c] = TK_ADD(TK_SUB(psum[c], pnew[c]), E[c]); pnew[c] = E[c]; }
-                ynew = yE; moved = true;
-            }
-        } else if (yR >= ynhi) { /* :102 contraction */
-            const double yC = accR ? y23.x : y23.y;
-            iter++;
-            if (yC < ynew) {
-#pragma unroll
-                for (int c = 0; c < CJ; c++) {
-                    const double Cv = accR ? Co[c] : Ci[c];
-                    psum[c] = TK_ADD(TK_SUB(psum[c], pnew[c]), Cv); pnew[c] = Cv;
-                }
-                ynew = yC; moved = true;
-            } else { /* :106-113 shrink toward the best vertex, re-evaluate, re-sum */
-                if (moved) {
-#pragma unroll
-                    for (int c = 0; c < CJ; c++)
-                        if (lane + 32 * c < nx) p[ihi * nx + jj[c]] = pnew[c];
-                }
-                if (lane == 0) ys[nx] = ynew;
-                moved = false;
-                __syncwarp();
-                /* MINLOC: the lowest vertex index among the minima */
-                unsigned cand_lo = 0xffffffffu;
-                for (int e = lane; e < np; e += 32)
-                    if (ys[e] == ylo) cand_lo = min(cand_lo, (unsigned)rows[e]);
-                const int ilo = (int)__reduce_min_sync(FULL, cand_lo);
-                __syncthreads(); /* all warps have stored vertex ihi and chosen ilo */
-                if (w == 0) { /* one warp halves the simplex (:107); the others wait */
-#pragma unroll
-                    for (int c = 0; c < CJ; c++) {
-                        if (lane + 32 * c >= nx) continue;
-                        const double pl = p[ilo * nx + jj[c]];
-                        for (int i = 0; i < np; i++)
-                            if (i != ilo) p[i * nx + jj[c]] = TK_MUL(0.5, TK_ADD(p[i * nx + jj[c]], pl));
-                    }
-                }
-                __syncthreads();
-                for (int v = w; v < np; v += 4) {
-                    if (v == ilo) continue;
-                    double xv[CJ];
-#pragma unroll
-                    for (int c = 0; c < CJ; c++) xv[c] = p[v * nx + jj[c]];
-                    const double yc2 = nm_eval_warp_wide<Obj, CJ>(ctx, scr, xv, blj, buj, lane, nx, nt);
-                    if (lane == 0) yv[v] = yc2;
-                }
-                __syncthreads();
-                for (int e = lane; e < np; e += 32)
-                    if (rows[e] != ilo) ys[e] = yv[rows[e]];
-                iter += nx;
-                nm_full_sort_wide<CJ>(ys, rows, np, lane, scr_y, scr_r);
-#pragma unroll
-                for (int c = 0; c < CJ; c++) {
-                    double s_ = 0.0;
-                    for (int i = 0; i < np; i++) s_ = TK_ADD(s_, p[i * nx + jj[c]]);
-                    psum[c] = s_;
-                }
-                __syncthreads(); /* yv / p may change again only after every warp is done with them */
+            if (lane + 32 * c < nx) {
+                xcand[jj[c]] = R[c]; xcand[ts + jj[c]] = E[c]; xcand[2 * ts + jj[c]] = Co[c]; xcand[3 * ts + jj[c]] = Ci[c];
             }
         }
-        if (moved) { /* vertex ihi takes (pnew, ynew): drop position nx, insert at its sorted position */
-            int pos = 0;
-            double ye[CJ]; int re[CJ];
-#pragma unroll
-            for (int c = 0; c < CJ; c++) {
-                const int e = lane + 32 * c;
-                if (e < nx) p[ihi * nx + e] = pnew[c];
-                ye[c] = (e < nx) ? ys[e] : 0.0; re[c] = (e < nx) ? rows[e] : 0;
-                pos += __popc(__ballot_sync(FULL, e < nx && nm_before(ye[c], re[c], ynew, ihi)));
-            }
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < CJ; c++) {
-                const int e = lane + 32 * c;
-                if (e < nx && e >= pos) { ys[e + 1] = ye[c]; rows[e + 1] = re[c]; }
-            }
-            if (lane == 0) { ys[pos] = ynew; rows[pos] = ihi; }
-        }
-        __syncwarp();
+        if (lane == 0) ctl[0] = NMW_EVAL4;
     }
     /* runAmoeba :631-632 returns the first minimal vertex; completeSearch :582 re-evaluates objFun there:
      * same point, same value. */
-    if (w == 0) {
+    if (master) {
         unsigned cand_lo = 0xffffffffu;
         for (int e = lane; e < np; e += 32)
             if (ys[e] == ylo) cand_lo = min(cand_lo, (unsigned)rows[e]);
@@ -1152,7 +1177,7 @@ int tk_nm_wave_capacity(tiktak_handle* h) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_quad_kernel<Obj, 0>, 128, shmem);
         } else if (nx <= 127 && Obj::nterms(nx) <= nx) {
             const int ts = (nx + 2) & ~1;
-            const size_t shmem = (size_t)(4 * ts + 8 + (nx + 1) * nx + 4 * 8 * ts) * sizeof(double);
+            const size_t shmem = (size_t)(8 * ts + 6 + (nx + 1) * nx + 4 * ts + 4 * 4 * ts) * sizeof(double);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_quad_wide_kernel<Obj, 2>, 128, shmem);
         }
         return TIKTAK_OK;
@@ -1225,7 +1250,7 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
             }
         } else if (nx <= 127 && Obj::nterms(nx) <= nx) { /* four warps per restart, CJ coordinates per lane */
             const int ts = (nx + 2) & ~1;
-            const size_t shmem = (size_t)(4 * ts + 8 + np * nx + 4 * 8 * ts) * sizeof(double);
+            const size_t shmem = (size_t)(8 * ts + 6 + np * nx + 4 * ts + 4 * 4 * ts) * sizeof(double);
             const int cj = (np + 31) / 32;
             auto go = [&]<int CJ>() -> int {
                 TK_CUDA(cudaFuncSetAttribute(nm_quad_wide_kernel<Obj, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
