@@ -5,13 +5,16 @@
 
 One "step" = one pass of the hot path over one synthetic job: Sobol pre-test of qr_ndraw points
 (solveAtSobolPoints) -> start selection (chooseSobol) -> all Nelder-Mead restarts
-(LocalMinimizations), device-resident.  N=1 runs BASELINE.json configs[1] (Griewank 10-D, 1e6 Sobol
+(LocalMinimizations: rounds of round_size restarts, later rounds started early on idle SMs and kept
+while the best row is unchanged -- same rows as strictly sequential rounds), device-resident.  N=1 runs BASELINE.json configs[1] (Griewank 10-D, 1e6 Sobol
 points, 1000+1 restarts).  N>1 (torchrun, one rank per GPU, NCCL) shards the Sobol index range and
 each round's restarts over the ranks with one all-gather per round; per-GPU work is held fixed
 (qr_ndraw, maxpoints and round_size scale with N): "scaling": "weak".
 
 JSON keys beyond the base contract:
   restarts_per_s   local restarts/s of the same step (second half of BASELINE.json's metric)
+  roofline_local   the restart kernel (dominant in the step's kernel time, latency-bound): algorithmic FP64
+                   flops of its objective evaluations / stage time, against the same FP64 peak
   roofline         the Sobol evaluation kernel (the stage BASELINE.json sets the >=50 % target on):
                    algorithmic FP64 flops per evaluation x evaluations per launch /
                    CUDA-event duration on the library's stream, vs the FP64 DFMA peak measured on
