@@ -453,3 +453,79 @@ def test_early_started_rounds_equal_sequential_rounds(built, name, alg, B):
         assert fb == o.getBestLine()[0]
     n_rounds = -(-cfg.p_maxpoints // B)
     assert runs[0][3] == n_rounds and runs[None][3] < n_rounds
+
+
+def _run_both(cfg, alg="a"):
+    with TikTakSearch(cfg) as s:
+        _, ne, nl = s.solveAtSobolPoints()
+        fv = s.sobolFnVal() if ne > 0 else np.empty(0)
+        xs = s.chooseSobol()
+        idx = s.sobol_idx.copy()
+        s.LocalMinimizations(alg)
+        out = (ne, nl, fv, xs, idx, s.searchStart, s.searchResults, s.evals, s.getBestLine())
+    o = Oracle(cfg, MATH_TK)
+    _, one, onl = o.solveAtSobolPoints()
+    oxs = o.chooseSobol(mode=1)
+    o.LocalMinimizations(1 if alg == "a" else 0)
+    return out, o, (one, onl, oxs)
+
+
+def test_edge_no_sobol_points(built):
+    """qr_ndraw = 0 -> maxpoints = 0 (genericParams.f90:325-326): one local search from p_init, nothing else"""
+    cfg = make_config(nx=4, nm=2, qr_ndraw=0, maxpoints=5, lo=-1.0, hi=1.0, bound=[[-3.0, 3.0]] * 4, init=[0.8, -0.2, 0.3, 0.2],
+                      objective_id=OBJ_TEMPLATE)
+    assert cfg.p_maxpoints == 1
+    (ne, nl, fv, xs, idx, st, rs, ev, best), o, (one, onl, oxs) = _run_both(cfg)
+    assert (ne, nl) == (one, onl) == (0, 0)
+    assert np.array_equal(xs, oxs) and xs.shape == (1, 5)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+
+
+@pytest.mark.parametrize("alg", ["a", "b"])
+def test_edge_one_parameter(built, alg):
+    """nx = 1: a two-vertex simplex / npt = 3 interpolation points"""
+    cfg = make_config(nx=1, nm=2, qr_ndraw=300, maxpoints=6, lo=-40.0, hi=60.0, init=[10.0], objective_id=OBJ_GRIEWANK, round_size=3)
+    (ne, nl, fv, xs, idx, st, rs, ev, best), o, (one, onl, oxs) = _run_both(cfg, alg)
+    assert (ne, nl) == (one, onl) and np.array_equal(fv, o.sobolFnVal())
+    assert np.array_equal(xs, oxs) and np.array_equal(idx, o.sobol_idx)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+
+
+def test_edge_largest_supported_dimension(built):
+    """nx = 128 (the build's limit; runtime-nx Sobol kernel, fallback Nelder-Mead kernel with a short evaluation cap)"""
+    cfg = make_config(nx=128, nm=1, qr_ndraw=600, maxpoints=3, lo=-2.0, hi=2.0, init=[0.5] * 128, objective_id=OBJ_ROSENBROCK,
+                      round_size=2, nm_itmax=400)
+    (ne, nl, fv, xs, idx, st, rs, ev, best), o, (one, onl, oxs) = _run_both(cfg)
+    assert (ne, nl) == (one, onl) and np.array_equal(fv, o.sobolFnVal())
+    assert np.array_equal(xs, oxs) and np.array_equal(idx, o.sobol_idx)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+
+
+def test_edge_every_point_selected_and_none_legitimate(built):
+    """maxpoints = qr_ndraw (every evaluated point becomes a start) and fvalmax below every value (no legitimate point):
+    selection ignores validity (:882), invalid rows simply take part"""
+    cfg = cfg_of("griewank7", qr_ndraw=37, maxpoints=37, fvalmax=1.0e-3, legitimate=5, round_size=8)
+    (ne, nl, fv, xs, idx, st, rs, ev, best), o, (one, onl, oxs) = _run_both(cfg)
+    assert (ne, nl) == (one, onl) == (37, 0)
+    assert sorted(idx[1:].tolist()) == list(range(1, 38))
+    assert np.array_equal(xs, oxs) and np.array_equal(idx, o.sobol_idx)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+
+
+def test_edge_invalid_configurations_are_refused(built):
+    """the reference stops (`stop 0`) on these; the library returns a status instead"""
+    from tiktak_b200.lib import TikTakError
+    cfg = cfg_of("griewank7")
+    cfg.maxpoints = cfg.qr_ndraw + 1  # maxpoints > # sobol points (genericParams.f90:331-333)
+    with pytest.raises(TikTakError):
+        TikTakSearch(cfg)
+    cfg = cfg_of("griewank7", search_type=2)  # unknown selectionMethod (TiktakGlobalSearch.f90:709-715)
+    with pytest.raises(TikTakError):
+        TikTakSearch(cfg)
+    cfg = cfg_of("griewank7")
+    with TikTakSearch(cfg) as s:
+        with pytest.raises(TikTakError):
+            s.chooseSobol()  # stage out of order
+        s.solveAtSobolPoints()
+        with pytest.raises(TikTakError):
+            s.LocalMinimizations("a")  # before chooseSobol
