@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def summary(self):
         if not self.ok or not self.samples:
