@@ -30,6 +30,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <string>
 #include <vector>
 
 #include "../include/tiktak_cuda.h" /* tiktak_config layout only */
@@ -908,6 +909,42 @@ int orc_indexx(int n, const double* arr, int32_t* index) {
     return rc;
 }
 double orc_text4020(double x) { return text4020(x); }
+
+/* solveAtSobolPoints WITH the reference's file protocol (TiktakGlobalSearch.f90:426-463, stateControl.f90:83-148,
+ * 187-201): per point one getNextNumber on lastSobol.dat (read cycle + replace cycle), one writeToLog append, one
+ * getNextNumber / getNumber on legitSobol.dat and one append to sobolFnVal.dat -- five to six open/close cycles
+ * around an objective evaluation.  Only used to time what a user of the reference's process-per-core scheme pays
+ * (bench.py cpu_baseline "faithful"); `dir` must exist and be private to the caller.  Returns points evaluated. */
+static long file_get_number(const std::string& f) { long y = 0; FILE* h = fopen(f.c_str(), "r"); if (h) { if (fscanf(h, "%ld", &y) != 1) y = 0; fclose(h); } return y; }
+static long file_get_next_number(const std::string& f) {
+    const long y = file_get_number(f) + 1;
+    FILE* h = fopen(f.c_str(), "w");
+    if (h) { fprintf(h, " %11ld\n", y); fclose(h); }
+    return y;
+}
+long orc_pretest_faithful(void* hh, const char* dir, long npoints) {
+    Oracle* o = (Oracle*)hh;
+    const int nx = o->c.nx;
+    const std::string d(dir);
+    const std::string lastSobol = d + "/lastSobol.dat", legit = d + "/legitSobol.dat", fnval = d + "/sobolFnVal.dat", logfile = d + "/logFile.txt";
+    for (const std::string& f : {lastSobol, legit}) { FILE* h = fopen(f.c_str(), "w"); if (!h) return -1; fprintf(h, " %11d\n", 0); fclose(h); }
+    for (const std::string& f : {fnval, logfile}) { FILE* h = fopen(f.c_str(), "w"); if (!h) return -1; fclose(h); }
+    Sobol sb;
+    if (sb.insobl(nx, o->c.qr_ndraw)) return -1;
+    std::vector<double> q(nx), x(nx);
+    long whichPoint = file_get_next_number(lastSobol), legitSobol = file_get_number(legit), done = 0;
+    while (whichPoint <= npoints && legitSobol < o->c.legitimate) {
+        { FILE* h = fopen(logfile.c_str(), "a"); if (h) { fprintf(h, " Sequence# %5d is solving sobol point %6ld\n", 1, whichPoint); fclose(h); } }
+        if (sb.next(q.data(), 0)) return -2;
+        for (int i = 0; i < nx; i++) x[i] = o->lo_r()[i] + q[i] * (o->hi_r()[i] - o->lo_r()[i]);
+        const double fval = o->objFun(x.data());
+        legitSobol = (fval < o->c.fvalmax) ? file_get_next_number(legit) : file_get_number(legit);
+        { FILE* h = fopen(fnval.c_str(), "a"); if (h) { fprintf(h, "%8ld%40.20f", whichPoint, fval); for (int i = 0; i < nx; i++) fprintf(h, "%40.20f", x[i]); fputc('\n', h); fclose(h); } }
+        done++;
+        whichPoint = file_get_next_number(lastSobol);
+    }
+    return done;
+}
 
 /* the lottery's random numbers (include/tiktak_rng.h) */
 void orc_philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) { tk_philox4x32_10(c, k0, k1); }
