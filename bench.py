@@ -349,8 +349,8 @@ def run_graft(args, rank, world, local_rank):
         else:
             achieved_tf = per_gpu_evals * F_ALG[name] / (eval_ms * 1e-3) / 1e12
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` captures
-            # (profiles/r01b_full_*.csv); the 8 MB of results of a 1e6-point launch stay in the 126 MB L2
-            traffic = {"C2": 38400, "C3": 741096704}.get(name) if world == 1 else None
+            # (profiles/r01c_full_*.csv); the 8 MB of results of a 1e6-point launch stay in the 126 MB L2
+            traffic = {"C2": 22528, "C3": 741874944}.get(name) if world == 1 else None
             roofline = {"bound": "fp64", "kernel": "sobol_eval_kernel", "achieved": achieved_tf, "peak": peak_tf,
                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                         "flops_per_eval": F_ALG[name], "evals_per_launch": per_gpu_evals, "kernel_ms": eval_ms,
