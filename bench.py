@@ -51,16 +51,21 @@ def parse_args():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--round-size", type=int, default=0)
+    ap.add_argument("--nm-shrink-mode", type=int, default=-1, choices=[-1, 0, 1],
+                    help="initial-simplex rule: 0 = the reference code, 1 = README.md:36 (bounds from the best minima so far); "
+                         "default 0 everywhere: the rule is not in the reference's code (SURVEY finding 3) and on C4 it ends at a "
+                         "worse minimum (3.42 against 1.002), so the parity configuration keeps the code's behaviour")
     ap.add_argument("--no-local", action="store_true", help="time only the Sobol stage + selection")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     return ap.parse_args()
 
 
-def workload_config(name, world, round_size=0):
+def workload_config(name, world, round_size=0, nm_shrink_mode=-1):
     from tiktak_b200 import baseline_config, smm_config
 
     cfg = smm_config(**C5_SIZES) if name == "C5" else baseline_config(name)
+    cfg.nm_shrink_mode = 0 if nm_shrink_mode < 0 else nm_shrink_mode
     if world > 1:  # weak scaling: per-GPU work fixed
         cfg.qr_ndraw *= world
         cfg.maxpoints *= world
@@ -230,7 +235,7 @@ def run_graft(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     name = args.workload
-    cfg = workload_config(name, world, args.round_size)
+    cfg = workload_config(name, world, args.round_size, args.nm_shrink_mode)
     L = lib.load()
     s = TikTakSearch(cfg, device=local_rank, rank=rank, world=world)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
@@ -376,7 +381,7 @@ def run_graft(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: {['', 'template', 'Griewank', 'Rastrigin', 'Rosenbrock', 'synthetic SMM'][int(name[1])]} "
                                    f"{cfg.nx}-D, qr_ndraw={npts}, maxpoints={cfg.maxpoints} (+1 = {nrest} Nelder-Mead restarts), "
-                                   f"round_size={cfg.round_size}, nm_itmax={cfg.nm_itmax}, ftol={cfg.nm_ftol}",
+                                   f"round_size={cfg.round_size}, nm_itmax={cfg.nm_itmax}, ftol={cfg.nm_ftol}, nm_shrink_mode={cfg.nm_shrink_mode}",
                        "parallelism": f"sobol index blocks + restarts sharded over {world} GPU(s)",
                        "l2": "256 MB buffer rewritten between steps (L2 flush)", "timing": timing},
             "restarts_per_s": restarts_s,
