@@ -243,7 +243,7 @@ def test_start_selection_large_m(built):
         cfg = cfg_of("griewank10", qr_ndraw=nd, maxpoints=maxpoints)
         with TikTakSearch(cfg) as s:
             s.solveAtSobolPoints(wait=False)
-            assert s.n_legit is None  # queued only; resolved by chooseSobol
+            assert s._n_legit is None  # queued only; the valid count is read back on first use
             xs = s.chooseSobol()
             idx = s.sobol_idx.copy()
             nl = s.n_legit

@@ -605,19 +605,16 @@ int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first, int64_t count, d
 
 /* the k=0 record [seqNo, 0, 0, fval(p_init), p_init] (TiktakGlobalSearch.f90:496-501) */
 static int push_init_row(tiktak_handle* h) {
-    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
-    std::vector<double> row0(nx + 1);
-    TK_CUDA(cudaMemcpyAsync(&row0[0], h->d_xstarts, 8, cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
-    for (int d = 0; d < nx; d++) row0[1 + d] = h->init[d];
-    std::vector<double> rows(nx + 4);
-    rows[0] = 1; rows[1] = 0; rows[2] = 0;
-    rows[3] = h->cfg.text_roundtrip ? tk_f4020_roundtrip(row0[0]) : row0[0];
-    for (int d = 0; d < nx; d++) rows[4 + d] = h->cfg.text_roundtrip ? tk_f4020_roundtrip(row0[1 + d]) : row0[1 + d];
+    /* on the device, without a host round trip; the host mirror of row 0 is read back only if push_results needs it */
+    const int K = h->cfg.maxpoints_plus1;
     std::fill(h->h_res_valid.begin(), h->h_res_valid.end(), 0);
-    h->n_rows = 0;
     TK_CUDA(cudaMemsetAsync(h->d_res_valid, 0, (size_t)(K + 1) * sizeof(int), h->stream));
-    return tiktak_cuda_push_results(h, rows.data(), 1);
+    int rc = tk_launch_init_results(h);
+    if (rc) return rc;
+    h->n_rows = 1;
+    h->row0_on_device_only = true;
+    h->best_dirty = false;
+    return TIKTAK_OK;
 }
 
 static int export_starts(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
@@ -639,9 +636,7 @@ int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
     if (!h) return TIKTAK_ERR_ARG;
     if (!h->pretest_done) { tk_set_error("choose: pretest has not completed"); return TIKTAK_ERR_STATE; }
     TK_CUDA(cudaSetDevice(h->device));
-    int rc = resolve_legit(h);
-    if (rc) return rc;
-    rc = begin_timer(h);
+    int rc = begin_timer(h); /* the valid count (legitSobol.dat) is not needed to select: tiktak_cuda_pretest_result reads it */
     if (rc) return rc;
     rc = tk_select_top(h, h->cfg.maxpoints_plus1 - 1);
     if (rc) return rc;
@@ -712,6 +707,13 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
     TK_CUDA(cudaSetDevice(h->device));
     std::vector<double> host((size_t)n * (nx + 4));
     if (n == 0) return TIKTAK_OK;
+    if (h->row0_on_device_only) { /* the #improvements bookkeeping below needs the k = 0 value on the host */
+        double f0 = 0;
+        TK_CUDA(cudaMemcpyAsync(&f0, h->d_res, 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        h->h_res_f[0] = f0; h->h_res_valid[0] = 1; h->h_res_imp[0] = 0;
+        h->row0_on_device_only = false;
+    }
     h->best_dirty = true;
     TK_CUDA(cudaMemcpy(host.data(), rows, host.size() * 8, cudaMemcpyDefault));
     /* running best, for the #improvements column (completeSearch :585-589) */

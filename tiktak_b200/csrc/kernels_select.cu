@@ -258,7 +258,27 @@ __global__ void init_row_kernel(const double* init, const double* finit, int nx,
     for (int d = threadIdx.x; d < nx; d += blockDim.x) xs[(size_t)(d + 1) * K] = init[d];
 }
 
+/* the k = 0 record [fval(p_init), p_init] (TiktakGlobalSearch.f90:496-501) as the only row of the results table, through
+ * the f40.20 record like every searchResults.dat row; it is also the best row so far.  valid[] was cleared before. */
+__global__ void init_results_kernel(const double* xs, int nx, int K, int roundtrip, double* res, int* valid, double* best) {
+    const double f = roundtrip ? tk_f4020_roundtrip(xs[0]) : xs[0];
+    if (threadIdx.x == 0) { res[0] = f; valid[0] = 1; best[0] = f; best[1] = 0.0; best[2] = 1.0; }
+    for (int d = threadIdx.x; d < nx; d += blockDim.x) {
+        const double x = roundtrip ? tk_f4020_roundtrip(xs[(size_t)(d + 1) * K]) : xs[(size_t)(d + 1) * K];
+        res[1 + d] = x;
+        best[3 + d] = x;
+    }
+}
+
 } /* namespace */
+
+int tk_launch_init_results(tiktak_handle* h) {
+    init_results_kernel<<<1, 64, 0, h->stream>>>(h->d_xstarts, h->cfg.nx, h->cfg.maxpoints_plus1, h->cfg.text_roundtrip, h->d_res,
+                                                 h->d_res_valid, h->d_best);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
 
 int tk_sort_candidates(tiktak_handle* h, double* d_f, unsigned int* d_i, int64_t n, double* d_sf, unsigned int* d_si);
 

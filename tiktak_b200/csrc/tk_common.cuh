@@ -108,6 +108,7 @@ struct tiktak_handle {
     int* d_shr_have = nullptr;
     double* d_arch_starts = nullptr; /* (K, nx) column-major: the searchStart.dat rows of every restart */
     int* d_arch_evals = nullptr;     /* [K+1]: objective evaluations of restart k */
+    bool row0_on_device_only = false; /* the k = 0 record was written by init_results_kernel; host mirror not filled yet */
     bool best_dirty = true;          /* d_best must be recomputed from the rows (after push_results) */
     cudaEvent_t evl0 = nullptr, evl1 = nullptr, evp0 = nullptr, evp1 = nullptr;
     bool local_timing_open = false, pretest_timing_open = false;
@@ -139,6 +140,7 @@ int tk_launch_objfun(tiktak_handle* h, const double* d_x, int64_t n, double* d_f
 int tk_launch_find_cut(tiktak_handle* h, int64_t cb, unsigned long long need, unsigned long long* d_result);
 int tk_select_top(tiktak_handle* h, int64_t M);
 int tk_build_starts(tiktak_handle* h);
+int tk_launch_init_results(tiktak_handle* h);
 int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count);

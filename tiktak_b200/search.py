@@ -48,12 +48,20 @@ class TikTakSearch:
         self._h = C.c_void_p()
         _lib.check(self._L.tiktak_cuda_create(C.byref(self._h), C.byref(self._c)), "tiktak_cuda_create")
         self.n_evaluated = None
-        self.n_legit = None
+        self._n_legit = None
         self.x_starts = None
         self.sobol_idx = None
         self.searchStart = None  # rows of searchStart.dat: (K, nx)
         self.searchResults = None  # rows of searchResults.dat: (K, nx+4) = seqNo, k, #improv, fval, x
         self.evals = None
+
+    @property
+    def n_legit(self):
+        """#(fval < fvalmax) among the evaluated points (the final legitSobol.dat value); read back from the device on
+        first use when the stage did not need it to place the cut"""
+        if self._n_legit is None and self.n_evaluated is not None:
+            self._resolve_legit()
+        return self._n_legit
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -120,10 +128,9 @@ class TikTakSearch:
         """Returns (complete, n_evaluated, n_legit) -- `complete` as in :465.
 
         wait=False: when the `legitimate` cut cannot fire (legitimate > qr_ndraw) the evaluation is only queued on
-        the device and n_legit comes back as None; it is filled in (self.n_legit) by chooseSobol."""
+        the device and n_legit comes back as None; the `n_legit` property reads it back on first use."""
         out = self._solve(wait)
-        if wait and self.n_legit is None:
-            self._resolve_legit()
+        if wait and self._n_legit is None:
             out = (out[0], out[1], self.n_legit)
         return out
 
@@ -131,7 +138,7 @@ class TikTakSearch:
         nl = C.c_int64()
         _lib.check(self._L.tiktak_cuda_pretest_result(self._h, None, C.byref(nl)), "pretest_result")
         if self.world == 1:
-            self.n_legit = nl.value
+            self._n_legit = nl.value
         else:  # a shard knows its own count only
             import torch
 
@@ -139,7 +146,7 @@ class TikTakSearch:
 
             counts = torch.zeros(self.cfg.qr_ndraw // SOBOL_BLOCK + 1, dtype=torch.int64, device=torch.device("cuda", self.device))
             _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), counts.numel()), "pretest_counts")
-            self.n_legit = int(D.reduce_counts(counts.sum().reshape(1), self.group).item())
+            self._n_legit = int(D.reduce_counts(counts.sum().reshape(1), self.group).item())
 
     def _solve(self, wait):
         ne, nl = C.c_int64(), C.c_int64()
@@ -147,10 +154,10 @@ class TikTakSearch:
             if not wait and self.cfg.legitimate > self.cfg.qr_ndraw > 0:
                 # the cut cannot fire: the evaluation is only queued; n_legit is read back by chooseSobol
                 _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), None), "solveAtSobolPoints")
-                self.n_evaluated, self.n_legit = ne.value, None
+                self.n_evaluated, self._n_legit = ne.value, None
                 return True, ne.value, None
             _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), C.byref(nl)), "solveAtSobolPoints")
-            self.n_evaluated, self.n_legit = ne.value, nl.value
+            self.n_evaluated, self._n_legit = ne.value, nl.value
             return True, ne.value, nl.value
         return self._solve_sharded()
 
@@ -168,12 +175,12 @@ class TikTakSearch:
         if N == 0 or Lg <= 0:
             _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, 0, 0), "pretest_wave")
             _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, 0, 0), "pretest_set_cut")
-            self.n_evaluated, self.n_legit = 0, 0
+            self.n_evaluated, self._n_legit = 0, 0
             return True, 0, 0
         if Lg > N:
             _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, 0, nblocks), "pretest_wave")
             _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, N, -1), "pretest_set_cut")
-            self.n_evaluated, self.n_legit = N, None  # n_legit is known after chooseSobol
+            self.n_evaluated, self._n_legit = N, None  # n_legit is known after chooseSobol
             return True, N, None
         dev = torch.device("cuda", self.device)
         wave = 64 * self.world
@@ -195,7 +202,7 @@ class TikTakSearch:
         if kcut < 0:
             kcut, nleg = N, cum
         _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, kcut, nleg), "pretest_set_cut")
-        self.n_evaluated, self.n_legit = kcut, nleg
+        self.n_evaluated, self._n_legit = kcut, nleg
         return True, kcut, nleg
 
     def sobolFnVal(self, first=1, count=None, out=None):
@@ -221,10 +228,6 @@ class TikTakSearch:
         idx = np.zeros(K, dtype=np.int32)
         if self.world == 1:
             _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
-            if self.n_legit is None:
-                nl = C.c_int64()
-                _lib.check(self._L.tiktak_cuda_pretest_result(self._h, None, C.byref(nl)), "pretest_result")
-                self.n_legit = nl.value
         else:
             import torch
 
@@ -238,8 +241,8 @@ class TikTakSearch:
                 allc = D.gather_candidates(cand, self.world, self.group)
                 _lib.check(self._L.tiktak_cuda_choose_merge(self._h, allc.data_ptr(), allc.shape[0], xs.ctypes.data,
                                                             idx.ctypes.data), "choose_merge")
-                if self.n_legit is None:  # no-cut run: the global valid count travelled in the trailer rows
-                    self.n_legit = int(allc.view(self.world, K, 2)[:, K - 1, 0].sum().item())
+                if self._n_legit is None:  # no-cut run: the global valid count travelled in the trailer rows
+                    self._n_legit = int(allc.view(self.world, K, 2)[:, K - 1, 0].sum().item())
         self.x_starts = xs.T.copy()  # (K, nx+1) = [fval, x]
         self.sobol_idx = idx
         return self.x_starts
