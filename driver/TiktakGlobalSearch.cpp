@@ -26,6 +26,7 @@
  * 2 Rastrigin, 3 Rosenbrock), TIKTAK_ROUND_SIZE (default 1 = the sequential reference order), TIKTAK_DEVICE,
  * TIKTAK_WRITE_SOBOL (1 = also dump sobol.dat like setupSobol does).
  */
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -239,14 +240,28 @@ int main(int argc, char** argv) {
         }
         const int B = tc.round_size < 1 ? 1 : tc.round_size;
         int k0 = resume_k + 1, kend = option == 5 ? 1 : K; /* option 5: only the initial guess (:151-197) */
-        for (; k0 <= kend; k0 += B) {
-            const int nk = std::min(B, kend - k0 + 1);
+        /* Rounds of B restarts (B = 1: the single-instance order of the reference).  A launch holds one resident wave
+         * of restarts, i.e. several rounds started early against the current best row; the library accepts them
+         * while that row stays the best one and the rest is queued again -- same rows as one round after the other. */
+        int32_t window = 0;
+        CHECK(tiktak_cuda_local_capacity(h, alg, &window));
+        const int per_launch = std::max(B, (window / B) * B);
+        const int kfirst = k0;
+        while (k0 <= kend) {
+            const int nk = std::min(per_launch, kend - k0 + 1);
+            int32_t acc = 0;
+            CHECK(tiktak_cuda_local_enqueue(h, alg, k0, nk, nullptr));
+            CHECK(tiktak_cuda_local_ingest_rounds(h, k0, nk, B, nullptr, &acc));
+            k0 += acc;
+        }
+        if (kend >= kfirst) {
+            const int nk = kend - kfirst + 1;
             std::vector<double> st((size_t)nk * nx), rs((size_t)nk * (nx + 4));
             std::vector<int32_t> ev(nk);
-            CHECK(tiktak_cuda_local(h, alg, k0, nk, st.data(), rs.data(), ev.data()));
+            CHECK(tiktak_cuda_local_fetch(h, kfirst, nk, st.data(), rs.data(), ev.data()));
             for (int s = 0; s < nk; s++) {
-                fprintf(fs, "%10d%10d", seqNo, k0 + s); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[(size_t)d * nk + s]); fputc('\n', fs);
-                fprintf(fr, "%10d%10d%10d", seqNo, k0 + s, (int)rs[(size_t)2 * nk + s]);
+                fprintf(fs, "%10d%10d", seqNo, kfirst + s); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[(size_t)d * nk + s]); fputc('\n', fs);
+                fprintf(fr, "%10d%10d%10d", seqNo, kfirst + s, (int)rs[(size_t)2 * nk + s]);
                 for (int d = 3; d < nx + 4; d++) fprintf(fr, "%40.20f", rs[(size_t)d * nk + s]);
                 fputc('\n', fr);
             }
