@@ -529,3 +529,69 @@ def test_edge_invalid_configurations_are_refused(built):
         s.solveAtSobolPoints()
         with pytest.raises(TikTakError):
             s.LocalMinimizations("a")  # before chooseSobol
+
+
+def test_full_size_c2_against_oracle(built):
+    """BASELINE.json configs[1] at full size (Griewank 10-D, 1e6 Sobol points, 1001 Nelder-Mead restarts in rounds of
+    128): every stage bit for bit against the CPU oracle"""
+    cfg = baseline_config("C2")
+    cfg.round_size = 128
+    with TikTakSearch(cfg) as s:
+        _, ne, nl = s.solveAtSobolPoints()
+        f = s.sobolFnVal()
+        xs = s.chooseSobol()
+        idx = s.sobol_idx.copy()
+        s.LocalMinimizations("a")
+        st, rs, ev, best = s.searchStart, s.searchResults, s.evals, s.getBestLine()
+        ff, xf, it = s.lastSearch()
+    o = Oracle(cfg, MATH_TK)
+    _, one, onl = o.solveAtSobolPoints()
+    assert (ne, nl) == (one, onl) == (1_000_000, 1_000_000)
+    assert np.array_equal(f, o.sobolFnVal())
+    assert np.array_equal(xs, o.chooseSobol(mode=1)) and np.array_equal(idx, o.sobol_idx)
+    o.LocalMinimizations(1)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+    ob = o.getBestLine()
+    assert best[0] == ob[0] and best[2] == ob[2]
+    of, ox, oit = o.lastSearch()
+    assert abs(ff - of) <= 1e-6 * abs(of) and ff == of and np.array_equal(xf, ox)
+
+
+@pytest.mark.parametrize("name,npts", [("C4", 10_000_000), ("C3", 100_000_000)])
+def test_full_size_selection_properties(built, name, npts):
+    """BASELINE.json configs[2] and [3] at full size, where the serial oracle would take minutes: size-independent
+    properties of the Sobol stage and of the start selection.
+      - the selected rows are in ascending (fval, index) order and no unselected point beats the last one;
+      - every selected row is the Sobol point of its index (regenerated) and its fval is objFun of that point
+        (re-evaluated through a different kernel): generation, evaluation and selection agree with one another;
+      - the valid count equals the number of stored values below fvalmax;
+      - selection is idempotent."""
+    cfg = baseline_config(name)
+    assert cfg.qr_ndraw == npts
+    K, nx = cfg.p_maxpoints, cfg.nx
+    with TikTakSearch(cfg) as s:
+        _, ne, nl = s.solveAtSobolPoints()
+        assert ne == npts
+        xs = s.chooseSobol()
+        idx = s.sobol_idx.copy()
+        xs2 = s.chooseSobol()
+        assert np.array_equal(xs, xs2) and np.array_equal(idx, s.sobol_idx)
+        fsel, sel = xs[1:, 0], idx[1:].astype(np.int64)
+        assert len(set(sel.tolist())) == K - 1 and sel.min() >= 1 and sel.max() <= npts
+        order = np.lexsort((sel, fsel))
+        assert np.array_equal(order, np.arange(K - 1))  # ascending fval, ties by ascending Sobol index
+        # threshold: count of stored values <= the last selected value, chunk by chunk
+        last_f, below, legit = fsel[-1], 0, 0
+        chunk = 10_000_000
+        for first in range(1, npts + 1, chunk):
+            f = s.sobolFnVal(first, min(chunk, npts - first + 1))
+            below += int(np.count_nonzero(f < last_f))
+            legit += int(np.count_nonzero(f < cfg.fvalmax))
+            inside = sel[(sel >= first) & (sel < first + len(f))]
+            assert np.array_equal(f[inside - first], fsel[np.isin(sel, inside)])  # the stored value of every selected index
+        assert below <= K - 2 and legit == nl
+        # regenerate the selected points one by one and re-evaluate them
+        for r in range(0, K - 1, max(1, (K - 1) // 200)):
+            pt = s.setupSobol(int(sel[r]), 1)[0]
+            assert np.array_equal(pt, xs[1 + r, 1:])
+        assert np.array_equal(s.objFun(xs[1:, 1:]), fsel)
