@@ -595,3 +595,34 @@ def test_full_size_selection_properties(built, name, npts):
             pt = s.setupSobol(int(sel[r]), 1)[0]
             assert np.array_equal(pt, xs[1 + r, 1:])
         assert np.array_equal(s.objFun(xs[1:, 1:]), fsel)
+
+
+def test_full_size_local_stage_properties_c4(built):
+    """BASELINE.json configs[3] at full size (Rosenbrock 50-D, 20 001 Nelder-Mead restarts): properties of the restart
+    stage that hold for any size -- the reported value is objFun at the reported point, evaluation counts respect
+    amoeba's cap, blended starts stay inside the Sobol box, the #improvements column is the running count of strict
+    improvements over the k = 0 record, and getBestLine is the first minimum."""
+    cfg = baseline_config("C4")
+    cfg.round_size = 1184
+    K, nx = cfg.p_maxpoints, cfg.nx
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(wait=False)
+        xs = s.chooseSobol()
+        s.LocalMinimizations("a")
+        st, rs, ev = s.searchStart, s.searchResults, s.evals
+        fb, xb, kb = s.getBestLine()
+        f_again = s.objFun(rs[:, 4:])
+    assert np.array_equal(rs[:, 1], np.arange(1, K + 1))
+    assert np.array_equal(f_again, rs[:, 3])  # f40.20 keeps values >= 2^-14 exactly
+    assert ev.min() >= nx + 2 and ev.max() <= cfg.nm_itmax + 2 * nx + 3
+    lo, hi = np.asarray(cfg.range)[:, 0], np.asarray(cfg.range)[:, 1]
+    assert np.all(st >= lo - 1e-12) and np.all(st <= hi + 1e-12)
+    run_best, imp, want = xs[0, 0], 0, []
+    for f in rs[:, 3]:
+        if f < run_best:
+            imp, run_best = imp + 1, f
+        want.append(imp)
+    assert np.array_equal(rs[:, 2], np.asarray(want, dtype=float))
+    k_first_min = int(np.argmin(rs[:, 3])) + 1
+    assert (fb, kb) == ((rs[k_first_min - 1, 3], k_first_min) if rs[k_first_min - 1, 3] < xs[0, 0] else (xs[0, 0], 0))
+    assert np.array_equal(xb, rs[kb - 1, 4:] if kb > 0 else xs[0, 1:])
