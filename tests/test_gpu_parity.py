@@ -626,3 +626,27 @@ def test_full_size_local_stage_properties_c4(built):
     k_first_min = int(np.argmin(rs[:, 3])) + 1
     assert (fb, kb) == ((rs[k_first_min - 1, 3], k_first_min) if rs[k_first_min - 1, 3] < xs[0, 0] else (xs[0, 0], 0))
     assert np.array_equal(xb, rs[kb - 1, 4:] if kb > 0 else xs[0, 1:])
+
+
+def test_smm_full_moment_count_properties(built):
+    """BASELINE.json configs[4] shape (1200 moments, 7 parameters, T = 40; panel of 32768 persons): the `legitimate` cut
+    stops at the first index where the valid count is reached, stored values are objFun of the regenerated points, and
+    the DFNLS minima are re-evaluated to the reported values"""
+    cfg = smm_config(np_persons=32768, T=40, qr_ndraw=2000, legitimate=20, maxpoints=15, fvalmax=50.0, round_size=16)
+    assert cfg.nm == 1200
+    with TikTakSearch(cfg) as s:
+        _, ne, nl = s.solveAtSobolPoints()
+        f = s.sobolFnVal()
+        assert nl == 20 and ne < 2000 and len(f) == ne
+        valid = f < cfg.fvalmax
+        assert int(valid.sum()) == 20 and valid[-1] and int(valid[:-1].sum()) == 19  # the prefix ends at the 20th valid point
+        pts = s.setupSobol(1, ne)
+        probe = np.linspace(0, ne - 1, 40).astype(int)
+        assert np.array_equal(s.objFun(pts[probe]), f[probe])
+        xs = s.chooseSobol()
+        assert np.array_equal(np.sort(xs[1:, 0]), xs[1:, 0]) and xs[1, 0] == f.min()
+        s.LocalMinimizations("b")
+        rs, ev = s.searchResults, s.evals
+        assert np.array_equal(s.objFun(rs[:, 4:]), rs[:, 3])
+        assert ev.max() <= cfg.maxeval + 1 and ev.min() >= 2 * cfg.nx + 2
+        assert rs[:, 3].min() <= xs[:, 0].min()  # the local stage does not lose the best start
