@@ -275,7 +275,8 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
-                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_counts_spare};
+                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_counts_spare,
+                    h->d_objfun_x, h->d_objfun_f};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -362,23 +363,27 @@ int tiktak_cuda_objfun(tiktak_handle* h, const double* x, int64_t n, double* fva
     TK_CUDA(cudaSetDevice(h->device));
     const size_t xb = (size_t)n * h->cfg.nx * sizeof(double), fb = (size_t)n * sizeof(double);
     const bool xdev = is_device_ptr(x), fdev = is_device_ptr(fval);
-    double *dx = nullptr, *df = nullptr;
-    int rc = TIKTAK_OK;
-    if (!xdev) {
-        TK_CUDA(cudaMalloc(&dx, xb));
-        TK_CUDA(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, h->stream));
+    /* staging for host arguments lives in the handle (lastSearch calls this hundreds of times with a few points) */
+    if ((!xdev || !fdev) && h->objfun_scratch_pts < n) {
+        if (h->d_objfun_x) cudaFree(h->d_objfun_x);
+        if (h->d_objfun_f) cudaFree(h->d_objfun_f);
+        h->d_objfun_x = h->d_objfun_f = nullptr; h->objfun_scratch_pts = 0;
+        const int64_t cap = std::max<int64_t>(n, 256);
+        TK_CUDA(cudaMalloc(&h->d_objfun_x, (size_t)cap * h->cfg.nx * sizeof(double)));
+        TK_CUDA(cudaMalloc(&h->d_objfun_f, (size_t)cap * sizeof(double)));
+        h->objfun_scratch_pts = cap;
     }
-    if (!fdev) TK_CUDA(cudaMalloc(&df, fb));
-    rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_objfun(h, xdev ? x : dx, n, fdev ? fval : df)
-                                                  : tk_launch_objfun(h, xdev ? x : dx, n, fdev ? fval : df);
+    double* dx = xdev ? nullptr : h->d_objfun_x;
+    double* df = fdev ? nullptr : h->d_objfun_f;
+    if (!xdev) TK_CUDA(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, h->stream));
+    int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_objfun(h, xdev ? x : dx, n, fdev ? fval : df)
+                                                      : tk_launch_objfun(h, xdev ? x : dx, n, fdev ? fval : df);
     if (!rc && !fdev) {
         cudaError_t e = cudaMemcpyAsync(fval, df, fb, cudaMemcpyDeviceToHost, h->stream);
         if (e != cudaSuccess) { tk_set_error("objfun copy: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess && !rc) { tk_set_error("objfun: %s", cudaGetErrorString(e)); rc = TIKTAK_ERR_CUDA; }
-    if (dx) cudaFree(dx);
-    if (df) cudaFree(df);
     return rc;
 }
 

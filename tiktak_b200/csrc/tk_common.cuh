@@ -121,6 +121,8 @@ struct tiktak_handle {
     int lot_cum_n = 0;
     int n_rows = 0;                   /* result rows known to the handle (k = 0 record included) */
     int* d_accepted = nullptr;        /* restarts ingested by the last multi-round ingest */
+    double *d_objfun_x = nullptr, *d_objfun_f = nullptr; /* staging of tiktak_cuda_objfun for host arguments */
+    int64_t objfun_scratch_pts = 0;
     /* DFNLS */
     double* d_dfnls_slab = nullptr;
     size_t dfnls_slab_doubles = 0;
