@@ -1,19 +1,22 @@
-/* kernels_nm.cu -- batched warm-start Nelder-Mead: one restart per warp.
+/* kernels_nm.cu -- the restart stage on the device: theta-blend, batched warm-start Nelder-Mead, result table.
  *
  * Replaces, per restart k: getBestLine/getModifiedParam (TiktakGlobalSearch.f90:683-720, 781-823: the
- * theta-blend toward the best local minimum so far, which the reference obtains by re-reading and
- * re-sorting searchResults.dat), runAmoeba (:602-633: regular simplex from simplex_coordinates2 scaled
- * by range/K^(1/nx), clamped to the bounds, nx+1 evaluations) and amoeba/amotry (minimize.f90:7-135).
+ * theta-blend toward the best local minimum so far -- or toward a rank-lottery row, getLotteryPoint :722-766 --
+ * which the reference obtains by re-reading and re-sorting searchResults.dat), runAmoeba (:602-633: regular
+ * simplex from simplex_coordinates2 scaled by range/K^(1/nx), clamped to the bounds, nx+1 evaluations),
+ * amoeba/amotry (minimize.f90:7-135) and the bookkeeping of completeSearch (:582-597).
  *
- * Mapping: a warp owns a restart.  The simplex (nx+1 vertices x nx), y, psum live in the warp's slice
- * of shared memory; lanes parallelise the coordinate-wise vector updates, warp shuffles give
- * argmin/argmax (first occurrence, like MINLOC/MAXLOC) and the shrink re-evaluates its nx vertices on
- * nx lanes at once.  The sequential part of amoeba -- reflect, then expand OR contract -- is collapsed
- * into one evaluation phase per iteration by evaluating the four possible trial points (reflection R,
- * expansion from R, contraction after an accepted R, contraction after a rejected R) on four lanes at
- * once; which of them count, and the `iter` bookkeeping, follow minimize.f90:97-114 exactly, so the
- * trajectory is the sequential one.  All arithmetic is unfused, in the reference's order; psum is
- * updated incrementally (minimize.f90:130) and only re-summed after a shrink (:112).
+ * Three Nelder-Mead kernels, same arithmetic and decisions, chosen by nx:
+ *   nm_quad_kernel       nx <= 31   one restart per block of four warps; every warp carries the simplex state
+ *                                   (sorted across lanes) and evaluates one of the four trial points
+ *   nm_quad_wide_kernel  nx <= 127  one master warp keeps the state, all four warps evaluate
+ *   nm_kernel            fallback   one restart per warp, state in the warp's shared memory
+ * The sequential part of amoeba -- reflect, then expand OR contract -- is collapsed into one evaluation phase per
+ * iteration by evaluating the four possible trial points (reflection R, expansion from R, contraction after an
+ * accepted R, contraction after a rejected R) at once; which of them count, and the `iter` bookkeeping, follow
+ * minimize.f90:97-114 exactly, so the trajectory is the sequential one.  All arithmetic is unfused, in the
+ * reference's order; psum is updated incrementally (minimize.f90:130) and only re-summed after a shrink (:112).
+ * ingest_kernel / blend_kernel / shrink_width_kernel / pack_kernel keep searchResults on the device between rounds.
  */
 #include <float.h>
 
