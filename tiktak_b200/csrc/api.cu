@@ -393,9 +393,8 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     TK_CUDA(cudaSetDevice(h->device));
     const bool first_wave = (cb0 == 0);
     if (first_wave) { /* the stage starts here: its device time runs from evp0 to the evp1 of the last wave */
-        TK_CUDA(cudaEventRecord(h->evp0, h->stream));
         std::swap(h->d_counts, h->d_counts_spare); /* a buffer zeroed behind the previous job's kernel: no memset in front */
-        TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+        if (ncb == 0) { TK_CUDA(cudaEventRecord(h->evp0, h->stream)); TK_CUDA(cudaEventRecord(h->evp1, h->stream)); }
         h->pretest_timing_open = true;
         h->cblocks_done = 0; h->kcut = -1; h->pretest_done = false; h->starts_ready = false;
         h->ms_pretest_eval = 0; h->wave_pending = false;
@@ -412,6 +411,7 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
         TK_CUDA(cudaEventSynchronize(h->evw1));
         float ms = 0; cudaEventElapsedTime(&ms, h->evw0, h->evw1); h->ms_pretest_eval += ms; h->wave_pending = false;
     }
+    if (first_wave) TK_CUDA(cudaEventRecord(h->evp0, h->stream)); /* directly in front of the stage's first device operation */
     TK_CUDA(cudaEventRecord(h->evw0, h->stream));
     int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
     TK_CUDA(cudaEventRecord(h->evw1, h->stream));
