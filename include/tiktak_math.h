@@ -67,6 +67,7 @@ TK_HD double tk_u2d(uint64_t u) {
 #define TK_PIO2_3 (-1.4973849048591698e-33) /* 0xb91f1976b7ed8fbc */
 #define TK_2OPI 0.6366197723675814          /* 0x3fe45f306dc9c883 */
 #define TK_RMAGIC 6755399441055744.0        /* 1.5 * 2^52 */
+#define TK_TRIG_DOMAIN 1073741824.0         /* tk_cos/tk_sin are defined for |x| < 2^30 */
 
 /* Shared core: reduce x = k*pi/2 + r, |r| <= pi/4(1+eps), n = k + shift (shift = 1 for cos, 0 for
  * sin: cos(x) = sin(x + pi/2)); then sin(x + shift*pi/2) = (n&1 ? cos(r) : sin(r)), negated when n&2.
@@ -84,18 +85,40 @@ static __constant__ double tk_sc_tab[16] = {
     /* reduction */ TK_2OPI, TK_PIO2_1, TK_PIO2_2, TK_PIO2_3};
 #endif
 
-TK_HD double tk_sincos_core(double x, int shift) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
+/* coefficients by parity of the quadrant, highest degree first (see tk_cos_n) */
+static __constant__ __align__(16) double tk_sel_tab[12] = {
+    /* parity 0 (sin): S6..S1 */ 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    /* parity 1 (cos): C6..C1 */ -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+/* The four constants that meet a second constant inside one FMA (x*2/pi + magic, z*S6 + S5, z*C6 + C5,
+ * z*(-0.5) + 1).  A DFMA takes one constant-bank/uniform operand, so each of these costs two register
+ * moves per call unless the value already sits in registers: a kernel loads them ONCE per thread
+ * (tk_trig_load) and hands them to tk_cos/tk_sin -- 8 issue slots less per call, same operations, same
+ * roundings.  `zero` must be a run-time 0.0 (a kernel argument): constant + zero is a real FP64
+ * instruction, which ptxas keeps in a register instead of re-materialising the constant at every use. */
+struct tk_trig_regs { double twoopi, s6, c6, mhalf; const double2* sel; /* coefficient table of tk_cos_n: tk_sel_tab or a shared-memory copy */ };
+__device__ __forceinline__ tk_trig_regs tk_trig_load(double zero) {
+    tk_trig_regs k;
+    k.twoopi = __dadd_rn(tk_sc_tab[12], zero);
+    k.s6 = __dadd_rn(tk_sc_tab[5], zero);
+    k.c6 = __dadd_rn(tk_sc_tab[11], zero);
+    k.mhalf = __dadd_rn(-0.5, zero);
+    k.sel = reinterpret_cast<const double2*>(tk_sel_tab);
+    return k;
+}
+__device__ __forceinline__ double tk_sincos_core_dev(double x, int shift, double k_twoopi, double k_s6, double k_c6, double k_mhalf) {
     const double* const T = tk_sc_tab;
-    const double t = __fma_rn(x, T[12], TK_RMAGIC);
+    const double t = __fma_rn(x, k_twoopi, TK_RMAGIC);
     const int n = __double2loint(t) + shift;
     const double kd = __dsub_rn(t, TK_RMAGIC);
     double r = __fma_rn(-kd, T[13], x);
     r = __fma_rn(-kd, T[14], r);
     r = __fma_rn(-kd, T[15], r);
     const double z = __dmul_rn(r, r);
-    double ps = __fma_rn(z, T[5], T[4]);
-    double pc = __fma_rn(z, T[11], T[10]);
+    double ps = __fma_rn(z, k_s6, T[4]);
+    double pc = __fma_rn(z, k_c6, T[10]);
     ps = __fma_rn(z, ps, T[3]);
     pc = __fma_rn(z, pc, T[9]);
     ps = __fma_rn(z, ps, T[2]);
@@ -105,11 +128,19 @@ TK_HD double tk_sincos_core(double x, int shift) {
     ps = __fma_rn(z, ps, T[0]);
     pc = __fma_rn(z, pc, T[6]);
     const double vs = __fma_rn(__dmul_rn(z, r), ps, r);
-    const double vc = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, -0.5, 1.0));
-    double v = (n & 1) ? vc : vs;
-    /* negate when n&2: flip the sign bit with integer logic */
-    v = __hiloint2double(__double2hiint(v) ^ ((n & 2) << 30), __double2loint(v));
-    return (fabs(x) < 1073741824.0) ? v : __longlong_as_double(0x7ff8000000000000LL);
+    const double vc = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, k_mhalf, 1.0));
+    const double v = (n & 1) ? vc : vs;
+    /* sign (n&2) and the domain test |x| < 2^30 are folded into the high word with integer logic: the
+     * FP64 pipe is the scarce one.  Outside the domain the result is a NaN (payload unspecified). */
+    const int hx = __double2hiint(x) & 0x7fffffff;
+    const int nanmask = (hx < 0x41d00000) ? 0 : 0x7ff80000;
+    return __hiloint2double((__double2hiint(v) ^ ((n & 2) << 30)) | nanmask, __double2loint(v));
+}
+#endif
+
+TK_HD double tk_sincos_core(double x, int shift) {
+#if defined(__CUDA_ARCH__)
+    return tk_sincos_core_dev(x, shift, tk_sc_tab[12], tk_sc_tab[5], tk_sc_tab[11], -0.5);
 #else
     if (!(fabs(x) < 1073741824.0)) return tk_u2d(0x7ff8000000000000ULL);
     const double t = TK_FMA(x, TK_2OPI, TK_RMAGIC);
@@ -141,6 +172,69 @@ TK_HD double tk_sincos_core(double x, int shift) {
 
 TK_HD double tk_cos(double x) { return tk_sincos_core(x, 1); }
 TK_HD double tk_sin(double x) { return tk_sincos_core(x, 0); }
+#if defined(__CUDACC__)
+/* N independent arguments at once, stage by stage ("breadth first"), and with the branch of the host version:
+ * the parity of n picks ONE coefficient set (S or C, read through k.sel with a per-lane index: three 16-byte
+ * loads when the kernel has copied tk_sel_tab to shared memory) and one polynomial is evaluated -- the operations of the selected branch of tk_sincos_core,
+ * hence the same values, with 14 FP64 instructions per argument instead of 20.  On sm_100a an FP64 instruction
+ * holds the issue port for two cycles, so this is the cheaper form wherever the coefficient loads are not the
+ * bottleneck; the N dependency chains sit side by side in the instruction stream, so a single warp keeps the
+ * pipe fed (~10 registers per element).  CHECK = false leaves out the domain test (|x| < 2^30): for callers
+ * that have verified the domain on the host. */
+template <int N, bool CHECK>
+__device__ __forceinline__ void tk_cos_n(const double (&x)[N], double (&y)[N], const tk_trig_regs& k) {
+    const double* const T = tk_sc_tab;
+    double t[N], r[N], z[N], p[N], h[N];
+    double2 c65[N], c43[N], c21[N];
+    int n[N], par[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = __fma_rn(x[i], k.twoopi, TK_RMAGIC);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        n[i] = __double2loint(t[i]) + 1;
+        par[i] = n[i] & 1;
+        const double2* tab = reinterpret_cast<const double2*>(reinterpret_cast<const char*>(k.sel) + 48 * par[i]);
+        c65[i] = tab[0]; c43[i] = tab[1]; c21[i] = tab[2];
+        t[i] = __dsub_rn(t[i], TK_RMAGIC);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = __fma_rn(-t[i], T[13], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = __fma_rn(-t[i], T[14], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = __fma_rn(-t[i], T[15], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) z[i] = __dmul_rn(r[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = __fma_rn(z[i], c65[i].x, c65[i].y);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = __fma_rn(z[i], p[i], c43[i].x);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = __fma_rn(z[i], p[i], c43[i].y);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = __fma_rn(z[i], p[i], c21[i].x);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = __fma_rn(z[i], p[i], c21[i].y);
+#pragma unroll
+    for (int i = 0; i < N; i++) h[i] = __fma_rn(z[i], k.mhalf, 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const bool odd = par[i] != 0;
+        const double m = odd ? z[i] : r[i]; /* cos: (z*z)*C + (1 - z/2);  sin: (z*r)*S + r */
+        const double a = odd ? h[i] : r[i];
+        const double v = __fma_rn(__dmul_rn(z[i], m), p[i], a);
+        int hi = __double2hiint(v) ^ ((n[i] & 2) << 30);
+        if (CHECK) {
+            const int hx = __double2hiint(x[i]) & 0x7fffffff;
+            hi |= (hx < 0x41d00000) ? 0 : 0x7ff80000;
+        }
+        y[i] = __hiloint2double(hi, __double2loint(v));
+    }
+}
+/* same values, constants from registers (device code that calls them in a loop) */
+__device__ __forceinline__ double tk_cos(double x, const tk_trig_regs& k) { return tk_sincos_core_dev(x, 1, k.twoopi, k.s6, k.c6, k.mhalf); }
+__device__ __forceinline__ double tk_sin(double x, const tk_trig_regs& k) { return tk_sincos_core_dev(x, 0, k.twoopi, k.s6, k.c6, k.mhalf); }
+#endif
 
 /* Round trip of a value through the reference's '200f40.20' text records (sobolFnVal.dat written at
  * TiktakGlobalSearch.f90:451,467 and re-read by chooseSobol :860; searchResults.dat written :594 and

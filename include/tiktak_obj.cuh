@@ -16,6 +16,9 @@
  *     static __device__ void   fold(double& s, double& p, double a, double b);
  *     static __device__ double finish(const tk_obj_ctx&, double s, double p);
  *     static constexpr bool kTermLocal;                  // true when term(.,i,.) reads x[i] only
+ *     template <int G, bool TRUSTED, class X>            // optional: G consecutive terms at once
+ *     static __device__ void   terms(const tk_obj_ctx&, const X& x, int i0, double (&a)[G], double (&b)[G]);
+ *     static bool domain_ok(int nx, const double* lo, const double* hi, const double* aux);   // optional, host
  * Together they are the user part of dfovec (objective.f90:96-117), i.e. the scalar v_err that the
  * shipped template replicates over the nm moments:
  *     fold_init(s,p); for i = 0 .. nterms-1 { term(x,i,a,b); fold(s,p,a,b); }  v_err = finish(s,p)
@@ -31,7 +34,8 @@
  *
  * Arithmetic rules for plugin authors: use TK_MUL/TK_ADD/... or plain operators (the library is
  * compiled with -fmad=false, so nothing is contracted behind your back), call tk_cos/tk_sin from
- * tiktak_math.h instead of cos/sin if you need CPU/GPU trajectories to agree bit for bit, and return
+ * tiktak_math.h instead of cos/sin if you need CPU/GPU trajectories to agree bit for bit (the
+ * two-argument form tk_cos(x, c.trig) is the same function with its constants kept in registers), and return
  * a finite value >= fvalmax where the model is undefined (README.md:34) -- never NaN.
  *
  * Objectives with vector-valued, per-moment residuals (DFNLS, TIKTAK_OBJ_SMM) additionally provide
@@ -54,6 +58,9 @@ struct tk_obj_ctx {
     double fvalmax, penalty0, penaltyc, max_penalty;
     double sqrt_nm;    /* DSQRT(DBLE(nm)), objective.f90:94 */
     const void* user;
+#ifdef __CUDACC__
+    tk_trig_regs trig; /* register-resident constants of tk_cos/tk_sin: call tk_cos(x, c.trig) */
+#endif
 };
 
 #define TK_MYEPS 2.220446049250313e-16 /* EPSILON(1.0_DP), objective.f90:24 */
@@ -100,6 +107,29 @@ __device__ __forceinline__ double tk_value_seq(const tk_obj_ctx& c, const X& x) 
         double a, b;
         Obj::term(c, x, i, a, b);
         Obj::fold(s, p, a, b);
+    }
+    return Obj::finish(c, s, p);
+}
+
+/* The same value with the terms taken G at a time through the plugin's optional batched form
+ *     template <int G, bool TRUSTED, class X> static __device__ void terms(ctx, x, i0, double (&a)[G], double (&b)[G]);
+ * (terms i0 .. i0+G-1, each computed by the operations of `term`); the fold stays in index order, so
+ * nothing is rounded differently.  NT = nterms, known at compile time; G must divide NT.  TRUSTED: the caller
+ * has checked on the host, through the plugin's optional
+ *     static bool domain_ok(int nx, const double* lo, const double* hi, const double* aux);
+ * that every tk_cos/tk_sin argument stays inside the functions' domain for all x in the box [lo, hi], so the
+ * per-call domain test may be left out (tk_cos_n<N, false>). */
+template <class Obj, int NT, int G, bool TRUSTED, class X>
+__device__ __forceinline__ double tk_value_grouped(const tk_obj_ctx& c, const X& x) {
+    static_assert(NT % G == 0, "group size must divide the number of terms");
+    double s, p;
+    Obj::fold_init(c, s, p);
+#pragma unroll
+    for (int i0 = 0; i0 < NT; i0 += G) {
+        double a[G], b[G];
+        Obj::template terms<G, TRUSTED>(c, x, i0, a, b);
+#pragma unroll
+        for (int g = 0; g < G; g++) Obj::fold(s, p, a[g], b[g]);
     }
     return Obj::finish(c, s, p);
 }

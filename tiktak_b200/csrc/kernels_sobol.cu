@@ -19,6 +19,28 @@
 
 #include "tk_common.cuh"
 
+#ifndef TK_SOBOL_MB
+#define TK_SOBOL_MB 6 /* resident blocks per SM the grouped kernels are compiled for (register budget 65536 / (MB * 128)) */
+#endif
+#ifndef TK_SOBOL_G
+#define TK_SOBOL_G 5 /* terms per group of the breadth-first evaluation */
+#endif
+
+#ifdef TK_SOBOL_TRACE /* experiment build: cycle stamps of block 0 / thread 0 (tools/sobol_trace.py) */
+__device__ unsigned long long tk_trace_buf[32];
+__device__ __forceinline__ unsigned long long tk_gtime() { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); return g; }
+#define TK_TRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { tk_trace_buf[2 * (i)] = clock64(); tk_trace_buf[2 * (i) + 1] = tk_gtime(); } } while (0)
+__device__ unsigned long long tk_blk_trace[3 * 8192]; /* per block: globaltimer at entry, at exit, SM id */
+#define TK_BLK_IN() do { if (threadIdx.x == 0 && blockIdx.x < 8192) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tk_blk_trace[3 * blockIdx.x] = tk_gtime(); tk_blk_trace[3 * blockIdx.x + 2] = sm; } } while (0)
+#define TK_BLK_OUT() do { if (threadIdx.x == 0 && blockIdx.x < 8192) tk_blk_trace[3 * blockIdx.x + 1] = tk_gtime(); } while (0)
+extern "C" int tiktak_cuda_debug_trace(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, tk_trace_buf, sizeof(tk_trace_buf)); }
+extern "C" int tiktak_cuda_debug_blocks(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, tk_blk_trace, sizeof(tk_blk_trace)); }
+#else
+#define TK_TRACE(i) do { } while (0)
+#define TK_BLK_IN() do { } while (0)
+#define TK_BLK_OUT() do { } while (0)
+#endif
+
 namespace {
 
 template <int NX>
@@ -32,74 +54,124 @@ __device__ __forceinline__ uint32_t tk_gray_point_coord(const uint32_t* Vd, uint
 /* INB: the host has verified that the whole Sobol box lies inside the bounds (lo >= bl and fl(lo + w) <= bu; every
  * point is <= fl(lo + w) because q < 1 and rounding is monotonic), so getPenalty is identically 0 and the per-point
  * bounds test (2 DSETP per coordinate on the FP64 pipe) is compiled out -- same values. */
-template <class Obj, int NX, int BT, int P, bool INB>
-__global__ void __launch_bounds__(BT)
+template <class Obj, int NX, int BT, int P, bool INB, int G>
+__global__ void __launch_bounds__(BT, G > 0 ? TK_SOBOL_MB : 0)
 sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, const TkWave wv) {
-    constexpr int S = (BT == 64) ? 6 : (BT == 128) ? 7 : 8;
-    static_assert((1 << S) == BT, "block size must be 64, 128 or 256");
+    constexpr int S = TK_SOBOL_S;
+    static_assert((1 << S) == BT, "the step table is built for blocks of 2^TK_SOBOL_S threads");
     constexpr int CH = BT * P;
     constexpr int CPB = TIKTAK_SOBOL_BLOCK / CH;
     static_assert(CPB * CH == TIKTAK_SOBOL_BLOCK, "chunk must divide the count block");
+    constexpr int NXP = TK_SOBOL_NXP(NX);
+    /* Direction numbers, bit-major: sV[j][d] = V[d][j]; sD[c][d] = what the step n -> n + BT does to the state of
+     * coordinate d when it flips Gray bits S-1 and S+c.  They are copied from global memory by the whole block
+     * (independent coalesced loads: one memory latency) instead of being read as constant-bank operands: a
+     * constant operand that misses stalls the warp, the misses of a fresh SM come one after the other, and the
+     * table spans 2 NX lines -- 5 us of a 34 us launch at C2, 14 us at C4 (tools/sobol_fixed_cost.py). */
+    __shared__ __align__(16) uint32_t sV[TK_MAXBIT * NXP];
+    __shared__ __align__(16) uint32_t sD[TK_MAXBIT * NXP];
     __shared__ uint32_t qhi[NX];
     __shared__ unsigned int blk_cnt;
+    __shared__ double strig[4][32]; /* one copy per lane of the tk_cos register constants (see below) */
+    __shared__ __align__(16) double ssel[12]; /* tk_sel_tab: per-lane coefficient reads become LDS.128 */
 
-    const int64_t lcb = blockIdx.x / CPB;
-    const int64_t cbf = wv.cb0 + (((int64_t)wv.rank - wv.cb0 % wv.world) + wv.world) % wv.world;
-    const int64_t cb = cbf + lcb * wv.world;
+    TK_TRACE(0);
+    TK_BLK_IN();
+    /* count block of this CUDA block: the wave's first owned count block (wv.cbf, found by the launcher: no
+     * 64-bit division in the kernel) + world * (blocks of CPB chunks in front of it) */
+    const int lcb = (int)(blockIdx.x / CPB);
+    const int64_t cb = wv.cbf + (int64_t)lcb * wv.world;
     if (cb >= wv.cb0 + wv.ncb) return;
-    const int64_t base = cb * TIKTAK_SOBOL_BLOCK + (int64_t)(blockIdx.x % CPB) * CH;
+    const int coff = (int)(blockIdx.x % CPB) * CH; /* offset of the chunk inside its count block */
+    const int64_t base = cb * TIKTAK_SOBOL_BLOCK + coff;
     if (base > wv.N) return;
     const int t = threadIdx.x;
     const uint32_t h0 = (uint32_t)(base >> S);
+    const int nrow = T.nbits;
+    TK_TRACE(1); /* Gray bits in use: rows 0 .. nbits-1 */
+    {
+        const uint4* gV = reinterpret_cast<const uint4*>(T.tab);
+        const uint4* gD = reinterpret_cast<const uint4*>(T.tab + TK_MAXBIT * NXP);
+        uint4* s4V = reinterpret_cast<uint4*>(sV);
+        uint4* s4D = reinterpret_cast<uint4*>(sD);
+        for (int i = t; i < nrow * (NXP / 4); i += BT) { s4V[i] = __ldg(gV + i); s4D[i] = __ldg(gD + i); }
+    }
+    if (t == 0) blk_cnt = 0;
+    if (t >= 32 && t < 44) ssel[t - 32] = tk_sel_tab[t - 32];
+    if (t < 32) { const tk_trig_regs k = tk_trig_load(sc.zero); strig[0][t] = k.twoopi; strig[1][t] = k.s6; strig[2][t] = k.c6; strig[3][t] = k.mhalf; }
+    __syncthreads();
+    TK_TRACE(2);
 
     /* block-uniform part of the seed: Gray bits >= S come from h0 only */
     const uint32_t ghi = h0 ^ (h0 >> 1);
-    if (t == 0) blk_cnt = 0;
     for (int d = t; d < NX; d += BT) {
         uint32_t q = 0;
-        for (int j = 0; j + S < 32; j++)
-            if ((ghi >> j) & 1u) q ^= T.V[d][j + S];
+        for (int j = 0; j + S < nrow; j++)
+            if ((ghi >> j) & 1u) q ^= sV[(j + S) * NXP + d];
         qhi[d] = q;
     }
     __syncthreads();
+    TK_TRACE(3);
     /* thread part: Gray bits < S of n0 = base + t (bit S-1 mixes in the lowest bit of h0) */
     const uint32_t n0 = (uint32_t)base + (uint32_t)t;
     const uint32_t glo = (n0 ^ (n0 >> 1)) & (uint32_t)(BT - 1);
-    uint32_t q[NX];
+    uint32_t q[NXP]; /* state of coordinate d: the 32-bit numerator of the point (padding entries stay unused) */
 #pragma unroll
     for (int d = 0; d < NX; d++) {
         uint32_t v = qhi[d];
 #pragma unroll
         for (int j = 0; j < S; j++)
-            if ((glo >> j) & 1u) v ^= T.V[d][j];
+            if ((glo >> j) & 1u) v ^= sV[j * NXP + d];
         q[d] = v;
     }
+#pragma unroll
+    for (int d = NX; d < NXP; d++) q[d] = 0;
 
-    const tk_obj_ctx ctx = tk_make_ctx(sc, NX, T.bl, T.bu, T.aux);
-    const int64_t lbase = tk_local_index(base, wv.world);
+    TK_TRACE(4);
+    tk_obj_ctx ctx = tk_make_ctx(sc, NX, T.bl, T.bu, T.aux);
+    { /* the register-resident constants of tk_cos come from a per-lane shared-memory copy: a value loaded from a
+       * lane-dependent address is neither re-materialised inside the loop nor moved to the uniform registers
+       * (which a DFMA that also carries an immediate cannot read) */
+        const int l = t & 31;
+        ctx.trig.twoopi = strig[0][l]; ctx.trig.s6 = strig[1][l]; ctx.trig.c6 = strig[2][l]; ctx.trig.mhalf = strig[3][l];
+        ctx.trig.sel = reinterpret_cast<const double2*>(ssel);
+    }
+    const int64_t lbase = (wv.cbf_q + lcb) * TIKTAK_SOBOL_BLOCK + coff; /* = tk_local_index(base, world) */
     unsigned int cnt = 0;
 #pragma unroll 1
     for (int j = 0; j < P; j++) {
         const int64_t n = base + (int64_t)j * BT + t;
         TkRegX<NX> x;
 #pragma unroll
-        for (int d = 0; d < NX; d++) x.v[d] = __dadd_rn(T.lo[d], __dmul_rn(tk_q2unit(q[d]), T.w[d]));
-        const double f = INB ? tk_objfun_finish(ctx, tk_value_seq<Obj>(ctx, x), 0.0) : tk_objfun<Obj>(ctx, x);
+        for (int d = 0; d < NX; d++) {
+            const double u = tk_q2unit(q[d]);
+            x.v[d] = __dadd_rn(T.lo[d], __dmul_rn(u, T.w[d]));
+        }
+        double f;
+        if constexpr (INB && G > 0) f = tk_objfun_finish(ctx, tk_value_grouped<Obj, Obj::nterms(NX), G, true>(ctx, x), 0.0);
+        else f = INB ? tk_objfun_finish(ctx, tk_value_seq<Obj>(ctx, x), 0.0) : tk_objfun<Obj>(ctx, x);
         if (n >= 1 && n <= wv.N) {
             wv.fval[lbase + (int64_t)j * BT + t] = f;
             cnt += (f < sc.fvalmax) ? 1u : 0u;
         }
-        /* advance to n + BT */
+        TK_TRACE(5 + (j < 3 ? j : 3));
+        /* advance to n + BT: Gray bits S-1 and S+c flip (one row of sD, broadcast reads) */
         const uint32_t h = h0 + (uint32_t)j;
         const int c = __ffs((int)~h) - 1;
+        const uint4* row = reinterpret_cast<const uint4*>(sD + c * NXP);
 #pragma unroll
-        for (int d = 0; d < NX; d++) q[d] ^= T.V[d][S - 1] ^ T.V[d][S + c];
+        for (int g = 0; g < NXP / 4; g++) {
+            const uint4 w = row[g];
+            q[4 * g] ^= w.x; q[4 * g + 1] ^= w.y; q[4 * g + 2] ^= w.z; q[4 * g + 3] ^= w.w;
+        }
     }
     /* valid count of this chunk -> its count block */
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((t & 31) == 0 && cnt) atomicAdd(&blk_cnt, cnt);
     __syncthreads();
     if (t == 0 && blk_cnt) atomicAdd(&wv.counts[cb], (unsigned long long)blk_cnt);
+    TK_TRACE(9);
+    TK_BLK_OUT();
 }
 
 /* runtime-nx fallback of the same kernel (nx <= TK_NX_GENERIC_MAX): tables in global memory,
@@ -203,27 +275,65 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
     TkTables<NX> T;
     memset(&T, 0, sizeof T);
     for (int d = 0; d < NX; d++) {
-        for (int j = 0; j < 32; j++) T.V[d][j] = h->V[(size_t)d * 32 + j];
         T.lo[d] = h->range[d];
         T.w[d] = h->range[NX + d] - h->range[d];
         T.bl[d] = h->bound[d];
         T.bu[d] = h->bound[NX + d];
         T.aux[d] = h->aux[d];
     }
+    constexpr int NXP = TK_SOBOL_NXP(NX);
+    if (!h->d_sobtab) { /* bit-major direction numbers + step table, once per handle */
+        std::vector<uint32_t> tab((size_t)2 * TK_MAXBIT * NXP, 0u);
+        for (int d = 0; d < NX; d++) {
+            const uint32_t* Vd = h->V.data() + (size_t)d * 32;
+            for (int j = 0; j < TK_MAXBIT; j++) tab[(size_t)j * NXP + d] = Vd[j];
+            for (int c = 0; c + TK_SOBOL_S < TK_MAXBIT; c++) {
+                tab[(size_t)(TK_MAXBIT + c) * NXP + d] = Vd[TK_SOBOL_S - 1] ^ Vd[TK_SOBOL_S + c];
+            }
+        }
+        TK_CUDA(cudaMalloc(&h->d_sobtab, tab.size() * sizeof(uint32_t)));
+        TK_CUDA(cudaMemcpyAsync(h->d_sobtab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream)); /* tab is a local */
+    }
+    T.tab = h->d_sobtab;
+    { /* rows in use: bit length of the largest index a block may touch (qr_ndraw rounded up to a chunk) */
+        const uint64_t top = (uint64_t)h->cfg.qr_ndraw + TIKTAK_SOBOL_BLOCK;
+        int nb = 0;
+        while ((top >> nb) != 0) nb++;
+        T.nbits = std::min(nb + 1, TK_MAXBIT);
+    }
     /* points per thread P: the smallest P whose grid is resident in ONE wave (no tail wave, seeding
      * amortised as little as necessary); a job too big for that takes the longest stride. */
-    bool inb = true; /* Sobol box inside the bounds? */
+    bool inb = true; /* Sobol box inside the bounds (and inside the plugin's declared domain)? */
     for (int d = 0; d < NX; d++) inb = inb && (T.lo[d] >= T.bl[d]) && (T.lo[d] + T.w[d] <= T.bu[d]);
+    if constexpr (requires(const double* p) { Obj::domain_ok(NX, p, p, p); }) {
+        double hi[NX];
+        for (int d = 0; d < NX; d++) hi[d] = T.lo[d] + T.w[d];
+        inb = inb && Obj::domain_ok(NX, T.lo, hi, T.aux);
+    }
+    TkWave wvk = wv; /* with the owned-block origin filled in */
+    wvk.cbf = wv.cb0 + (((int64_t)wv.rank - wv.cb0 % wv.world) + wv.world) % wv.world;
+    wvk.cbf_q = wvk.cbf / wv.world;
     auto try_launch = [&]<int BT, int P>(bool force) -> int {
+        static_assert(BT == (1 << TK_SOBOL_S), "the step table is built for blocks of 2^TK_SOBOL_S threads");
         const int64_t grid = owned_cbs * (TIKTAK_SOBOL_BLOCK / (BT * P));
-        static int per_sm[2] = {0, 0}; /* per instantiation: the occupancy query is host work in front of every launch */
-        if (per_sm[inb] == 0) {
-            if (inb) TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sobol_eval_kernel<Obj, NX, BT, P, true>, BT, 0));
-            else TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sobol_eval_kernel<Obj, NX, BT, P, false>, BT, 0));
-        }
-        if (!force && grid > (int64_t)per_sm[inb] * h->sm_count) return 1;
-        if (inb) sobol_eval_kernel<Obj, NX, BT, P, true><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
-        else sobol_eval_kernel<Obj, NX, BT, P, false><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wv);
+        auto go = [&]<bool INB, int G>() -> int {
+            static int per_sm = 0; /* per instantiation: the occupancy query is host work in front of every launch */
+            if (per_sm == 0) TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sobol_eval_kernel<Obj, NX, BT, P, INB, G>, BT, 0));
+            if (!force && grid > (int64_t)per_sm * h->sm_count) return 1;
+            sobol_eval_kernel<Obj, NX, BT, P, INB, G><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wvk);
+            return TIKTAK_OK;
+        };
+        /* terms per group of the breadth-first evaluation (0: one term after the other) */
+        constexpr bool kHasTerms = requires(const tk_obj_ctx& c, const TkRegX<NX>& x, double (&a)[1], double (&b)[1]) { Obj::template terms<1, true>(c, x, 0, a, b); };
+        constexpr int NT = Obj::nterms(NX);
+        constexpr int GA = !kHasTerms ? 0 : (NT % TK_SOBOL_G == 0 ? TK_SOBOL_G : (NT % 5 == 0 ? 5 : (NT % 4 == 0 ? 4 : 0)));
+        static const int gsel = getenv("TIKTAK_SOBOL_GROUP") ? atoi(getenv("TIKTAK_SOBOL_GROUP")) : 1;
+        int rc;
+        if (!inb) rc = go.template operator()<false, 0>();
+        else if (gsel == 0 || GA == 0) rc = go.template operator()<true, 0>();
+        else rc = go.template operator()<true, GA>();
+        if (rc != TIKTAK_OK) return rc;
         h->launches++;
         TK_CUDA(cudaGetLastError());
         return TIKTAK_OK;
@@ -233,6 +343,7 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
     if (shape) {
         int bt = 0, pp = 0;
         if (sscanf(shape, "%dx%d", &bt, &pp) == 2) {
+            if (bt == 128 && pp == 2) return try_launch.template operator()<128, 2>(true);
             if (bt == 128 && pp == 4) return try_launch.template operator()<128, 4>(true);
             if (bt == 128 && pp == 8) return try_launch.template operator()<128, 8>(true);
             if (bt == 128 && pp == 16) return try_launch.template operator()<128, 16>(true);

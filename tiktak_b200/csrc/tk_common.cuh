@@ -11,6 +11,7 @@
 
 #define TK_MAXBIT 30          /* utilities.f90:54: atmost < 2^30 */
 #define TK_NX_GENERIC_MAX 128 /* largest nx of the runtime-nx fallback kernels */
+#define TK_SOBOL_S 7          /* log2 of the Sobol kernel's block size (128 threads) */
 
 void tk_set_error(const char* fmt, ...);
 #define TK_CUDA(call)                                                                         \
@@ -25,13 +26,16 @@ void tk_set_error(const char* fmt, ...);
 /* tables that ride along as __grid_constant__ kernel parameters (constant bank, broadcast reads) */
 template <int NX>
 struct TkTables {
-    uint32_t V[NX][32]; /* V[d][j]: direction number of Gray-code bit j, scaled so that q = lastq * 2^-32 */
     double lo[NX], w[NX], bl[NX], bu[NX], aux[NX];
+    const uint32_t* tab; /* device memory: Vt[TK_MAXBIT][NXP] bit-major direction numbers, then Dt[TK_MAXBIT][NXP] step table */
+    int nbits;           /* Gray bits in use (rows of the tables a block copies) */
 };
+#define TK_SOBOL_NXP(nx) (((nx) + 3) & ~3) /* row length of the tables, padded to 16 bytes */
 struct TkScalars {
     int nx, nm;
     double fvalmax, penalty0, penaltyc, max_penalty, sqrt_nm;
     const void* user;
+    double zero; /* 0.0 at run time (see tk_trig_load) */
 };
 
 /* pointers to the same tables in global memory, for the runtime-nx kernels */
@@ -49,6 +53,7 @@ struct TkWave {
     double* fval;         /* local store, indexed by local n (see tk_local_index) */
     unsigned long long* counts; /* per GLOBAL count block */
     int64_t n_lo = 1, n_hi = -1; /* optional sub-range of indices (expensive objectives: finer early-stop grain); n_hi < 0: all */
+    int64_t cbf = 0, cbf_q = 0;  /* filled by the launcher: first count block of the wave owned by this rank, and cbf / world */
 };
 
 __host__ __device__ inline int64_t tk_local_index(int64_t n, int world) {
@@ -72,6 +77,7 @@ struct tiktak_handle {
     TkScalars sc;
     /* device copies */
     uint32_t* d_V = nullptr;
+    uint32_t* d_sobtab = nullptr; /* bit-major tables of the fixed-nx Sobol kernel (kernels_sobol.cu) */
     double *d_lo = nullptr, *d_w = nullptr, *d_bl = nullptr, *d_bu = nullptr, *d_aux = nullptr, *d_init = nullptr;
     double *d_simplex = nullptr, *d_w11 = nullptr;
     /* pre-test state */
@@ -186,6 +192,7 @@ __device__ __forceinline__ tk_obj_ctx tk_make_ctx(const TkScalars& s, int nx, co
     c.nx = nx; c.nm = s.nm; c.bl = bl; c.bu = bu; c.aux = aux;
     c.fvalmax = s.fvalmax; c.penalty0 = s.penalty0; c.penaltyc = s.penaltyc; c.max_penalty = s.max_penalty;
     c.sqrt_nm = s.sqrt_nm; c.user = s.user;
+    c.trig = tk_trig_load(__dmul_rn(s.zero, (double)threadIdx.x)); /* 0.0, and not provably the same in every lane: stays in vector registers */
     return c;
 }
 /* 32-bit Sobol numerator -> double in [0,1), exact: build 1.q in [1,2) and subtract 1 */

@@ -10,7 +10,7 @@ import os
 from ._abi import TiktakConfig, c_double_p, c_int32_p, c_int64_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtiktak_cuda.so")
+LIB_PATH = os.environ.get("TIKTAK_CUDA_LIB") or os.path.join(_HERE, "libtiktak_cuda.so")  # override: experiment builds
 
 #: name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
