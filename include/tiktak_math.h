@@ -93,20 +93,16 @@ static __constant__ __align__(16) double tk_sel_tab[12] = {
     /* parity 1 (cos): C6..C1 */ -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
     2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 /* The four constants that meet a second constant inside one FMA (x*2/pi + magic, z*S6 + S5, z*C6 + C5,
- * z*(-0.5) + 1).  A DFMA takes one constant-bank/uniform operand, so each of these costs two register
- * moves per call unless the value already sits in registers: a kernel loads them ONCE per thread
- * (tk_trig_load) and hands them to tk_cos/tk_sin -- 8 issue slots less per call, same operations, same
- * roundings.  `zero` must be a run-time 0.0 (a kernel argument): constant + zero is a real FP64
- * instruction, which ptxas keeps in a register instead of re-materialising the constant at every use. */
+ * z*(-0.5) + 1), and the coefficient table of tk_cos_n.  A DFMA takes one constant-bank/uniform operand, so
+ * each of these costs two register moves per call unless the value already sits in a register.  tk_trig_plain()
+ * returns them as plain constants (ptxas re-materialises them at every use: right for latency-bound code such
+ * as the Nelder-Mead kernels, where holding them in registers measured 7 % slower).  A throughput kernel with a
+ * hot loop over tk_cos replaces them by values it has LOADED (per lane, from a shared-memory copy): a loaded
+ * value is neither re-materialised nor moved to the uniform registers, which saves 8 issue slots per call --
+ * same operations, same roundings (kernels_sobol.cu). */
 struct tk_trig_regs { double twoopi, s6, c6, mhalf; const double2* sel; /* coefficient table of tk_cos_n: tk_sel_tab or a shared-memory copy */ };
-__device__ __forceinline__ tk_trig_regs tk_trig_load(double zero) {
-    tk_trig_regs k;
-    k.twoopi = __dadd_rn(tk_sc_tab[12], zero);
-    k.s6 = __dadd_rn(tk_sc_tab[5], zero);
-    k.c6 = __dadd_rn(tk_sc_tab[11], zero);
-    k.mhalf = __dadd_rn(-0.5, zero);
-    k.sel = reinterpret_cast<const double2*>(tk_sel_tab);
-    return k;
+__device__ __forceinline__ tk_trig_regs tk_trig_plain() {
+    return tk_trig_regs{tk_sc_tab[12], tk_sc_tab[5], tk_sc_tab[11], -0.5, reinterpret_cast<const double2*>(tk_sel_tab)};
 }
 __device__ __forceinline__ double tk_sincos_core_dev(double x, int shift, double k_twoopi, double k_s6, double k_c6, double k_mhalf) {
     const double* const T = tk_sc_tab;

@@ -188,7 +188,6 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     h->sc.max_penalty = 1000.0 * h->sc.penalty0;
     h->sc.sqrt_nm = sqrt((double)cfg->nm);
     h->sc.user = nullptr;
-    h->sc.zero = 0.0;
     h->aux.assign(nx, 0.0);
     int rc = TIKTAK_OK;
     if (cfg->objective_id != TIKTAK_OBJ_SMM)
@@ -298,15 +297,15 @@ int tiktak_cuda_stage_ms(tiktak_handle* h, const char* stage, double* ms) {
     if (!h || !stage || !ms) return TIKTAK_ERR_ARG;
     if (!strcmp(stage, "pretest")) {
         if (h->pretest_timing_open) {
-            TK_CUDA(cudaEventSynchronize(h->evp1));
-            float w = 0; cudaEventElapsedTime(&w, h->evp0, h->evp1); h->ms_pretest = w; h->pretest_timing_open = false;
+            TK_CUDA(cudaEventSynchronize(h->ev_stage_end));
+            float w = 0; cudaEventElapsedTime(&w, h->evp0, h->ev_stage_end); h->ms_pretest = w; h->pretest_timing_open = false;
         }
         *ms = h->ms_pretest;
     }
     else if (!strcmp(stage, "pretest_eval")) {
         if (h->wave_pending) {
             TK_CUDA(cudaEventSynchronize(h->evw1));
-            float w = 0; cudaEventElapsedTime(&w, h->evw0, h->evw1); h->ms_pretest_eval += w; h->wave_pending = false;
+            float w = 0; cudaEventElapsedTime(&w, h->ev_wave_start, h->evw1); h->ms_pretest_eval += w; h->wave_pending = false;
         }
         *ms = h->ms_pretest_eval;
     }
@@ -395,7 +394,7 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     const bool first_wave = (cb0 == 0);
     if (first_wave) { /* the stage starts here: its device time runs from evp0 to the evp1 of the last wave */
         std::swap(h->d_counts, h->d_counts_spare); /* a buffer zeroed behind the previous job's kernel: no memset in front */
-        if (ncb == 0) { TK_CUDA(cudaEventRecord(h->evp0, h->stream)); TK_CUDA(cudaEventRecord(h->evp1, h->stream)); }
+        if (ncb == 0) { TK_CUDA(cudaEventRecord(h->evp0, h->stream)); TK_CUDA(cudaEventRecord(h->evp1, h->stream)); h->ev_stage_end = h->evp1; }
         h->pretest_timing_open = true;
         h->cblocks_done = 0; h->kcut = -1; h->pretest_done = false; h->starts_ready = false;
         h->ms_pretest_eval = 0; h->wave_pending = false;
@@ -410,13 +409,16 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
     if (!h->evw0) { TK_CUDA(cudaEventCreate(&h->evw0)); TK_CUDA(cudaEventCreate(&h->evw1)); }
     if (h->wave_pending) { /* fold the previous wave's duration in before the events are reused */
         TK_CUDA(cudaEventSynchronize(h->evw1));
-        float ms = 0; cudaEventElapsedTime(&ms, h->evw0, h->evw1); h->ms_pretest_eval += ms; h->wave_pending = false;
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev_wave_start, h->evw1); h->ms_pretest_eval += ms; h->wave_pending = false;
     }
-    if (first_wave) TK_CUDA(cudaEventRecord(h->evp0, h->stream)); /* directly in front of the stage's first device operation */
-    TK_CUDA(cudaEventRecord(h->evw0, h->stream));
+    /* one event in front of the wave and one behind it: the first wave's start event is the stage's start event and the
+     * last wave's end event is the stage's end event (an event record costs ~1.3 us of stream time on this GPU, so a
+     * second pair around the same kernel would add 2.6 us to a 33 us stage) */
+    h->ev_wave_start = first_wave ? h->evp0 : h->evw0;
+    TK_CUDA(cudaEventRecord(h->ev_wave_start, h->stream));
     int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
     TK_CUDA(cudaEventRecord(h->evw1, h->stream));
-    TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+    h->ev_stage_end = h->evw1;
     if (first_wave) /* clear the other counts buffer for the next job, behind this wave */
         TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
     h->wave_pending = true;
@@ -464,6 +466,7 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
     int rc = TIKTAK_OK;
     auto end_stage = [&]() -> int { /* the find_cut / count reads after the last wave belong to the stage */
         TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+        h->ev_stage_end = h->evp1;
         h->pretest_timing_open = true;
         return TIKTAK_OK;
     };

@@ -72,7 +72,7 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
     __shared__ __align__(16) uint32_t sD[TK_MAXBIT * NXP];
     __shared__ uint32_t qhi[NX];
     __shared__ unsigned int blk_cnt;
-    __shared__ double strig[4][32]; /* one copy per lane of the tk_cos register constants (see below) */
+    __shared__ double strig[5][32]; /* one copy per lane of the register constants: tk_cos's four and 2^-32 (see below) */
     __shared__ __align__(16) double ssel[12]; /* tk_sel_tab: per-lane coefficient reads become LDS.128 */
 
     TK_TRACE(0);
@@ -87,8 +87,15 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
     if (base > wv.N) return;
     const int t = threadIdx.x;
     const uint32_t h0 = (uint32_t)(base >> S);
-    const int nrow = T.nbits;
-    TK_TRACE(1); /* Gray bits in use: rows 0 .. nbits-1 */
+    const int nrow = T.nbits; /* Gray bits in use: rows 0 .. nbits-1 */
+    TK_TRACE(1);
+    static_assert(P >= 2, "the thread part of the seed assumes chunks of at least 2 BT points");
+    uint4 low[NXP / 4]; /* row t of the thread-part table: issued first, needed last */
+    {
+        const uint4* gL = reinterpret_cast<const uint4*>(T.tab + 2 * TK_MAXBIT * NXP) + t * (NXP / 4);
+#pragma unroll
+        for (int g = 0; g < NXP / 4; g++) low[g] = __ldg(gL + g);
+    }
     {
         const uint4* gV = reinterpret_cast<const uint4*>(T.tab);
         const uint4* gD = reinterpret_cast<const uint4*>(T.tab + TK_MAXBIT * NXP);
@@ -98,7 +105,7 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
     }
     if (t == 0) blk_cnt = 0;
     if (t >= 32 && t < 44) ssel[t - 32] = tk_sel_tab[t - 32];
-    if (t < 32) { const tk_trig_regs k = tk_trig_load(sc.zero); strig[0][t] = k.twoopi; strig[1][t] = k.s6; strig[2][t] = k.c6; strig[3][t] = k.mhalf; }
+    if (t < 32) { const tk_trig_regs k = tk_trig_plain(); strig[0][t] = k.twoopi; strig[1][t] = k.s6; strig[2][t] = k.c6; strig[3][t] = k.mhalf; strig[4][t] = 0x1p-32; }
     __syncthreads();
     TK_TRACE(2);
 
@@ -112,20 +119,15 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
     }
     __syncthreads();
     TK_TRACE(3);
-    /* thread part: Gray bits < S of n0 = base + t (bit S-1 mixes in the lowest bit of h0) */
-    const uint32_t n0 = (uint32_t)base + (uint32_t)t;
-    const uint32_t glo = (n0 ^ (n0 >> 1)) & (uint32_t)(BT - 1);
+    /* thread part: Gray bits < S of n0 = base + t.  base is a multiple of 2 BT (P >= 2), so they are the Gray code of
+     * t alone, the same in every block: row t of a table the host built once, read at the top of the kernel */
     uint32_t q[NXP]; /* state of coordinate d: the 32-bit numerator of the point (padding entries stay unused) */
 #pragma unroll
-    for (int d = 0; d < NX; d++) {
-        uint32_t v = qhi[d];
-#pragma unroll
-        for (int j = 0; j < S; j++)
-            if ((glo >> j) & 1u) v ^= sV[j * NXP + d];
-        q[d] = v;
+    for (int g = 0; g < NXP / 4; g++) {
+        q[4 * g] = low[g].x; q[4 * g + 1] = low[g].y; q[4 * g + 2] = low[g].z; q[4 * g + 3] = low[g].w;
     }
 #pragma unroll
-    for (int d = NX; d < NXP; d++) q[d] = 0;
+    for (int d = 0; d < NX; d++) q[d] ^= qhi[d];
 
     TK_TRACE(4);
     tk_obj_ctx ctx = tk_make_ctx(sc, NX, T.bl, T.bu, T.aux);
@@ -136,6 +138,7 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
         ctx.trig.twoopi = strig[0][l]; ctx.trig.s6 = strig[1][l]; ctx.trig.c6 = strig[2][l]; ctx.trig.mhalf = strig[3][l];
         ctx.trig.sel = reinterpret_cast<const double2*>(ssel);
     }
+    const double k2m32 = strig[4][t & 31]; /* 2^-32 in a register: the FMA below also reads lo[d] from the constant bank */
     const int64_t lbase = (wv.cbf_q + lcb) * TIKTAK_SOBOL_BLOCK + coff; /* = tk_local_index(base, world) */
     unsigned int cnt = 0;
 #pragma unroll 1
@@ -144,8 +147,10 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
         TkRegX<NX> x;
 #pragma unroll
         for (int d = 0; d < NX; d++) {
-            const double u = tk_q2unit(q[d]);
-            x.v[d] = __dadd_rn(T.lo[d], __dmul_rn(u, T.w[d]));
+            /* lo + u*w with u = q * 2^-32 (:834, unfused): the power of two commutes with the rounding of the
+             * product, fl(u*w) = fl(q*w) * 2^-32 exactly, so an integer conversion, a product and an FMA whose
+             * product is exact give the reference's two roundings with one FP64 instruction less */
+            x.v[d] = __fma_rn(__dmul_rn((double)q[d], T.w[d]), k2m32, T.lo[d]);
         }
         double f;
         if constexpr (INB && G > 0) f = tk_objfun_finish(ctx, tk_value_grouped<Obj, Obj::nterms(NX), G, true>(ctx, x), 0.0);
@@ -283,12 +288,21 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
     }
     constexpr int NXP = TK_SOBOL_NXP(NX);
     if (!h->d_sobtab) { /* bit-major direction numbers + step table, once per handle */
-        std::vector<uint32_t> tab((size_t)2 * TK_MAXBIT * NXP, 0u);
+        std::vector<uint32_t> tab((size_t)(2 * TK_MAXBIT + (1 << TK_SOBOL_S)) * NXP, 0u);
         for (int d = 0; d < NX; d++) {
             const uint32_t* Vd = h->V.data() + (size_t)d * 32;
             for (int j = 0; j < TK_MAXBIT; j++) tab[(size_t)j * NXP + d] = Vd[j];
             for (int c = 0; c + TK_SOBOL_S < TK_MAXBIT; c++) {
                 tab[(size_t)(TK_MAXBIT + c) * NXP + d] = Vd[TK_SOBOL_S - 1] ^ Vd[TK_SOBOL_S + c];
+            }
+        }
+        for (int t = 0; t < (1 << TK_SOBOL_S); t++) { /* thread part of the seed: XOR of the direction numbers picked by gray(t) */
+            const uint32_t g = (uint32_t)t ^ ((uint32_t)t >> 1);
+            for (int d = 0; d < NX; d++) {
+                uint32_t x = 0;
+                for (int j = 0; j < TK_SOBOL_S; j++)
+                    if ((g >> j) & 1u) x ^= h->V[(size_t)d * 32 + j];
+                tab[(size_t)(2 * TK_MAXBIT + t) * NXP + d] = x;
             }
         }
         TK_CUDA(cudaMalloc(&h->d_sobtab, tab.size() * sizeof(uint32_t)));
@@ -302,8 +316,9 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
         while ((top >> nb) != 0) nb++;
         T.nbits = std::min(nb + 1, TK_MAXBIT);
     }
-    /* points per thread P: the smallest P whose grid is resident in ONE wave (no tail wave, seeding
-     * amortised as little as necessary); a job too big for that takes the longest stride. */
+    /* points per thread P: the smallest P whose grid is at most TWO resident waves (blocks of the second wave start as
+     * blocks of the first one retire, which evens out the SMs; measured at C2: P = 4 and 8 within 1 %, 16 is 15 % slower,
+     * 2 pays the seeding twice as often); a job too big for that takes the longest stride. */
     bool inb = true; /* Sobol box inside the bounds (and inside the plugin's declared domain)? */
     for (int d = 0; d < NX; d++) inb = inb && (T.lo[d] >= T.bl[d]) && (T.lo[d] + T.w[d] <= T.bu[d]);
     if constexpr (requires(const double* p) { Obj::domain_ok(NX, p, p, p); }) {
@@ -320,7 +335,7 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
         auto go = [&]<bool INB, int G>() -> int {
             static int per_sm = 0; /* per instantiation: the occupancy query is host work in front of every launch */
             if (per_sm == 0) TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sobol_eval_kernel<Obj, NX, BT, P, INB, G>, BT, 0));
-            if (!force && grid > (int64_t)per_sm * h->sm_count) return 1;
+            if (!force && grid > 2 * (int64_t)per_sm * h->sm_count) return 1;
             sobol_eval_kernel<Obj, NX, BT, P, INB, G><<<(unsigned)grid, BT, 0, h->stream>>>(T, h->sc, wvk);
             return TIKTAK_OK;
         };

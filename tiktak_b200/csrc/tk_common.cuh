@@ -27,7 +27,7 @@ void tk_set_error(const char* fmt, ...);
 template <int NX>
 struct TkTables {
     double lo[NX], w[NX], bl[NX], bu[NX], aux[NX];
-    const uint32_t* tab; /* device memory: Vt[TK_MAXBIT][NXP] bit-major direction numbers, then Dt[TK_MAXBIT][NXP] step table */
+    const uint32_t* tab; /* device memory: Vt[TK_MAXBIT][NXP] bit-major direction numbers, Dt[TK_MAXBIT][NXP] step table, Lt[2^S][NXP] thread part of the seed */
     int nbits;           /* Gray bits in use (rows of the tables a block copies) */
 };
 #define TK_SOBOL_NXP(nx) (((nx) + 3) & ~3) /* row length of the tables, padded to 16 bytes */
@@ -35,7 +35,6 @@ struct TkScalars {
     int nx, nm;
     double fvalmax, penalty0, penaltyc, max_penalty, sqrt_nm;
     const void* user;
-    double zero; /* 0.0 at run time (see tk_trig_load) */
 };
 
 /* pointers to the same tables in global memory, for the runtime-nx kernels */
@@ -118,6 +117,7 @@ struct tiktak_handle {
     bool best_dirty = true;          /* d_best must be recomputed from the rows (after push_results) */
     cudaEvent_t evl0 = nullptr, evl1 = nullptr, evp0 = nullptr, evp1 = nullptr;
     bool local_timing_open = false, pretest_timing_open = false;
+    cudaEvent_t ev_wave_start = nullptr, ev_stage_end = nullptr; /* which of the events above bracket the current wave / close the stage */
     bool rho_ready = false;
     /* selectType = 1 (lottery) */
     double *d_lot_f = nullptr, *d_lot_sf = nullptr, *d_lot_cum = nullptr;
@@ -192,7 +192,7 @@ __device__ __forceinline__ tk_obj_ctx tk_make_ctx(const TkScalars& s, int nx, co
     c.nx = nx; c.nm = s.nm; c.bl = bl; c.bu = bu; c.aux = aux;
     c.fvalmax = s.fvalmax; c.penalty0 = s.penalty0; c.penaltyc = s.penaltyc; c.max_penalty = s.max_penalty;
     c.sqrt_nm = s.sqrt_nm; c.user = s.user;
-    c.trig = tk_trig_load(__dmul_rn(s.zero, (double)threadIdx.x)); /* 0.0, and not provably the same in every lane: stays in vector registers */
+    c.trig = tk_trig_plain(); /* kernels with a hot loop over tk_cos swap in register-resident copies (kernels_sobol.cu) */
     return c;
 }
 /* 32-bit Sobol numerator -> double in [0,1), exact: build 1.q in [1,2) and subtract 1 */
