@@ -1,0 +1,72 @@
+! tiktak_cuda_mod.f90 -- ISO_C_BINDING interface of libtiktak_cuda (include/tiktak_cuda.h) for the reference driver.
+!
+! The reference (TiktakGlobalSearch.f90) keeps its state machine, CLI, config.txt parser and .dat writers; the bodies
+! of setupSobol (:825-838), solveAtSobolPoints (:405-471), chooseSobol (:840-899), LocalMinimizations (:473-544) and
+! lastSearch (:635-681) call the functions below instead (INTEGRATION.md section 2 lists the replacement per procedure).
+! Add this file before minimize.o in the reference Makefile's object list and link with -ltiktak_cuda -lcudart.
+! No Fortran compiler exists in the build image: this source is reviewed, not compiled here;
+! tests/test_abi_and_config.py checks that every NAME= below is declared in the header and exported by the library.
+MODULE tiktak_cuda_mod
+  USE, INTRINSIC :: ISO_C_BINDING
+  IMPLICIT NONE
+  TYPE, BIND(C) :: tiktak_config            ! include/tiktak_cuda.h: struct tiktak_config
+     INTEGER(C_INT32_T) :: nx, nm, maxeval, qr_ndraw, legitimate, maxpoints_plus1, search_type, lottery_points
+     REAL(C_DOUBLE)     :: fvalmax
+     TYPE(C_PTR)        :: range, init, bound          ! p_range(nx,2), p_init(nx), p_bound(nx,2): column-major as is
+     INTEGER(C_INT32_T) :: objective_id, device, rank, world
+     INTEGER(C_INT32_T) :: nm_itmax, nm_shrink_mode, sobol_quirk, text_roundtrip, round_size
+     REAL(C_DOUBLE)     :: nm_ftol
+     TYPE(C_PTR)        :: user
+  END TYPE
+  INTERFACE
+     INTEGER(C_INT) FUNCTION tiktak_cuda_create(h, cfg) BIND(C, NAME='tiktak_cuda_create')
+       IMPORT; TYPE(C_PTR), INTENT(OUT) :: h; TYPE(tiktak_config), INTENT(IN) :: cfg
+     END FUNCTION
+     SUBROUTINE tiktak_cuda_destroy(h) BIND(C, NAME='tiktak_cuda_destroy')
+       IMPORT; TYPE(C_PTR), VALUE :: h
+     END SUBROUTINE
+     INTEGER(C_INT) FUNCTION tiktak_cuda_sobol_points(h, first, count, out) BIND(C, NAME='tiktak_cuda_sobol_points')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT64_T), VALUE :: first, count; REAL(C_DOUBLE) :: out(*)
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_pretest(h, n_eval, n_legit) BIND(C, NAME='tiktak_cuda_pretest')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT64_T), INTENT(OUT) :: n_eval, n_legit
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_pretest_values(h, first, count, fval) BIND(C, NAME='tiktak_cuda_pretest_values')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT64_T), VALUE :: first, count; REAL(C_DOUBLE) :: fval(*)
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_choose(h, x_starts, sobol_idx) BIND(C, NAME='tiktak_cuda_choose')
+       IMPORT; TYPE(C_PTR), VALUE :: h; REAL(C_DOUBLE) :: x_starts(*); INTEGER(C_INT32_T) :: sobol_idx(*)
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local(h, alg, first_k, n_k, starts, results, evals) BIND(C, NAME='tiktak_cuda_local')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, first_k, n_k
+       REAL(C_DOUBLE) :: starts(*), results(*); INTEGER(C_INT32_T) :: evals(*)
+     END FUNCTION
+     ! the same round without host synchronisation: queue every round, read once (include/tiktak_cuda.h)
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_enqueue(h, alg, first_k, n_k, send) BIND(C, NAME='tiktak_cuda_local_enqueue')
+       IMPORT; TYPE(C_PTR), VALUE :: h, send; INTEGER(C_INT32_T), VALUE :: alg, first_k, n_k
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_ingest(h, first_k, n_k, recv) BIND(C, NAME='tiktak_cuda_local_ingest')
+       IMPORT; TYPE(C_PTR), VALUE :: h, recv; INTEGER(C_INT32_T), VALUE :: first_k, n_k
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_ingest_rounds(h, first_k, n_k, round_size, recv, accepted) &
+          BIND(C, NAME='tiktak_cuda_local_ingest_rounds')
+       IMPORT; TYPE(C_PTR), VALUE :: h, recv; INTEGER(C_INT32_T), VALUE :: first_k, n_k, round_size
+       INTEGER(C_INT32_T), INTENT(OUT) :: accepted
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_capacity(h, alg, restarts) BIND(C, NAME='tiktak_cuda_local_capacity')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg; INTEGER(C_INT32_T), INTENT(OUT) :: restarts
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_fetch(h, first_k, n_k, starts, results, evals) BIND(C, NAME='tiktak_cuda_local_fetch')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k
+       REAL(C_DOUBLE) :: starts(*), results(*); INTEGER(C_INT32_T) :: evals(*)
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_last_search(h, fval, x, iters) BIND(C, NAME='tiktak_cuda_last_search')
+       IMPORT; TYPE(C_PTR), VALUE :: h; REAL(C_DOUBLE), INTENT(OUT) :: fval; REAL(C_DOUBLE) :: x(*)
+       INTEGER(C_INT32_T), INTENT(OUT) :: iters
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_best(h, fbest, xbest, k) BIND(C, NAME='tiktak_cuda_best')
+       IMPORT; TYPE(C_PTR), VALUE :: h; REAL(C_DOUBLE), INTENT(OUT) :: fbest; REAL(C_DOUBLE) :: xbest(*)
+       INTEGER(C_INT32_T), INTENT(OUT) :: k
+     END FUNCTION
+  END INTERFACE
+END MODULE

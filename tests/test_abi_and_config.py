@@ -29,6 +29,33 @@ def test_library_exports_every_header_symbol(built):
     assert sorted(lib.SIGNATURES) == names, "tiktak_b200/lib.py binds a different set than the header declares"
 
 
+def test_fortran_interface_binds_exported_symbols(built):
+    """fortran/tiktak_cuda_mod.f90 (the ISO_C_BINDING side of the boundary) and INTEGRATION.md name only functions that
+    the header declares and the library exports, with the header's argument counts; the BIND(C) struct has the
+    header's field order"""
+    f90 = open(os.path.join(ROOT, "fortran", "tiktak_cuda_mod.f90")).read()
+    assert f90.split("MODULE tiktak_cuda_mod", 1)[1].strip() in open(os.path.join(ROOT, "INTEGRATION.md")).read().replace("\r", ""), \
+        "INTEGRATION.md shows a different module than fortran/tiktak_cuda_mod.f90"
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tiktak_cuda.h")).read(), flags=re.S)
+    L = C.CDLL(lib.LIB_PATH)
+    binds = re.findall(r"(?:FUNCTION|SUBROUTINE)\s+(\w+)\s*\(([^)]*)\)\s*&?\s*BIND\(C, NAME='(\w+)'\)", f90, flags=re.S)
+    assert len(binds) >= 14
+    for fname, fargs, cname in binds:
+        assert fname == cname
+        assert hasattr(L, cname), f"{cname} bound in Fortran but not exported"
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % cname, hdr, flags=re.S)
+        assert m, f"{cname} not declared in the header"
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == len([a for a in fargs.split(",") if a.strip()]), cname
+    # field order of TYPE, BIND(C) :: tiktak_config against the ctypes mirror (itself checked against the C struct below)
+    body = f90.split("TYPE, BIND(C) :: tiktak_config", 1)[1].split("END TYPE", 1)[0]
+    fields = []
+    for line in body.splitlines():
+        line = line.split("!")[0]
+        if "::" in line:
+            fields += [v.strip() for v in line.split("::", 1)[1].split(",")]
+    assert fields == [f[0] for f in TiktakConfig._fields_]
+
+
 def test_struct_layout_matches_c(built):
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "tiktak_cuda.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tiktak_config), offsetof(tiktak_config,fvalmax), offsetof(tiktak_config,range), offsetof(tiktak_config,objective_id), offsetof(tiktak_config,nm_ftol), offsetof(tiktak_config,user));return 0;}'
     with tempfile.TemporaryDirectory() as d:
