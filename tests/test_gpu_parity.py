@@ -66,6 +66,42 @@ def test_pretest_values(built, name):
     assert np.max(np.abs(f - fl) / np.abs(fl)) <= 1e-12  # tolerance from BASELINE.json
 
 
+@pytest.mark.parametrize("name,blo,bhi,fvalmax", [("template4", -0.5, 0.75, 1e4), ("griewank10", -300.0, 500.0, 1e4),
+                                                  ("rastrigin20", -4.0, 5.0, 1e7), ("rosenbrock50", -4.9, 9.9, 1e18),
+                                                  ("griewank7", -30.0, 50.0, 1e4)])
+def test_pretest_values_box_outside_bounds(built, name, blo, bhi, fvalmax):
+    """Sobol box wider than the bounds: the getPenalty branch of dfovec / objFun (objective.f90:51-74, 92-95) inside the
+    Sobol kernel (the bounds test is compiled out only when the host has verified that the box lies inside the bounds)"""
+    nx = SMALL[name]["nx"]
+    cfg = cfg_of(name, bound=[[blo, bhi]] * nx, fvalmax=fvalmax, legitimate=-1)
+    with TikTakSearch(cfg) as s:
+        _, ne, nl = s.solveAtSobolPoints()
+        f = s.sobolFnVal()
+    o = Oracle(cfg, MATH_TK)
+    _, one, onl = o.solveAtSobolPoints()
+    fo = o.sobolFnVal()
+    assert (ne, nl) == (one, onl)
+    assert np.array_equal(f, fo)
+    assert 0 < np.count_nonzero(f >= cfg.fvalmax) < len(f), "the case must mix penalised and regular points"
+
+
+def test_pretest_values_outside_trig_domain(built):
+    """arguments beyond tk_cos's domain (|x| >= 2^30): the plugin's domain_ok fails on the host, the kernel keeps the
+    per-call domain test, and device and oracle agree on which values are NaN and on every other value"""
+    cfg = cfg_of("griewank10", lo=-3.0e9, hi=3.0e9, qr_ndraw=6000, init=[1.0] * 10)
+    with TikTakSearch(cfg) as s:
+        _, ne, nl = s.solveAtSobolPoints()
+        f = s.sobolFnVal()
+    o = Oracle(cfg, MATH_TK)
+    _, one, onl = o.solveAtSobolPoints()
+    fo = o.sobolFnVal()
+    assert (ne, nl) == (one, onl)
+    assert np.array_equal(np.isnan(f), np.isnan(fo))
+    ok = ~np.isnan(fo)
+    assert 0 < np.count_nonzero(ok) < len(fo)
+    assert np.array_equal(f[ok], fo[ok])
+
+
 @pytest.mark.parametrize("name", ["griewank10", "rastrigin20", "griewank7"])
 def test_legitimate_cut(built, name):
     """finite fvalmax and legitimate < #valid: the evaluated set is the prefix 1..Kcut (:429-464)"""
