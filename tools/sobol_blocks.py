@@ -1,4 +1,4 @@
-"""experiment (library built with -DTK_SOBOL_TRACE): Gantt data of one C2 launch -- when every block starts and ends
+"""experiment (trace build: `make -C tiktak_b200/csrc trace`, passed as TIKTAK_CUDA_LIB): Gantt data of one C2 launch -- when every block starts and ends
 (globaltimer), on which SM; summarised as resident blocks per SM over time"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,4 @@
-"""experiment (needs a library built with -DTK_SOBOL_TRACE, passed as TIKTAK_CUDA_LIB): where block 0 of the Sobol
+"""experiment (needs the trace build: `make -C tiktak_b200/csrc trace`, passed as TIKTAK_CUDA_LIB): where block 0 of the Sobol
 kernel spends its time -- SM cycle stamps and globaltimer stamps at the phase boundaries, beside the event time"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
