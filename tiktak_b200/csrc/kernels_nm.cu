@@ -640,8 +640,11 @@ __device__ __forceinline__ void nm_full_sort_wide(double* ys, int* rows, int np,
  * three of four warps now run only the evaluation (no redundant bookkeeping): ~2.4x fewer instructions per iteration
  * than carrying the state in every warp. */
 enum { NMW_EVAL4 = 0, NMW_VERTS = 1, NMW_STOP = 2 };
+#ifndef TK_NMW_MB
+#define TK_NMW_MB 0 /* resident blocks per SM the wide kernel is compiled for (0: ptxas decides) */
+#endif
 template <class Obj, int CJ>
-__global__ void __launch_bounds__(128) nm_quad_wide_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+__global__ void __launch_bounds__(128, TK_NMW_MB) nm_quad_wide_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
     extern __shared__ double smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
