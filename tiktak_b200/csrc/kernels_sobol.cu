@@ -139,11 +139,17 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
         ctx.trig.sel = reinterpret_cast<const double2*>(ssel);
     }
     const double k2m32 = strig[4][t & 31]; /* 2^-32 in a register: the FMA below also reads lo[d] from the constant bank */
-    const int64_t lbase = (wv.cbf_q + lcb) * TIKTAK_SOBOL_BLOCK + coff; /* = tk_local_index(base, world) */
+    /* Loop-carried bookkeeping: the index of the current point (32 bits: qr_ndraw < 2^30), where its value goes and
+     * the block-uniform step counter.  The empty asm makes them opaque, so ptxas keeps them in three registers instead
+     * of re-deriving them from blockIdx and the kernel arguments in every iteration (45 instructions per point). */
+    uint32_t n32 = (uint32_t)base + (uint32_t)t;
+    double* out = wv.fval + ((wv.cbf_q + lcb) * TIKTAK_SOBOL_BLOCK + coff) + t; /* fval[tk_local_index(base, world) + t] */
+    uint32_t hh = h0;
+    const uint32_t N32 = (uint32_t)wv.N;
+    asm volatile("" : "+r"(n32), "+l"(out), "+r"(hh));
     unsigned int cnt = 0;
 #pragma unroll 1
     for (int j = 0; j < P; j++) {
-        const int64_t n = base + (int64_t)j * BT + t;
         TkRegX<NX> x;
 #pragma unroll
         for (int d = 0; d < NX; d++) {
@@ -155,14 +161,16 @@ sobol_eval_kernel(const __grid_constant__ TkTables<NX> T, const TkScalars sc, co
         double f;
         if constexpr (INB && G > 0) f = tk_objfun_finish(ctx, tk_value_grouped<Obj, Obj::nterms(NX), G, true>(ctx, x), 0.0);
         else f = INB ? tk_objfun_finish(ctx, tk_value_seq<Obj>(ctx, x), 0.0) : tk_objfun<Obj>(ctx, x);
-        if (n >= 1 && n <= wv.N) {
-            wv.fval[lbase + (int64_t)j * BT + t] = f;
+        if (n32 - 1u < N32) { /* 1 <= n <= qr_ndraw */
+            asm volatile("st.global.f64 [%0], %1;" ::"l"(out), "d"(f) : "memory"); /* `out` is opaque to the compiler: name the state space */
             cnt += (f < sc.fvalmax) ? 1u : 0u;
         }
+        n32 += BT;
+        out += BT;
         TK_TRACE(5 + (j < 3 ? j : 3));
         /* advance to n + BT: Gray bits S-1 and S+c flip (one row of sD, broadcast reads) */
-        const uint32_t h = h0 + (uint32_t)j;
-        const int c = __ffs((int)~h) - 1;
+        const int c = __ffs((int)~hh) - 1;
+        hh++;
         const uint4* row = reinterpret_cast<const uint4*>(sD + c * NXP);
 #pragma unroll
         for (int g = 0; g < NXP / 4; g++) {
