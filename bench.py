@@ -355,7 +355,7 @@ def run_graft(args, rank, world, local_rank):
             achieved_tf = per_gpu_evals * F_ALG[name] / (eval_ms * 1e-3) / 1e12
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` captures
             # (profiles/r01d_full_*.csv); the 8 MB of results of a 1e6-point launch stay in the 126 MB L2
-            traffic = {"C2": 25088, "C3": 741538048, "C4": 21462528}.get(name) if world == 1 else None
+            traffic = {"C2": 25088, "C3": 742264320, "C4": 21494528}.get(name) if world == 1 else None
             roofline = {"bound": "fp64", "kernel": "sobol_eval_kernel", "achieved": achieved_tf, "peak": peak_tf,
                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                         "flops_per_eval": F_ALG[name], "evals_per_launch": per_gpu_evals, "kernel_ms": eval_ms,
@@ -364,7 +364,7 @@ def run_graft(args, rank, world, local_rank):
                         "share_of_step": eval_ms / step_ms if step_ms > 0 else None,
                         "note": "CUDA-event duration: an EMPTY kernel between the same two events takes 6.3-7.5 us on this "
                                 "GPU (tools/micro/launch_floor.cu, gpurun_out/launch_floor.txt), which is inside kernel_ms; "
-                                "ncu's gpu__time_duration of the C2 launch is 27.6 us (profiles/r01d_full_c2_sobol.csv)"}
+                                "ncu's gpu__time_duration of the C2 launch is 26.8 us (profiles/r01d_full_c2_sobol.csv)"}
         # the local stage's kernel dominates the STEP (profiles/: ~95 % of the kernel time at C2) but is a chain of
         # dependent simplex iterations, not a throughput kernel: reported for completeness against the same FP64 peak
         roofline_local = None
