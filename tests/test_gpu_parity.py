@@ -291,6 +291,24 @@ def test_start_selection_large_m(built):
         assert np.array_equal(xs, oxs)
 
 
+@pytest.mark.parametrize("lo,hi,nd,maxpoints", [(-0.01, 0.01, 600_000, 50), (-400.0, 600.0, 300_000, 700), (-1e-9, 1e-9, 40_000, 30)])
+def test_start_selection_threshold_list(built, lo, hi, nd, maxpoints):
+    """the radix select's short list of elements that share the threshold's top 16 key bits: a narrow box puts EVERY value
+    into one such bucket (the list overflows its capacity of an eighth of the points and the later passes fall back to
+    the array), the C2 box leaves a small bucket, and a box of width 2e-9 makes most values exactly equal (ties at the
+    threshold resolved by Sobol index through the list)"""
+    cfg = cfg_of("griewank10", lo=lo, hi=hi, qr_ndraw=nd, maxpoints=maxpoints, init=[0.5 * (lo + hi)] * 10)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        xs = s.chooseSobol()
+        idx = s.sobol_idx.copy()
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    oxs = o.chooseSobol(mode=1)
+    assert np.array_equal(idx, o.sobol_idx)
+    assert np.array_equal(xs, oxs)
+
+
 def test_blocking_round_api_matches_queued_rounds(built):
     """tiktak_cuda_local (one blocking call per round) and the queued enqueue/ingest/fetch form give the same rows"""
     import ctypes as C

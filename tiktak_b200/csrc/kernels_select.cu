@@ -3,9 +3,12 @@
  * Replaces chooseSobol (TiktakGlobalSearch.f90:840-899): the reference re-reads every evaluated row
  * from sobolFnVal.dat, index-sorts ALL of them with indexx (utilities.f90:1334-1424) and keeps the
  * first K-1.  Only the K-1 smallest are ever used, so the device does an exact radix SELECT on the
- * order-preserving 64-bit image of fval (8 histogram passes of 8 bits over the fval array, most
- * significant digit first; the last block of a pass scans the bins), resolves a tie at the threshold by
- * Sobol index (4 more passes, skipped when there is none), compacts the <= K-1 winners and orders them by
+ * order-preserving 64-bit image of fval (8 histogram passes of 8 bits, most significant digit first; the
+ * last block of a pass scans the bins).  Only the first two passes read the fval array: once the top 16
+ * bits of the threshold are known, the elements that share them -- the only ones the later digits depend
+ * on -- are copied to a short (key, index) list and the remaining passes read that list (four sweeps over
+ * the array per selection instead of thirteen).  A tie at the threshold is resolved by Sobol index (4 more
+ * passes over the list, skipped when there is none); then the <= K-1 winners are compacted and ordered by
  * (fval, index) with a chunk sort + merge-by-rank passes.  Order among exactly equal fvals is ascending Sobol index (indexx's order
  * among equal keys is an artefact of its partitioning; DESIGN.md "ties").
  */
@@ -28,7 +31,11 @@ struct SelView {
     int64_t nlocal; /* local elements (multiple of the count block) */
     int64_t kcut;
     int rank, world;
+    unsigned long long* list_key; /* elements whose key shares the threshold's top 16 bits (filled after pass 2) */
+    unsigned int* list_n;
+    unsigned long long list_cap;
 };
+/* selstate[5] = elements in the list, selstate[6] = 1 when they did not fit (later passes read the array again) */
 __device__ __forceinline__ int64_t tk_global_n(const SelView& v, int64_t li) {
     return ((li / TIKTAK_SOBOL_BLOCK) * v.world + v.rank) * (int64_t)TIKTAK_SOBOL_BLOCK + (li % TIKTAK_SOBOL_BLOCK);
 }
@@ -46,10 +53,19 @@ select_hist_kernel(const SelView v, unsigned long long* state, unsigned long lon
     __syncthreads();
     const unsigned long long prefix = state[0], iprefix = state[2];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; li < v.nlocal; li += stride) {
-        const int64_t n = tk_global_n(v, li);
-        if (n < 1 || n > v.kcut) continue;
-        const unsigned long long key = tk_order_key(v.fval[li]);
+    const bool from_list = !(phase == 0 && shift >= 48) && state[6] == 0; /* the list exists and is complete */
+    const int64_t count = from_list ? (int64_t)state[5] : v.nlocal;
+    for (int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; li < count; li += stride) {
+        unsigned long long key;
+        int64_t n;
+        if (from_list) {
+            key = v.list_key[li];
+            n = (int64_t)v.list_n[li];
+        } else {
+            n = tk_global_n(v, li);
+            if (n < 1 || n > v.kcut) continue;
+            key = tk_order_key(v.fval[li]);
+        }
         if (phase == 0) {
             const bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
             if (match) atomicAdd(&sh[(key >> shift) & 255u], 1u);
@@ -97,6 +113,39 @@ select_hist_kernel(const SelView v, unsigned long long* state, unsigned long lon
     }
     __syncthreads();
     hist[threadIdx.x] = 0;
+}
+
+/* after the pass with shift 48: copy the elements whose key has the threshold's top 16 bits to the list (one atomic per
+ * warp); the order in the list is arbitrary, the passes that read it only count */
+__global__ void __launch_bounds__(256)
+select_compact_kernel(const SelView v, unsigned long long* state) {
+    const unsigned long long top = state[0] >> 48;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (v.nlocal + stride - 1) / stride;
+    const int lane = threadIdx.x & 31;
+    int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t r = 0; r < rounds; r++, li += stride) { /* whole warps stay in the loop: the ballot below is warp-wide */
+        bool take = false;
+        unsigned long long key = 0;
+        int64_t n = 0;
+        if (li < v.nlocal) {
+            n = tk_global_n(v, li);
+            if (n >= 1 && n <= v.kcut) {
+                key = tk_order_key(v.fval[li]);
+                take = (key >> 48) == top;
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, take);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == __ffs((int)m) - 1) base = atomicAdd(&state[5], (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+        if (take) {
+            const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+            if (pos < v.list_cap) { v.list_key[pos] = key; v.list_n[pos] = (unsigned int)n; }
+            else state[6] = 1; /* does not fit: the later passes fall back to the array */
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -301,7 +350,13 @@ int tk_select_top(tiktak_handle* h, int64_t M) {
     const int64_t m = M < owned ? M : owned;
     h->n_cand = m;
     if (m <= 0) return TIKTAK_OK;
-    SelView v{h->d_fval, h->n_local_cblocks * (int64_t)TIKTAK_SOBOL_BLOCK, h->kcut, rank, world};
+    if (!h->d_sel_list_key) { /* list of the elements that share the threshold's top 16 bits: an eighth of the shard (+ slack) */
+        h->sel_list_cap = (unsigned long long)(h->n_local_cblocks * (int64_t)TIKTAK_SOBOL_BLOCK) / 8 + 65536;
+        TK_CUDA(cudaMalloc(&h->d_sel_list_key, h->sel_list_cap * sizeof(unsigned long long)));
+        TK_CUDA(cudaMalloc(&h->d_sel_list_n, h->sel_list_cap * sizeof(unsigned int)));
+    }
+    SelView v{h->d_fval, h->n_local_cblocks * (int64_t)TIKTAK_SOBOL_BLOCK, h->kcut, rank, world,
+              h->d_sel_list_key, h->d_sel_list_n, h->sel_list_cap};
     /* only scan the count blocks that can hold n <= kcut */
     {
         const int64_t lastcb = h->kcut / TIKTAK_SOBOL_BLOCK;
@@ -321,6 +376,10 @@ int tk_select_top(tiktak_handle* h, int64_t M) {
         for (int shift = top; shift >= 0; shift -= 8) {
             select_hist_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate, h->d_hist, h->d_ticket, phase, shift);
             h->launches++;
+            if (phase == 0 && shift == 48) {
+                select_compact_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate);
+                h->launches++;
+            }
         }
     }
     select_collect_kernel<<<grid, 256, 0, h->stream>>>(v, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n,

@@ -95,6 +95,9 @@ struct tiktak_handle {
     unsigned int* d_cand_i = nullptr;
     unsigned int* d_cand_n = nullptr;
     unsigned int* d_ticket = nullptr;   /* last-block ticket of the radix-select passes */
+    unsigned long long* d_sel_list_key = nullptr; /* radix select: elements sharing the threshold's top 16 bits */
+    unsigned int* d_sel_list_n = nullptr;
+    unsigned long long sel_list_cap = 0;
     double* d_sorted_f = nullptr;
     unsigned int* d_sorted_i = nullptr;
     int64_t n_cand = 0;
