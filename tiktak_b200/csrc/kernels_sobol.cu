@@ -351,11 +351,7 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
         constexpr bool kHasTerms = requires(const tk_obj_ctx& c, const TkRegX<NX>& x, double (&a)[1], double (&b)[1]) { Obj::template terms<1, true>(c, x, 0, a, b); };
         constexpr int NT = Obj::nterms(NX);
         constexpr int GA = !kHasTerms ? 0 : (NT % TK_SOBOL_G == 0 ? TK_SOBOL_G : (NT % 5 == 0 ? 5 : (NT % 4 == 0 ? 4 : 0)));
-        static const int gsel = getenv("TIKTAK_SOBOL_GROUP") ? atoi(getenv("TIKTAK_SOBOL_GROUP")) : 1;
-        int rc;
-        if (!inb) rc = go.template operator()<false, 0>();
-        else if (gsel == 0 || GA == 0) rc = go.template operator()<true, 0>();
-        else rc = go.template operator()<true, GA>();
+        const int rc = !inb ? go.template operator()<false, 0>() : go.template operator()<true, GA>();
         if (rc != TIKTAK_OK) return rc;
         h->launches++;
         TK_CUDA(cudaGetLastError());
@@ -366,7 +362,6 @@ int launch_wave_fixed(tiktak_handle* h, const TkWave& wv, int64_t owned_cbs) {
     if (shape) {
         int bt = 0, pp = 0;
         if (sscanf(shape, "%dx%d", &bt, &pp) == 2) {
-            if (bt == 128 && pp == 2) return try_launch.template operator()<128, 2>(true);
             if (bt == 128 && pp == 4) return try_launch.template operator()<128, 4>(true);
             if (bt == 128 && pp == 8) return try_launch.template operator()<128, 8>(true);
             if (bt == 128 && pp == 16) return try_launch.template operator()<128, 16>(true);
