@@ -1,4 +1,7 @@
-"""torchrun --nproc-per-node N tools/mgpu_check.py : sharded run vs the single-instance oracle (rank 0 checks)."""
+"""torchrun --nproc-per-node N tests/mgpu_check.py : sharded run vs the single-instance oracle (rank 0 checks).
+
+A multi-process GPU parity test (not collected by pytest: it needs torchrun and N GPUs); it lives under tests/ because
+it imports the oracle, which only test code may do."""
 import os
 import sys
 
