@@ -271,3 +271,58 @@ def test_lottery_selection_oracle(built):
             hits[match[0] + 1] += 1
         rows.append((o.searchResults[k - 1, 3], k, o.searchResults[k - 1, 4:]))
     assert hits[1] > hits[3] and hits[2] > 0  # rank 1 is drawn most often, lower ranks do occur
+
+
+def test_affine_map_identity_used_by_the_sobol_kernel():
+    """kernels_sobol.cu maps a point with I2F, DMUL, DFMA: fma(fl(q * w), 2^-32, lo).  The reference computes
+    lo + fl(u * w) with u = q * 2^-32 (TiktakGlobalSearch.f90:834).  Scaling by a power of two is exact and commutes
+    with rounding (no underflow at these magnitudes), so both give the same double -- checked here bit for bit on the
+    CPU for the BASELINE boxes and for awkward widths; the product q * w * 2^-32 being exact, the FMA equals a plain add."""
+    rng = np.random.default_rng(20261020)
+    q = rng.integers(1, 2**32, size=200_000, dtype=np.uint64)
+    q[:64] = [1 << (i % 32) for i in range(64)]
+    for lo, hi in ((-400.0, 600.0), (-4.12, 5.12), (-5.0, 10.0), (-1.0, 1.0), (1e-3, 1e-3 + 2.0**-20), (-3.0e9, 3.0e9),
+                   (0.1, 0.3), (-1e-9, 1e-9)):
+        w = np.float64(hi) - np.float64(lo)
+        u = q.astype(np.float64) * np.float64(2.0**-32)            # exact
+        ref = np.float64(lo) + u * w                                   # two roundings, as the reference
+        dev = np.float64(lo) + (q.astype(np.float64) * w) * np.float64(2.0**-32)  # fl(q*w) scaled exactly, then one add
+        assert np.array_equal(ref, dev), (lo, hi)
+
+
+def test_sobol_kernel_table_algebra(L):
+    """the index algebra of sobol_eval_kernel, restated with numpy on the oracle's direction numbers: a block of 128
+    threads owning the indices [base, base + 128 P) seeds thread t with (XOR of the rows picked by the Gray bits >= 7 of
+    base) ^ Lt[t], where Lt[t] = XOR of the rows picked by gray(t) (the same in every block because base is a multiple of
+    256), and steps n -> n + 128 with Dt[c] = V[6] ^ V[7 + c], c = ctz(~(n >> 7)).  Every point produced that way must be
+    the oracle's point (q * 2^-32 in the unit cube)."""
+    nx, S, P, BT = 10, 7, 8, 128
+    atmost = 2**30 - 1
+    V = np.zeros((nx, 32), dtype=np.uint32)
+    assert L.orc_sobol_dirnums(nx, atmost, V.ctypes.data) == 0
+    V = V.astype(np.uint64)
+    Lt = np.zeros((BT, nx), dtype=np.uint64)
+    for t in range(BT):
+        g = t ^ (t >> 1)
+        for j in range(S):
+            if (g >> j) & 1:
+                Lt[t] ^= V[:, j]
+    Dt = np.stack([V[:, S - 1] ^ V[:, S + c] for c in range(30 - S)])
+    ref = unit_points(L, nx, 3 * BT * P + 5000, atmost=atmost)  # points 1 .. N
+    for base in (0, BT * P, 2 * BT * P, 4096):
+        h0 = base >> S
+        ghi = h0 ^ (h0 >> 1)
+        qhi = np.zeros(nx, dtype=np.uint64)
+        for j in range(30 - S):
+            if (ghi >> j) & 1:
+                qhi ^= V[:, j + S]
+        q = Lt ^ qhi[None, :]                                   # (thread, coordinate)
+        hh = h0
+        for j in range(P):
+            n = base + j * BT + np.arange(BT)
+            ok = n >= 1
+            pts = q.astype(np.float64) * 2.0**-32
+            assert np.array_equal(pts[ok], ref[n[ok] - 1]), (base, j)
+            c = (~hh & (hh + 1)).bit_length() - 1               # ctz(~hh)
+            q = q ^ Dt[c][None, :]
+            hh += 1
