@@ -5,14 +5,16 @@
  * bracketed by ~6 lock-file cycles).  Here no point is ever stored: a thread derives its first point
  * from the Gray code of its index (closed form of the Antonov-Saleev recurrence utilities.f90:1086-1106:
  * point n = XOR of the direction numbers selected by the bits of n ^ (n>>1)), then strides through the
- * sequence with ONE 3-input XOR per coordinate per point, maps it to the search box with the
- * reference's unfused lo + q*(hi-lo) (:834) and evaluates the objective plugin in registers.
+ * sequence with ONE XOR per coordinate per point, maps it to the search box with the two roundings of
+ * the reference's unfused lo + q*(hi-lo) (:834) and evaluates the objective plugin in registers.
  * Output: 8 bytes per point (fval) + one valid-count per TIKTAK_SOBOL_BLOCK-point count block.
  *
  * Work decomposition: a CUDA block of BT = 2^S threads owns BT*P consecutive Sobol indices; thread t
  * handles n = base + j*BT + t, j = 0..P-1, so the fval stores of a warp are contiguous and the step
  * n -> n+BT flips exactly two Gray-code bits, S-1 and S+ctz(~(n>>S)) -- the same two for the whole
- * block (block-uniform constant-bank reads).
+ * block: one row of a precomputed step table, which every block copies to shared memory together with
+ * the bit-major direction numbers (fixed-nx kernel; DESIGN.md section 3 tells why the tables do not
+ * travel as kernel arguments any more).  The runtime-nx kernel further down is the plain fallback.
  */
 #include <stdio.h>
 #include <stdlib.h>
