@@ -390,6 +390,7 @@ def run_graft(args, rank, world, local_rank):
             "restarts_per_s": restarts_s,
             "mean_evals_per_restart": float(np.mean(s.evals)) if s.evals is not None else None,
             "stage_ms": {"pretest": pre_ms, "pretest_eval_kernel": eval_ms, "choose": choose_ms, "local": local_ms},
+            "pretest_ms_steps": [round(float(d["pretest_ms"]), 5) for d in dev_steps],  # this rank's timed steps, one by one
             "roofline": roofline,
             "roofline_local": roofline_local,
             "cpu_baseline": cpu,
