@@ -68,5 +68,30 @@ MODULE tiktak_cuda_mod
        IMPORT; TYPE(C_PTR), VALUE :: h; REAL(C_DOUBLE), INTENT(OUT) :: fbest; REAL(C_DOUBLE) :: xbest(*)
        INTEGER(C_INT32_T), INTENT(OUT) :: k
      END FUNCTION
+     ! objFun at n points, x(n, nx) column-major (objective.f90:125-142): chooseSobol's p_init row, CLI option d
+     INTEGER(C_INT) FUNCTION tiktak_cuda_objfun(h, x, n, fval) BIND(C, NAME='tiktak_cuda_objfun')
+       IMPORT; TYPE(C_PTR), VALUE :: h; REAL(C_DOUBLE) :: x(*); INTEGER(C_INT64_T), VALUE :: n; REAL(C_DOUBLE) :: fval(*)
+     END FUNCTION
+     ! counts of the queued pre-test (read when first needed: lastSobol.dat / legitSobol.dat)
+     INTEGER(C_INT) FUNCTION tiktak_cuda_pretest_result(h, n_eval, n_legit) BIND(C, NAME='tiktak_cuda_pretest_result')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT64_T), INTENT(OUT) :: n_eval, n_legit
+     END FUNCTION
+     ! update options 2 / 3 (genericParams.f90:118-251): the rows of searchResults.dat, (n, nx+4) column-major, re-enter the device table
+     INTEGER(C_INT) FUNCTION tiktak_cuda_push_results(h, rows, n) BIND(C, NAME='tiktak_cuda_push_results')
+       IMPORT; TYPE(C_PTR), VALUE :: h; REAL(C_DOUBLE) :: rows(*); INTEGER(C_INT32_T), VALUE :: n
+     END FUNCTION
+     ! the -1 defaults of config.txt (genericParams.f90:307-372), applied in place
+     INTEGER(C_INT) FUNCTION tiktak_cuda_config_defaults(nx, maxeval, qr_ndraw, legitimate, fvalmax, maxpoints, lottery_points) &
+          BIND(C, NAME='tiktak_cuda_config_defaults')
+       IMPORT; INTEGER(C_INT32_T), VALUE :: nx; INTEGER(C_INT32_T) :: maxeval, qr_ndraw, legitimate, maxpoints, lottery_points
+       REAL(C_DOUBLE) :: fvalmax
+     END FUNCTION
+     ! messages: C strings (use C_F_POINTER / a loop up to the NUL to copy them into a CHARACTER variable for exitState)
+     TYPE(C_PTR) FUNCTION tiktak_cuda_strerror(code) BIND(C, NAME='tiktak_cuda_strerror')
+       IMPORT; INTEGER(C_INT), VALUE :: code
+     END FUNCTION
+     TYPE(C_PTR) FUNCTION tiktak_cuda_last_error() BIND(C, NAME='tiktak_cuda_last_error')
+       IMPORT
+     END FUNCTION
   END INTERFACE
 END MODULE
