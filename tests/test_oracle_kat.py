@@ -326,3 +326,47 @@ def test_sobol_kernel_table_algebra(L):
             c = (~hh & (hh + 1)).bit_length() - 1               # ctz(~hh)
             q = q ^ Dt[c][None, :]
             hh += 1
+
+
+def test_radix_select_with_list_restated():
+    """the selection algorithm of kernels_select.cu restated with numpy: order-preserving 64-bit key, radix select most
+    significant byte first, the list of elements sharing the threshold's top 16 bits after two passes, the remaining
+    digits (and the tie-break by index) from the list only -- against a plain lexicographic sort by (value, index),
+    for distributions with one bucket, many buckets, negative values and heavy ties"""
+    def key(f):
+        u = f.view(np.uint64)
+        return np.where(u >> np.uint64(63) != 0, ~u, u | np.uint64(1 << 63))
+
+    def select(f, m):
+        k = key(f)
+        n = np.arange(1, len(f) + 1, dtype=np.uint64)
+        prefix, rem = np.uint64(0), m
+        src_k, src_n = k, n
+        for shift in range(56, -8, -8):
+            sh = np.uint64(shift)
+            match = np.ones(len(src_k), bool) if shift == 56 else (src_k >> (sh + np.uint64(8))) == (prefix >> (sh + np.uint64(8)))
+            hist = np.bincount(((src_k[match] >> sh) & np.uint64(255)).astype(np.int64), minlength=256)
+            cum = np.concatenate([[0], np.cumsum(hist)])
+            b = int(np.searchsorted(cum[1:], rem, side="left"))
+            b = min(b, 255)
+            rem -= int(cum[b])
+            prefix |= np.uint64(b) << sh
+            if shift == 48:  # compaction: only these can still matter
+                keep = (k >> np.uint64(48)) == (prefix >> np.uint64(48))
+                src_k, src_n = k[keep], n[keep]
+        eq = src_k == prefix
+        n_thr = np.uint64(0xFFFFFFFF)
+        if int(eq.sum()) > rem:  # more keys equal to the threshold than still needed: lowest indices win
+            n_thr = np.sort(src_n[eq])[rem - 1]
+        win = (k < prefix) | ((k == prefix) & (n <= n_thr))
+        return np.flatnonzero(win)
+
+    rng = np.random.default_rng(7)
+    cases = [rng.random(50_000) * 1e-4 + 1.0, rng.lognormal(3.0, 4.0, 50_000), rng.normal(0.0, 10.0, 50_000),
+             np.round(rng.random(50_000) * 20.0), np.ones(5_000)]
+    for f in cases:
+        f = f.astype(np.float64)
+        for m in (1, 37, 1000, len(f) - 1, len(f)):
+            got = select(f, m)
+            order = np.lexsort((np.arange(len(f)), f))[:m]
+            assert np.array_equal(np.sort(got), np.sort(order)), (len(f), m)
