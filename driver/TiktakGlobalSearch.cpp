@@ -250,8 +250,7 @@ int main(int argc, char** argv) {
         while (k0 <= kend) {
             const int nk = std::min(per_launch, kend - k0 + 1);
             int32_t acc = 0;
-            CHECK(tiktak_cuda_local_enqueue(h, alg, k0, nk, nullptr));
-            CHECK(tiktak_cuda_local_ingest_rounds(h, k0, nk, B, nullptr, &acc));
+            CHECK(tiktak_cuda_local_launch(h, alg, k0, nk, B, &acc));
             k0 += acc;
         }
         if (kend >= kfirst) {

@@ -196,6 +196,12 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
 int tiktak_cuda_local_ingest_rounds(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t round_size, const double* recv,
                                     int32_t* accepted);
 int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts);
+/* world == 1: local_enqueue + local_ingest_rounds of restarts first_k .. first_k+n_k-1 as ONE call.  With the throughput
+ * form of the Nelder-Mead kernel this is one launch: restarts are handed to sub-warp groups by a device-side queue, the
+ * group that finishes the last restart of a round commits the complete rounds in order into the results table
+ * (completeSearch :582-597), and the first round that changes the best row stops the launch (`accepted` < n_k); how far
+ * restarts may be started ahead of the committed rounds is bounded inside the kernel, so n_k may be "all that is left". */
+int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t round_size, int32_t* accepted);
 /* make rows computed elsewhere (other ranks, or a resumed searchResults.dat) known to the handle;
  * rows is (n, nx+4) column-major.  Rows whose fval is NaN are ignored.  Also how the k=0 row
  * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */

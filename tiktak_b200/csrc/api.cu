@@ -275,7 +275,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_sorted_i, h->d_xstarts, h->d_res, h->d_res_valid, h->d_best, h->d_starts, h->d_out_x,
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
-                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_counts_spare,
+                    h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_nmq, h->d_counts_spare,
                     h->d_objfun_x, h->d_objfun_f, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -798,7 +798,7 @@ int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, con
     TK_CUDA(cudaSetDevice(h->device));
     int rc = tk_launch_ingest(h, first_k, n_k, n_k, h->cfg.world > 1 ? recv : nullptr, nullptr);
     if (rc) return rc;
-    h->n_rows += n_k;
+    h->n_rows += n_k; /* upper bound (rows with a NaN value are skipped on the device); exact after ingest_rounds / local_launch */
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
     return TIKTAK_OK;
 }
@@ -815,9 +815,48 @@ int tiktak_cuda_local_ingest_rounds(tiktak_handle* h, int32_t first_k, int32_t n
     if (rc) return rc;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
     int acc = 0;
+    double rows = 0; /* the row count comes from the device: restarts whose value is NaN are not rows (ingest_kernel skips them) */
     TK_CUDA(cudaMemcpyAsync(&acc, h->d_accepted, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(&rows, h->d_best + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
-    h->n_rows += acc;
+    h->n_rows = (int)rows;
+    *accepted = acc;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t round_size, int32_t* accepted) {
+    if (!h || !accepted || first_k < 1 || n_k < 0 || round_size < 1 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    *accepted = 0;
+    if (n_k == 0) return TIKTAK_OK;
+    if (h->cfg.world > 1) { tk_set_error("local_launch: world > 1 exchanges the rows between enqueue and ingest_rounds"); return TIKTAK_ERR_UNSUPPORTED; }
+    const bool fused = alg == TIKTAK_ALG_AMOEBA && h->cfg.objective_id != TIKTAK_OBJ_SMM && tk_nm_use_w4(h);
+    if (!fused) { /* DFNLS, or a configuration only the latency form is built for: kernel, then the ingest kernel */
+        int rc = tiktak_cuda_local_enqueue(h, alg, first_k, n_k, nullptr);
+        if (rc) return rc;
+        return tiktak_cuda_local_ingest_rounds(h, first_k, n_k, round_size, nullptr, accepted);
+    }
+    if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
+    TK_CUDA(cudaSetDevice(h->device));
+    int rc;
+    if (!h->local_timing_open) {
+        TK_CUDA(cudaEventRecord(h->evl0, h->stream));
+        h->local_timing_open = true;
+    }
+    if (h->best_dirty) {
+        if ((rc = tk_launch_best(h))) return rc;
+        h->best_dirty = false;
+    }
+    if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows) : tk_launch_blend(h, first_k, n_k))) return rc;
+    if (h->cfg.nm_shrink_mode == 1 && (rc = tk_launch_shrink_width(h))) return rc;
+    if ((rc = tk_launch_nm(h, first_k, n_k, round_size))) return rc;
+    TK_CUDA(cudaEventRecord(h->evl1, h->stream));
+    int acc = 0;
+    double rows = 0;
+    TK_CUDA(cudaMemcpyAsync(&acc, h->d_nmq + 4 /* NMQ_ACCEPTED */, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(&rows, h->d_best + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (acc <= 0 || acc > n_k) { tk_set_error("local_launch: the kernel committed %d of %d restarts", acc, n_k); return TIKTAK_ERR_STATE; }
+    h->n_rows = (int)rows;
     *accepted = acc;
     return TIKTAK_OK;
 }
@@ -828,7 +867,10 @@ int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts)
     /* later rounds only depend on earlier ones through the best row, so they can be started early when the search
      * mode makes the start a function of that row alone (not of the 10 best rows / the rank lottery) */
     const bool speculate = h->cfg.search_type == 0 && !(alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1);
-    *restarts = speculate ? tk_nm_wave_capacity(h) * h->cfg.world : 0;
+    int cap = tk_nm_wave_capacity(h) * h->cfg.world;
+    /* nm_w4_kernel bounds the early starts itself (restart queue + in-kernel commit): a launch may hold all that is left */
+    if (alg == TIKTAK_ALG_AMOEBA && h->cfg.world == 1 && h->cfg.objective_id != TIKTAK_OBJ_SMM && tk_nm_use_w4(h)) cap = std::max(cap, (int)h->cfg.maxpoints_plus1);
+    *restarts = speculate ? cap : 0;
     return TIKTAK_OK;
 }
 

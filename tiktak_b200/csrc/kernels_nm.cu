@@ -19,33 +19,17 @@
  * ingest_kernel / blend_kernel / shrink_width_kernel / pack_kernel keep searchResults on the device between rounds.
  */
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
-#include "tk_common.cuh"
+#include "nm_common.cuh"
 #include "../../include/tiktak_rng.h"
 
-namespace {
+using namespace tknm;
 
-struct NmArgs {
-    int n_run;            /* restarts this launch runs */
-    int n_k;              /* restarts of the round (column length of starts/out_x) */
-    int rank, world;      /* restart slot = rank + r*world */
-    int first_k, K;       /* restart number of slot 0; p_maxpoints */
-    const double* starts; /* (n_k, nx) column-major */
-    const double* width;  /* nx: p_range(:,2)-p_range(:,1) */
-    const double* wshr;   /* nx: simplex width from the best minima so far (nm_shrink_mode = 1), else NULL */
-    const int* shr_have;  /* device flag: wshr is defined (>= 2 finished restarts), else NULL */
-    const double* simplex; /* (nx, nx+1) column-major unit simplex */
-    double scale;          /* DBLE(p_maxpoints)**(1/nx) */
-    double ftol;
-    int itmax;
-    double fac1r, fac2r, fac1e, fac2e, fac1c, fac2c; /* amotry's fac1/fac2 for fac = -1, 2, 0.5 */
-    double tiny;
-    double* out_x; /* (n_k, nx) column-major */
-    double* out_f; /* n_k */
-    int* out_evals;
-};
+namespace {
 
 __device__ __forceinline__ void warp_argmin(const double* y, int np, int lane, int& idx) {
     double v = DBL_MAX; int bi = 0x7fffffff;
@@ -276,8 +260,6 @@ struct TkLaneX { /* accessor for plugins whose term i reads x[i] only: the lane'
     double v;
     __device__ __forceinline__ double operator[](int) const { return v; }
 };
-/* (ya, ra) sorts before (yb, rb): y ascending, vertex index descending among equal y */
-__device__ __forceinline__ bool nm_before(double ya, int ra, double yb, int rb) { return ya < yb || (ya == yb && ra > rb); }
 
 /* sort the np (y, vertex) pairs held one per lane; every lane returns the pair of its sorted position */
 __device__ __forceinline__ void nm_full_sort(double& y, int& row, int np, int lane, double* scr_y, int* scr_r) {
@@ -369,8 +351,11 @@ __device__ __forceinline__ double nm_eval_warp(const tk_obj_ctx& ctx, const NmSc
     return yc;
 }
 
+#ifndef TK_NMQ_MINB
+#define TK_NMQ_MINB 0 /* ptxas decides (72 registers, 6-7 resident blocks per SM); 8 (64 registers) measured slower: C2 4.8 against 4.2 ms, C3 39.7 against 35.9 ms */
+#endif
 template <class Obj, int NXC>
-__global__ void __launch_bounds__(128) nm_quad_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+__global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
     extern __shared__ double smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -526,16 +511,6 @@ __global__ void __launch_bounds__(128) nm_quad_kernel(const TkTablesG T, const T
             a.out_evals[slot] = np + iter + 1;
         }
     }
-}
-
-/* amoeba's stopping test rtol < ftol (:84-85); the division is only formed when the product test is within 2^-40 */
-__device__ __forceinline__ bool nm_converged(const NmArgs& a, double ylo, double yhi) {
-    const double num = TK_MUL(2.0, fabs(TK_SUB(yhi, ylo)));
-    const double den = TK_ADD(TK_ADD(fabs(yhi), fabs(ylo)), a.tiny);
-    const double thr = TK_MUL(a.ftol, den);
-    bool conv = num < TK_MUL(thr, 0.99999999999909051);
-    if (!conv && !(num > TK_MUL(thr, 1.00000000000090949))) conv = TK_DIV(num, den) < a.ftol;
-    return conv;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -1172,10 +1147,13 @@ int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, con
 }
 
 /* how many restarts of the local-search kernel are resident at once on this GPU (one wave) */
+bool tk_nm_use_w4(tiktak_handle* h);
+int tk_nm_w4_capacity(tiktak_handle* h);
 int tk_nm_wave_capacity(tiktak_handle* h) {
     const int nx = h->cfg.nx;
     int per_sm = 1;
     if (h->cfg.objective_id == TIKTAK_OBJ_SMM) return h->sm_count;
+    if (tk_nm_use_w4(h)) return std::max(1, tk_nm_w4_capacity(h));
     tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
         if (nx <= 31 && Obj::nterms(nx) <= nx) {
             const int ts = (nx + 2) & ~1;
@@ -1216,7 +1194,26 @@ static int nm_launch_warp(tiktak_handle* h, const TkTablesG& T, const NmArgs& a,
     return TIKTAK_OK;
 }
 
-int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
+bool tk_nm_w4_supported(tiktak_handle* h);
+int tk_nm_w4_capacity(tiktak_handle* h);
+int tk_launch_nm_w4(tiktak_handle* h, const NmArgs& a, const NmQueue& q);
+
+/* which Nelder-Mead form runs: one warp per restart + device queue (kernels_nm_w4.cu) wherever it is built for the
+ * configuration; TIKTAK_NM_FORM=quad forces the four-warp form of this file (experiments, cross-check of one form against the other) */
+bool tk_nm_use_w4(tiktak_handle* h) {
+    if (h->nm_form < 0) {
+        const char* e = getenv("TIKTAK_NM_FORM");
+        /* measured (B200, round 2): four warps per restart are ~2x faster per evaluation than one warp where the quad kernel
+         * exists (nx <= 31); above that the one-warp kernel wins (C4: 97 ms against 254 ms) */
+        const bool want_w4 = (e && !strcmp(e, "w4")) || (!(e && !strcmp(e, "quad")) && h->cfg.nx > 31);
+        h->nm_form = (want_w4 && tk_nm_w4_supported(h)) ? 1 : 0;
+    }
+    return h->nm_form == 1;
+}
+
+/* commit_round_size > 0 (world == 1, throughput form): the kernel itself commits complete rounds into the results
+ * table and stops the launch at the first round that changes the best row; h->d_nmq[NMQ_ACCEPTED] = restarts committed */
+int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size) {
     const int nx = h->cfg.nx, np = nx + 1;
     NmArgs a;
     a.n_k = n_k;
@@ -1242,6 +1239,22 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k) {
     a.out_x = h->d_out_x;
     a.out_f = h->d_out_f;
     a.out_evals = h->d_out_evals;
+    if (tk_nm_use_w4(h)) {
+        NmQueue q;
+        const int K = h->cfg.maxpoints_plus1;
+        if (!h->d_nmq) TK_CUDA(cudaMalloc(&h->d_nmq, (size_t)(NMQ_DONE0 + K + 1) * sizeof(int)));
+        q.commit = (commit_round_size > 0 && h->cfg.world == 1) ? 1 : 0;
+        q.round_size = q.commit ? commit_round_size : n_k;
+        q.n_rounds = (n_k + q.round_size - 1) / q.round_size;
+        TK_CUDA(cudaMemsetAsync(h->d_nmq, 0, (size_t)(NMQ_DONE0 + q.n_rounds) * sizeof(int), h->stream));
+        /* restarts that may run ahead of the committed rounds: a round, or what two warps per SM sub-partition hold */
+        q.depth0 = std::max(q.round_size, h->sm_count * 8);
+        q.roundtrip = h->cfg.text_roundtrip;
+        q.nx = nx;
+        q.ctl = h->d_nmq; q.res = h->d_res; q.valid = h->d_res_valid; q.arch_evals = h->d_arch_evals; q.best = h->d_best;
+        return tk_launch_nm_w4(h, a, q);
+    }
+    if (commit_round_size > 0) { tk_set_error("nm: in-kernel commit needs nm_w4_kernel"); return TIKTAK_ERR_STATE; }
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
         int rc = TIKTAK_OK;

@@ -89,6 +89,7 @@ struct ObjRastrigin { /* f = 10 n + sum (x^2 - 10 cos(2 pi x)) */
     static constexpr int kId = TIKTAK_OBJ_RASTRIGIN;
     static constexpr bool kVector = false;
     static constexpr bool kTermLocal = true;
+    static constexpr bool kFoldUsesB = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }
@@ -124,6 +125,7 @@ struct ObjRosenbrock { /* f = sum_{i<n} 100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2 */
     static constexpr int kId = TIKTAK_OBJ_ROSENBROCK;
     static constexpr bool kVector = false;
     static constexpr bool kTermLocal = false;
+    static constexpr bool kFoldUsesB = false;
     static void host_init(int nx, double* aux) {
         for (int i = 0; i < nx; i++) aux[i] = 0.0;
     }

@@ -130,6 +130,8 @@ struct tiktak_handle {
     int lot_cum_n = 0;
     int n_rows = 0;                   /* result rows known to the handle (k = 0 record included) */
     int* d_accepted = nullptr;        /* restarts ingested by the last multi-round ingest */
+    int* d_nmq = nullptr;             /* control words of the throughput Nelder-Mead kernel's restart queue (nm_common.cuh) */
+    int nm_form = -1;                 /* 1: one warp per restart (kernels_nm_w4.cu), 0: four warps per restart (kernels_nm.cu), -1: not decided yet */
     double *d_objfun_x = nullptr, *d_objfun_f = nullptr; /* staging of tiktak_cuda_objfun for host arguments */
     int64_t objfun_scratch_pts = 0;
     /* DFNLS */
@@ -155,7 +157,8 @@ int tk_launch_init_results(tiktak_handle* h);
 int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count);
-int tk_launch_nm(tiktak_handle* h, int first_k, int n_k);
+int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size = 0);
+bool tk_nm_use_w4(tiktak_handle* h);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, const double* pack, int* d_accepted);
 int tk_nm_wave_capacity(tiktak_handle* h);

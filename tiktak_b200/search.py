@@ -144,9 +144,10 @@ class TikTakSearch:
 
             from . import dist as D
 
-            counts = torch.zeros(self.cfg.qr_ndraw // SOBOL_BLOCK + 1, dtype=torch.int64, device=torch.device("cuda", self.device))
-            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), counts.numel()), "pretest_counts")
-            self._n_legit = int(D.reduce_counts(counts.sum().reshape(1), self.group).item())
+            with torch.cuda.stream(self.torch_stream()):  # the copy overwrites every element: no fill kernel on another stream
+                counts = torch.empty(self.cfg.qr_ndraw // SOBOL_BLOCK + 1, dtype=torch.int64, device=torch.device("cuda", self.device))
+                _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), counts.numel()), "pretest_counts")
+                self._n_legit = int(D.reduce_counts(counts.sum().reshape(1), self.group).item())
 
     def _solve(self, wait):
         ne, nl = C.c_int64(), C.c_int64()
@@ -184,7 +185,8 @@ class TikTakSearch:
             return True, N, None
         dev = torch.device("cuda", self.device)
         wave = 64 * self.world
-        counts = torch.zeros(nblocks, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(self.torch_stream()):  # pretest_counts overwrites every element on that stream
+            counts = torch.empty(nblocks, dtype=torch.int64, device=dev)
         cum, kcut, nleg, cb0 = 0, -1, 0, 0
         while cb0 < nblocks and kcut < 0:
             ncb = min(wave, nblocks - cb0)
@@ -235,8 +237,8 @@ class TikTakSearch:
 
             # shard-local top-(K-1), exported on the device, one all-gather, merged on the device
             _lib.check(self._L.tiktak_cuda_choose(self._h, None, None), "chooseSobol")
-            cand = torch.empty((K, 2), dtype=torch.float64, device=torch.device("cuda", self.device))
             with torch.cuda.stream(self.torch_stream()):
+                cand = torch.empty((K, 2), dtype=torch.float64, device=torch.device("cuda", self.device))
                 _lib.check(self._L.tiktak_cuda_choose_candidates(self._h, cand.data_ptr()), "choose_candidates")
                 allc = D.gather_candidates(cand, self.world, self.group)
                 _lib.check(self._L.tiktak_cuda_choose_merge(self._h, allc.data_ptr(), allc.shape[0], xs.ctypes.data,
@@ -272,7 +274,7 @@ class TikTakSearch:
         if window is None:
             cap = C.c_int32()
             _lib.check(self._L.tiktak_cuda_local_capacity(self._h, alg, C.byref(cap)), "local_capacity")
-            window = cap.value
+            window = cap.value  # 0 = the mode forbids early starts: one round per launch
         per_launch = max(B, (int(window) // B) * B)  # whole rounds
         send = recv = None
         if W > 1:
@@ -282,20 +284,22 @@ class TikTakSearch:
 
             cap = D.n_max(min(per_launch, K), W) * (nx + 2)
             dev = torch.device("cuda", self.device)
-            send = torch.empty(cap, dtype=torch.float64, device=dev)
-            recv = torch.empty(W * cap, dtype=torch.float64, device=dev)
+            with torch.cuda.stream(self.torch_stream()):  # allocated and used on the library's stream only
+                send = torch.empty(cap, dtype=torch.float64, device=dev)
+                recv = torch.empty(W * cap, dtype=torch.float64, device=dev)
         k, acc = 1, C.c_int32()
         self.local_launches = 0
         while k <= K:
             n = min(per_launch, K - k + 1)
-            _lib.check(self._L.tiktak_cuda_local_enqueue(self._h, alg, k, n, send.data_ptr() if W > 1 else None),
-                       "LocalMinimizations")
-            if W > 1:
+            if W == 1:
+                _lib.check(self._L.tiktak_cuda_local_launch(self._h, alg, k, n, B, C.byref(acc)), "LocalMinimizations")
+            else:
+                _lib.check(self._L.tiktak_cuda_local_enqueue(self._h, alg, k, n, send.data_ptr()), "LocalMinimizations")
                 cnt = D.n_max(n, W) * (nx + 2)
                 with torch.cuda.stream(self.torch_stream()):
                     D.gather_rows(recv[: W * cnt], send[:cnt], self.group)
-            _lib.check(self._L.tiktak_cuda_local_ingest_rounds(self._h, k, n, B, recv.data_ptr() if W > 1 else None,
-                                                               C.byref(acc)), "LocalMinimizations")
+                _lib.check(self._L.tiktak_cuda_local_ingest_rounds(self._h, k, n, B, recv.data_ptr(), C.byref(acc)),
+                           "LocalMinimizations")
             assert 0 < acc.value <= n
             k += acc.value
             self.local_launches += 1
