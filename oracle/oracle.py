@@ -185,5 +185,30 @@ class Oracle:
         self.L.orc_run_amoeba(self.h, dptr(p), C.byref(it))
         return p, it.value
 
+    def sobolFnValRange(self, first, count):
+        """objFun at Sobol points first..first+count-1 (seeks by the Gray code; no points before `first` are generated)"""
+        f = np.empty(count)
+        self.L.orc_objfun_range.restype = C.c_long
+        self.L.orc_objfun_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, c_double_p]
+        nl = self.L.orc_objfun_range(self.h, first, count, dptr(f))
+        assert nl >= 0, nl
+        return f, int(nl)
+
+    def sobolPointsRange(self, first, count):
+        out = np.empty((self.cfg.nx, count))
+        self.L.orc_points_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, c_double_p]
+        assert self.L.orc_points_range(self.h, first, count, dptr(out)) == 0
+        return out.T
+
+    def completeSearch(self, algor, k, start):
+        """one restart from a given start: (result point, fn_val of the re-evaluation :582, objective evaluations)"""
+        x = as_f64(start).copy()
+        f = C.c_double()
+        self.L.orc_complete_search.restype = C.c_int
+        self.L.orc_complete_search.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
+        ne = self.L.orc_complete_search(self.h, algor, k, dptr(x), C.byref(f))
+        assert ne >= 0, ne
+        return x, f.value, ne
+
     def nfev(self):
         return int(self.L.orc_nfev(self.h))

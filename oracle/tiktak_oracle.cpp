@@ -961,6 +961,75 @@ int orc_dfnls(void* h, double* x, double rhobeg, double rhoend, int maxfun, int3
     if (nrescue) *nrescue = n2;
     return rc;
 }
+/* objFun at the Sobol points first..first+count-1 without generating the points before them: the generator's state
+ * after n calls is lastq = XOR of the columns v(:,j) over the set bits j of the Gray code n ^ (n >> 1) (SURVEY 8a3;
+ * checked against the sequential generator by tests/test_oracle_kat.py), Scount = n.  Lets P processes share a
+ * large pre-test (C3: 1e8 points) by index range.  Returns the number of values below fvalmax, or < 0. */
+long orc_objfun_range(void* h, int64_t first, int64_t count, double* fval) {
+    Oracle* o = (Oracle*)h;
+    Sobol sb;
+    if (first < 1 || count < 0 || sb.insobl(o->c.nx, o->c.qr_ndraw)) return -1;
+    const int64_t n0 = first - 1;
+    const int64_t g = n0 ^ (n0 >> 1);
+    for (int j = 1; j <= sb.maxcol; j++)
+        if ((g >> (j - 1)) & 1)
+            for (int d = 1; d <= sb.s; d++) sb.lastq[d] ^= sb.v[d][j];
+    sb.scount = (int)n0;
+    std::vector<double> q(o->c.nx), x(o->c.nx);
+    long legit = 0;
+    for (int64_t r = 0; r < count; r++) {
+        if (sb.next(q.data(), 0)) return -2;
+        for (int i = 0; i < o->c.nx; i++) x[i] = o->lo_r()[i] + q[i] * (o->hi_r()[i] - o->lo_r()[i]); /* :834 */
+        fval[r] = o->objFun(x.data());
+        if (fval[r] < o->c.fvalmax) legit++;
+    }
+    return legit;
+}
+/* the Sobol points themselves for such a range: (count, nx) column-major, same seek */
+int orc_points_range(void* h, int64_t first, int64_t count, double* out) {
+    Oracle* o = (Oracle*)h;
+    Sobol sb;
+    if (first < 1 || count < 0 || sb.insobl(o->c.nx, o->c.qr_ndraw)) return -1;
+    const int64_t n0 = first - 1;
+    const int64_t g = n0 ^ (n0 >> 1);
+    for (int j = 1; j <= sb.maxcol; j++)
+        if ((g >> (j - 1)) & 1)
+            for (int d = 1; d <= sb.s; d++) sb.lastq[d] ^= sb.v[d][j];
+    sb.scount = (int)n0;
+    std::vector<double> q(o->c.nx);
+    for (int64_t r = 0; r < count; r++) {
+        if (sb.next(q.data(), 0)) return -2;
+        for (int i = 0; i < o->c.nx; i++) out[(size_t)i * count + r] = o->lo_r()[i] + q[i] * (o->hi_r()[i] - o->lo_r()[i]);
+    }
+    return 0;
+}
+/* completeSearch (TiktakGlobalSearch.f90:546-600) for restart k from a GIVEN start (evalParam): the local search with the
+ * radii / simplex of restart k, then the re-evaluation :582.  x: in = start, out = result; returns objective evaluations. */
+int orc_complete_search(void* h, int alg, int k, double* x, double* fn_val) {
+    Oracle* o = (Oracle*)h;
+    const int nx = o->c.nx, K = o->c.maxpoints_plus1;
+    std::vector<double> p(x, x + nx);
+    const long nfev0 = o->nfev;
+    if (alg == TIKTAK_ALG_AMOEBA) {
+        std::vector<double> w(nx);
+        for (int i = 0; i < nx; i++) w[i] = o->hi_r()[i] - o->lo_r()[i];
+        int it = 0;
+        o->runAmoeba(p, w, it);
+    } else if (alg == TIKTAK_ALG_DFNLS) {
+        double itratio = (double)((float)k / (float)K); /* :564 */
+        double mn = o->bu()[0] - o->bl()[0];
+        for (int i = 1; i < nx; i++) mn = std::min(mn, o->bu()[i] - o->bl()[i]);
+        double rhobeg, rhoend;
+        if (itratio > 0.5) { rhobeg = (mn / 2.5) / (4 * itratio); rhoend = 1.0e-3 / (4 * itratio); } /* :565-571 */
+        else { rhobeg = mn / 2.50; rhoend = 1.0e-3; }
+        int nf = 0, nresc = 0;
+        o->dfnls(p, rhobeg, rhoend, o->c.maxeval, nf, nresc);
+    } else return -2;
+    const double f = o->objFun(p.data()); /* :582 */
+    for (int i = 0; i < nx; i++) x[i] = p[i];
+    if (fn_val) *fn_val = f;
+    return (int)(o->nfev - nfev0);
+}
 /* runtime self-check that this build does not contract a*b+c (the reference build has no FMA) */
 int orc_unfused_selfcheck(void) {
     volatile double a = 1.0 + ldexp(1.0, -30), b = 1.0 - ldexp(1.0, -30), cc = -1.0;

@@ -65,6 +65,20 @@ def test_sobol_dims_1_2_match_scipy(L):
     assert np.array_equal(ours, ref)
 
 
+def test_sobol_seek_by_gray_code_equals_sequential_generation(built):
+    """orc_objfun_range / orc_points_range start in the middle of the sequence (state = XOR of the columns picked by the
+    Gray code of the previous index): same points and values as generating from point 1 -- what lets the full-size
+    GPU tests share 1e8 oracle evaluations between processes"""
+    cfg = make_config(20, 1, 70000, 10, -4.12, 5.12, init=[1.0] * 20, objective_id=OBJ_RASTRIGIN)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    f, pts = o.sobolFnVal(), o.setupSobol()
+    for first, count in [(1, 50), (2, 3), (4096, 10), (4097, 200), (32768, 5), (65535, 3), (69990, 11), (33333, 1)]:
+        g, nl = o.sobolFnValRange(first, count)
+        assert np.array_equal(g, f[first - 1:first - 1 + count]) and nl == count
+        assert np.array_equal(o.sobolPointsRange(first, count), pts[first - 1:first - 1 + count])
+
+
 def test_sobol_single_precision_quirk(L):
     """utilities.f90:1090 `i = floor(real(i/2))`: identical to the integer rule up to Scount 33,554,434,
     first mismatch at 33,554,435 (l_ref = 2, l_true = 3), then only columns 1..2 are ever used."""
