@@ -24,9 +24,13 @@
  *      appending to searchStart.dat / searchResults.dat.
  * Knobs outside the reference surface come from the environment: TIKTAK_OBJECTIVE (0 template, 1 Griewank,
  * 2 Rastrigin, 3 Rosenbrock), TIKTAK_ROUND_SIZE (default 1 = the sequential reference order), TIKTAK_DEVICE,
- * TIKTAK_WRITE_SOBOL (1 = also dump sobol.dat like setupSobol does).
+ * TIKTAK_WRITE_SOBOL (1 = also dump sobol.dat like setupSobol does), TIKTAK_NGPU (default 1: shard the Sobol index range and
+ * the restarts of every launch over the first n GPUs of the box; the library's NCCL communicator does the exchanges,
+ * one host thread per GPU makes the stage calls, this thread -- rank 0 -- also writes the files).
  */
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +38,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/tiktak_cuda.h"
@@ -176,19 +181,58 @@ int main(int argc, char** argv) {
     tiktak_handle* h = nullptr;
     const int K = tc.maxpoints_plus1, nx = c.nx, seqNo = 1;
     write_int("state.dat", 0);
-    CHECK(tiktak_cuda_create(&h, &tc));
+    const int ngpu = std::max(1, envi("TIKTAK_NGPU", 1));
+    std::vector<tiktak_handle*> hs(ngpu, nullptr);
+    for (int r = 0; r < ngpu; r++) { /* rank r of ngpu on device TIKTAK_DEVICE + r */
+        tiktak_config tr = tc;
+        tr.rank = r; tr.world = ngpu; tr.device = tc.device + r;
+        CHECK(tiktak_cuda_create(&hs[r], &tr));
+    }
+    h = hs[0];
+    if (ngpu > 1) CHECK(tiktak_cuda_comm_init_all(hs.data(), ngpu));
     write_int("seqNo.dat", seqNo);
     if (option == 4) { /* :138-149 */
         double f;
         printf(" Running diagnostics for the initial guess:\n");
         CHECK(tiktak_cuda_objfun(h, c.init.data(), 1, &f));
         printf("Objective value = %12.6f\n", f);
-        tiktak_cuda_destroy(h);
+        for (int r = 0; r < ngpu; r++) tiktak_cuda_destroy(hs[r]);
         return 0;
     }
     if (alg == 2 && option != 5) { logmsg("<main:search> dfpmin as the stage-7 algorithm is not built; use a or b"); tiktak_cuda_destroy(h); return 1; }
     if (option == 3) { for (const char* fn : {"sobolFnVal.dat", "FinalStart.dat", "FinalResults.dat"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); } }
     else for (const char* fn : {"sobolFnVal.dat", "searchStart.dat", "searchResults.dat", "FinalStart.dat", "FinalResults.dat", "logFile.txt"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); }
+    /* ranks 1.. of a multi-GPU run: the same stage calls (each is collective over the handles), no files */
+    std::vector<std::thread> helpers;
+    std::vector<int> helper_rc(ngpu, 0);
+    std::atomic<bool> values_read{false}; /* rank 0 has copied every shard's values out for sobolFnVal.dat: the handles are free again */
+    {
+        const int n_old = (int)old_rows.size();
+        std::vector<double> old_cm((size_t)n_old * (nx + 4));
+        for (int r = 0; r < n_old; r++) for (int cc = 0; cc < nx + 4; cc++) old_cm[(size_t)cc * n_old + r] = old_rows[r][cc];
+        for (int r = 1; r < ngpu; r++)
+            helpers.emplace_back([&, r, old_cm, n_old]() {
+                tiktak_handle* hr = hs[r];
+                int64_t e = 0, l = 0;
+                int rc = tiktak_cuda_pretest(hr, &e, &l);
+                while (!values_read.load()) std::this_thread::sleep_for(std::chrono::microseconds(200));
+                if (!rc) rc = tiktak_cuda_choose(hr, nullptr, nullptr);
+                if (!rc && n_old > 0) rc = tiktak_cuda_push_results(hr, old_cm.data(), n_old);
+                const int B = tc.round_size < 1 ? 1 : tc.round_size;
+                int k0 = resume_k + 1;
+                const int kend = option == 5 ? 1 : K;
+                int32_t window = 0;
+                if (!rc) rc = tiktak_cuda_local_capacity(hr, alg, &window);
+                const int per_launch = std::max(B, (window / B) * B);
+                while (!rc && k0 <= kend) {
+                    int32_t acc = 0;
+                    rc = tiktak_cuda_local_launch(hr, alg, k0, std::min(per_launch, kend - k0 + 1), B, &acc);
+                    k0 += acc;
+                }
+                helper_rc[r] = rc;
+            });
+    }
+    struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.detach(); } } joiner{helpers};
     /* states 2-5 */
     write_int("state.dat", 2);
     if (envi("TIKTAK_WRITE_SOBOL", 0) && c.qr > 0) {
@@ -206,6 +250,13 @@ int main(int argc, char** argv) {
         for (int64_t first = 1; first <= ne; first += chunk) {
             const int64_t cnt = std::min<int64_t>(chunk, ne - first + 1);
             CHECK(tiktak_cuda_pretest_values(h, first, cnt, fv.data()));
+            if (ngpu > 1) { /* a shard returns NaN for the count blocks of the others: take each value from its owner */
+                std::vector<double> part(cnt);
+                for (int r = 1; r < ngpu; r++) {
+                    CHECK(tiktak_cuda_pretest_values(hs[r], first, cnt, part.data()));
+                    for (int64_t q = 0; q < cnt; q++) if (part[q] == part[q]) fv[q] = part[q];
+                }
+            }
             CHECK(tiktak_cuda_sobol_points(h, first, cnt, pts.data()));
             for (int64_t r = 0; r < cnt; r++) {
                 fprintf(f, "%8lld%40.20f", (long long)(first + r), fv[r]);
@@ -215,6 +266,7 @@ int main(int argc, char** argv) {
         }
         fclose(f);
     }
+    values_read.store(true);
     write_int("lastSobol.dat", (long)ne + 1);
     write_int("legitSobol.dat", (long)nl);
     { char b[200]; snprintf(b, sizeof b, "%d has evaluated %lld sobol points, %lld legitimate", seqNo, (long long)ne, (long long)nl); logmsg(b); }
@@ -282,6 +334,8 @@ int main(int argc, char** argv) {
         char b[300]; snprintf(b, sizeof b, "The best final point is %.12f (restart %d), after the final search %.12f", fb, kb, ff); logmsg(b);
     }
     { char b[100]; snprintf(b, sizeof b, "%d has no more tasks.", seqNo); logmsg(b); }
-    tiktak_cuda_destroy(h);
+    for (auto& t : helpers) if (t.joinable()) t.join();
+    for (int r = 1; r < ngpu; r++) if (helper_rc[r]) { char b[200]; snprintf(b, sizeof b, "EXIT STATE: rank %d: %s", r, tiktak_cuda_strerror(helper_rc[r])); logmsg(b); return 1; }
+    for (int r = 0; r < ngpu; r++) tiktak_cuda_destroy(hs[r]);
     return 0;
 }

@@ -207,6 +207,21 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
  * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */
 int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n);
 
+/* Multi-GPU: the handle owns its NCCL communicator.  The reference's instances coordinate through lock files on a
+ * shared directory (stateControl.f90:12-216: getNextNumber / setState / waitState); here rank r of `world` (tiktak_config)
+ * owns the Sobol count blocks r, r+world, ... and the restart slots r, r+world, ... of every launch, and once a
+ * communicator exists tiktak_cuda_pretest / _choose / _local_launch do their exchanges themselves, on the handle's stream
+ * (per-wave all-reduce of the valid counts when the `legitimate` cut can fire; one all-gather of candidate rows; one
+ * all-gather of result rows per launch) and return the same global results on every rank.  NCCL is loaded with dlopen.
+ *   one process per GPU : rank 0 calls comm_unique_id, the launcher carries the 128 bytes to the other ranks (MPI,
+ *                         torch.distributed, a file), every rank calls comm_init -- a collective.
+ *   one process, n GPUs : create n handles (rank r on device r) and call comm_init_all once; then one host thread per
+ *                         handle makes the stage calls (each is collective over the n handles). */
+#define TIKTAK_COMM_ID_BYTES 128
+int tiktak_cuda_comm_unique_id(void* id, int32_t bytes);
+int tiktak_cuda_comm_init(tiktak_handle* h, const void* id, int32_t bytes);
+int tiktak_cuda_comm_init_all(tiktak_handle** handles, int32_t n_handles);
+
 /* getBestLine (TiktakGlobalSearch.f90:781-802): best row so far. */
 int tiktak_cuda_best(tiktak_handle* h, double* fbest, double* xbest, int32_t* k);
 

@@ -350,7 +350,7 @@ def test_sharded_protocol_on_one_gpu(built, name, alg, world):
     dev = torch.device("cuda", 0)
     o = Oracle(cfg, MATH_TK)
     o.solveAtSobolPoints(); oxs = o.chooseSobol(mode=1); o.LocalMinimizations(1 if alg == "a" else 0)
-    hs = [TikTakSearch(cfg, device=0, rank=r, world=world) for r in range(world)]
+    hs = [TikTakSearch(cfg, device=0, rank=r, world=world, comm=False) for r in range(world)]
     try:
         # --- Sobol stage: every shard evaluates its own count blocks, no exchange (legitimate > qr_ndraw)
         for s in hs:

@@ -269,6 +269,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    tk_comm_destroy(h);
     tk_smm_free(h);
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
                     h->d_counts, h->d_hist, h->d_selstate, h->d_cand_f, h->d_cand_i, h->d_cand_n, h->d_sorted_f,
@@ -276,7 +277,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
                     h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_nmq, h->d_counts_spare,
-                    h->d_objfun_x, h->d_objfun_f, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n};
+                    h->d_objfun_x, h->d_objfun_f, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -459,6 +460,69 @@ int tiktak_cuda_pretest_set_cut(tiktak_handle* h, int64_t kcut, int64_t n_legit)
     return TIKTAK_OK;
 }
 
+/* exchange buffers of the handle's communicator: send `n` doubles per rank, receive world * n */
+static int comm_buffers(tiktak_handle* h, size_t n) {
+    if (h->xbuf_doubles >= n) return TIKTAK_OK;
+    if (h->d_xsend) cudaFree(h->d_xsend);
+    if (h->d_xrecv) cudaFree(h->d_xrecv);
+    h->d_xsend = h->d_xrecv = nullptr; h->xbuf_doubles = 0;
+    TK_CUDA(cudaMalloc(&h->d_xsend, n * sizeof(double)));
+    TK_CUDA(cudaMalloc(&h->d_xrecv, n * sizeof(double) * (size_t)h->cfg.world));
+    h->xbuf_doubles = n;
+    return TIKTAK_OK;
+}
+
+/* world > 1 with the handle's communicator: count blocks are dealt block-cyclically; when the `legitimate` cut cannot
+ * fire every rank evaluates its blocks and nothing is exchanged (the valid count travels with choose's candidate rows);
+ * otherwise blocks are evaluated in waves of 64 per rank with one all-reduce of the per-block valid counts per wave, and
+ * the owner of the block that holds the L-th valid point finds its index (solveAtSobolPoints :429-464 on shards) */
+static int pretest_sharded(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit) {
+    const int64_t N = h->cfg.qr_ndraw, L = h->cfg.legitimate;
+    int rc;
+    h->counts_global = false;
+    if (L > N) {
+        if ((rc = tiktak_cuda_pretest_wave(h, 0, h->n_cblocks))) return rc;
+        h->kcut = N; h->nlegit = -1; h->pretest_done = true;
+        if (n_evaluated) *n_evaluated = N;
+        if (n_legit) { /* the caller wants the count now: one all-reduce of the shard totals */
+            if ((rc = tiktak_cuda_pretest_result(h, nullptr, n_legit))) return rc;
+        }
+        return TIKTAK_OK;
+    }
+    const int64_t wave = 64 * (int64_t)h->cfg.world;
+    int64_t cum = 0, kcut = -1, nleg = 0;
+    for (int64_t cb0 = 0; cb0 < h->n_cblocks && kcut < 0; cb0 += wave) {
+        const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
+        if ((rc = tiktak_cuda_pretest_wave(h, cb0, ncb))) return rc;
+        if ((rc = tk_comm_allreduce_sum_u64(h, h->d_counts + cb0, (size_t)ncb))) return rc;
+        TK_CUDA(cudaMemcpyAsync(h->h_counts.data() + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        for (int64_t cb = cb0; cb < cb0 + ncb; cb++) {
+            const int64_t c = (int64_t)h->h_counts[cb];
+            if (cum + c >= L) { /* the L-th valid point lives in this count block: its owner finds the index */
+                TK_CUDA(cudaMemsetAsync(h->d_selstate, 0, 8, h->stream));
+                if (cb % h->cfg.world == h->cfg.rank && (rc = tk_launch_find_cut(h, cb, (unsigned long long)(L - cum), h->d_selstate))) return rc;
+                if ((rc = tk_comm_allreduce_max_u64(h, h->d_selstate, 1))) return rc;
+                unsigned long long r = 0;
+                TK_CUDA(cudaMemcpyAsync(&r, h->d_selstate, 8, cudaMemcpyDeviceToHost, h->stream));
+                TK_CUDA(cudaStreamSynchronize(h->stream));
+                kcut = (int64_t)r; nleg = L;
+                break;
+            }
+            cum += c;
+        }
+    }
+    if (kcut < 0) { kcut = N; nleg = cum; }
+    h->counts_global = true;
+    h->kcut = kcut; h->nlegit = nleg; h->pretest_done = true;
+    if (n_evaluated) *n_evaluated = kcut;
+    if (n_legit) *n_legit = nleg;
+    TK_CUDA(cudaEventRecord(h->evp1, h->stream));
+    h->ev_stage_end = h->evp1;
+    h->pretest_timing_open = true;
+    return TIKTAK_OK;
+}
+
 int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit) {
     if (!h) return TIKTAK_ERR_ARG;
     TK_CUDA(cudaSetDevice(h->device));
@@ -477,6 +541,7 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
         if (n_legit) *n_legit = 0;
         return end_stage();
     }
+    if (h->cfg.world > 1 && tk_comm_ready(h)) return pretest_sharded(h, n_evaluated, n_legit);
     const bool can_cut = (L <= N) && h->cfg.world == 1;
     const int64_t wave = can_cut ? 64 : h->n_cblocks;
     int64_t cum = 0, kcut = -1, nleg = 0;
@@ -559,7 +624,16 @@ static int resolve_legit(tiktak_handle* h) {
     TK_CUDA(cudaStreamSynchronize(h->stream));
     int64_t tot = 0;
     for (int64_t cb = 0; cb < h->n_cblocks; cb++) tot += (int64_t)h->h_counts[cb];
-    if (h->cfg.world == 1) h->nlegit = tot; /* a shard only knows its own count; the host sums the shards */
+    if (h->cfg.world == 1 || h->counts_global) h->nlegit = tot;
+    else if (tk_comm_ready(h)) { /* shard totals summed over the communicator (a collective: every rank calls it) */
+        unsigned long long v = (unsigned long long)tot;
+        TK_CUDA(cudaMemcpyAsync(h->d_selstate, &v, 8, cudaMemcpyHostToDevice, h->stream));
+        int rc = tk_comm_allreduce_sum_u64(h, h->d_selstate, 1);
+        if (rc) return rc;
+        TK_CUDA(cudaMemcpyAsync(&v, h->d_selstate, 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        h->nlegit = (int64_t)v;
+    } /* else: a shard only knows its own count; the caller sums the shards */
     return TIKTAK_OK;
 }
 
@@ -649,6 +723,25 @@ int tiktak_cuda_choose(tiktak_handle* h, double* x_starts, int32_t* sobol_idx) {
     if (rc) return rc;
     rc = tk_select_top(h, h->cfg.maxpoints_plus1 - 1);
     if (rc) return rc;
+    if (h->cfg.world > 1 && tk_comm_ready(h)) {
+        /* every shard's K candidate rows [fval, idx] (+ trailer [valid count, rows filled]) in ONE all-gather; the merged
+         * list is built identically on every rank (chooseSobol :840-899 over the union of the shards) */
+        const int K = h->cfg.maxpoints_plus1, W = h->cfg.world;
+        if ((rc = comm_buffers(h, (size_t)2 * K))) return rc;
+        if ((rc = tk_export_candidates(h, h->d_xsend))) return rc;
+        if ((rc = tk_comm_allgather_f64(h, h->d_xsend, h->d_xrecv, (size_t)2 * K))) return rc;
+        unsigned int tot = 0;
+        if (K > 1) {
+            if ((rc = tk_merge_candidates(h, h->d_xrecv))) return rc;
+            TK_CUDA(cudaMemcpyAsync(&tot, h->d_cand_n, sizeof tot, cudaMemcpyDeviceToHost, h->stream));
+        }
+        std::vector<double> trailer((size_t)W);
+        for (int r = 0; r < W; r++) /* the shards' valid counts ride in the trailer rows */
+            TK_CUDA(cudaMemcpyAsync(&trailer[r], h->d_xrecv + ((size_t)r * K + (K - 1)) * 2, 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        h->n_cand = tot;
+        if (h->nlegit < 0) { double sum = 0; for (double v : trailer) sum += v; h->nlegit = (int64_t)sum; }
+    }
     rc = tk_build_starts(h);
     if (rc) return rc;
     rc = end_timer(h, &h->ms_choose);
@@ -828,7 +921,17 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
     if (!h || !accepted || first_k < 1 || n_k < 0 || round_size < 1 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
     *accepted = 0;
     if (n_k == 0) return TIKTAK_OK;
-    if (h->cfg.world > 1) { tk_set_error("local_launch: world > 1 exchanges the rows between enqueue and ingest_rounds"); return TIKTAK_ERR_UNSUPPORTED; }
+    if (h->cfg.world > 1) {
+        /* slot s of the launch is run by rank s % world; one all-gather of the ranks' rows [fval, x, #evaluations], then every
+         * rank ingests the same rows in the same order (replicated results table and best row) */
+        if (!tk_comm_ready(h)) { tk_set_error("local_launch: world > 1 needs tiktak_cuda_comm_init (or enqueue / all-gather / ingest_rounds by the caller)"); return TIKTAK_ERR_STATE; }
+        const size_t cnt = (size_t)((n_k + h->cfg.world - 1) / h->cfg.world) * (h->cfg.nx + 2);
+        int rc = comm_buffers(h, std::max(cnt, (size_t)2 * h->cfg.maxpoints_plus1));
+        if (rc) return rc;
+        if ((rc = tiktak_cuda_local_enqueue(h, alg, first_k, n_k, h->d_xsend))) return rc;
+        if ((rc = tk_comm_allgather_f64(h, h->d_xsend, h->d_xrecv, cnt))) return rc;
+        return tiktak_cuda_local_ingest_rounds(h, first_k, n_k, round_size, h->d_xrecv, accepted);
+    }
     const bool fused = alg == TIKTAK_ALG_AMOEBA && h->cfg.objective_id != TIKTAK_OBJ_SMM && tk_nm_use_w4(h);
     if (!fused) { /* DFNLS, or a configuration only the latency form is built for: kernel, then the ingest kernel */
         int rc = tiktak_cuda_local_enqueue(h, alg, first_k, n_k, nullptr);

@@ -130,6 +130,11 @@ struct tiktak_handle {
     int lot_cum_n = 0;
     int n_rows = 0;                   /* result rows known to the handle (k = 0 record included) */
     int* d_accepted = nullptr;        /* restarts ingested by the last multi-round ingest */
+    /* multi-GPU: NCCL communicator owned by the handle (comm.cu) + exchange buffers */
+    void* comm = nullptr;
+    double *d_xsend = nullptr, *d_xrecv = nullptr;
+    size_t xbuf_doubles = 0;
+    bool counts_global = false;       /* d_counts holds the all-reduced (global) per-block counts */
     int* d_nmq = nullptr;             /* control words of the throughput Nelder-Mead kernel's restart queue (nm_common.cuh) */
     int nm_form = -1;                 /* 1: one warp per restart (kernels_nm_w4.cu), 0: four warps per restart (kernels_nm.cu), -1: not decided yet */
     double *d_objfun_x = nullptr, *d_objfun_f = nullptr; /* staging of tiktak_cuda_objfun for host arguments */
@@ -165,6 +170,11 @@ int tk_nm_wave_capacity(tiktak_handle* h);
 int tk_launch_pack(tiktak_handle* h, int n_k, double* pack);
 int tk_launch_shrink_width(tiktak_handle* h);
 int tk_fp64_peak(int device, double* flops, double* ms);
+bool tk_comm_ready(const tiktak_handle* h);
+int tk_comm_allgather_f64(tiktak_handle* h, const double* send, double* recv, size_t count);
+int tk_comm_allreduce_sum_u64(tiktak_handle* h, unsigned long long* buf, size_t count);
+int tk_comm_allreduce_max_u64(tiktak_handle* h, unsigned long long* buf, size_t count);
+void tk_comm_destroy(tiktak_handle* h);
 
 /* objective dispatch: calls f.template operator()<Obj>() for the configured plugin */
 #include "objectives.cuh"

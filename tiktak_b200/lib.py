@@ -37,6 +37,9 @@ SIGNATURES = {
     "tiktak_cuda_local_ingest_rounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_int32_p]),
     "tiktak_cuda_local_capacity": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_launch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p]),
+    "tiktak_cuda_comm_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
+    "tiktak_cuda_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "tiktak_cuda_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32]),
     "tiktak_cuda_push_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "tiktak_cuda_best": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int32_p]),
     "tiktak_cuda_last_search": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int32_p]),

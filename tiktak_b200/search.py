@@ -10,9 +10,10 @@ PROGRAM TiktakGlobalSearch (TiktakGlobalSearch.f90:404-1148) for the hot path:
     getBestLine           :781-802     best searchResults row so far
     run                   :217-401     the state machine 1 -> 2 -> 3 -> 6 -> 7 (-> 10) of one cold start
 
-All compute happens in libtiktak_cuda (CUDA, sm_100a).  torch is used only for device memory
-hand-off and torch.distributed (NCCL) when world > 1: the Sobol index range and each round's
-restarts are sharded over the ranks and the per-round result rows are all-gathered.
+All compute happens in libtiktak_cuda (CUDA, sm_100a).  With world > 1 the Sobol index range and each
+launch's restarts are sharded over the ranks; the exchanges (valid counts, candidate rows, result rows)
+are NCCL collectives issued by the library itself on the handle's communicator -- torch.distributed only
+carries the communicator's 128-byte id from rank 0 to the other ranks when the instance is created.
 """
 import ctypes as C
 
@@ -28,7 +29,7 @@ _ALG = {"a": ALG_AMOEBA, "b": ALG_DFNLS, "amoeba": ALG_AMOEBA, "dfnls": ALG_DFNL
 class TikTakSearch:
     """One "instance" of the reference program bound to one GPU (rank of a torch.distributed group or alone)."""
 
-    def __init__(self, cfg: TikTakConfig, device=0, rank=0, world=1, group=None):
+    def __init__(self, cfg: TikTakConfig, device=0, rank=0, world=1, group=None, comm=True):
         self.cfg = cfg
         self.rank, self.world, self.group = rank, world, group
         self.device = device
@@ -47,6 +48,8 @@ class TikTakSearch:
             round_size=cfg.round_size, nm_ftol=cfg.nm_ftol, user=C.cast(C.pointer(self._user), C.c_void_p) if self._user is not None else None)
         self._h = C.c_void_p()
         _lib.check(self._L.tiktak_cuda_create(C.byref(self._h), C.byref(self._c)), "tiktak_cuda_create")
+        if world > 1 and comm:  # comm=False: the caller drives the exchanges itself (enqueue / gather / ingest of the C ABI)
+            self._init_comm()
         self.n_evaluated = None
         self._n_legit = None
         self.x_starts = None
@@ -54,6 +57,18 @@ class TikTakSearch:
         self.searchStart = None  # rows of searchStart.dat: (K, nx)
         self.searchResults = None  # rows of searchResults.dat: (K, nx+4) = seqNo, k, #improv, fval, x
         self.evals = None
+
+    def _init_comm(self):
+        """the handle's NCCL communicator: rank 0 creates the id, the process group carries it to the other ranks"""
+        import torch.distributed as dist
+
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(self._L.tiktak_cuda_comm_unique_id(buf, 128), "comm_unique_id")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        ident = C.create_string_buffer(box[0], 128)
+        _lib.check(self._L.tiktak_cuda_comm_init(self._h, ident, 128), "comm_init")
 
     @property
     def n_legit(self):
@@ -135,77 +150,20 @@ class TikTakSearch:
         return out
 
     def _resolve_legit(self):
-        nl = C.c_int64()
+        nl = C.c_int64()  # world > 1 and not known yet: a collective over the handle's communicator (every rank calls it)
         _lib.check(self._L.tiktak_cuda_pretest_result(self._h, None, C.byref(nl)), "pretest_result")
-        if self.world == 1:
-            self._n_legit = nl.value
-        else:  # a shard knows its own count only
-            import torch
-
-            from . import dist as D
-
-            with torch.cuda.stream(self.torch_stream()):  # the copy overwrites every element: no fill kernel on another stream
-                counts = torch.empty(self.cfg.qr_ndraw // SOBOL_BLOCK + 1, dtype=torch.int64, device=torch.device("cuda", self.device))
-                _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), counts.numel()), "pretest_counts")
-                self._n_legit = int(D.reduce_counts(counts.sum().reshape(1), self.group).item())
+        self._n_legit = nl.value
 
     def _solve(self, wait):
         ne, nl = C.c_int64(), C.c_int64()
-        if self.world == 1:
-            if not wait and self.cfg.legitimate > self.cfg.qr_ndraw > 0:
-                # the cut cannot fire: the evaluation is only queued; n_legit is read back by chooseSobol
-                _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), None), "solveAtSobolPoints")
-                self.n_evaluated, self._n_legit = ne.value, None
-                return True, ne.value, None
-            _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), C.byref(nl)), "solveAtSobolPoints")
-            self.n_evaluated, self._n_legit = ne.value, nl.value
-            return True, ne.value, nl.value
-        return self._solve_sharded()
-
-    def _solve_sharded(self):
-        """world > 1: count blocks are dealt block-cyclically.  When the `legitimate` cut cannot fire
-        (legitimate > qr_ndraw, the default) every rank just evaluates its blocks -- no exchange at all; the
-        global valid count rides along with the candidate all-gather of chooseSobol.  Otherwise blocks are
-        evaluated in waves with one all-reduce of the per-block valid counts per wave."""
-        import torch
-
-        from . import dist as D
-
-        N, Lg = self.cfg.qr_ndraw, self.cfg.legitimate
-        nblocks = N // SOBOL_BLOCK + 1
-        if N == 0 or Lg <= 0:
-            _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, 0, 0), "pretest_wave")
-            _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, 0, 0), "pretest_set_cut")
-            self.n_evaluated, self._n_legit = 0, 0
-            return True, 0, 0
-        if Lg > N:
-            _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, 0, nblocks), "pretest_wave")
-            _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, N, -1), "pretest_set_cut")
-            self.n_evaluated, self._n_legit = N, None  # n_legit is known after chooseSobol
-            return True, N, None
-        dev = torch.device("cuda", self.device)
-        wave = 64 * self.world
-        with torch.cuda.stream(self.torch_stream()):  # pretest_counts overwrites every element on that stream
-            counts = torch.empty(nblocks, dtype=torch.int64, device=dev)
-        cum, kcut, nleg, cb0 = 0, -1, 0, 0
-        while cb0 < nblocks and kcut < 0:
-            ncb = min(wave, nblocks - cb0)
-            _lib.check(self._L.tiktak_cuda_pretest_wave(self._h, cb0, ncb), "pretest_wave")
-            _lib.check(self._L.tiktak_cuda_pretest_counts(self._h, counts.data_ptr(), nblocks), "pretest_counts")
-            with torch.cuda.stream(self.torch_stream()):
-                D.reduce_counts(counts, self.group)
-                cg = counts.cpu().numpy()
-            b, need, cum = D.find_cut(cg[: cb0 + ncb], cb0, Lg, cum)
-            if b >= 0:
-                n = C.c_int64()
-                _lib.check(self._L.tiktak_cuda_pretest_find(self._h, b, need, C.byref(n)), "pretest_find")
-                kcut, nleg = D.agree_max(n.value, self.group, dev), Lg
-            cb0 += ncb
-        if kcut < 0:
-            kcut, nleg = N, cum
-        _lib.check(self._L.tiktak_cuda_pretest_set_cut(self._h, kcut, nleg), "pretest_set_cut")
-        self.n_evaluated, self._n_legit = kcut, nleg
-        return True, kcut, nleg
+        if not wait and self.cfg.legitimate > self.cfg.qr_ndraw > 0:
+            # the cut cannot fire: the evaluation is only queued; the valid count is read back by chooseSobol / n_legit
+            _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), None), "solveAtSobolPoints")
+            self.n_evaluated, self._n_legit = ne.value, None
+            return True, ne.value, None
+        _lib.check(self._L.tiktak_cuda_pretest(self._h, C.byref(ne), C.byref(nl)), "solveAtSobolPoints")
+        self.n_evaluated, self._n_legit = ne.value, nl.value
+        return True, ne.value, nl.value
 
     def sobolFnVal(self, first=1, count=None, out=None):
         """fval column of sobolFnVal.dat rows first.. (:467); NaN for points of other shards / beyond the cut.
@@ -228,23 +186,10 @@ class TikTakSearch:
         K, nx = self.K, self.cfg.nx
         xs = np.empty((nx + 1, K), dtype=np.float64)
         idx = np.zeros(K, dtype=np.int32)
-        if self.world == 1:
-            _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
-        else:
-            import torch
-
-            from . import dist as D
-
-            # shard-local top-(K-1), exported on the device, one all-gather, merged on the device
-            _lib.check(self._L.tiktak_cuda_choose(self._h, None, None), "chooseSobol")
-            with torch.cuda.stream(self.torch_stream()):
-                cand = torch.empty((K, 2), dtype=torch.float64, device=torch.device("cuda", self.device))
-                _lib.check(self._L.tiktak_cuda_choose_candidates(self._h, cand.data_ptr()), "choose_candidates")
-                allc = D.gather_candidates(cand, self.world, self.group)
-                _lib.check(self._L.tiktak_cuda_choose_merge(self._h, allc.data_ptr(), allc.shape[0], xs.ctypes.data,
-                                                            idx.ctypes.data), "choose_merge")
-                if self._n_legit is None:  # no-cut run: the global valid count travelled in the trailer rows
-                    self._n_legit = int(allc.view(self.world, K, 2)[:, K - 1, 0].sum().item())
+        # world > 1: shard-local top-(K-1), one all-gather of the candidate rows inside the library, merged on the device
+        _lib.check(self._L.tiktak_cuda_choose(self._h, xs.ctypes.data, idx.ctypes.data), "chooseSobol")
+        if self._n_legit is None and self.world > 1:  # no-cut run: the global valid count travelled in the trailer rows
+            self._resolve_legit()
         self.x_starts = xs.T.copy()  # (K, nx+1) = [fval, x]
         self.sobol_idx = idx
         return self.x_starts
@@ -276,30 +221,11 @@ class TikTakSearch:
             _lib.check(self._L.tiktak_cuda_local_capacity(self._h, alg, C.byref(cap)), "local_capacity")
             window = cap.value  # 0 = the mode forbids early starts: one round per launch
         per_launch = max(B, (int(window) // B) * B)  # whole rounds
-        send = recv = None
-        if W > 1:
-            import torch
-
-            from . import dist as D
-
-            cap = D.n_max(min(per_launch, K), W) * (nx + 2)
-            dev = torch.device("cuda", self.device)
-            with torch.cuda.stream(self.torch_stream()):  # allocated and used on the library's stream only
-                send = torch.empty(cap, dtype=torch.float64, device=dev)
-                recv = torch.empty(W * cap, dtype=torch.float64, device=dev)
         k, acc = 1, C.c_int32()
         self.local_launches = 0
         while k <= K:
             n = min(per_launch, K - k + 1)
-            if W == 1:
-                _lib.check(self._L.tiktak_cuda_local_launch(self._h, alg, k, n, B, C.byref(acc)), "LocalMinimizations")
-            else:
-                _lib.check(self._L.tiktak_cuda_local_enqueue(self._h, alg, k, n, send.data_ptr()), "LocalMinimizations")
-                cnt = D.n_max(n, W) * (nx + 2)
-                with torch.cuda.stream(self.torch_stream()):
-                    D.gather_rows(recv[: W * cnt], send[:cnt], self.group)
-                _lib.check(self._L.tiktak_cuda_local_ingest_rounds(self._h, k, n, B, recv.data_ptr(), C.byref(acc)),
-                           "LocalMinimizations")
+            _lib.check(self._L.tiktak_cuda_local_launch(self._h, alg, k, n, B, C.byref(acc)), "LocalMinimizations")
             assert 0 < acc.value <= n
             k += acc.value
             self.local_launches += 1
