@@ -131,6 +131,10 @@ int tiktak_cuda_pretest_result(tiktak_handle* h, int64_t* n_evaluated, int64_t* 
 /* the shard's own fval store in one copy: count blocks rank, rank+world, ... (TIKTAK_SOBOL_BLOCK values each, point n of
  * block b at [(b/world)*TIKTAK_SOBOL_BLOCK + n%TIKTAK_SOBOL_BLOCK]) up to the block holding the cut; n_local = values copied. */
 int tiktak_cuda_pretest_values_shard(tiktak_handle* h, double* fval_local, int64_t capacity, int64_t* n_local);
+/* the same copy queued on a second stream, behind the evaluation and beside whatever the handle does next (selection,
+ * restarts); pretest_values_wait returns when it has landed.  The host buffer should be pinned. */
+int tiktak_cuda_pretest_values_shard_async(tiktak_handle* h, double* fval_local, int64_t capacity, int64_t* n_local);
+int tiktak_cuda_pretest_values_wait(tiktak_handle* h);
 /* fval of points first..first+count-1 (the rows of sobolFnVal.dat, :467); points this shard
  * does not own or beyond the cut come back as NaN. */
 int tiktak_cuda_pretest_values(tiktak_handle* h, int64_t first_1based, int64_t count, double* fval);

@@ -269,6 +269,8 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     tk_comm_destroy(h);
     tk_smm_free(h);
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
@@ -659,6 +661,32 @@ int tiktak_cuda_pretest_values_shard(tiktak_handle* h, double* fval_local, int64
     TK_CUDA(cudaSetDevice(h->device));
     if (n > 0) TK_CUDA(cudaMemcpyAsync(fval_local, h->d_fval, (size_t)n * 8, cudaMemcpyDefault, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
+    return TIKTAK_OK;
+}
+
+/* the same copy on a second stream, behind the evaluation and beside whatever the handle's stream does next (selection,
+ * restarts): sobolFnVal.dat is the only consumer of the values on the host, nothing on the path waits for it */
+int tiktak_cuda_pretest_values_shard_async(tiktak_handle* h, double* fval_local, int64_t capacity, int64_t* n_local) {
+    if (!h || !fval_local) return TIKTAK_ERR_ARG;
+    if (!h->pretest_done) return TIKTAK_ERR_STATE;
+    const int64_t lastcb = h->kcut / TIKTAK_SOBOL_BLOCK;
+    const int64_t nl = (lastcb >= h->cfg.rank) ? ((lastcb - h->cfg.rank) / h->cfg.world + 1) : 0;
+    const int64_t n = nl * (int64_t)TIKTAK_SOBOL_BLOCK;
+    if (n_local) *n_local = n;
+    if (capacity < n) { tk_set_error("pretest_values_shard_async: capacity %lld < %lld", (long long)capacity, (long long)n); return TIKTAK_ERR_ARG; }
+    TK_CUDA(cudaSetDevice(h->device));
+    if (!h->copy_stream) {
+        TK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        TK_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    }
+    TK_CUDA(cudaEventRecord(h->ev_copy, h->stream)); /* the values exist once everything queued so far has run */
+    TK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+    if (n > 0) TK_CUDA(cudaMemcpyAsync(fval_local, h->d_fval, (size_t)n * 8, cudaMemcpyDefault, h->copy_stream));
+    return TIKTAK_OK;
+}
+int tiktak_cuda_pretest_values_wait(tiktak_handle* h) {
+    if (!h) return TIKTAK_ERR_ARG;
+    if (h->copy_stream) { TK_CUDA(cudaSetDevice(h->device)); TK_CUDA(cudaStreamSynchronize(h->copy_stream)); }
     return TIKTAK_OK;
 }
 

@@ -132,6 +132,8 @@ struct tiktak_handle {
     int* d_accepted = nullptr;        /* restarts ingested by the last multi-round ingest */
     /* multi-GPU: NCCL communicator owned by the handle (comm.cu) + exchange buffers */
     void* comm = nullptr;
+    cudaStream_t copy_stream = nullptr; /* asynchronous copy of the stored values to the host (pretest_values_shard_async) */
+    cudaEvent_t ev_copy = nullptr;
     double *d_xsend = nullptr, *d_xrecv = nullptr;
     size_t xbuf_doubles = 0;
     bool counts_global = false;       /* d_counts holds the all-reduced (global) per-block counts */

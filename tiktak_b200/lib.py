@@ -22,6 +22,8 @@ SIGNATURES = {
     "tiktak_cuda_pretest": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
     "tiktak_cuda_pretest_result": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
     "tiktak_cuda_pretest_values_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_int64_p]),
+    "tiktak_cuda_pretest_values_shard_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_int64_p]),
+    "tiktak_cuda_pretest_values_wait": (C.c_int, [C.c_void_p]),
     "tiktak_cuda_pretest_values": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "tiktak_cuda_pretest_wave": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "tiktak_cuda_pretest_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),

@@ -181,6 +181,17 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_pretest_values_shard(self._h, f.ctypes.data, f.size, C.byref(n)), "sobolFnValShard")
         return f[: n.value]
 
+    def sobolFnValShardAsync(self, out):
+        """queue the copy of this shard's stored values into `out` (pinned host memory) on a second stream; returns the number
+        of values; sobolFnValWait() returns when they have landed.  Nothing on the path waits for them (they are
+        sobolFnVal.dat's fval column), so the copy runs beside selection and the restarts."""
+        n = C.c_int64()
+        _lib.check(self._L.tiktak_cuda_pretest_values_shard_async(self._h, out.ctypes.data, out.size, C.byref(n)), "sobolFnValShardAsync")
+        return n.value
+
+    def sobolFnValWait(self):
+        _lib.check(self._L.tiktak_cuda_pretest_values_wait(self._h), "sobolFnValWait")
+
     # ------------------------------------------------------------------ stage 6
     def chooseSobol(self):
         K, nx = self.K, self.cfg.nx
