@@ -310,6 +310,13 @@ int main(int argc, char** argv) {
             std::vector<double> st((size_t)nk * nx), rs((size_t)nk * (nx + 4));
             std::vector<int32_t> ev(nk);
             CHECK(tiktak_cuda_local_fetch(h, kfirst, nk, st.data(), rs.data(), ev.data()));
+            {
+                std::vector<int32_t> stt(nk);
+                CHECK(tiktak_cuda_local_status(h, kfirst, nk, stt.data()));
+                int n1 = 0;
+                for (int s = 0; s < nk; s++) n1 += stt[s] != 0;
+                if (n1) { char b[200]; snprintf(b, sizeof b, "%d: %d local search(es) stopped early (status != 0: DFNLS would have called RESCUE_H, or refused its start)", seqNo, n1); logmsg(b); }
+            }
             for (int s = 0; s < nk; s++) {
                 fprintf(fs, "%10d%10d", seqNo, kfirst + s); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[(size_t)d * nk + s]); fputc('\n', fs);
                 fprintf(fr, "%10d%10d%10d", seqNo, kfirst + s, (int)rs[(size_t)2 * nk + s]);

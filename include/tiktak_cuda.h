@@ -81,8 +81,8 @@ typedef struct tiktak_config {
     int32_t qr_ndraw;        /* p_qr_ndraw, must be < 2^30 (utilities.f90:937) */
     int32_t legitimate;      /* p_legitimate */
     int32_t maxpoints_plus1; /* p_maxpoints = config maxpoints + 1 (genericParams.f90:369) */
-    int32_t search_type;     /* p_searchType: only 0 (best point) is implemented */
-    int32_t lottery_points;  /* p_lotteryPoints (unused while search_type == 0) */
+    int32_t search_type;     /* p_searchType: 0 = best point so far, 1 = rank lottery (getLotteryPoint :722-766) */
+    int32_t lottery_points;  /* p_lotteryPoints: rows the lottery draws from (search_type == 1) */
     double fvalmax;          /* p_fvalmax */
     const double* range;     /* p_range(nx,2) column-major: lo[0..nx), hi[0..nx) */
     const double* init;      /* p_init(nx) */
@@ -93,7 +93,8 @@ typedef struct tiktak_config {
     int32_t rank, world;     /* shard of the Sobol index range / restart set owned by this handle */
     int32_t nm_itmax;        /* amoeba evaluation cap; reference value 5000 (minimize.f90:27-35) */
     int32_t nm_shrink_mode;  /* 0 = code behaviour; 1 = README.md:36 simplex bounds from best minima */
-    int32_t sobol_quirk;     /* 1 = reproduce the single-precision rightmost-zero search (utilities.f90:1090) */
+    int32_t sobol_quirk;     /* 1 = the reference's single-precision rightmost-zero search (utilities.f90:1090): identical to 0 up to
+                              * Sobol index 33,554,435; beyond it (a degenerate 4-point cycle) create() returns TIKTAK_ERR_UNSUPPORTED */
     int32_t text_roundtrip;  /* 1 = values pass through the f40.20 records like the reference's .dat files */
     int32_t round_size;      /* restarts blended against the same best-so-far; 1 = sequential reference order */
     double nm_ftol;          /* p_tolf_amoeba = 1e-4 (genericParams.f90:25) */
@@ -188,6 +189,10 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
 int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, const double* recv);
 int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, double* starts, double* results,
                             int32_t* evals);
+/* how each restart's local search ended: 0 = as the reference's would; 1 = DFNLS stopped where the reference calls RESCUE_H
+ * (a denominator damaged by cancellation, minimize.f90:746-751, :782-787 -- RESCUE_H is not built on the device, the
+ * result row is the best point so far); 2 = DFNLS refused the start (bounds closer than 2 rhobeg, :354-362). */
+int tiktak_cuda_local_status(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* status);
 /* Rounds started early.  A round depends on the earlier ones only through the best row, which changes in few
  * rounds (the #improvements column).  local_enqueue may therefore be given SEVERAL consecutive rounds at once
  * (n_k = a multiple of round_size, or up to the last restart): all of them start from the best row known now.

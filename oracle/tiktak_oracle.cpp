@@ -266,6 +266,16 @@ struct Oracle {
             for (int m = 0; m < c.nm; m++) F[m] = f;
         } else if (c.objective_id == TIKTAK_OBJ_SMM) {
             smm.residuals(x, F);
+        } else if (c.objective_id == 100) { /* TEST ONLY (not in the library): Rosenbrock as residuals, nm = 2 (nx - 1) [+ 1: a constant
+                                              * residual 0.5, so that F_min = 0.25 and the F <= 1e-12 exit (:831) cannot fire] */
+            for (int i = 0; i + 1 < c.nx; i++) { F[2 * i] = 10.0 * (x[i + 1] - x[i] * x[i]); F[2 * i + 1] = 1.0 - x[i]; }
+            for (int m = 2 * (c.nx - 1); m < c.nm; m++) F[m] = 0.5;
+        } else if (c.objective_id == 101) { /* TEST ONLY: linear residuals A x - b with a fixed dense A (nm rows) */
+            for (int m = 0; m < c.nm; m++) {
+                double r = -(0.5 + 0.25 * cos(1.0 + m));
+                for (int j = 0; j < c.nx; j++) r = r + sin(1.3 * (m + 1) + 0.7 * (j + 1) + 0.1 * (m + 1) * (j + 1)) * x[j];
+                F[m] = r;
+            }
         } else {
             double v = model_value(x);
             for (int m = 0; m < c.nm; m++) F[m] = v;
@@ -1029,6 +1039,34 @@ int orc_complete_search(void* h, int alg, int k, double* x, double* fn_val) {
     for (int i = 0; i < nx; i++) x[i] = p[i];
     if (fn_val) *fn_val = f;
     return (int)(o->nfev - nfev0);
+}
+/* one DFNLS run that records the model state at every entry of label 60 (minimize.f90:525) for the invariant checks of
+ * tests/test_oracle_pins.py.  Each snapshot = [KOPT, NF, XBASE(n), XOPT(n), XPT(npt,n), FVAL_V(mv,npt), GQV(mv,n), HQV(mv,nh),
+ * PQV(mv,npt), BMAT(ndim,n), ZMAT(npt,nptm)], arrays column-major as in the Fortran.  Returns the number of snapshots. */
+int orc_dfnls_trace(void* h, double* x, double rhobeg, double rhoend, int maxfun, int max_snap, double* out, int32_t* nf) {
+    Oracle* o = (Oracle*)h;
+    Dfnls d;
+    d.dfovec = [o](const double* xx, double* F) { o->nfev++; o->dfovec(xx, F); };
+    d.getPenalty = [o](const double* xx) { return o->getPenalty(xx); };
+    int nsnap = 0;
+    double* w = out;
+    d.trace = [&](const Dfnls& s, int KOPT, int NF) {
+        if (nsnap >= max_snap) return;
+        *w++ = KOPT; *w++ = NF;
+        auto put = [&](const std::vector<double>& v, size_t n) { for (size_t i = 0; i < n; i++) *w++ = v[i]; };
+        put(s.XBASE, s.N); put(s.XOPT, s.N); put(s.XPT, (size_t)s.NPT * s.N); put(s.FVAL_V, (size_t)s.mv * s.NPT);
+        put(s.GQV, (size_t)s.mv * s.N); put(s.HQV, (size_t)s.mv * s.NH); put(s.PQV, (size_t)s.mv * s.NPT);
+        put(s.BMAT, (size_t)s.NDIM * s.N); put(s.ZMAT, (size_t)s.NPT * s.NPTM);
+        nsnap++;
+    };
+    const int n = o->c.nx, npt = 2 * n + 1;
+    std::vector<double> p(x, x + n);
+    int n1 = 0;
+    d.BOBYQA_H(n, npt, p.data(), o->bl(), o->bu(), rhobeg, rhoend, maxfun, o->c.nm, n1);
+    for (int i = 0; i < n; i++) x[i] = p[i];
+    if (nf) *nf = n1;
+    if (getenv("TK_DFNLS_DEBUG")) fprintf(stderr, "dfnls exit_line %d nf %d\n", d.exit_line, n1);
+    return nsnap;
 }
 /* runtime self-check that this build does not contract a*b+c (the reference build has no FMA) */
 int orc_unfused_selfcheck(void) {

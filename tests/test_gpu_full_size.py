@@ -160,6 +160,7 @@ def test_c5_full_size_against_oracle(built):
         xs = s.chooseSobol()
         s.LocalMinimizations("b")
         st, rs, ev = s.searchStart.copy(), s.searchResults.copy(), s.evals.copy()
+        assert not s.status.any(), "a DFNLS restart stopped where the reference calls RESCUE_H (not built on the device)"
     assert (nl == cfg.legitimate and fv[ne - 1] < cfg.fvalmax) or (ne == cfg.qr_ndraw and nl < cfg.legitimate)  # :429
     assert int(np.count_nonzero(fv < cfg.fvalmax)) == nl
     _CFG = cfg

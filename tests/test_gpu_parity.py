@@ -566,6 +566,26 @@ def test_edge_every_point_selected_and_none_legitimate(built):
     assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
 
 
+def test_nan_objective_values_sort_last(built):
+    """An objective that returns NaN on part of the box (here: tk_cos outside its domain |x| < 2^30 -- sign bit set or not)
+    must not win the start selection: every NaN has one radix key above +inf, so numbers come first in (fval, index) order
+    and NaN rows are taken, by ascending index, only when fewer than K-1 numbers exist."""
+    for maxpoints in (6, 400):
+        cfg = make_config(2, 1, 3000, maxpoints, -4.0e9, 4.0e9, init=[1.0, 2.0], objective_id=OBJ_GRIEWANK)
+        with TikTakSearch(cfg) as s:
+            _, ne, nl = s.solveAtSobolPoints()
+            fv = s.sobolFnVal()
+            xs = s.chooseSobol()
+            idx = s.sobol_idx[1:].astype(np.int64)
+        nan = np.isnan(fv)
+        assert nan.any() and (~nan).sum() > 6 and nl == int((fv < cfg.fvalmax).sum())
+        n = np.arange(1, ne + 1)
+        order = np.concatenate([n[~nan][np.lexsort((n[~nan], fv[~nan]))], n[nan]])[:maxpoints]
+        assert np.array_equal(idx, order), (maxpoints, idx[:10], order[:10])
+        k_num = min(maxpoints, int((~nan).sum()))
+        assert np.array_equal(xs[1:1 + k_num, 0], fv[order[:k_num] - 1]) and np.isnan(xs[1 + k_num:, 0]).all()
+
+
 def test_edge_invalid_configurations_are_refused(built):
     """the reference stops (`stop 0`) on these; the library returns a status instead"""
     from tiktak_b200.lib import TikTakError
@@ -576,6 +596,11 @@ def test_edge_invalid_configurations_are_refused(built):
     cfg = cfg_of("griewank7", search_type=2)  # unknown selectionMethod (TiktakGlobalSearch.f90:709-715)
     with pytest.raises(TikTakError):
         TikTakSearch(cfg)
+    cfg = baseline_config("C3", sobol_quirk=1)  # 1e8 points: the literal reference sequence degenerates after 33,554,435 -- not built
+    with pytest.raises(TikTakError):
+        TikTakSearch(cfg)
+    with TikTakSearch(cfg_of("griewank7", sobol_quirk=1)) as s:  # below that index both sequences coincide: accepted
+        assert np.array_equal(s.setupSobol(1, 64), Oracle(cfg_of("griewank7", sobol_quirk=1), MATH_TK).setupSobol(1, 64, quirk=1))
     cfg = cfg_of("griewank7")
     with TikTakSearch(cfg) as s:
         with pytest.raises(TikTakError):

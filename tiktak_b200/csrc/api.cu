@@ -154,6 +154,13 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
         return TIKTAK_ERR_ARG;
     }
     if (cfg->search_type == 1 && cfg->lottery_points < 1) { tk_set_error("create: lotteryPoints must be >= 1"); return TIKTAK_ERR_ARG; }
+    if (cfg->sobol_quirk != 0 && cfg->qr_ndraw > 33554435) {
+        /* the reference's rightmost-zero search goes through single-precision REAL() (utilities.f90:1090) and degenerates to a
+         * 4-point cycle from Sobol index 33,554,436 on (SURVEY finding 2); the device generates the intended sequence only.
+         * Up to that index both sequences are identical, so the flag is accepted there. */
+        tk_set_error("create: sobol_quirk = 1 with qr_ndraw > 33554435 is not built (the degenerate 4-point cycle of the reference); use sobol_quirk = 0");
+        return TIKTAK_ERR_UNSUPPORTED;
+    }
     if (cfg->nx > TK_NX_GENERIC_MAX) { tk_set_error("create: nx > %d not supported by this build", TK_NX_GENERIC_MAX); return TIKTAK_ERR_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -1043,7 +1050,20 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
     }
     if (starts) TK_CUDA(cudaMemcpy(starts, st.data(), st.size() * 8, cudaMemcpyDefault));
     if (results) TK_CUDA(cudaMemcpy(results, rows.data(), rows.size() * 8, cudaMemcpyDefault));
+    for (int& e : hev) e &= 0xffffff; /* the high byte is the local search's status (tiktak_cuda_local_status) */
     if (evals) TK_CUDA(cudaMemcpy(evals, hev.data() + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDefault));
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_local_status(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* status) {
+    if (!h || !status || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (n_k == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    std::vector<int> hev(n_k);
+    TK_CUDA(cudaMemcpyAsync(hev.data(), h->d_arch_evals + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    for (int& e : hev) e = (e >> 24) & 0xff;
+    TK_CUDA(cudaMemcpy(status, hev.data(), (size_t)n_k * sizeof(int), cudaMemcpyDefault));
     return TIKTAK_OK;
 }
 

@@ -19,8 +19,14 @@
 
 namespace {
 
+/* order-preserving image of a double.  Every NaN (either sign, any payload: CUDA's canonical NaN has the sign bit set, and
+ * a plugin objective may return one, e.g. tk_cos outside its domain) maps to ONE key above +inf and below the padding key
+ * ~0: NaN rows sort last, after every number, and are selected only when fewer than K-1 numbers exist.  (The reference's
+ * indexx has no defined order for NaN; README.md:34 asks objectives to return a large finite value instead.) */
+#define TK_KEY_NAN 0xFFFFFFFFFFFFFFFEULL
 __device__ __forceinline__ unsigned long long tk_order_key(double f) {
     unsigned long long u = (unsigned long long)__double_as_longlong(f);
+    if (f != f) return TK_KEY_NAN;
     return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
 }
 
@@ -182,7 +188,7 @@ chunk_sort_kernel(const double* cf, const unsigned int* ci, unsigned int m, doub
     const unsigned int base = blockIdx.x * SORT_CHUNK;
     for (unsigned int t = threadIdx.x; t < SORT_CHUNK; t += blockDim.x) {
         const unsigned int e = base + t;
-        /* padding sorts last: NaN never reaches here, so the all-ones key is free */
+        /* padding sorts last: every NaN has the key TK_KEY_NAN, so the all-ones key is free */
         k[t] = (e < m) ? tk_order_key(cf[e]) : ~0ULL;
         n[t] = (e < m) ? ci[e] : 0xffffffffu;
     }

@@ -246,6 +246,9 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_local_fetch(self._h, 1, K, s.ctypes.data, r.ctypes.data, e.ctypes.data),
                    "LocalMinimizations")
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
+        st = np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_status(self._h, 1, K, st.ctypes.data_as(C.POINTER(C.c_int32))), "local_status")
+        self.status = st  # 0 = ended like the reference's search; 1 = DFNLS stopped where the reference would call RESCUE_H
         return True
 
     # ------------------------------------------------------------------ queries
