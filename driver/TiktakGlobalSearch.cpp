@@ -99,15 +99,21 @@ static void mywrite2(const char* file, const double* a, int rows, int cols) { /*
     for (int r = 0; r < rows; r++) { fputc(' ', f); for (int c = 0; c < cols; c++) fprintf(f, "   %30.15f", a[(size_t)c * rows + r]); fputc('\n', f); }
     fclose(f);
 }
-static int exit_state(const std::string& m) { /* exitState, stateControl.f90:203-216 */
-    logmsg("EXIT STATE: " + m);
+static void broadcast_exit() { /* exitState, stateControl.f90:203-216: state -1 and poisoned work counters stop every instance on the directory */
     write_int("state.dat", -1);
+    write_int("lastSobol.dat", -10000000);
+    write_int("lastParam.dat", -10000000);
+    write_int("seqNo.dat", -10000000);
+}
+static int exit_state(const std::string& m) {
+    logmsg("EXIT STATE: " + m);
+    broadcast_exit();
     return 1;
 }
 struct Cfg;
 static void write_internal_config(const Cfg& c);
 #define CHECK(call) do { int rc_ = (call); if (rc_) { char b_[1200]; snprintf(b_, sizeof b_, "EXIT STATE: %s: %s; %s", #call, tiktak_cuda_strerror(rc_), tiktak_cuda_last_error()); \
-    logmsg(b_); write_int("state.dat", -1); return 1; } } while (0)
+    logmsg(b_); broadcast_exit(); return 1; } } while (0)
 
 static void write_internal_config(const Cfg& c) { /* genericParams.f90:154-174; parse_config reads it back (maxpoints is stored raw) */
     FILE* f = fopen("internalConfig.dat", "w");
@@ -127,7 +133,11 @@ int main(int argc, char** argv) {
     const char* algarg = option == 1 ? (argc >= 3 ? argv[2] : nullptr) : (argc >= 4 ? argv[3] : nullptr); /* warm start: alg is arg 2 */
     if (algarg) { if (algarg[0] == 'a') alg = 1; else if (algarg[0] == 'b') alg = 0; else if (algarg[0] == 'd') alg = 2; else { usage(); return 0; } }
     if (option < -1 || option > 5) { usage(); return 0; }
-    if (option == -1) { write_int("state.dat", -1); logmsg("exit state written; no other instance is attached to device-resident state"); return 0; }
+    if (option == -1) { /* :219-223: tell every instance that shares the directory (CPU instances of the reference included) to stop */
+        broadcast_exit();
+        logmsg("exit state written: state.dat = -1, lastSobol/lastParam/seqNo poisoned");
+        return 0;
+    }
     if (option == 1) {
         logmsg("option 1 joins a multi-process CPU run through the .dat lock files; the GPU library keeps that state "
                "on the device and runs the whole job in one process (options 0, 2, 3). Nothing to do.");
@@ -166,7 +176,8 @@ int main(int argc, char** argv) {
                 snprintf(b, sizeof b, "Update LocalMinimizations: numsolved > p_maxpoints %d %d Change p_maxpoints to > %d", oldc.maxpoints + 1, c.maxpoints + 1, resume_k + 1);
                 return exit_state(b);
             }
-            if ((int)old_rows.size() != resume_k) return exit_state("Update LocalMinimizations: searchResults.dat has gaps; the missing-work sweep of the reference is not built");
+            /* gaps (restarts a killed instance never reported) are legal: the run continues after the largest k (genericParams.f90:
+             * 229-236) and the missing-search sweep of states 8-9 fills them afterwards (:1048-1146) */
         }
     }
     write_internal_config(c);
@@ -207,11 +218,17 @@ int main(int argc, char** argv) {
     std::vector<int> helper_rc(ngpu, 0);
     std::atomic<bool> values_read{false}; /* rank 0 has copied every shard's values out for sobolFnVal.dat: the handles are free again */
     {
+        std::vector<int> helper_missing; /* the same list rank 0 derives below (states 8-9) */
+        if (option != 5) {
+            std::vector<char> solved(K + 1, 0);
+            for (auto& r : old_rows) if ((int)r[1] >= 1 && (int)r[1] <= K) solved[(int)r[1]] = 1;
+            for (int k = 1; k <= resume_k; k++) if (!solved[k]) helper_missing.push_back(k);
+        }
         const int n_old = (int)old_rows.size();
         std::vector<double> old_cm((size_t)n_old * (nx + 4));
         for (int r = 0; r < n_old; r++) for (int cc = 0; cc < nx + 4; cc++) old_cm[(size_t)cc * n_old + r] = old_rows[r][cc];
         for (int r = 1; r < ngpu; r++)
-            helpers.emplace_back([&, r, old_cm, n_old]() {
+            helpers.emplace_back([&, r, old_cm, n_old, helper_missing]() {
                 tiktak_handle* hr = hs[r];
                 int64_t e = 0, l = 0;
                 int rc = tiktak_cuda_pretest(hr, &e, &l);
@@ -229,6 +246,7 @@ int main(int argc, char** argv) {
                     rc = tiktak_cuda_local_launch(hr, alg, k0, std::min(per_launch, kend - k0 + 1), B, &acc);
                     k0 += acc;
                 }
+                for (size_t q = 0; !rc && q < helper_missing.size(); q++) rc = tiktak_cuda_local_missing(hr, alg, helper_missing[q]);
                 helper_rc[r] = rc;
             });
     }
@@ -269,6 +287,10 @@ int main(int argc, char** argv) {
     values_read.store(true);
     write_int("lastSobol.dat", (long)ne + 1);
     write_int("legitSobol.dat", (long)nl);
+    /* states 4-5 (setupMissingSobol / solveMissingSobol, :901-1046): the device evaluates the whole prefix 1..Kcut in one stage, so
+     * no Sobol point can be missing from sobolFnVal.dat; the reference's bookkeeping files are written for the instances that read them */
+    { FILE* f = fopen("missingSobol.dat", "w"); if (f) fclose(f); }
+    write_int("legitSobolMiss.dat", (long)nl);
     { char b[200]; snprintf(b, sizeof b, "%d has evaluated %lld sobol points, %lld legitimate", seqNo, (long long)ne, (long long)nl); logmsg(b); }
     /* state 6 */
     write_int("state.dat", 6);
@@ -323,6 +345,26 @@ int main(int argc, char** argv) {
                 for (int d = 3; d < nx + 4; d++) fprintf(fr, "%40.20f", rs[(size_t)d * nk + s]);
                 fputc('\n', fr);
             }
+        }
+        /* states 8-9: setupMissingSearch / SolveMissingSearch (:1048-1146) -- restarts missing from searchResults.dat */
+        std::vector<int> missing;
+        if (option != 5) {
+            std::vector<char> solved(K + 1, 0);
+            for (auto& r : old_rows) if ((int)r[1] >= 1 && (int)r[1] <= K) solved[(int)r[1]] = 1;
+            for (int k = 1; k <= resume_k; k++) if (!solved[k]) missing.push_back(k);
+        }
+        { FILE* f = fopen("missingSearch.dat", "w"); if (f) { for (int k : missing) fprintf(f, "%10d\n", k); fclose(f); } }
+        if (!missing.empty()) {
+            write_int("state.dat", 9);
+            for (int k : missing) {
+                char b[200]; snprintf(b, sizeof b, "%d searching using sobol point %d (missing from searchResults.dat)", seqNo, k); logmsg(b);
+                CHECK(tiktak_cuda_local_missing(h, alg, k));
+                std::vector<double> st(nx), rs(nx + 4); int32_t ev = 0;
+                CHECK(tiktak_cuda_local_fetch(h, k, 1, st.data(), rs.data(), &ev));
+                fprintf(fs, "%10d%10d", seqNo, k); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[d]); fputc('\n', fs);
+                fprintf(fr, "%10d%10d%10d", seqNo, k, (int)rs[2]); for (int d = 3; d < nx + 4; d++) fprintf(fr, "%40.20f", rs[d]); fputc('\n', fr);
+            }
+            { FILE* f = fopen("missingSearch.dat", "w"); if (f) fclose(f); } /* the list is consumed entry by entry (:1112-1118) */
         }
         fclose(fr); fclose(fs);
         write_int("lastParam.dat", (long)kend + 1);

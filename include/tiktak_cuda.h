@@ -211,6 +211,11 @@ int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts)
  * (completeSearch :582-597), and the first round that changes the best row stops the launch (`accepted` < n_k); how far
  * restarts may be started ahead of the committed rounds is bounded inside the kernel, so n_k may be "all that is left". */
 int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t round_size, int32_t* accepted);
+/* SolveMissingSearch (TiktakGlobalSearch.f90:1104-1146), states 8-9: one restart k that is missing from searchResults.dat (an
+ * instance was killed before it reported).  Start = getModifiedParam(p_maxpoints, x_starts(k,2:)) (:1121: the blend weight of
+ * the last restart number, toward the best row known now), then completeSearch(alg, k).  Push the rows that do exist with
+ * tiktak_cuda_push_results first.  The row lands in the results table like any other (local_fetch reads it). */
+int tiktak_cuda_local_missing(tiktak_handle* h, int32_t alg, int32_t k);
 /* make rows computed elsewhere (other ranks, or a resumed searchResults.dat) known to the handle;
  * rows is (n, nx+4) column-major.  Rows whose fval is NaN are ignored.  Also how the k=0 row
  * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */

@@ -166,6 +166,20 @@ class Oracle:
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
         return True
 
+    def set_rows(self, rows):
+        """rows (n, nx+4) = the records of an interrupted run in file order, the k = 0 record first"""
+        rin = np.ascontiguousarray(np.asarray(rows, dtype=np.float64).T)
+        self.L.orc_set_rows.argtypes = [C.c_void_p, c_double_p, C.c_int]
+        assert self.L.orc_set_rows(self.h, dptr(rin), len(rows)) == 0
+
+    def SolveMissingSearch(self, algor, k):
+        """states 8-9 for one missing restart k (TiktakGlobalSearch.f90:1104-1146): (start, searchResults row, evaluations)"""
+        nx = self.cfg.nx
+        st, row, ne = np.empty(nx), np.empty(nx + 4), C.c_int32()
+        self.L.orc_missing_search.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_int32_p]
+        assert self.L.orc_missing_search(self.h, algor, k, dptr(st), dptr(row), C.byref(ne)) == 0
+        return st, row, ne.value
+
     def getBestLine(self):
         f, k = C.c_double(), C.c_int32()
         x = np.empty(self.cfg.nx)

@@ -644,8 +644,58 @@ struct Oracle {
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first = 1);
+    int missing_search(int alg, int k, double* start_out, double* row_out, int32_t* evals_out);
     int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
 };
+
+/* SolveMissingSearch (TiktakGlobalSearch.f90:1104-1146) for one missing restart k: getModifiedParam is called with whichPoint =
+ * p_maxpoints (:1121), so the blend weight is that of the LAST restart number; completeSearch(alg, k) follows (:1126) */
+int Oracle::missing_search(int alg, int k, double* start_out, double* row_out, int32_t* evals_out) {
+    const int K = c.maxpoints_plus1, nx = c.nx;
+    if (k < 1 || k > K || rows.empty()) return -1;
+    const int count = (int)rows.size();
+    const std::vector<Row> snapshot(rows.begin(), rows.end());
+    std::vector<double> evalParam(nx);
+    const double* evalPoint = &x_starts[(size_t)(k - 1) * (nx + 1) + 1];
+    if (count <= 1) {
+        for (int i = 0; i < nx; i++) evalParam[i] = evalPoint[i];
+    } else {
+        const std::vector<double>& base = (c.search_type == 1) ? snapshot[lottery_row(snapshot, count, k)].x : snapshot[best_row(snapshot, count)].x;
+        float wf = sqrtf((float)K / (float)K);
+        wf = std::min(std::max(0.10f, wf), 0.95f);
+        const double w11 = (double)wf;
+        for (int i = 0; i < nx; i++) evalParam[i] = w11 * base[i] + (1.0 - w11) * evalPoint[i];
+    }
+    if (start_out) for (int i = 0; i < nx; i++) start_out[i] = evalParam[i];
+    const long nfev0 = nfev;
+    if (alg == TIKTAK_ALG_AMOEBA) {
+        std::vector<double> width;
+        simplex_width(k, snapshot, count, width);
+        int iters = 0;
+        runAmoeba(evalParam, width, iters);
+    } else if (alg == TIKTAK_ALG_DFNLS) {
+        double itratio = (double)((float)k / (float)K);
+        double mn = bu()[0] - bl()[0];
+        for (int i = 1; i < nx; i++) mn = std::min(mn, bu()[i] - bl()[i]);
+        double rhobeg, rhoend;
+        if (itratio > 0.5) { rhobeg = (mn / 2.5) / (4 * itratio); rhoend = 1.0e-3 / (4 * itratio); }
+        else { rhobeg = mn / 2.50; rhoend = 1.0e-3; }
+        int nf = 0, nresc = 0;
+        dfnls(evalParam, rhobeg, rhoend, c.maxeval, nf, nresc);
+    } else return -2;
+    const double fn_val = objFun(evalParam.data());
+    if (evals_out) *evals_out = (int32_t)(nfev - nfev0);
+    const int b = best_row(rows, (int)rows.size());
+    int imp = rows[b].imp;
+    if (fn_val < rows[b].fval) imp++;
+    write_row(1, k, imp, fn_val, evalParam.data());
+    if (row_out) {
+        const Row& r = rows.back();
+        row_out[0] = r.seq; row_out[1] = r.k; row_out[2] = r.imp; row_out[3] = r.fval;
+        for (int i = 0; i < nx; i++) row_out[4 + i] = r.x[i];
+    }
+    return 0;
+}
 
 /* k_first > 1: continue an earlier run (option 3, genericParams.f90:133-251): `rows` already holds the k = 0 record and
  * the finished restarts 1..k_first-1 (orc_set_rows), as re-read from searchResults.dat */
@@ -970,6 +1020,23 @@ int orc_dfnls(void* h, double* x, double rhobeg, double rhoend, int maxfun, int3
     if (nf) *nf = n1;
     if (nrescue) *nrescue = n2;
     return rc;
+}
+/* the rows of an interrupted run (k = 0 record first, then the finished restarts in file order; (n, nx+4) column-major) become
+ * the oracle's searchResults; orc_missing_search then runs one missing restart (states 8-9) and returns its start, its
+ * searchResults row (seq, k, #improvements, fval, x) and its evaluation count */
+int orc_set_rows(void* h, const double* rows_in, int n) {
+    Oracle* o = (Oracle*)h;
+    const int nx = o->c.nx;
+    o->rows.clear();
+    for (int r = 0; r < n; r++) {
+        std::vector<double> x(nx);
+        for (int i = 0; i < nx; i++) x[i] = rows_in[(size_t)(4 + i) * n + r];
+        o->write_row((int)rows_in[(size_t)0 * n + r], (int)rows_in[(size_t)1 * n + r], (int)rows_in[(size_t)2 * n + r], rows_in[(size_t)3 * n + r], x.data());
+    }
+    return 0;
+}
+int orc_missing_search(void* h, int alg, int k, double* start_out, double* row_out, int32_t* evals_out) {
+    return ((Oracle*)h)->missing_search(alg, k, start_out, row_out, evals_out);
 }
 /* objFun at the Sobol points first..first+count-1 without generating the points before them: the generator's state
  * after n calls is lastq = XOR of the columns v(:,j) over the set bits j of the Gray code n ^ (n >> 1) (SURVEY 8a3;

@@ -910,7 +910,7 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
         if ((rc = tk_launch_best(h))) return rc;
         h->best_dirty = false;
     }
-    if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows) : tk_launch_blend(h, first_k, n_k))) return rc;
+    if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows, h->blend_w_idx) : tk_launch_blend(h, first_k, n_k, h->blend_w_idx))) return rc;
     if (alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1 && (rc = tk_launch_shrink_width(h))) return rc;
     rc = (alg == TIKTAK_ALG_AMOEBA) ? tk_launch_nm(h, first_k, n_k) : tk_launch_dfnls(h, first_k, n_k);
     if (rc) return rc;
@@ -984,7 +984,7 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
         if ((rc = tk_launch_best(h))) return rc;
         h->best_dirty = false;
     }
-    if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows) : tk_launch_blend(h, first_k, n_k))) return rc;
+    if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows, h->blend_w_idx) : tk_launch_blend(h, first_k, n_k, h->blend_w_idx))) return rc;
     if (h->cfg.nm_shrink_mode == 1 && (rc = tk_launch_shrink_width(h))) return rc;
     if ((rc = tk_launch_nm(h, first_k, n_k, round_size))) return rc;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
@@ -997,6 +997,20 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
     h->n_rows = (int)rows;
     *accepted = acc;
     return TIKTAK_OK;
+}
+
+/* SolveMissingSearch (TiktakGlobalSearch.f90:1104-1146): a restart that an earlier (killed) instance never reported.  Its start
+ * is getModifiedParam(p_maxpoints, x_starts(k,2:), ...) (:1121) -- the blend weight of the LAST restart number, toward the best
+ * row known now -- then completeSearch(alg, k, ...) as usual (the DFNLS radii follow k).  One restart per call, like the
+ * reference's sweep; every rank of a multi-GPU run makes the call (rank 0 runs the search, the row is exchanged). */
+int tiktak_cuda_local_missing(tiktak_handle* h, int32_t alg, int32_t k) {
+    if (!h || k < 1 || k > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    h->blend_w_idx = h->cfg.maxpoints_plus1;
+    int32_t acc = 0;
+    const int rc = tiktak_cuda_local_launch(h, alg, k, 1, 1, &acc);
+    h->blend_w_idx = -1;
+    if (!rc && acc != 1) { tk_set_error("local_missing: restart %d was not committed", k); return TIKTAK_ERR_STATE; }
+    return rc;
 }
 
 int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts) {

@@ -872,7 +872,7 @@ __global__ void best_kernel(const double* res, const int* valid, int nrows, int 
 
 /* getModifiedParam (:683-720): start = w11*best + (1-w11)*x_starts(k), unfused; w11 is the
  * single-precision weight widened to double (computed on the host, h->w11). */
-__global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11,
+__global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11, int w_idx,
                              const double* best, double* starts, double* arch_starts) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_k * nx) return;
@@ -880,7 +880,7 @@ __global__ void blend_kernel(const double* xs, int K, int nx, int first_k, int n
     const double ev = xs[(size_t)(d + 1) * K + (k - 1)];
     double out = ev;
     if (best[2] > 1.0) { /* count <= 1: no finished local minimisation yet (:701) */
-        const double w = w11[k];
+        const double w = w11[w_idx > 0 ? w_idx : k]; /* SolveMissingSearch calls getModifiedParam with whichPoint = p_maxpoints (:1121) */
         out = TK_ADD(TK_MUL(w, best[3 + d]), TK_MUL(TK_SUB(1.0, w), ev));
     }
     starts[(size_t)d * n_k + s] = out;
@@ -899,7 +899,7 @@ __global__ void lottery_collect_kernel(const double* res, const int* valid, int 
     f[pos] = res[(size_t)r * (nx + 1)];
     kk[pos] = (unsigned int)r;
 }
-__global__ void blend_lottery_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11, int count,
+__global__ void blend_lottery_kernel(const double* xs, int K, int nx, int first_k, int n_k, const double* w11, int w_idx, int count,
                                      int num_points, const double* cum, const unsigned int* sorted_k, const double* res,
                                      double* starts, double* arch_starts, int* lot_point) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -916,7 +916,7 @@ __global__ void blend_lottery_kernel(const double* xs, int K, int nx, int first_
             if (u < cum[mid]) hi = mid; else lo = mid + 1;
         }
         lot = (int)sorted_k[lo];
-        const double w = w11[k];
+        const double w = w11[w_idx > 0 ? w_idx : k];
         out = TK_ADD(TK_MUL(w, res[(size_t)lot * (nx + 1) + 1 + d]), TK_MUL(TK_SUB(1.0, w), ev));
     }
     starts[(size_t)d * n_k + s] = out;
@@ -1081,10 +1081,10 @@ int tk_launch_best(tiktak_handle* h) {
     return TIKTAK_OK;
 }
 
-int tk_launch_blend(tiktak_handle* h, int first_k, int n_k) {
+int tk_launch_blend(tiktak_handle* h, int first_k, int n_k, int w_idx) {
     const int tot = n_k * h->cfg.nx;
     blend_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, h->cfg.maxpoints_plus1, h->cfg.nx, first_k, n_k,
-                                                            h->d_w11, h->d_best, h->d_starts, h->d_arch_starts);
+                                                            h->d_w11, w_idx, h->d_best, h->d_starts, h->d_arch_starts);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;
@@ -1093,7 +1093,7 @@ int tk_launch_blend(tiktak_handle* h, int first_k, int n_k) {
 int tk_sort_candidates(tiktak_handle* h, double* d_f, unsigned int* d_i, int64_t n, double* d_sf, unsigned int* d_si);
 
 /* the blend of a round under selectType = 1 (lottery); `count` = result rows known to the handle */
-int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count) {
+int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count, int w_idx) {
     const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
     if (!h->d_lot_f) {
         TK_CUDA(cudaMalloc(&h->d_lot_f, (size_t)(K + 1) * 8)); TK_CUDA(cudaMalloc(&h->d_lot_sf, (size_t)(K + 1) * 8));
@@ -1123,7 +1123,7 @@ int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count) {
         }
     }
     const int tot = n_k * nx;
-    blend_lottery_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, K, nx, first_k, n_k, h->d_w11, count, num_points,
+    blend_lottery_kernel<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_xstarts, K, nx, first_k, n_k, h->d_w11, w_idx, count, num_points,
                                                                     h->d_lot_cum, h->d_lot_sk, h->d_res, h->d_starts,
                                                                     h->d_arch_starts, h->d_lot_point);
     h->launches++;

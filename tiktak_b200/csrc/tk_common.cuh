@@ -138,6 +138,7 @@ struct tiktak_handle {
     size_t xbuf_doubles = 0;
     bool counts_global = false;       /* d_counts holds the all-reduced (global) per-block counts */
     int* d_nmq = nullptr;             /* control words of the throughput Nelder-Mead kernel's restart queue (nm_common.cuh) */
+    int blend_w_idx = -1;             /* > 0: the next launch blends with the weight of restart number blend_w_idx (missing-search sweep) */
     int nm_form = -1;                 /* 1: one warp per restart (kernels_nm_w4.cu), 0: four warps per restart (kernels_nm.cu), -1: not decided yet */
     double *d_objfun_x = nullptr, *d_objfun_f = nullptr; /* staging of tiktak_cuda_objfun for host arguments */
     int64_t objfun_scratch_pts = 0;
@@ -162,8 +163,8 @@ int tk_select_top(tiktak_handle* h, int64_t M);
 int tk_build_starts(tiktak_handle* h);
 int tk_launch_init_results(tiktak_handle* h);
 int tk_launch_best(tiktak_handle* h);
-int tk_launch_blend(tiktak_handle* h, int first_k, int n_k);
-int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count);
+int tk_launch_blend(tiktak_handle* h, int first_k, int n_k, int w_idx = -1);
+int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count, int w_idx = -1);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size = 0);
 bool tk_nm_use_w4(tiktak_handle* h);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);

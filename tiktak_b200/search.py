@@ -251,6 +251,24 @@ class TikTakSearch:
         self.status = st  # 0 = ended like the reference's search; 1 = DFNLS stopped where the reference would call RESCUE_H
         return True
 
+    def pushResults(self, rows):
+        """rows (n, nx+4) = seqNo, k, #improvements, fval, x re-read from searchResults.dat (options 3, missing-work sweep)"""
+        rows = np.asarray(rows, dtype=np.float64)
+        rin = np.ascontiguousarray(rows.T)
+        _lib.check(self._L.tiktak_cuda_push_results(self._h, rin.ctypes.data, len(rows)), "pushResults")
+
+    def SolveMissingSearch(self, algor, missing):
+        """states 8-9 (:1048-1146): the restarts `missing` (never reported by a killed instance), one after the other; each
+        starts from getModifiedParam(p_maxpoints, x_starts(k,2:)) and ends in completeSearch(alg, k).  Returns the rows."""
+        alg, nx = _ALG[algor], self.cfg.nx
+        out = []
+        for k in missing:
+            _lib.check(self._L.tiktak_cuda_local_missing(self._h, alg, int(k)), "SolveMissingSearch")
+            s = np.empty((nx, 1)); r = np.empty((nx + 4, 1)); e = np.zeros(1, dtype=np.int32)
+            _lib.check(self._L.tiktak_cuda_local_fetch(self._h, int(k), 1, s.ctypes.data, r.ctypes.data, e.ctypes.data), "SolveMissingSearch")
+            out.append((s[:, 0].copy(), r[:, 0].copy(), int(e[0])))
+        return out
+
     # ------------------------------------------------------------------ queries
     def getBestLine(self):
         f, k = C.c_double(), C.c_int32()
