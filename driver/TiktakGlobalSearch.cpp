@@ -210,7 +210,6 @@ int main(int argc, char** argv) {
         for (int r = 0; r < ngpu; r++) tiktak_cuda_destroy(hs[r]);
         return 0;
     }
-    if (alg == 2 && option != 5) { logmsg("<main:search> dfpmin as the stage-7 algorithm is not built; use a or b"); tiktak_cuda_destroy(h); return 1; }
     if (option == 3) { for (const char* fn : {"sobolFnVal.dat", "FinalStart.dat", "FinalResults.dat"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); } }
     else for (const char* fn : {"sobolFnVal.dat", "searchStart.dat", "searchResults.dat", "FinalStart.dat", "FinalResults.dat", "logFile.txt"}) { FILE* f = fopen(fn, "w"); if (f) fclose(f); }
     /* ranks 1.. of a multi-GPU run: the same stage calls (each is collective over the handles), no files */
@@ -246,7 +245,7 @@ int main(int argc, char** argv) {
                     rc = tiktak_cuda_local_launch(hr, alg, k0, std::min(per_launch, kend - k0 + 1), B, &acc);
                     k0 += acc;
                 }
-                for (size_t q = 0; !rc && q < helper_missing.size(); q++) rc = tiktak_cuda_local_missing(hr, alg, helper_missing[q]);
+                for (size_t q = 0; !rc && q < helper_missing.size(); q++) rc = tiktak_cuda_local_missing(hr, alg, helper_missing[q], nullptr, nullptr, nullptr);
                 helper_rc[r] = rc;
             });
     }
@@ -358,9 +357,8 @@ int main(int argc, char** argv) {
             write_int("state.dat", 9);
             for (int k : missing) {
                 char b[200]; snprintf(b, sizeof b, "%d searching using sobol point %d (missing from searchResults.dat)", seqNo, k); logmsg(b);
-                CHECK(tiktak_cuda_local_missing(h, alg, k));
                 std::vector<double> st(nx), rs(nx + 4); int32_t ev = 0;
-                CHECK(tiktak_cuda_local_fetch(h, k, 1, st.data(), rs.data(), &ev));
+                CHECK(tiktak_cuda_local_missing(h, alg, k, st.data(), rs.data(), &ev));
                 fprintf(fs, "%10d%10d", seqNo, k); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[d]); fputc('\n', fs);
                 fprintf(fr, "%10d%10d%10d", seqNo, k, (int)rs[2]); for (int d = 3; d < nx + 4; d++) fprintf(fr, "%40.20f", rs[d]); fputc('\n', fr);
             }

@@ -214,8 +214,10 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
 /* SolveMissingSearch (TiktakGlobalSearch.f90:1104-1146), states 8-9: one restart k that is missing from searchResults.dat (an
  * instance was killed before it reported).  Start = getModifiedParam(p_maxpoints, x_starts(k,2:)) (:1121: the blend weight of
  * the last restart number, toward the best row known now), then completeSearch(alg, k).  Push the rows that do exist with
- * tiktak_cuda_push_results first.  The row lands in the results table like any other (local_fetch reads it). */
-int tiktak_cuda_local_missing(tiktak_handle* h, int32_t alg, int32_t k);
+ * tiktak_cuda_push_results first (in file order) and fetch the restarts this handle ran itself (local_fetch) before the sweep.
+ * Outputs (host memory, may be NULL): start (nx) = the searchStart.dat row, row (nx+4) = seqNo, k, #improvements, fval, x =
+ * the searchResults.dat row, evals.  #improvements counts against the best of ALL rows known, as completeSearch :585-589 does. */
+int tiktak_cuda_local_missing(tiktak_handle* h, int32_t alg, int32_t k, double* start, double* row, int32_t* evals);
 /* make rows computed elsewhere (other ranks, or a resumed searchResults.dat) known to the handle;
  * rows is (n, nx+4) column-major.  Rows whose fval is NaN are ignored.  Also how the k=0 row
  * [fval(p_init), p_init] (:496-507) gets in: tiktak_cuda_choose pushes it automatically. */

@@ -750,6 +750,9 @@ int Oracle::local(int alg, int round_size, double* starts_out, double* results_o
                 }
                 int nf = 0, nresc = 0;
                 dfnls(evalParam, rhobeg, rhoend, c.maxeval, nf, nresc);
+            } else if (alg == TIKTAK_ALG_DFPMIN) { /* CASE (2), :575-576 */
+                double fret = 0;
+                dfpmin(evalParam, fret, 1000, 1.0e-6);
             } else return -2;
             double fn_val = objFun(evalParam.data()); /* :582 */
             if (evals_out) evals_out[k - 1] = (int32_t)(nfev - nfev0);

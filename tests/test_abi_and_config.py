@@ -114,3 +114,16 @@ def test_parse_config_defaults_and_errors(tmp_path):
     p.write_text("3\n2\n")
     with pytest.raises(ValueError):
         parse_config(str(p))
+
+
+def test_driver_exit_broadcast(built, tmp_path):
+    """option -1 = exitState (stateControl.f90:203-216): state.dat = -1 and poisoned work counters, so that every instance
+    sharing the directory -- CPU instances of the reference included -- stops at its next getNextNumber / getState"""
+    import subprocess
+
+    exe = os.path.join(ROOT, "driver", "TiktakGlobalSearch")
+    assert os.path.exists(exe)
+    subprocess.check_call([exe, "-1"], cwd=tmp_path)
+    assert int(open(tmp_path / "state.dat").read().split()[0]) == -1
+    for f in ("lastSobol.dat", "lastParam.dat", "seqNo.dat"):
+        assert int(open(tmp_path / f).read().split()[0]) == -10000000

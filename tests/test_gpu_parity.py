@@ -566,6 +566,49 @@ def test_edge_every_point_selected_and_none_legitimate(built):
     assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
 
 
+@pytest.mark.parametrize("alg", ["a", "b"])
+def test_missing_search_sweep(built, alg):
+    """States 8-9 (setupMissingSearch / SolveMissingSearch, TiktakGlobalSearch.f90:1048-1146): restarts that a killed instance
+    never reported are run afterwards, one by one, each from getModifiedParam(p_maxpoints, x_starts(k,2:)) -- the blend weight
+    of the last restart number toward the best row of the file as it is then -- and appended with #improvements counted
+    against every row known.  Rows of a complete run minus three restarts are pushed back; the sweep must reproduce what the
+    oracle's SolveMissingSearch does with the same file."""
+    cfg = cfg_of("griewank7", round_size=4, maxpoints=19) if alg == "a" else cfg_of("griewank7", round_size=4, maxpoints=9, nm=3)
+    K = cfg.p_maxpoints
+    missing = [3, 7, K]
+    algid = 1 if alg == "a" else 0
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); xs = s.chooseSobol(); s.LocalMinimizations(alg)
+        full = s.searchResults.copy()
+    keep = full[[k - 1 for k in range(1, K + 1) if k not in missing]]
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol()
+        s.pushResults(keep)
+        got = s.SolveMissingSearch(alg, missing)
+        fb, xb, kb = s.getBestLine()
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1)
+    row0 = np.concatenate([[1.0, 0.0, 0.0], xs[0]])  # the k = 0 record: [seqNo, 0, 0, fval(p_init), p_init]
+    o.set_rows(np.vstack([row0, keep]))
+    for k, (st, row, ev) in zip(missing, got):
+        ost, orow, oev = o.SolveMissingSearch(algid, k)
+        assert np.array_equal(st, ost) and np.array_equal(row, orow) and ev == oev, (k, row[:4], orow[:4], ev, oev)
+    assert fb == o.getBestLine()[0]
+
+
+def test_local_minimizations_dfpmin(built):
+    """the CLI's third algorithm, `d`: completeSearch CASE (2) = EST_dfpmin from the blended start (TiktakGlobalSearch.f90:575-576,
+    minimize.f90:2572-2816), every objective evaluation on the device -- rows, starts and evaluation counts vs the oracle"""
+    cfg = cfg_of("griewank7", round_size=3, maxpoints=8)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations("d")
+        st, rs, ev, best = s.searchStart, s.searchResults, s.evals, s.getBestLine()
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(2)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+    assert best[0] == o.getBestLine()[0]
+
+
 def test_nan_objective_values_sort_last(built):
     """An objective that returns NaN on part of the box (here: tk_cos outside its domain |x| < 2^30 -- sign bit set or not)
     must not win the start selection: every NaN has one radix key above +inf, so numbers come first in (fval, index) order

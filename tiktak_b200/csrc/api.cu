@@ -108,6 +108,8 @@ bool is_device_ptr(const void* p) {
 
 extern "C" {
 
+static int tk_est_dfpmin(tiktak_handle* h, std::vector<double>& p, double* fret_out, int* its_out, long* nfev);
+
 const char* tiktak_cuda_last_error(void) { return g_err; }
 const char* tiktak_cuda_version(void) { return "tiktak_b200 0.1 (sm_100a)"; }
 const char* tiktak_cuda_strerror(int code) {
@@ -890,10 +892,40 @@ int tiktak_cuda_push_results(tiktak_handle* h, const double* rows, int32_t n) {
     return flush();
 }
 
+/* completeSearch CASE (2) (TiktakGlobalSearch.f90:575-576): EST_dfpmin from the blended start of every restart this rank owns.
+ * The CLI's algorithm `d`; the BFGS recurrences are host arithmetic in the reference's order (minimize.f90:2572-2816), every
+ * objective evaluation goes through the device plugin -- the same code as lastSearch.  Restarts run one after the other: this
+ * is the reference's rarely used third option, provided for completeness, not a throughput path. */
+static int local_dfpmin(tiktak_handle* h, int n_k) {
+    const int nx = h->cfg.nx;
+    std::vector<double> st((size_t)n_k * nx), ox((size_t)n_k * nx, 0.0), of(n_k, NAN);
+    std::vector<int> oe(n_k, 0);
+    TK_CUDA(cudaMemcpyAsync(st.data(), h->d_starts, st.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    for (int s = h->cfg.rank; s < n_k; s += h->cfg.world) {
+        std::vector<double> p(nx);
+        for (int d = 0; d < nx; d++) p[d] = st[(size_t)d * n_k + s];
+        double fret = 0, fn = 0;
+        int its = 0;
+        long nfev = 0;
+        int rc = tk_est_dfpmin(h, p, &fret, &its, &nfev);
+        if (rc) return rc;
+        if ((rc = tiktak_cuda_objfun(h, p.data(), 1, &fn))) return rc; /* :582 fn_val = objFun(evalParam) */
+        for (int d = 0; d < nx; d++) ox[(size_t)d * n_k + s] = p[d];
+        of[s] = fn;
+        oe[s] = (int)nfev + 1;
+    }
+    TK_CUDA(cudaMemcpyAsync(h->d_out_x, ox.data(), ox.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->d_out_f, of.data(), of.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->d_out_evals, oe.data(), oe.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream)); /* the staging vectors are locals */
+    return TIKTAK_OK;
+}
+
 int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, double* send) {
     if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
-    if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) { tk_set_error("local: algorithm %d not available in this build", alg); return TIKTAK_ERR_UNSUPPORTED; }
+    if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS && alg != TIKTAK_ALG_DFPMIN) { tk_set_error("local: unknown search method %d", alg); return TIKTAK_ERR_ARG; }
     if (n_k == 0) return TIKTAK_OK;
     if (alg == TIKTAK_ALG_AMOEBA && h->cfg.objective_id == TIKTAK_OBJ_SMM) {
         tk_set_error("local: Nelder-Mead is not built for the vector-valued SMM objective; use DFNLS");
@@ -912,7 +944,8 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
     }
     if ((rc = h->cfg.search_type == 1 ? tk_launch_blend_lottery(h, first_k, n_k, h->n_rows, h->blend_w_idx) : tk_launch_blend(h, first_k, n_k, h->blend_w_idx))) return rc;
     if (alg == TIKTAK_ALG_AMOEBA && h->cfg.nm_shrink_mode == 1 && (rc = tk_launch_shrink_width(h))) return rc;
-    rc = (alg == TIKTAK_ALG_AMOEBA) ? tk_launch_nm(h, first_k, n_k) : tk_launch_dfnls(h, first_k, n_k);
+    if (alg == TIKTAK_ALG_DFPMIN) rc = local_dfpmin(h, n_k);
+    else rc = (alg == TIKTAK_ALG_AMOEBA) ? tk_launch_nm(h, first_k, n_k) : tk_launch_dfnls(h, first_k, n_k);
     if (rc) return rc;
     if (h->cfg.world > 1 && (rc = tk_launch_pack(h, n_k, send))) return rc;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
@@ -1002,15 +1035,39 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
 /* SolveMissingSearch (TiktakGlobalSearch.f90:1104-1146): a restart that an earlier (killed) instance never reported.  Its start
  * is getModifiedParam(p_maxpoints, x_starts(k,2:), ...) (:1121) -- the blend weight of the LAST restart number, toward the best
  * row known now -- then completeSearch(alg, k, ...) as usual (the DFNLS radii follow k).  One restart per call, like the
- * reference's sweep; every rank of a multi-GPU run makes the call (rank 0 runs the search, the row is exchanged). */
-int tiktak_cuda_local_missing(tiktak_handle* h, int32_t alg, int32_t k) {
+ * reference's sweep; every rank of a multi-GPU run makes the call (rank 0 runs the search, the row is exchanged).
+ * start (nx), row (nx+4 = seqNo, k, #improvements, fval, x) and evals may be NULL. */
+int tiktak_cuda_local_missing(tiktak_handle* h, int32_t alg, int32_t k, double* start, double* row, int32_t* evals) {
     if (!h || k < 1 || k > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
-    h->blend_w_idx = h->cfg.maxpoints_plus1;
+    const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1;
+    /* the best row BEFORE the search, for the #improvements column (completeSearch :585-589 sees every row of the file) */
+    std::vector<double> hres((size_t)(K + 1) * (nx + 1));
+    std::vector<int> hval(K + 1);
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaMemcpyAsync(hres.data(), h->d_res, hres.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hval.data(), h->d_res_valid, hval.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    double best_f = 1.0e7; int best_imp = 0; bool any = false;
+    for (int q = 0; q <= K; q++)
+        if (q != k && hval[q] && (!any || hres[(size_t)q * (nx + 1)] < best_f)) { best_f = hres[(size_t)q * (nx + 1)]; best_imp = h->h_res_imp[q]; any = true; }
+    h->blend_w_idx = K;
     int32_t acc = 0;
-    const int rc = tiktak_cuda_local_launch(h, alg, k, 1, 1, &acc);
+    int rc = tiktak_cuda_local_launch(h, alg, k, 1, 1, &acc);
     h->blend_w_idx = -1;
-    if (!rc && acc != 1) { tk_set_error("local_missing: restart %d was not committed", k); return TIKTAK_ERR_STATE; }
-    return rc;
+    if (rc) return rc;
+    if (acc != 1) { tk_set_error("local_missing: restart %d was not committed", k); return TIKTAK_ERR_STATE; }
+    std::vector<double> r1(nx + 1), st(nx);
+    int ev = 0;
+    TK_CUDA(cudaMemcpyAsync(r1.data(), h->d_res + (size_t)k * (nx + 1), (size_t)(nx + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(&ev, h->d_arch_evals + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    for (int d = 0; d < nx; d++) TK_CUDA(cudaMemcpyAsync(&st[d], h->d_arch_starts + (size_t)d * K + (k - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    const int imp = best_imp + ((any && r1[0] < best_f) ? 1 : 0);
+    h->h_res_f[k] = r1[0]; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
+    if (start) for (int d = 0; d < nx; d++) start[d] = st[d];
+    if (row) { row[0] = 1.0; row[1] = (double)k; row[2] = (double)imp; row[3] = r1[0]; for (int d = 0; d < nx; d++) row[4 + d] = r1[1 + d]; }
+    if (evals) *evals = ev & 0xffffff;
+    return TIKTAK_OK;
 }
 
 int tiktak_cuda_local_capacity(tiktak_handle* h, int32_t alg, int32_t* restarts) {
@@ -1119,17 +1176,12 @@ int tiktak_cuda_best(tiktak_handle* h, double* fbest, double* xbest, int32_t* k)
  * best row.  It runs once per job; the BFGS recurrences (O(nx^2) per iteration) are host arithmetic in the
  * reference's order, every objective evaluation goes through the device plugin: the 2 nx points of a central-
  * difference gradient as one batch, line-search trial points one by one. */
-int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* iters) {
-    if (!h) return TIKTAK_ERR_ARG;
+static int tk_est_dfpmin(tiktak_handle* h, std::vector<double>& p, double* fret_out, int* its_out, long* nfev) {
     const int nn = h->cfg.nx, itmax = 1000;
     const double gtol = 1.0e-6; /* itmax_DFPMIN, gtol_DFPMIN (genericParams.f90:27-28) */
-    double fbest = 0;
-    std::vector<double> p(nn);
-    int kb = 0;
-    int rc = tiktak_cuda_best(h, &fbest, p.data(), &kb);
-    if (rc) return rc;
+    int rc = TIKTAK_OK;
     const double stpmx = 100.0, eps = 2.220446049250313e-16, tolx = 4.0 * eps, xinc = 1.0e-5;
-    auto func = [&](const std::vector<double>& xx, double& out) -> int { return tiktak_cuda_objfun(h, xx.data(), 1, &out); };
+    auto func = [&](const std::vector<double>& xx, double& out) -> int { if (nfev) (*nfev)++; return tiktak_cuda_objfun(h, xx.data(), 1, &out); };
     auto dograd = [&](const std::vector<double>& xx, std::vector<double>& grad) -> int {
         std::vector<double> dh(nn), pts((size_t)2 * nn * nn), f((size_t)2 * nn);
         const double tolera = 10.0 * xinc;
@@ -1142,6 +1194,7 @@ int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* 
             }
         int r = tiktak_cuda_objfun(h, pts.data(), n, f.data());
         if (r) return r;
+        if (nfev) *nfev += n;
         grad.resize(nn);
         for (int i = 0; i < nn; i++) grad[i] = (f[2 * i + 1] - f[2 * i]) / (2.0 * dh[i]);
         return TIKTAK_OK;
@@ -1223,9 +1276,23 @@ int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* 
         }
         for (int i = 0; i < nn; i++) { double sm = 0.0; for (int j = 0; j < nn; j++) sm = sm + hessin[(size_t)i * nn + j] * g[j]; xi[i] = -sm; }
     }
+    if (fret_out) *fret_out = fret;
+    if (its_out) *its_out = its_done;
+    return TIKTAK_OK;
+}
+
+int tiktak_cuda_last_search(tiktak_handle* h, double* fval, double* x, int32_t* iters) {
+    if (!h) return TIKTAK_ERR_ARG;
+    const int nn = h->cfg.nx;
+    double fbest = 0, fret = 0;
+    std::vector<double> p(nn);
+    int kb = 0, its = 0;
+    int rc = tiktak_cuda_best(h, &fbest, p.data(), &kb);
+    if (rc) return rc;
+    if ((rc = tk_est_dfpmin(h, p, &fret, &its, nullptr))) return rc;
     if (fval) *fval = fret;
     if (x) for (int i = 0; i < nn; i++) x[i] = p[i];
-    if (iters) *iters = its_done;
+    if (iters) *iters = its;
     return TIKTAK_OK;
 }
 

@@ -23,7 +23,7 @@ from . import lib as _lib
 from ._abi import ALG_AMOEBA, ALG_DFNLS, SOBOL_BLOCK, TiktakConfig, as_f64, dptr, smm_user
 from .config import TikTakConfig
 
-_ALG = {"a": ALG_AMOEBA, "b": ALG_DFNLS, "amoeba": ALG_AMOEBA, "dfnls": ALG_DFNLS, 0: ALG_DFNLS, 1: ALG_AMOEBA}
+_ALG = {"a": ALG_AMOEBA, "b": ALG_DFNLS, "d": 2, "amoeba": ALG_AMOEBA, "dfnls": ALG_DFNLS, "dfpmin": 2, 0: ALG_DFNLS, 1: ALG_AMOEBA, 2: 2}
 
 
 class TikTakSearch:
@@ -263,10 +263,9 @@ class TikTakSearch:
         alg, nx = _ALG[algor], self.cfg.nx
         out = []
         for k in missing:
-            _lib.check(self._L.tiktak_cuda_local_missing(self._h, alg, int(k)), "SolveMissingSearch")
-            s = np.empty((nx, 1)); r = np.empty((nx + 4, 1)); e = np.zeros(1, dtype=np.int32)
-            _lib.check(self._L.tiktak_cuda_local_fetch(self._h, int(k), 1, s.ctypes.data, r.ctypes.data, e.ctypes.data), "SolveMissingSearch")
-            out.append((s[:, 0].copy(), r[:, 0].copy(), int(e[0])))
+            st, row, ev = np.empty(nx), np.empty(nx + 4), C.c_int32()
+            _lib.check(self._L.tiktak_cuda_local_missing(self._h, alg, int(k), dptr(st), dptr(row), C.byref(ev)), "SolveMissingSearch")
+            out.append((st, row, ev.value))
         return out
 
     # ------------------------------------------------------------------ queries
