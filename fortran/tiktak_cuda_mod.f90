@@ -53,6 +53,26 @@ MODULE tiktak_cuda_mod
        IMPORT; TYPE(C_PTR), VALUE :: h, recv; INTEGER(C_INT32_T), VALUE :: first_k, n_k, round_size
        INTEGER(C_INT32_T), INTENT(OUT) :: accepted
      END FUNCTION
+     ! enqueue + commit of restarts first_k.. as ONE call (what fortran/TiktakGlobalSearch.patch uses): `accepted` restarts were
+     ! committed to the device-resident searchResults table; queue the rest again.  Collective when world > 1.
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_launch(h, alg, first_k, n_k, round_size, accepted) &
+          BIND(C, NAME='tiktak_cuda_local_launch')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, first_k, n_k, round_size
+       INTEGER(C_INT32_T), INTENT(OUT) :: accepted
+     END FUNCTION
+     ! 0 = the search ended like the reference's; 1 = DFNLS stopped where the reference calls RESCUE_H; 2 = DFNLS refused the start
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_status(h, first_k, n_k, status) BIND(C, NAME='tiktak_cuda_local_status')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: status(*)
+     END FUNCTION
+     ! SolveMissingSearch (:1104-1146) for one restart missing from searchResults.dat; start(nx), row(nx+4), evals
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_missing(h, alg, k, start, row, evals) BIND(C, NAME='tiktak_cuda_local_missing')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, k
+       REAL(C_DOUBLE) :: start(*), row(*); INTEGER(C_INT32_T), INTENT(OUT) :: evals
+     END FUNCTION
+     ! several GPUs in one process: handles(1:n) created with rank = 0..n-1, world = n, device = rank; one communicator for all
+     INTEGER(C_INT) FUNCTION tiktak_cuda_comm_init_all(handles, n) BIND(C, NAME='tiktak_cuda_comm_init_all')
+       IMPORT; TYPE(C_PTR) :: handles(*); INTEGER(C_INT32_T), VALUE :: n
+     END FUNCTION
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_capacity(h, alg, restarts) BIND(C, NAME='tiktak_cuda_local_capacity')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg; INTEGER(C_INT32_T), INTENT(OUT) :: restarts
      END FUNCTION

@@ -127,3 +127,25 @@ def test_driver_exit_broadcast(built, tmp_path):
     assert int(open(tmp_path / "state.dat").read().split()[0]) == -1
     for f in ("lastSobol.dat", "lastParam.dat", "seqNo.dat"):
         assert int(open(tmp_path / f).read().split()[0]) == -10000000
+
+
+def test_fortran_patch_applies_to_the_reference(tmp_path):
+    """fortran/TiktakGlobalSearch.patch is a unified diff against the reference's driver: it must apply cleanly, and the patched
+    file must call the library where the stage bodies were (the reference tree only exists in the build container)"""
+    import shutil
+    import subprocess
+
+    ref = "/root/reference/TiktakGlobalSearch.f90"
+    if not os.path.exists(ref) or shutil.which("patch") is None:
+        pytest.skip("reference tree or patch(1) not available here")
+    shutil.copy(ref, tmp_path / "TiktakGlobalSearch.f90")
+    patch = os.path.join(ROOT, "fortran", "TiktakGlobalSearch.patch")
+    subprocess.check_call(["patch", "-p1", "--dry-run", "-i", patch], cwd=tmp_path, stdout=subprocess.DEVNULL)
+    subprocess.check_call(["patch", "-p1", "-i", patch], cwd=tmp_path, stdout=subprocess.DEVNULL)
+    out = open(tmp_path / "TiktakGlobalSearch.f90", encoding="latin-1").read()
+    for call in ("tiktak_cuda_create", "tiktak_cuda_sobol_points", "tiktak_cuda_pretest(", "tiktak_cuda_choose", "tiktak_cuda_local_launch",
+                 "tiktak_cuda_local_fetch", "tiktak_cuda_last_search"):
+        assert call in out, call
+    f90 = open(os.path.join(ROOT, "fortran", "tiktak_cuda_mod.f90")).read()
+    for name in re.findall(r"(tiktak_cuda_\w+)\(", out):
+        assert f"NAME='{name}'" in f90, name  # every call of the patched driver is bound by the interface module
