@@ -38,8 +38,10 @@
  * two-argument form tk_cos(x, c.trig) is the same function with its constants kept in registers), and return
  * a finite value >= fvalmax where the model is undefined (README.md:34) -- never NaN.
  *
- * Objectives with vector-valued, per-moment residuals (DFNLS, TIKTAK_OBJ_SMM) additionally provide
- * a batched residual kernel; see tiktak_b200/csrc/smm.cuh.
+ * Objectives whose dfovec fills a genuine VECTOR of moments (TIKTAK_OBJ_SMM) use the block-wide plugin form instead
+ * (tiktak_b200/csrc/smm.cuh: kVector = true, `dfovec_block(user, theta, F, scratch)` computed by all threads of a block,
+ * `smem_doubles`): DFNLS consumes the residuals per moment, Nelder-Mead and the Sobol stage take objFun = DOT_PRODUCT(F, F)
+ * in index order + getPenalty from the same evaluation (kernels_dfnls.cu: dfnls_kernel, nm_vec_kernel; kernels_smm.cu).
  */
 #ifndef TIKTAK_OBJ_CUH
 #define TIKTAK_OBJ_CUH

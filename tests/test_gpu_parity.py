@@ -596,6 +596,20 @@ def test_missing_search_sweep(built, alg):
     assert fb == o.getBestLine()[0]
 
 
+def test_nelder_mead_on_a_vector_valued_objective(built):
+    """amoeba through objFun = DOT_PRODUCT(dfovec, dfovec) + getPenalty (objective.f90:125-142) where dfovec fills a genuine
+    vector of moments (the synthetic SMM: 600 moments from a simulated panel): one restart per block, block-wide evaluations"""
+    cfg = smm_config(np_persons=1024, T=20, qr_ndraw=200, legitimate=30, maxpoints=5, fvalmax=20000.0, round_size=3)
+    cfg.nm_itmax = 60  # an evaluation simulates the panel: keep the oracle's share of the test short
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints(); s.chooseSobol(); s.LocalMinimizations("a")
+        st, rs, ev, best = s.searchStart, s.searchResults, s.evals, s.getBestLine()
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizations(1)
+    assert np.array_equal(st, o.searchStart) and np.array_equal(rs, o.searchResults) and np.array_equal(ev, o.evals)
+    assert best[0] == o.getBestLine()[0] and ev.min() >= cfg.nx + 2
+
+
 def test_local_minimizations_dfpmin(built):
     """the CLI's third algorithm, `d`: completeSearch CASE (2) = EST_dfpmin from the blended start (TiktakGlobalSearch.f90:575-576,
     minimize.f90:2572-2816), every objective evaluation on the device -- rows, starts and evaluation counts vs the oracle"""

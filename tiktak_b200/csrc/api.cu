@@ -927,10 +927,6 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
     if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS && alg != TIKTAK_ALG_DFPMIN) { tk_set_error("local: unknown search method %d", alg); return TIKTAK_ERR_ARG; }
     if (n_k == 0) return TIKTAK_OK;
-    if (alg == TIKTAK_ALG_AMOEBA && h->cfg.objective_id == TIKTAK_OBJ_SMM) {
-        tk_set_error("local: Nelder-Mead is not built for the vector-valued SMM objective; use DFNLS");
-        return TIKTAK_ERR_UNSUPPORTED;
-    }
     if (h->cfg.world > 1 && !send) { tk_set_error("local: world > 1 needs the send buffer of the round's all-gather"); return TIKTAK_ERR_ARG; }
     TK_CUDA(cudaSetDevice(h->device));
     int rc;

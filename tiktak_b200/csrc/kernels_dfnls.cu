@@ -24,7 +24,7 @@
  * logs it, tests assert it).  Measured: 0 entries in the 1001 restarts of C5 at BASELINE size and in every test
  * configuration (tests/test_gpu_full_size.py asserts status 0 before comparing with the oracle, which has RESCUE_H).
  */
-#include "tk_common.cuh"
+#include "nm_common.cuh"
 #include "smm.cuh"
 
 namespace {
@@ -1301,7 +1301,111 @@ __global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const T
     d.bar();
 }
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Nelder-Mead for objectives whose dfovec fills a VECTOR of moments (objective.f90:76-123; here the plugin form
+ * `dfovec_block`: the whole block computes Fnout(1:nm) at one point -- TIKTAK_OBJ_SMM simulates its panel).  objFun =
+ * DOT_PRODUCT(F, F) in index order + getPenalty (:125-142), through the same eval_at_XC() as DFNLS.  One restart per block:
+ * thread 0 runs runAmoeba (TiktakGlobalSearch.f90:602-633) and amoeba/amotry (minimize.f90:7-135) as written -- first-occurrence
+ * MINLOC/MAXLOC, incremental psum (:130), re-sum after a shrink (:112) -- and every objective evaluation is the block's.
+ * An evaluation costs a panel pass, so the serial simplex bookkeeping is noise next to it.
+ * --------------------------------------------------------------------------------------------- */
+template <class Obj>
+__global__ void __launch_bounds__(512) nm_vec_kernel(const TkTablesG T, const TkScalars sc, const tknm::NmArgs a) {
+    extern __shared__ double sm[];
+    __shared__ DfCtl ctl;
+    __shared__ tk_obj_ctx sctx;
+    const int r = blockIdx.x;
+    if (r >= a.n_run) return;
+    const int slot = a.rank + r * a.world;
+    const int N = sc.nx, NPV = N + 1;
+    Df<Obj> d;
+    d.tid = threadIdx.x; d.nthr = blockDim.x;
+    d.N = N; d.NPT = 0; d.mv = sc.nm; d.NDIM = 0; d.NP = N + 1; d.NPTM = 0; d.NH = 0;
+    d.eps = 2.220446049250313e-16;
+    d.ctl = &ctl;
+    d.ctx = &sctx;
+    double* q = sm;
+    auto take = [&](int n) { double* t = q; q += n; return t; };
+    double* sbl = take(N); double* sbu = take(N); double* saux = take(N);
+    d.XL = sbl; d.XU = sbu;
+    d.XC = take(N);
+    double* P = take(NPV * N); double* Y = take(NPV); double* PSUM = take(N); double* PTRY = take(N);
+    d.VSH = take(d.mv); d.YSH = take(Obj::smem_doubles(sc.user, 0));
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
+    if (threadIdx.x == 0) { sctx = tk_make_ctx(sc, N, sbl, sbu, saux); ctl.op = -1; ctl.model_update = 0; }
+    __syncthreads();
+    d.v_err = d.VSH; /* OP_DFOVEC also stores the residuals to v_err: let it store them where they already are */
+    if (threadIdx.x != 0) { d.worker_loop(); return; }
+    /* ---- master ---- */
+    auto objfun = [&](const double* x) -> double {
+        for (int j = 0; j < N; j++) d.XC[j] = x[j];
+        return d.eval_at_XC();
+    };
+    const bool shr = a.shr_have && a.shr_have[0] && ((float)(a.first_k + slot) / (float)a.K > 0.5f);
+    const double* wsrc = shr ? a.wshr : a.width;
+    for (int ia = 0; ia < NPV; ia++) { /* runAmoeba :622-627 */
+        for (int i = 0; i < N; i++) {
+            double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * N + i], wsrc[i]), a.scale));
+            P[ia * N + i] = fmax(fmin(t, sbu[i]), sbl[i]);
+        }
+        Y[ia] = objfun(P + ia * N);
+    }
+    for (int j = 0; j < N; j++) { double s_ = 0.0; for (int i = 0; i < NPV; i++) s_ = TK_ADD(s_, P[i * N + j]); PSUM[j] = s_; } /* :49 */
+    int iter = 0, ilo = 0, ihi = 0, inhi = 0;
+    auto amotry = [&](double fac) -> double { /* :116-134 */
+        const double fac1 = TK_DIV(TK_SUB(1.0, fac), (double)N), fac2 = TK_SUB(fac1, fac);
+        for (int j = 0; j < N; j++) PTRY[j] = TK_SUB(TK_MUL(PSUM[j], fac1), TK_MUL(P[ihi * N + j], fac2));
+        const double ytry = objfun(PTRY);
+        if (ytry < Y[ihi]) {
+            Y[ihi] = ytry;
+            for (int j = 0; j < N; j++) { PSUM[j] = TK_ADD(TK_SUB(PSUM[j], P[ihi * N + j]), PTRY[j]); P[ihi * N + j] = PTRY[j]; }
+        }
+        return ytry;
+    };
+    for (;;) {
+        ilo = 0; for (int i = 1; i < NPV; i++) if (Y[i] < Y[ilo]) ilo = i;        /* iminloc: first occurrence */
+        ihi = 0; for (int i = 1; i < NPV; i++) if (Y[i] > Y[ihi]) ihi = i;        /* imaxloc */
+        { const double ytmp = Y[ihi]; Y[ihi] = Y[ilo]; inhi = 0; for (int i = 1; i < NPV; i++) if (Y[i] > Y[inhi]) inhi = i; Y[ihi] = ytmp; }
+        if (tknm::nm_converged(a, Y[ilo], Y[ihi]) || iter >= a.itmax) break;     /* :84-96 */
+        double ytry = amotry(-1.0);
+        iter++;
+        if (ytry <= Y[ilo]) { ytry = amotry(2.0); iter++; }
+        else if (ytry >= Y[inhi]) {
+            const double ysave = Y[ihi];
+            ytry = amotry(0.5);
+            iter++;
+            if (ytry >= ysave) { /* :106-113 */
+                for (int i = 0; i < NPV; i++)
+                    if (i != ilo) { for (int j = 0; j < N; j++) P[i * N + j] = TK_MUL(0.5, TK_ADD(P[i * N + j], P[ilo * N + j])); Y[i] = objfun(P + i * N); }
+                iter += N;
+                for (int j = 0; j < N; j++) { double s_ = 0.0; for (int i = 0; i < NPV; i++) s_ = TK_ADD(s_, P[i * N + j]); PSUM[j] = s_; }
+            }
+        }
+    }
+    /* runAmoeba :631-632 + completeSearch :582: the first minimal vertex and objFun there (same point, same value) */
+    for (int j = 0; j < N; j++) a.out_x[(size_t)j * a.n_k + slot] = P[ilo * N + j];
+    a.out_f[slot] = Y[ilo];
+    a.out_evals[slot] = NPV + iter + 1;
+    ctl.op = OP_EXIT;
+    d.bar();
+}
+
 } /* namespace */
+
+/* Nelder-Mead for vector-valued objectives (one restart per block; see nm_vec_kernel) */
+int tk_launch_nm_vec(tiktak_handle* h, const tknm::NmArgs& a) {
+    if (h->cfg.objective_id != TIKTAK_OBJ_SMM) { tk_set_error("nm_vec: objective %d has no block-wide dfovec", h->cfg.objective_id); return TIKTAK_ERR_UNSUPPORTED; }
+    const int nx = h->cfg.nx, mv = h->cfg.nm;
+    const size_t sh = (size_t)(4 * nx + (nx + 1) * nx + (nx + 1) + 2 * nx + mv + 2 * TK_SMM_SMEM_DOUBLES(h->smm_T) + mv) * sizeof(double);
+    if (sh > 226 * 1024) { tk_set_error("nm_vec: shared memory (nx=%d, nm=%d)", nx, mv); return TIKTAK_ERR_UNSUPPORTED; }
+    const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
+    TK_CUDA(cudaFuncSetAttribute(nm_vec_kernel<ObjSmm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    nm_vec_kernel<ObjSmm><<<a.n_run, 512, sh, h->stream>>>(T, h->sc, a);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
 
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
     const int nx = h->cfg.nx, mv = h->cfg.nm, npt = 2 * nx + 1; /* p_ninterppt, genericParams.f90:311 */

@@ -1194,6 +1194,7 @@ static int nm_launch_warp(tiktak_handle* h, const TkTablesG& T, const NmArgs& a,
     return TIKTAK_OK;
 }
 
+int tk_launch_nm_vec(tiktak_handle* h, const NmArgs& a);
 bool tk_nm_w4_supported(tiktak_handle* h);
 int tk_nm_w4_capacity(tiktak_handle* h);
 int tk_launch_nm_w4(tiktak_handle* h, const NmArgs& a, const NmQueue& q);
@@ -1239,6 +1240,10 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size) 
     a.out_x = h->d_out_x;
     a.out_f = h->d_out_f;
     a.out_evals = h->d_out_evals;
+    if (h->cfg.objective_id == TIKTAK_OBJ_SMM) { /* vector-valued dfovec: one restart per block, block-wide evaluations (kernels_dfnls.cu) */
+        if (commit_round_size > 0) { tk_set_error("nm: in-kernel commit needs nm_w4_kernel"); return TIKTAK_ERR_STATE; }
+        return tk_launch_nm_vec(h, a);
+    }
     if (tk_nm_use_w4(h)) {
         NmQueue q;
         const int K = h->cfg.maxpoints_plus1;
