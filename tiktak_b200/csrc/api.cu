@@ -232,7 +232,8 @@ int tiktak_cuda_create(tiktak_handle** out, const tiktak_config* cfg) {
     TK_TRY(dalloc(&h->d_counts_spare, (size_t)h->n_cblocks + 1));
     TK_CUDA(cudaMemsetAsync(h->d_counts, 0, ((size_t)h->n_cblocks + 1) * sizeof(unsigned long long), h->stream));
     TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, ((size_t)h->n_cblocks + 1) * sizeof(unsigned long long), h->stream));
-    h->h_counts.assign(h->n_cblocks, 0ULL);
+    TK_CUDA(cudaMallocHost(&h->h_counts, ((size_t)h->n_cblocks + 1) * sizeof(unsigned long long)));
+    memset(h->h_counts, 0, ((size_t)h->n_cblocks + 1) * sizeof(unsigned long long));
     TK_TRY(dalloc(&h->d_hist, 256));
     TK_TRY(dalloc(&h->d_selstate, 8));
     const size_t ncand = (size_t)std::max(K - 1, 1) * (size_t)std::max(cfg->world, 1);
@@ -280,6 +281,8 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    for (auto& g : h->stage_graph) if (g) cudaGraphExecDestroy(g);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
     tk_comm_destroy(h);
     tk_smm_free(h);
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
@@ -427,13 +430,47 @@ int tiktak_cuda_pretest_wave(tiktak_handle* h, int64_t cb0, int64_t ncb) {
      * last wave's end event is the stage's end event (an event record costs ~1.3 us of stream time on this GPU, so a
      * second pair around the same kernel would add 2.6 us to a 33 us stage) */
     h->ev_wave_start = first_wave ? h->evp0 : h->evw0;
-    TK_CUDA(cudaEventRecord(h->ev_wave_start, h->stream));
-    int rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
-    TK_CUDA(cudaEventRecord(h->evw1, h->stream));
+    int rc = TIKTAK_OK;
+    /* A stage that is ONE wave (no cut possible) goes to the device as one CUDA graph from its second run on: start event,
+     * kernel, end event and the memset of the spare counts are four stream commands, and with an idle stream the host
+     * time between them lies inside the event interval -- 2.4 us of a 31 us stage at C2 (tools/micro/launch_floor.cu,
+     * profiles/r02_sobol_dealing.txt).  Two graphs: the job's counts buffer alternates between d_counts and its twin. */
+    static const bool no_graph = [] { const char* e = getenv("TIKTAK_NO_GRAPH"); return e && atoi(e) != 0; }();
+    const bool whole_stage = first_wave && ncb == h->n_cblocks && h->cfg.objective_id != TIKTAK_OBJ_SMM && !no_graph;
+    const int gi = whole_stage ? ((h->d_counts == h->stage_graph_counts[0]) ? 0 : (h->d_counts == h->stage_graph_counts[1]) ? 1 : -1) : -1;
+    if (gi >= 0 && h->stage_graph[gi]) {
+        TK_CUDA(cudaGraphLaunch(h->stage_graph[gi], h->stream));
+        h->launches++;
+    } else {
+        /* captured from the second run on (the first one builds tables and asks for the occupancy: not capturable) */
+        int slot = -1;
+        if (whole_stage && h->stage_runs >= 1) {
+            slot = h->stage_graph_counts[0] ? (h->stage_graph_counts[1] ? -1 : 1) : 0;
+            if (slot >= 0 && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); slot = -1; }
+        }
+        if (slot >= 0) TK_CUDA(cudaEventRecordWithFlags(h->ev_wave_start, h->stream, cudaEventRecordExternal));
+        else TK_CUDA(cudaEventRecord(h->ev_wave_start, h->stream));
+        rc = (h->cfg.objective_id == TIKTAK_OBJ_SMM) ? tk_launch_smm_wave(h, wv) : tk_launch_sobol_wave(h, wv);
+        if (slot >= 0) TK_CUDA(cudaEventRecordWithFlags(h->evw1, h->stream, cudaEventRecordExternal));
+        else TK_CUDA(cudaEventRecord(h->evw1, h->stream));
+        if (whole_stage) /* every count to the pinned mirror: the stage's callers read them right behind it */
+            TK_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)h->n_cblocks * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (first_wave) /* clear the other counts buffer for the next job, behind this wave */
+            TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
+        if (slot >= 0) {
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&h->stage_graph[slot], g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess || rc) { tk_set_error("pre-test stage graph: %s", cudaGetErrorString(e)); cudaGetLastError(); return rc ? rc : TIKTAK_ERR_CUDA; }
+            h->stage_graph_counts[slot] = h->d_counts;
+            TK_CUDA(cudaGraphLaunch(h->stage_graph[slot], h->stream));
+        }
+        if (whole_stage) h->stage_runs++;
+    }
     h->ev_stage_end = h->evw1;
-    if (first_wave) /* clear the other counts buffer for the next job, behind this wave */
-        TK_CUDA(cudaMemsetAsync(h->d_counts_spare, 0, (size_t)h->n_cblocks * sizeof(unsigned long long), h->stream));
     h->wave_pending = true;
+    h->counts_copied = whole_stage;
     if (rc) return rc;
     h->cblocks_done = std::max(h->cblocks_done, cb0 + ncb);
     return TIKTAK_OK;
@@ -506,7 +543,7 @@ static int pretest_sharded(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_le
         const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
         if ((rc = tiktak_cuda_pretest_wave(h, cb0, ncb))) return rc;
         if ((rc = tk_comm_allreduce_sum_u64(h, h->d_counts + cb0, (size_t)ncb))) return rc;
-        TK_CUDA(cudaMemcpyAsync(h->h_counts.data() + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaMemcpyAsync(h->h_counts + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
         TK_CUDA(cudaStreamSynchronize(h->stream));
         for (int64_t cb = cb0; cb < cb0 + ncb; cb++) {
             const int64_t c = (int64_t)h->h_counts[cb];
@@ -604,7 +641,7 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
         const int64_t ncb = std::min(wave, h->n_cblocks - cb0);
         rc = tiktak_cuda_pretest_wave(h, cb0, ncb);
         if (rc) return rc;
-        TK_CUDA(cudaMemcpyAsync(h->h_counts.data() + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (!h->counts_copied) TK_CUDA(cudaMemcpyAsync(h->h_counts + cb0, h->d_counts + cb0, (size_t)ncb * 8, cudaMemcpyDeviceToHost, h->stream));
         TK_CUDA(cudaStreamSynchronize(h->stream));
         if (h->cfg.world > 1) continue;
         for (int64_t cb = cb0; cb < cb0 + ncb; cb++) {
@@ -631,7 +668,7 @@ int tiktak_cuda_pretest(tiktak_handle* h, int64_t* n_evaluated, int64_t* n_legit
 /* valid count of the evaluated prefix when it was not needed to place the cut (sum of the per-block counts) */
 static int resolve_legit(tiktak_handle* h) {
     if (h->nlegit >= 0 || !h->pretest_done) return TIKTAK_OK;
-    TK_CUDA(cudaMemcpyAsync(h->h_counts.data(), h->d_counts, (size_t)h->n_cblocks * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->counts_copied) TK_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)h->n_cblocks * 8, cudaMemcpyDeviceToHost, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     int64_t tot = 0;
     for (int64_t cb = 0; cb < h->n_cblocks; cb++) tot += (int64_t)h->h_counts[cb];

@@ -71,6 +71,9 @@ struct tiktak_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw0 = nullptr, evw1 = nullptr;
     bool wave_pending = false;
+    cudaGraphExec_t stage_graph[2] = {nullptr, nullptr}; /* the one-wave pre-test stage as a graph, per counts buffer (api.cu pretest_wave) */
+    const void* stage_graph_counts[2] = {nullptr, nullptr};
+    int stage_runs = 0;
     int sm_count = 148;
     int64_t launches = 0;
     TkScalars sc;
@@ -84,7 +87,8 @@ struct tiktak_handle {
     double* d_fval = nullptr;             /* local fvals */
     unsigned long long* d_counts = nullptr; /* [n_cblocks] */
     unsigned long long* d_counts_spare = nullptr; /* zeroed twin: the next job swaps to it */
-    std::vector<unsigned long long> h_counts;
+    unsigned long long* h_counts = nullptr; /* pinned host mirror of d_counts */
+    bool counts_copied = false;            /* the whole-stage path has queued the copy of all counts to h_counts already */
     int64_t cblocks_done = 0;
     int64_t kcut = -1, nlegit = 0;
     bool pretest_done = false;
