@@ -336,7 +336,11 @@ int main(int argc, char** argv) {
                 CHECK(tiktak_cuda_local_status(h, kfirst, nk, stt.data()));
                 int n1 = 0;
                 for (int s = 0; s < nk; s++) n1 += stt[s] != 0;
-                if (n1) { char b[200]; snprintf(b, sizeof b, "%d: %d local search(es) stopped early (status != 0: DFNLS would have called RESCUE_H, or refused its start)", seqNo, n1); logmsg(b); }
+                if (n1) { char b[200]; snprintf(b, sizeof b, "%d: %d local search(es) stopped early (status != 0: DFNLS refused its start)", seqNo, n1); logmsg(b); }
+                CHECK(tiktak_cuda_local_nrescue(h, kfirst, nk, stt.data()));
+                int nr = 0;
+                for (int s = 0; s < nk; s++) nr += stt[s];
+                if (nr) { char b[200]; snprintf(b, sizeof b, "%d: DFNLS rebuilt its interpolation system %d time(s) (RESCUE_H)", seqNo, nr); logmsg(b); }
             }
             for (int s = 0; s < nk; s++) {
                 fprintf(fs, "%10d%10d", seqNo, kfirst + s); for (int d = 0; d < nx; d++) fprintf(fs, "%40.20f", st[(size_t)d * nk + s]); fputc('\n', fs);

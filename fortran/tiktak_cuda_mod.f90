@@ -60,9 +60,13 @@ MODULE tiktak_cuda_mod
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, first_k, n_k, round_size
        INTEGER(C_INT32_T), INTENT(OUT) :: accepted
      END FUNCTION
-     ! 0 = the search ended like the reference's; 1 = DFNLS stopped where the reference calls RESCUE_H; 2 = DFNLS refused the start
+     ! 0 = the search ended like the reference's; 2 = DFNLS refused the start
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_status(h, first_k, n_k, status) BIND(C, NAME='tiktak_cuda_local_status')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: status(*)
+     END FUNCTION
+     ! RESCUE_H calls of each restart's DFNLS search (minimize.f90:643-650)
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_nrescue(h, first_k, n_k, nrescue) BIND(C, NAME='tiktak_cuda_local_nrescue')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: nrescue(*)
      END FUNCTION
      ! SolveMissingSearch (:1104-1146) for one restart missing from searchResults.dat; start(nx), row(nx+4), evals
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_missing(h, alg, k, start, row, evals) BIND(C, NAME='tiktak_cuda_local_missing')

@@ -189,10 +189,12 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
 int tiktak_cuda_local_ingest(tiktak_handle* h, int32_t first_k, int32_t n_k, const double* recv);
 int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, double* starts, double* results,
                             int32_t* evals);
-/* how each restart's local search ended: 0 = as the reference's would; 1 = DFNLS stopped where the reference calls RESCUE_H
- * (a denominator damaged by cancellation, minimize.f90:746-751, :782-787 -- RESCUE_H is not built on the device, the
- * result row is the best point so far); 2 = DFNLS refused the start (bounds closer than 2 rhobeg, :354-362). */
+/* how each restart's local search ended: 0 = as the reference's would; 2 = DFNLS refused the start (bounds closer than
+ * 2 rhobeg, minimize.f90:354-362).  (1 was "stopped where the reference calls RESCUE_H" while RESCUE_H was not on the device.) */
 int tiktak_cuda_local_status(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* status);
+/* how often restart k's DFNLS search rebuilt its interpolation system with RESCUE_H (minimize.f90:643-650, :1627-2023: after a
+ * denominator was damaged by cancellation, :746-747, :782-783); saturates at 31.  0 for Nelder-Mead. */
+int tiktak_cuda_local_nrescue(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* nrescue);
 /* Rounds started early.  A round depends on the earlier ones only through the best row, which changes in few
  * rounds (the #improvements column).  local_enqueue may therefore be given SEVERAL consecutive rounds at once
  * (n_k = a multiple of round_size, or up to the last restart): all of them start from the best row known now.

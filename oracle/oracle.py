@@ -54,6 +54,10 @@ def load():
         L.orc_best.argtypes = [C.c_void_p, c_double_p, c_double_p, c_int32_p]
         L.orc_run_amoeba.argtypes = [C.c_void_p, c_double_p, c_int32_p]
         L.orc_dfnls.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, c_int32_p, c_int32_p]
+        L.orc_set_dfnls_force_rescue.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_set_dfnls_force_rescue.restype = C.c_long
+        L.orc_dfnls_rescue_evals.argtypes = [C.c_void_p]
+        L.orc_dfnls_rescue_evals.restype = C.c_long
         L.orc_simplex_coordinates2.argtypes = [C.c_int, c_double_p]
         L.orc_indexx.argtypes = [C.c_int, c_double_p, c_int32_p]
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32]

@@ -646,6 +646,8 @@ struct Oracle {
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first = 1);
     int missing_search(int alg, int k, double* start_out, double* row_out, int32_t* evals_out);
     int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
+    int dfnls_force_first = 0, dfnls_force_every = 0; /* test hook (orc_set_dfnls_force_rescue) */
+    long nrescue_total = 0, rescue_evals_total = 0;    /* RESCUE_H calls of all dfnls runs of this oracle, evaluations made inside them */
 };
 
 /* SolveMissingSearch (TiktakGlobalSearch.f90:1104-1146) for one missing restart k: getModifiedParam is called with whichPoint =
@@ -1013,6 +1015,15 @@ long orc_pretest_faithful(void* hh, const char* dir, long npoints) {
 void orc_philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) { tk_philox4x32_10(c, k0, k1); }
 double orc_uniform01(uint32_t seed, uint32_t stream, uint64_t counter) { return tk_uniform01(seed, stream, counter); }
 float orc_w11(int k, int K) { float wf = sqrtf((float)k / (float)K); return std::min(std::max(0.10f, wf), 0.95f); }
+/* test hook: every later DFNLS run of this oracle treats the denominator tests (minimize.f90:746, :782) as failed when NF reaches
+ * `first` (and every `every` evaluations after it), i.e. calls RESCUE_H there; first <= 0 switches it off.  Returns the number of
+ * RESCUE_H calls so far. */
+long orc_set_dfnls_force_rescue(void* h, int first, int every) {
+    Oracle* o = (Oracle*)h;
+    o->dfnls_force_first = first; o->dfnls_force_every = every;
+    return o->nrescue_total;
+}
+long orc_dfnls_rescue_evals(void* h) { return ((Oracle*)h)->rescue_evals_total; }
 /* one DFNLS run (bobyqa_h) from x with explicit radii */
 int orc_dfnls(void* h, double* x, double rhobeg, double rhoend, int maxfun, int32_t* nf, int32_t* nrescue) {
     Oracle* o = (Oracle*)h;
@@ -1116,6 +1127,7 @@ int orc_complete_search(void* h, int alg, int k, double* x, double* fn_val) {
 int orc_dfnls_trace(void* h, double* x, double rhobeg, double rhoend, int maxfun, int max_snap, double* out, int32_t* nf) {
     Oracle* o = (Oracle*)h;
     Dfnls d;
+    d.force_first = o->dfnls_force_first; d.force_every = o->dfnls_force_every > 0 ? o->dfnls_force_every : 1 << 30;
     d.dfovec = [o](const double* xx, double* F) { o->nfev++; o->dfovec(xx, F); };
     d.getPenalty = [o](const double* xx) { return o->getPenalty(xx); };
     int nsnap = 0;
@@ -1135,6 +1147,7 @@ int orc_dfnls_trace(void* h, double* x, double rhobeg, double rhoend, int maxfun
     d.BOBYQA_H(n, npt, p.data(), o->bl(), o->bu(), rhobeg, rhoend, maxfun, o->c.nm, n1);
     for (int i = 0; i < n; i++) x[i] = p[i];
     if (nf) *nf = n1;
+    o->nrescue_total += d.nrescue; o->rescue_evals_total += d.rescue_evals;
     if (getenv("TK_DFNLS_DEBUG")) fprintf(stderr, "dfnls exit_line %d nf %d\n", d.exit_line, n1);
     return nsnap;
 }

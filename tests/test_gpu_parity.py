@@ -188,6 +188,85 @@ def test_local_minimizations_dfnls(built, name, B, nm):
     assert np.array_equal(gr, o.searchResults)
 
 
+@pytest.mark.parametrize("name,B,nm,first,every", [("template4", 4, 8, 11, 0), ("griewank7", 4, 3, 17, 0), ("griewank7", 4, 3, 26, 7),
+                                                   ("griewank10", 5, 6, 30, 9), ("rastrigin20", 8, 2, 45, 40), ("rosenbrock33", 3, 4, 70, 0)])
+def test_dfnls_rescue_forced(built, name, B, nm, first, every, monkeypatch):
+    """RESCUE_H on the device (minimize.f90:1627-2023, label 190 :643-675).  Rounding damages a denominator in almost no run
+    (0 entries in 3600 oracle runs over the four objectives, 0 at C5), so the test hook makes the denominator tests of :746 /
+    :782 count as failed at chosen evaluation numbers, in the kernel (TIKTAK_DFNLS_FORCE_RESCUE) and in the oracle
+    (orc_set_dfnls_force_rescue) alike.  Both must then walk RESCUE_H through the same exchanges of provisional and original
+    points, make the same evaluations inside it and end every restart on the same row, bit for bit."""
+    cfg = cfg_of(name, round_size=B, nm=nm, maxpoints=min(SMALL[name]["maxpoints"], 9))
+    monkeypatch.setenv("TIKTAK_DFNLS_FORCE_RESCUE", "%d,%d" % (first, every))
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizations("b")
+        gs, gr, ge, gn = s.searchStart, s.searchResults, s.evals, s.nrescue
+        assert np.all(s.status == 0)
+    o = Oracle(cfg, MATH_TK)
+    o.L.orc_set_dfnls_force_rescue(o.h, first, every)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizations(0)
+    n_resc = o.L.orc_set_dfnls_force_rescue(o.h, 0, 0)
+    assert n_resc >= cfg.p_maxpoints - 1 and int(gn.sum()) == n_resc, (gn, n_resc)  # (a restart may end before `first`)
+    assert np.array_equal(gs, o.searchStart)
+    assert np.array_equal(ge, o.evals)
+    assert np.array_equal(gr, o.searchResults)
+    # and the hook switched off gives the plain run again (the knob is read at every launch)
+    monkeypatch.delenv("TIKTAK_DFNLS_FORCE_RESCUE")
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizations("b")
+        assert int(s.nrescue.sum()) == 0
+
+
+@pytest.mark.parametrize("name,B,nm,K,first,every", [("griewank7", 5, 3, 9, 24, 2), ("rosenbrock33", 3, 4, 4, 70, 2)])
+def test_dfnls_rescue_forced_with_evaluations_inside(built, name, B, nm, K, first, every, monkeypatch):
+    """the second half of RESCUE_H (:1892-2019): provisional points that could not be exchanged for original ones stay, each
+    costs an evaluation and a model update -- the forced schedules below (a rescue every other evaluation) leave dozens in
+    (the oracle counts them); rows, evaluation counts and the number of rescues per job must agree"""
+    cfg = cfg_of(name, round_size=B, nm=nm, maxpoints=K)
+    monkeypatch.setenv("TIKTAK_DFNLS_FORCE_RESCUE", "%d,%d" % (first, every))
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizations("b")
+        gr, ge, gn = s.searchResults, s.evals, s.nrescue
+    o = Oracle(cfg, MATH_TK)
+    o.L.orc_set_dfnls_force_rescue(o.h, first, every)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizations(0)
+    assert o.L.orc_dfnls_rescue_evals(o.h) > 0
+    n_resc = o.L.orc_set_dfnls_force_rescue(o.h, 0, 0)
+    assert np.array_equal(ge, o.evals) and np.array_equal(gr, o.searchResults)
+    assert int(gn.sum()) == n_resc or np.any(gn == 31)  # the per-restart counter saturates at 31
+
+
+@pytest.mark.parametrize("nx,nm", [(64, 2), (100, 1)])
+def test_dfnls_up_to_nx_100(built, nx, nm):
+    """nmax = 100 of minimize.f90:416: above nx ~ 55 XPT, BMAT and ZMAT (560 KB at nx = 100) live in the restart's slab of
+    global memory instead of shared memory; same arithmetic, same rows"""
+    cfg = make_config(nx=nx, nm=nm, qr_ndraw=400, maxpoints=3, lo=-2.0, hi=2.0, init=[0.5] * nx, objective_id=OBJ_ROSENBROCK,
+                      round_size=2, maxeval=3 * nx + 40)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizations("b")
+        gs, gr, ge = s.searchStart, s.searchResults, s.evals
+        assert np.all(s.status == 0)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizations(0)
+    assert np.array_equal(gs, o.searchStart)
+    assert np.array_equal(ge, o.evals)
+    assert np.array_equal(gr, o.searchResults)
+
+
 def test_smm_objective_pretest_and_dfnls(built):
     """BASELINE config 5 at reduced panel size: synthetic SMM (30 T moments, 7 parameters, panel simulated per
     evaluation), legitimate cut with a finite fvalmax, DFNLS local stage."""

@@ -125,8 +125,10 @@ def _dfnls_cfg(obj, nx, nm, lo, hi, init):
     return make_config(nx, nm, 10, 1, lo, hi, init=init, objective_id=obj, fvalmax=1.0e8)
 
 
-def _run_dfnls(cfg, start, rhobeg, rhoend, maxfun, trace=0):
+def _run_dfnls(cfg, start, rhobeg, rhoend, maxfun, trace=0, force=None, info=None):
     o = Oracle(cfg, MATH_TK)
+    if force:
+        o.L.orc_set_dfnls_force_rescue(o.h, force[0], force[1])
     x = np.ascontiguousarray(np.asarray(start, dtype=np.float64))
     nf = C.c_int32()
     n, npt, mv = cfg.nx, 2 * cfg.nx + 1, cfg.nm
@@ -134,6 +136,8 @@ def _run_dfnls(cfg, start, rhobeg, rhoend, maxfun, trace=0):
         nr = C.c_int32()
         rc = o.L.orc_dfnls(o.h, dptr(x), rhobeg, rhoend, maxfun, C.byref(nf), C.byref(nr))
         assert rc == 0
+        if info is not None:
+            info.update(nrescue=nr.value, rescue_evals=o.L.orc_dfnls_rescue_evals(o.h))
         return x, nf.value, None
     nh, ndim, nptm = n * (n + 1) // 2, npt + n, npt - n - 1
     size = 2 + 2 * n + npt * n + mv * npt + mv * n + mv * nh + mv * npt + ndim * n + npt * nptm
@@ -141,6 +145,8 @@ def _run_dfnls(cfg, start, rhobeg, rhoend, maxfun, trace=0):
     o.L.orc_dfnls_trace.restype = C.c_int
     o.L.orc_dfnls_trace.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int, c_double_p, c_int32_p]
     ns = o.L.orc_dfnls_trace(o.h, dptr(x), rhobeg, rhoend, maxfun, trace, dptr(buf), C.byref(nf))
+    if info is not None:
+        info.update(nrescue=o.L.orc_set_dfnls_force_rescue(o.h, 0, 0), rescue_evals=o.L.orc_dfnls_rescue_evals(o.h))
     snaps = []
     for s in range(ns):
         w = buf[s * size:(s + 1) * size]
@@ -199,20 +205,10 @@ def test_dfnls_known_answers(built):
     assert np.isclose(x.max(), hi) and np.allclose(x, ref, atol=1e-5), (x, ref, nf)
 
 
-@pytest.mark.parametrize("case", ["rosen2", "rosen3", "lin3"])
-def test_dfnls_models_interpolate_and_kkt_inverse_holds_at_every_step(built, case):
-    if case.startswith("rosen"):
-        nx = int(case[-1])
-        cfg = _dfnls_cfg(OBJ_TEST_ROSENRES, nx, 2 * (nx - 1), -3.0, 3.0, [-1.2, 1.0, -0.5][:nx])
-        start, resid, rb = [-1.2, 1.0, -0.5][:nx], _rosen_res, 0.4
-    else:
-        nx, nm = 3, 8
-        A, b = _lin_Ab(nx, nm)
-        cfg = _dfnls_cfg(OBJ_TEST_LINRES, nx, nm, -10.0, 10.0, [0.3, -0.2, 0.1])
-        start, resid, rb = [0.3, -0.2, 0.1], (lambda v: A @ v - b), 0.5
-    x, nf, snaps = _run_dfnls(cfg, start, rb, 1.0e-7, 600, trace=400)
+def _model_and_kkt_errors(cfg, snaps, resid):
+    """largest violation, over the snapshots of a traced run, of (1) the interpolation conditions of the per-moment models and
+    (2) the Lagrange property of the functions BMAT / ZMAT define"""
     n, npt = cfg.nx, 2 * cfg.nx + 1
-    assert len(snaps) >= 10 and nf > npt
     iu = [(i, j) for j in range(n) for i in range(j + 1)]  # packed upper triangle by columns (IH runs j = 1..n, i = 1..j)
     worst_i = worst_l = 0.0
     for s in snaps:
@@ -239,5 +235,53 @@ def test_dfnls_models_interpolate_and_kkt_inverse_holds_at_every_step(built, cas
         lag = omega @ (q - q[:, [ko]]) + s["bmat"][:npt] @ (xpt - xpt[ko]).T   # [k, j] = l_k(x_j) - l_k(x_opt)
         want = np.eye(npt) - np.eye(npt)[:, [ko]]
         worst_l = max(worst_l, float(np.abs(lag - want).max()))
+    return worst_i, worst_l
+
+
+@pytest.mark.parametrize("case", ["rosen2", "rosen3", "lin3"])
+def test_dfnls_models_interpolate_and_kkt_inverse_holds_at_every_step(built, case):
+    if case.startswith("rosen"):
+        nx = int(case[-1])
+        cfg = _dfnls_cfg(OBJ_TEST_ROSENRES, nx, 2 * (nx - 1), -3.0, 3.0, [-1.2, 1.0, -0.5][:nx])
+        start, resid, rb = [-1.2, 1.0, -0.5][:nx], _rosen_res, 0.4
+    else:
+        nx, nm = 3, 8
+        A, b = _lin_Ab(nx, nm)
+        cfg = _dfnls_cfg(OBJ_TEST_LINRES, nx, nm, -10.0, 10.0, [0.3, -0.2, 0.1])
+        start, resid, rb = [0.3, -0.2, 0.1], (lambda v: A @ v - b), 0.5
+    x, nf, snaps = _run_dfnls(cfg, start, rb, 1.0e-7, 600, trace=400)
+    n, npt = cfg.nx, 2 * cfg.nx + 1
+    assert len(snaps) >= 10 and nf > npt
+    worst_i, worst_l = _model_and_kkt_errors(cfg, snaps, resid)
     assert worst_i < 1e-7, worst_i
     assert worst_l < 1e-6, worst_l
+
+
+@pytest.mark.parametrize("case,first,every", [("rosen3", 9, 0), ("rosen3", 12, 5), ("lin3", 10, 6), ("lin3", 8, 0),
+                                              ("rosen3", 8, 0), ("rosen5", 15, 0), ("rosen5", 24, 0)])
+def test_dfnls_rescue_keeps_the_interpolation_system(built, case, first, every):
+    """RESCUE_H (minimize.f90:1627-2023) has no counterpart in scipy and almost never runs on its own, so the oracle's
+    restatement is pinned through what it must leave behind.  With the test hook forcing label 190 at chosen evaluation
+    numbers: after EVERY later step BMAT / ZMAT -- which RESCUE_H rebuilds from scratch, exchanging provisional for original
+    points one UPDATE at a time -- still define Lagrange functions on the current points, whether or not provisional points
+    stayed (the last three cases: evaluations inside RESCUE_H, its second half :1892-2019), and the per-moment models still
+    interpolate the residuals at every point.  The run ends where the plain run ends."""
+    if case.startswith("rosen"):
+        nx = int(case[-1])
+        start = [-1.2, 1.0, -0.5, 0.8, -1.0][:nx]
+        cfg = _dfnls_cfg(OBJ_TEST_ROSENRES, nx, 2 * (nx - 1) + 1, -3.0, 3.0, start)
+        resid, rb = (lambda v: _rosen_res(v, 1)), 0.4
+    else:
+        nx, nm = 3, 8
+        A, b = _lin_Ab(nx, nm)
+        cfg = _dfnls_cfg(OBJ_TEST_LINRES, nx, nm, -10.0, 10.0, [0.3, -0.2, 0.1])
+        start, resid, rb = [0.3, -0.2, 0.1], (lambda v: A @ v - b), 0.5
+    info = {}
+    x, nf, snaps = _run_dfnls(cfg, start, rb, 1.0e-7, 900, trace=600, force=(first, every), info=info)
+    assert info["nrescue"] >= 1 and len(snaps) >= 10
+    assert (info["rescue_evals"] > 0) == ((case, first) in (("rosen3", 8), ("rosen5", 15), ("rosen5", 24)))
+    worst_i, worst_l = _model_and_kkt_errors(cfg, snaps, resid)
+    assert worst_l < 1e-6, worst_l
+    assert worst_i < 1e-7, worst_i
+    plain, _, _ = _run_dfnls(cfg, start, rb, 1.0e-7, 900)
+    assert np.allclose(x, plain, atol=2e-4), (x, plain)

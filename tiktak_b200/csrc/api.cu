@@ -1166,8 +1166,21 @@ int tiktak_cuda_local_status(tiktak_handle* h, int32_t first_k, int32_t n_k, int
     std::vector<int> hev(n_k);
     TK_CUDA(cudaMemcpyAsync(hev.data(), h->d_arch_evals + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
-    for (int& e : hev) e = (e >> 24) & 0xff;
+    for (int& e : hev) e = (e >> 24) & 0x3;
     TK_CUDA(cudaMemcpy(status, hev.data(), (size_t)n_k * sizeof(int), cudaMemcpyDefault));
+    return TIKTAK_OK;
+}
+
+/* how often restart k called RESCUE_H (minimize.f90:643-650; DFNLS only, saturates at 31) */
+int tiktak_cuda_local_nrescue(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* nrescue) {
+    if (!h || !nrescue || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (n_k == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    std::vector<int> hev(n_k);
+    TK_CUDA(cudaMemcpyAsync(hev.data(), h->d_arch_evals + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    for (int& e : hev) e = (e >> 26) & 0x1f;
+    TK_CUDA(cudaMemcpy(nrescue, hev.data(), (size_t)n_k * sizeof(int), cudaMemcpyDefault));
     return TIKTAK_OK;
 }
 

@@ -248,7 +248,10 @@ class TikTakSearch:
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
         st = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_local_status(self._h, 1, K, st.ctypes.data_as(C.POINTER(C.c_int32))), "local_status")
-        self.status = st  # 0 = ended like the reference's search; 1 = DFNLS stopped where the reference would call RESCUE_H
+        self.status = st  # 0 = ended like the reference's search; 2 = DFNLS refused the start
+        nr = np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_nrescue(self._h, 1, K, nr.ctypes.data_as(C.POINTER(C.c_int32))), "local_nrescue")
+        self.nrescue = nr  # RESCUE_H calls per restart (DFNLS)
         return True
 
     def pushResults(self, rows):
