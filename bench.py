@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--round-size", type=int, default=0)
+    ap.add_argument("--local-mode", choices=["auto", "rounds", "async"], default="auto",
+                    help="restart stage: rounds of round_size restarts, or round_size asynchronous instances (one launch; the reference's "
+                         "multi-process mode); auto = async where the library has it (Nelder-Mead, nx <= 31, one GPU)")
     ap.add_argument("--nm-shrink-mode", type=int, default=-1, choices=[-1, 0, 1],
                     help="initial-simplex rule: 0 = the reference code, 1 = README.md:36 (bounds from the best minima so far); "
                          "default 0: the rule is not in the reference's code (SURVEY finding 3)")
@@ -267,7 +270,7 @@ def run_reference(args, rank, world):
 class Job:
     """one workload bound to this rank's GPU: timed steps of the hot path, stage times from CUDA events on the library stream"""
 
-    def __init__(self, name, cfg, rank, world, local_rank, dist, no_local=False):
+    def __init__(self, name, cfg, rank, world, local_rank, dist, no_local=False, local_mode="auto"):
         import torch
 
         from tiktak_b200 import SOBOL_BLOCK, TikTakSearch
@@ -279,6 +282,9 @@ class Job:
         self.n_host = ((cfg.qr_ndraw // SOBOL_BLOCK + world) // world) * SOBOL_BLOCK
         self.pinned = None  # host side of the e2e copy, allocated on first use
         self.alg = "b" if name == "C5" else "a"
+        self.local_async = local_mode != "rounds" and world == 1 and self.s.asyncSupported(self.alg)
+        if local_mode == "async" and not self.local_async:
+            raise SystemExit("bench: --local-mode async is not available for this workload / world size")
 
     def close(self):
         self.s.close()
@@ -314,7 +320,10 @@ class Job:
         e3 = self.mark()
         t3 = time.perf_counter()
         if not self.no_local:
-            s.LocalMinimizations(self.alg)
+            if self.local_async:
+                s.LocalMinimizationsAsync(self.alg)
+            else:
+                s.LocalMinimizations(self.alg)
         e4 = self.mark()
         self.ext.synchronize()
         t4 = time.perf_counter()
@@ -360,8 +369,16 @@ class Job:
                "mean_evals_per_restart": float(np.mean(s.evals)) if s.evals is not None else None,
                "evals_in_restarts": float(np.sum(s.evals)) if s.evals is not None else None,
                "local_launches": getattr(s, "local_launches", None), "gpu_launches": int(launches),
+               "local_mode": "async" if self.local_async else "rounds",
+               "instances": getattr(s, "instances_used", None) if self.local_async else None,
                "pretest_ms_steps": [round(float(d["pretest_ms"]), 5) for d in dev],
                "best_fval": None if self.no_local else s.getBestLine()[0]}
+        if self.local_async and not self.no_local:  # the same restarts as rounds of round_size, beside (untimed steps)
+            self.local_async = False
+            rd = [self.step(flush, False) for _ in range(2)]
+            self.local_async = True
+            out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_launches": getattr(s, "local_launches", None),
+                             "restarts_per_s": cfg.p_maxpoints / (np.mean([d["local_ms"] for d in rd]) * 1e-3), "best_fval": s.getBestLine()[0]}
         if e2e:
             out["e2e_sobol_s"] = self.mx(np.mean([d["wall_pretest"] for d in e2e]))
             out["e2e_step_s"] = self.mx(np.mean([d["wall"] for d in e2e]))
@@ -402,11 +419,15 @@ def rooflines(name, cfg, m, world, peak_tf, hbm_gbs, hbm_src):
     local = None
     if m.get("evals_in_restarts") and m["stage_ms"]["local"] > 0 and name != "C5":
         ach = m["evals_in_restarts"] * F_ALG[name] / (m["stage_ms"]["local"] * 1e-3) / 1e12
-        local = {"bound": "latency", "kernel": "nm_quad_kernel (four warps per restart)" if cfg.nx <= 31 else "nm_w4_kernel (one warp per restart, device-side restart queue)",
+        asy = m.get("local_mode") == "async"
+        local = {"bound": "latency", "kernel": ("nm_quad_async_kernel (four warps per restart, %s asynchronous instances, one launch)" % m.get("instances")) if asy else
+                 ("nm_quad_kernel (four warps per restart)" if cfg.nx <= 31 else "nm_w4_kernel (one warp per restart, device-side restart queue)"),
                  "achieved": ach, "peak": peak_tf * world, "unit": "TFLOP/s", "frac": ach / (peak_tf * world),
                  "objective_evals_per_step": m["evals_in_restarts"], "share_of_step": m["stage_ms"]["local"] / step_ms,
-                 "note": "rounds are sequential (a round's starts depend on the best row of the rounds before it) and a round lasts as long "
-                         "as its longest restart: a chain of dependent simplex iterations, ~0.6-1.2 us per counted evaluation (DESIGN.md section 3)"}
+                 "note": ("every instance takes the next restart the moment it finishes one (virtual-time order, DESIGN.md section 3); a restart is a chain of "
+                          "dependent simplex iterations, ~0.6-1.2 us per counted evaluation") if asy else
+                         ("rounds are sequential (a round's starts depend on the best row of the rounds before it) and a round lasts as long "
+                          "as its longest restart: a chain of dependent simplex iterations, ~0.6-1.2 us per counted evaluation (DESIGN.md section 3)")}
     return roof, local
 
 
@@ -442,6 +463,18 @@ def parity_block(rank, world, local_rank):
                       "best": best[0] == o.getBestLine()[0]}
             detail[cname] = checks
             ok = ok and all(checks.values())
+        if world == 1:  # the asynchronous-instances form of the same restarts against the oracle's event simulation
+            with TikTakSearch(cfg, device=local_rank) as s:
+                if s.asyncSupported("a"):
+                    s.solveAtSobolPoints()
+                    s.chooseSobol()
+                    s.LocalMinimizationsAsync("a")
+                    res, st, ev, best, used = s.searchResults, s.searchStart, s.evals, s.getBestLine(), s.instances_used
+                    o.LocalMinimizationsAsync(used)
+                    checks = {"starts": bool(np.array_equal(st, o.searchStart)), "results": bool(np.array_equal(res, o.searchResults)),
+                              "evals": bool(np.array_equal(ev, o.evals)), "best": best[0] == o.getBestLine()[0], "instances": int(used)}
+                    detail[cname + "_async"] = checks
+                    ok = ok and all(bool(v) for v in checks.values())
     return {"ok": bool(ok), "world": world, "checked": "Sobol-stage cut and valid count, x_starts, searchStart, searchResults (bit for bit), evaluation counts, best row; "
             "sharded over this run's ranks vs the single-instance CPU oracle", "cases": detail}
 
@@ -467,7 +500,7 @@ def run_graft(args, rank, world, local_rank):
     steps, warmup = max(1, args.steps), max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    job = Job(name, cfg, rank, world, local_rank, dist, args.no_local)
+    job = Job(name, cfg, rank, world, local_rank, dist, args.no_local, args.local_mode)
     m = job.measure(flush, steps, warmup, sampler, e2e_steps=steps)
     job.close()
 
@@ -486,7 +519,7 @@ def run_graft(args, rank, world, local_rank):
                 if wn == name:
                     continue
                 wcfg = workload_config(wn, 1)
-                wj = Job(wn, wcfg, rank, 1, local_rank, None)
+                wj = Job(wn, wcfg, rank, 1, local_rank, None, local_mode=args.local_mode)
                 wm = wj.measure(flush, 1 if wn == "C5" else 2, 1, sampler)
                 wj.close()
                 roof, rl = rooflines(wn, wcfg, wm, 1, peak_tf, hbm_gbs, hbm_src)
@@ -497,7 +530,7 @@ def run_graft(args, rank, world, local_rank):
                     strong = dict(wm, n_gpus=1)
         else:
             scfg = workload_config("C3", world, weak=False)
-            sj = Job("C3", scfg, rank, world, local_rank, dist)
+            sj = Job("C3", scfg, rank, world, local_rank, dist, local_mode=args.local_mode)
             sm_ = sj.measure(flush, 2, 1, sampler)
             sj.close()
             strong = dict(sm_, n_gpus=world)
@@ -520,6 +553,7 @@ def run_graft(args, rank, world, local_rank):
                                  "stage's own device work; choose/local: events bracketing the host calls)"},
             "restarts_per_s": m["restarts_per_s"], "mean_evals_per_restart": m["mean_evals_per_restart"],
             "stage_ms": m["stage_ms"], "pretest_ms_steps": m["pretest_ms_steps"], "local_launches": m["local_launches"],
+            "local_mode": m["local_mode"], "instances": m["instances"], "rounds": m.get("rounds"),
             "roofline": roof, "roofline_local": rl, "cpu_baseline": cpu,
             "e2e": {"value": m["n_evaluated"] / m["e2e_sobol_s"], "unit": "evals/s",
                     "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": m["d2h_total"],

@@ -64,6 +64,14 @@ MODULE tiktak_cuda_mod
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_status(h, first_k, n_k, status) BIND(C, NAME='tiktak_cuda_local_status')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: status(*)
      END FUNCTION
+     ! asynchronous instances: restarts first_k.. by `instances` blocks that take the next restart when they finish one (:546-600)
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_async(h, alg, first_k, n_k, instances, used) BIND(C, NAME='tiktak_cuda_local_async')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, first_k, n_k, instances
+       INTEGER(C_INT32_T), INTENT(OUT) :: used
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_async_supported(h, alg, yes) BIND(C, NAME='tiktak_cuda_local_async_supported')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg; INTEGER(C_INT32_T), INTENT(OUT) :: yes
+     END FUNCTION
      ! RESCUE_H calls of each restart's DFNLS search (minimize.f90:643-650)
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_nrescue(h, first_k, n_k, nrescue) BIND(C, NAME='tiktak_cuda_local_nrescue')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: nrescue(*)

@@ -400,6 +400,7 @@ struct Oracle {
             for (int i = 1; i <= n; i++) X(i, j) = X(i, j) / s;
     }
 
+    int amoeba_trips = 0, amoeba_shrinks = 0; /* loop trips and shrink steps of the last amoeba call */
     /* amoeba + amotry (minimize.f90:7-135).  p is (ndim+1, ndim) ROW-major here (p[i][j]). */
     void amoeba(std::vector<double>& p, std::vector<double>& y, double ftol, int& iter, int ITMAX) {
         const double TINY = (double)1.0e-10f; /* REAL(dp), PARAMETER :: TINY=1.0e-10 -- SP literal (:28) */
@@ -424,6 +425,7 @@ struct Oracle {
             return ytry;
         };
         iter = 0;
+        amoeba_trips = 0; amoeba_shrinks = 0;
         sum_psum();
         for (;;) {
             int ilo = iminloc();
@@ -438,6 +440,7 @@ struct Oracle {
                 for (int j = 0; j < ndim; j++) std::swap(P(0, j), P(ilo, j));
                 return;
             }
+            amoeba_trips++; /* one pass of the loop: the virtual clock of the asynchronous-instances run (local_async) */
             double ytry = amotry(-1.0);
             iter++;
             if (ytry <= y[ilo]) {
@@ -455,6 +458,7 @@ struct Oracle {
                     for (int i = 0; i < np; i++)
                         if (i != ilo) y[i] = objFun(&P(i, 0));
                     iter += ndim;
+                    amoeba_shrinks++;
                     sum_psum();
                 }
             }
@@ -644,6 +648,7 @@ struct Oracle {
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first = 1);
+    int local_async(int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out);
     int missing_search(int alg, int k, double* start_out, double* row_out, int32_t* evals_out);
     int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
     int dfnls_force_first = 0, dfnls_force_every = 0; /* test hook (orc_set_dfnls_force_rescue) */
@@ -774,6 +779,102 @@ int Oracle::local(int alg, int round_size, double* starts_out, double* results_o
             for (int i = 0; i < nx; i++) results_out[(size_t)(4 + i) * K + (k - 1)] = r.x[i];
         }
     }
+    return 0;
+}
+
+/* The reference's multi-process mode as a sequential event simulation (restated on the device by nm_quad_async_kernel):
+ * P instances; an instance that finishes a restart appends its row and takes the next restart number; the new start is blended
+ * toward the best row of the file as it is then (completeSearch :546-600, getModifiedParam :683-720).  "Then" is a virtual time:
+ * a restart costs cb + c0 + trips + shrinks * c0 ticks (cb = TIKTAK_ASYNC_PICKUP_TICKS: taking the next restart; trips = passes of
+ * amoeba's loop; c0 = ceil((nx+1)/4): what the initial simplex and a shrink step cost four warps).  Restart numbers go out in the order of the finish times, ties by instance number; a start sees the
+ * rows with finish time <= its start time; the best row is the lowest value, ties by the order of the file (finish time, instance, k).
+ * Nelder-Mead, search_type 0, nm_shrink_mode 0. */
+int Oracle::local_async(int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out) {
+    const int K = c.maxpoints_plus1, nx = c.nx;
+    if ((int)x_starts.size() != K * (nx + 1)) return -1;
+    if (c.search_type != 0 || c.nm_shrink_mode != 0) return -2;
+    const int P = std::max(1, std::min(instances, K));
+    const int c0 = (nx + 1 + 3) / 4;
+    const int seqNo = 1;
+    rows.clear();
+    write_row(seqNo, 0, 0, x_starts[0], &x_starts[1]); /* :496-501: the k = 0 record */
+    std::vector<int> fin(K + 1, -1), inst(K + 1, -1);
+    fin[0] = 0;
+    std::vector<Row> byk(K + 1);
+    byk[0] = rows[0];
+    std::vector<long> free_at(P, 0); /* when instance i is free again */
+    auto before = [&](int a, int b) { /* row a before row b: lower value, then the order of the file */
+        if (byk[a].fval != byk[b].fval) return byk[a].fval < byk[b].fval;
+        if (fin[a] != fin[b]) return fin[a] < fin[b];
+        if (inst[a] != inst[b]) return inst[a] < inst[b];
+        return a < b;
+    };
+    for (int k = 1; k <= K; k++) {
+        int i = 0;
+        for (int q = 1; q < P; q++) if (free_at[q] < free_at[i]) i = q; /* earliest free instance, lowest number among equals */
+        const int T = (int)free_at[i];
+        int count = 0, b = -1;
+        for (int j = 0; j < k; j++) {
+            if (fin[j] < 0 || fin[j] > T) continue;
+            if (!(byk[j].fval == byk[j].fval)) continue;
+            count++;
+            if (b < 0 || before(j, b)) b = j;
+        }
+        std::vector<double> evalParam(nx);
+        const double* evalPoint = &x_starts[(size_t)(k - 1) * (nx + 1) + 1];
+        if (count <= 1) {
+            for (int d = 0; d < nx; d++) evalParam[d] = evalPoint[d];
+        } else {
+            float wf = sqrtf((float)k / (float)K);
+            wf = std::min(std::max(0.10f, wf), 0.95f);
+            const double w11 = (double)wf;
+            for (int d = 0; d < nx; d++) evalParam[d] = w11 * byk[b].x[d] + (1.0 - w11) * evalPoint[d];
+        }
+        if (starts_out) for (int d = 0; d < nx; d++) starts_out[(size_t)d * K + (k - 1)] = evalParam[d];
+        const long nfev0 = nfev;
+        std::vector<double> width;
+        simplex_width(k, rows, 1, width);
+        int iters = 0;
+        runAmoeba(evalParam, width, iters);
+        const int steps = TIKTAK_ASYNC_PICKUP_TICKS + c0 + amoeba_trips + amoeba_shrinks * c0;
+        const double fn_val = objFun(evalParam.data()); /* :582 */
+        if (evals_out) evals_out[k - 1] = (int32_t)(nfev - nfev0);
+        Row r;
+        r.seq = seqNo; r.k = k; r.imp = 0;
+        r.fval = c.text_roundtrip ? text4020(fn_val) : fn_val;
+        r.x.resize(nx);
+        for (int d = 0; d < nx; d++) r.x[d] = c.text_roundtrip ? text4020(evalParam[d]) : evalParam[d];
+        byk[k] = r;
+        fin[k] = T + steps;
+        inst[k] = i;
+        free_at[i] = fin[k];
+    }
+    /* the file: rows in the order of the finish events; the #improvements column as completeSearch :585-589 computes it there */
+    std::vector<int> order(K);
+    for (int k = 1; k <= K; k++) order[k - 1] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fin[a] != fin[b] ? fin[a] < fin[b] : (inst[a] != inst[b] ? inst[a] < inst[b] : a < b); });
+    double best_f = rows[0].fval;
+    int best_imp = 0;
+    for (int k : order) {
+        Row& r = byk[k];
+        if (!(r.fval == r.fval)) continue;
+        int imp = best_imp;
+        if (r.fval < best_f) { imp = best_imp + 1; best_f = r.fval; best_imp = imp; }
+        r.imp = imp;
+        rows.push_back(r);
+    }
+    if (results_out) {
+        for (int k = 1; k <= K; k++) {
+            const Row& r = byk[k];
+            results_out[(size_t)0 * K + (k - 1)] = r.seq;
+            results_out[(size_t)1 * K + (k - 1)] = r.k;
+            results_out[(size_t)2 * K + (k - 1)] = r.imp;
+            results_out[(size_t)3 * K + (k - 1)] = r.fval;
+            for (int d = 0; d < nx; d++) results_out[(size_t)(4 + d) * K + (k - 1)] = r.x[d];
+        }
+    }
+    if (fin_out) for (int k = 1; k <= K; k++) fin_out[k - 1] = fin[k];
+    if (inst_out) for (int k = 1; k <= K; k++) inst_out[k - 1] = inst[k];
     return 0;
 }
 
@@ -951,6 +1052,9 @@ long orc_nfev(void* h) { return ((Oracle*)h)->nfev; }
 long orc_best_tie_events(void* h) { return ((Oracle*)h)->best_tie_events; }
 
 /* one Nelder-Mead restart from `start` exactly as runAmoeba does it for restart k (width = p_range) */
+int orc_local_async(void* h, int instances, double* starts, double* results, int32_t* evals, int32_t* fin, int32_t* inst) {
+    return ((Oracle*)h)->local_async(instances, starts, results, evals, fin, inst);
+}
 int orc_run_amoeba(void* h, double* pt, int32_t* iters) {
     Oracle* o = (Oracle*)h;
     std::vector<double> p(pt, pt + o->c.nx), w(o->c.nx);

@@ -167,6 +167,52 @@ def test_local_minimizations_nm(built, name, B):
     assert abs(gbest[0] - ob[0]) <= 1e-6 * abs(ob[0]) and gbest[2] == ob[2]
 
 
+@pytest.mark.parametrize("name,P,nm,K", [("griewank10", 8, 1, 40), ("griewank10", 16, 3, 40), ("griewank10", 64, 1, 200), ("rastrigin20", 7, 1, 30),
+                                          ("rastrigin20", 30, 2, 30), ("template4", 3, 8, 3), ("griewank7", 4, 3, 10), ("griewank7", 1, 1, 10)])
+def test_asynchronous_instances(built, name, P, nm, K):
+    """the reference's multi-process mode on one GPU (tiktak_cuda_local_async, nm_quad_async_kernel): P blocks that take the
+    next restart the moment they finish one, every start blended toward the best row finished by then, reproducible through a
+    virtual clock -- against the oracle's sequential event simulation of P instances (Oracle::local_async): start rows, result
+    rows incl. the #improvements column in file order, evaluation counts and the best row, bit for bit"""
+    cfg = cfg_of(name, nm=nm, maxpoints=K, round_size=P)
+    with TikTakSearch(cfg) as s:
+        assert s.asyncSupported("a")
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizationsAsync("a")
+        gs, gr, ge, used = s.searchStart, s.searchResults, s.evals, s.instances_used
+        gbest = s.getBestLine()
+    assert used == min(P, cfg.p_maxpoints)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizationsAsync(used)
+    assert np.array_equal(gs, o.searchStart), "blended start points differ"
+    assert np.array_equal(ge, o.evals)
+    assert np.array_equal(gr, o.searchResults)
+    ob = o.getBestLine()
+    assert gbest[0] == ob[0] and gbest[2] == ob[2]
+    if P > 1:  # the instances did overlap: some restart was blended toward a row other than the best of all earlier restarts
+        assert len(set(o.inst.tolist())) == used
+        if cfg.p_maxpoints > 2 * used:
+            assert np.any(np.diff(o.fin) < 0)
+
+
+def test_one_asynchronous_instance_is_the_sequential_run(built):
+    """P = 1: the instance sees every earlier row -- the reference's single-process run, i.e. rounds of one restart"""
+    cfg = cfg_of("griewank10", maxpoints=25, round_size=1)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizationsAsync("a", instances=1)
+        a_s, a_r, a_e = s.searchStart, s.searchResults, s.evals
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizations("a")
+        assert np.array_equal(a_s, s.searchStart) and np.array_equal(a_r, s.searchResults) and np.array_equal(a_e, s.evals)
+
+
 @pytest.mark.parametrize("name,B,nm", [("template4", 1, 8), ("template4", 4, 8), ("griewank10", 5, 6), ("griewank7", 4, 3),
                                        ("rastrigin20", 8, 2), ("rosenbrock33", 3, 4)])
 def test_local_minimizations_dfnls(built, name, B, nm):

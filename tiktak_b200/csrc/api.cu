@@ -291,7 +291,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
                     h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_nmq, h->d_counts_spare,
-                    h->d_objfun_x, h->d_objfun_f, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
+                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -966,6 +966,7 @@ int tiktak_cuda_local_enqueue(tiktak_handle* h, int32_t alg, int32_t first_k, in
     if (n_k == 0) return TIKTAK_OK;
     if (h->cfg.world > 1 && !send) { tk_set_error("local: world > 1 needs the send buffer of the round's all-gather"); return TIKTAK_ERR_ARG; }
     TK_CUDA(cudaSetDevice(h->device));
+    h->async_rows = false; /* rows in restart order from here on */
     int rc;
     if (!h->local_timing_open) {
         TK_CUDA(cudaEventRecord(h->evl0, h->stream));
@@ -1041,6 +1042,7 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
     }
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
     TK_CUDA(cudaSetDevice(h->device));
+    h->async_rows = false;
     int rc;
     if (!h->local_timing_open) {
         TK_CUDA(cudaEventRecord(h->evl0, h->stream));
@@ -1062,6 +1064,46 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
     if (acc <= 0 || acc > n_k) { tk_set_error("local_launch: the kernel committed %d of %d restarts", acc, n_k); return TIKTAK_ERR_STATE; }
     h->n_rows = (int)rows;
     *accepted = acc;
+    return TIKTAK_OK;
+}
+
+/* Asynchronous instances: restarts first_k .. first_k + n_k - 1 run by `instances` blocks that take the next restart number the
+ * moment they finish one, each new start blended toward the best row finished by then -- the reference's own multi-process mode
+ * (TiktakGlobalSearch.f90:546-600), made reproducible by a virtual clock (kernels_nm.cu, nm_quad_async_kernel).
+ * One launch, no rounds, no host round trip; *used = instances actually run (<= the number of resident blocks). */
+int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used) {
+    if (!h || !used || first_k < 1 || n_k < 0 || instances < 1 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    *used = 0;
+    if (alg != TIKTAK_ALG_AMOEBA) { tk_set_error("local_async: Nelder-Mead only"); return TIKTAK_ERR_UNSUPPORTED; }
+    if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
+    if (n_k == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    if (!h->local_timing_open) {
+        TK_CUDA(cudaEventRecord(h->evl0, h->stream));
+        h->local_timing_open = true;
+    }
+    int u = 0;
+    int rc = tk_launch_nm_async(h, first_k, n_k, instances, &u);
+    if (rc) return rc;
+    TK_CUDA(cudaEventRecord(h->evl1, h->stream));
+    h->async_rows = true;
+    h->best_dirty = false;
+    h->n_rows = first_k + n_k; /* (rows with a NaN value are not rows; the exact count is d_best[2]) */
+    *used = u;
+    return TIKTAK_OK;
+}
+
+/* experiment hook (TIKTAK_ASYNC_DEBUG=1): per instance wait / scan / run cycles, restarts, polls of the last asynchronous launch */
+extern "C" int tiktak_cuda_debug_async(tiktak_handle* h, long long* out, int n) {
+    if (!h || !h->async_dbg) return TIKTAK_ERR_STATE;
+    cudaStreamSynchronize(h->stream);
+    return (int)cudaMemcpy(out, h->async_dbg, (size_t)n * 5 * sizeof(long long), cudaMemcpyDeviceToHost);
+}
+
+/* which instances tiktak_cuda_local_async would run: 0 = the configuration is not built for it */
+int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* yes) {
+    if (!h || !yes) return TIKTAK_ERR_ARG;
+    *yes = (alg == TIKTAK_ALG_AMOEBA && tk_nm_async_supported(h)) ? 1 : 0;
     return TIKTAK_OK;
 }
 
@@ -1134,7 +1176,22 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
     int best_imp = 0;
     bool any = false;
     std::vector<double> rows((size_t)n_k * (nx + 4)), st((size_t)n_k * nx);
-    for (int k = 0; k <= last; k++) {
+    std::vector<int> order(last + 1);
+    for (int k = 0; k <= last; k++) order[k] = k;
+    if (h->async_rows) { /* the file of an asynchronous run is in the order of the (virtual) finish times, ties by instance */
+        std::vector<TkAsyncRow> ev(last + 1);
+        TK_CUDA(cudaMemcpy(ev.data(), h->d_async_ev, ev.size() * sizeof(TkAsyncRow), cudaMemcpyDeviceToHost));
+        std::vector<int> fin(last + 1), slt(last + 1);
+        for (int k = 0; k <= last; k++) { fin[k] = ev[k].fin; slt[k] = ev[k].slt; }
+        std::stable_sort(order.begin() + 1, order.end(), [&](int x, int y) {
+            const int fx = std::max(fin[x], 0), fy = std::max(fin[y], 0);
+            if (fx != fy) return fx < fy;
+            if (slt[x] != slt[y]) return slt[x] < slt[y];
+            return x < y;
+        });
+    }
+    for (int kk = 0; kk <= last; kk++) {
+        const int k = order[kk];
         const bool valid = hval[k] != 0;
         const double fv = hres[(size_t)k * (nx + 1)];
         int imp = best_imp;

@@ -354,22 +354,24 @@ __device__ __forceinline__ double nm_eval_warp(const tk_obj_ctx& ctx, const NmSc
 #ifndef TK_NMQ_MINB
 #define TK_NMQ_MINB 0 /* ptxas decides (72 registers, 6-7 resident blocks per SM); 8 (64 registers) measured slower: C2 4.8 against 4.2 ms, C3 39.7 against 35.9 ms */
 #endif
-template <class Obj, int NXC>
-__global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
-    extern __shared__ double smem[];
+/* One restart by the four warps of a block (runAmoeba :622-627 + amoeba): shared by the per-launch kernel (one block per
+ * restart of the launch) and the asynchronous-instances kernel (a block is an instance and runs restart after restart).
+ * start(i): coordinate i of the blended start; tick(trips, shrinks): called by every thread once per loop trip (the
+ * asynchronous kernel publishes its clock there).  Every warp ends with the same sorted list: ylo, the first minimal
+ * vertex ilo (row of this warp's copy p of the simplex), amoeba's evaluation count iter, loop trips and shrink steps. */
+struct NmQuadOut {
+    double ylo;
+    int ilo, iter, trips, shrinks;
+    double* p;
+};
+template <class Obj, int NXC, class StartF, class TickF>
+__device__ __forceinline__ NmQuadOut nm_quad_search(const tk_obj_ctx& ctx, const NmArgs& a, int nx, bool shr, double* sbl, double* sbu,
+                                                    double* yv, double* yx, double* mine, StartF start, TickF tick) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nx = NXC ? NXC : sc.nx, np = nx + 1;
+    const int np = nx + 1;
     const int nt = Obj::nterms(nx);
     const int ts = (nx + 2) & ~1; /* even stride >= np */
-    /* block-shared */
-    double* sbl = smem;
-    double* sbu = sbl + ts;
-    double* saux = sbu + ts;
-    double* yv = saux + ts;                     /* yv[vertex]: values of re-evaluated vertices (start, shrink) */
-    double* yx = yv + ts;                       /* yx[parity*4 + c]: the four trial values of an iteration */
-    /* per warp */
-    double* mine = yx + 8 + (size_t)w * (5 * ts + (size_t)np * nx);
     NmScratch scr;
     scr.ta = mine;
     scr.tb = mine + ts;
@@ -377,20 +379,15 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTable
     scr.cand = mine + 3 * ts;
     int* scr_r = reinterpret_cast<int*>(mine + 4 * ts); /* sort scratch (with scr.cand) */
     double* p = mine + 5 * ts;                  /* p[i*nx + j]: this warp's copy of the simplex */
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
-    __syncthreads();
-    const int slot = a.rank + (int)blockIdx.x * a.world;
-    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
     const bool has_j = lane < nx, has_i = lane < np;
     const int j = has_j ? lane : 0;
     const double blj = sbl[j], buj = sbu[j];
 
     /* runAmoeba :622-627 -- initial simplex around the blended start */
-    const bool shr = a.shr_have && a.shr_have[0] && ((float)(a.first_k + slot) / (float)a.K > 0.5f);
     const double* wsrc = shr ? a.wshr : a.width;
     for (int e = lane; e < np * nx; e += 32) {
         const int ia = e / nx, i = e - ia * nx;
-        double t = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
+        double t = TK_ADD(start(i), TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
         t = fmax(fmin(t, sbu[i]), sbl[i]);
         p[e] = t;
     }
@@ -408,7 +405,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTable
     if (has_j)
         for (int i = 0; i < np; i++) psum = TK_ADD(psum, p[i * nx + j]);
 
-    int iter = 0;
+    int iter = 0, trips = 0, shrinks = 0;
     unsigned par = 0;
     double ylo;
     for (;;) {
@@ -430,6 +427,8 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTable
         bool conv = num < TK_MUL(thr, 0.99999999999909051);
         if (!conv && !(num > TK_MUL(thr, 1.00000000000090949))) conv = TK_DIV(num, den) < a.ftol;
         if (conv || iter >= a.itmax) break;
+        trips++;
+        tick(trips, shrinks);
 
         const double xc = (w == 0) ? R : (w == 1) ? E : (w == 2) ? Co : Ci;
         const double yc = nm_eval_warp<Obj, NXC>(ctx, scr, xc, blj, buj, lane, nx, nt);
@@ -464,6 +463,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTable
                 psum = TK_ADD(TK_SUB(psum, pnew), Cv);
                 pnew = Cv; ynew = yC; moved = true;
             } else { /* :106-113 shrink toward the best vertex, re-evaluate, re-sum */
+                shrinks++;
                 if (moved && has_j) p[ihi * nx + j] = pnew;
                 if (lane == nx) ys = ynew;
                 moved = false;
@@ -501,15 +501,237 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTable
         }
         __syncwarp();
     }
+    NmQuadOut o;
+    o.ylo = ylo;
+    o.ilo = (int)__reduce_min_sync(FULL, (has_i && ys == ylo) ? (unsigned)row : 0xffffffffu);
+    o.iter = iter; o.trips = trips; o.shrinks = shrinks; o.p = p;
+    return o;
+}
+
+template <class Obj, int NXC>
+__global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nx = NXC ? NXC : sc.nx, np = nx + 1;
+    const int ts = (nx + 2) & ~1; /* even stride >= np */
+    /* block-shared */
+    double* sbl = smem;
+    double* sbu = sbl + ts;
+    double* saux = sbu + ts;
+    double* yv = saux + ts;                     /* yv[vertex]: values of re-evaluated vertices (start, shrink) */
+    double* yx = yv + ts;                       /* yx[parity*4 + c]: the four trial values of an iteration */
+    double* mine = yx + 8 + (size_t)w * (5 * ts + (size_t)np * nx); /* per warp: term scratch, sort scratch, simplex */
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
+    __syncthreads();
+    const int slot = a.rank + (int)blockIdx.x * a.world;
+    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
+    const bool shr = a.shr_have && a.shr_have[0] && ((float)(a.first_k + slot) / (float)a.K > 0.5f);
+    const NmQuadOut o = nm_quad_search<Obj, NXC>(ctx, a, nx, shr, sbl, sbu, yv, yx, mine,
+                                                 [&](int i) { return a.starts[(size_t)i * a.n_k + slot]; }, [](int, int) {});
     /* runAmoeba :631-632 returns the first minimal vertex; completeSearch :582 re-evaluates objFun there:
      * same point, same value. */
     if (w == 0) {
-        const int ilo = (int)__reduce_min_sync(FULL, (has_i && ys == ylo) ? (unsigned)row : 0xffffffffu);
-        if (has_j) a.out_x[(size_t)j * a.n_k + slot] = p[ilo * nx + j];
+        if (lane < nx) a.out_x[(size_t)lane * a.n_k + slot] = o.p[o.ilo * nx + lane];
         if (lane == 0) {
-            a.out_f[slot] = ylo;
-            a.out_evals[slot] = np + iter + 1;
+            a.out_f[slot] = o.ylo;
+            a.out_evals[slot] = np + o.iter + 1;
         }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Asynchronous instances (DESIGN.md "asynchronous instances").  The reference's own parallel mode is P independent
+ * processes: an instance that finishes restart k' appends its row to searchResults.dat and takes the next restart
+ * number; the new start is blended toward the best row of the file AS IT IS THEN (TiktakGlobalSearch.f90:546-600,
+ * 683-720).  Nobody waits for a round to end.  Here a block is an instance.  To keep the run reproducible, "then" is
+ * a VIRTUAL time that advances by one per loop trip of amoeba (a trip costs the four warps the same real time
+ * whatever it counts as evaluations; the initial simplex and a shrink step count c0 = ceil((nx+1)/4) trips):
+ *   * an instance that finishes at virtual time F takes restart number first_k + P + #(finish events before (F, id)),
+ *     i.e. restarts are handed out in the order of the virtual finish times, ties by instance number;
+ *   * its start is blended toward the best row among the rows that finished at virtual times <= F
+ *     (lowest value; ties by (finish time, instance, k) -- the order of the file);
+ * which is exactly what a sequential event simulation of P instances computes (the oracle's local_async).  On the
+ * device an instance may only act at virtual time F when no other instance can still produce a finish event <= F:
+ * every block publishes a lower bound of its next finish time (clk), and waits until all the others' exceed F.
+ * Real time per trip is nearly the same on every SM, so the wait is short; the instance with the smallest F never
+ * waits for long (every running clock grows), hence no deadlock -- PROVIDED all P blocks are resident: the launcher
+ * asks the occupancy calculator and launches cooperatively.
+ * The block itself writes the row (completeSearch :582-597 through the f40.20 record), so there is no ingest kernel.
+ * --------------------------------------------------------------------------------------------- */
+struct NmAsync {
+    int first_k, last_k;   /* restarts of the launch */
+    int K, nx, roundtrip;
+    const double* xs;      /* x_starts (K, nx+1) column-major */
+    const double* w11;     /* blend weight per restart number */
+    double* res;           /* (K+1) x (nx+1) result rows [fval, x] */
+    int* valid;
+    int* arch_evals;
+    double* arch_starts;   /* (K, nx) column-major */
+    TkAsyncRow* ev;        /* [K+1] value, virtual finish time (-1: not finished; 0: rows known before the launch) and instance (-1: known
+                              before) of row k, one 16-byte record per row for the scans */
+    int* clk;              /* [P] lower bound of the instance's next finish time; clk[P]: highest restart number handed out */
+    long long* dbg;        /* experiment: per instance [wait cycles, scan cycles, run cycles, restarts, polls] or NULL */
+    int c0, cb;            /* ticks of the initial simplex / of a shrink step; ticks an instance needs between two restarts */
+};
+
+#define TK_GVT_COPIES 16
+__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+/* (f, fin, slt, k) of row A before row B: lower value first, then the order of the (virtual) file */
+__device__ __forceinline__ bool nm_row_before(double fa, int ta, int sa, int ka, double fb, int tb, int sb, int kb) {
+    if (fa != fb) return fa < fb;
+    if (ta != tb) return ta < tb;
+    if (sa != sb) return sa < sb;
+    return ka < kb;
+}
+
+__global__ void nm_async_init_kernel(const NmAsync q, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= q.K) {
+        const bool known = i < q.first_k && q.valid[i];
+        TkAsyncRow r;
+        r.fv = known ? q.res[(size_t)i * (q.nx + 1)] : 0.0;
+        r.fin = known ? 0 : -1;
+        r.slt = -1;
+        q.ev[i] = r;
+        if (i >= q.first_k && i <= q.last_k) q.valid[i] = 0;
+    }
+    if (i < P) q.clk[i] = q.cb + q.c0;
+    if (i == P) q.clk[P] = min(q.last_k, q.first_k + P - 1);
+    if (i < TK_GVT_COPIES) q.clk[P + 32 + i * 32] = 0; /* the time keeper's words */
+}
+
+template <class Obj, int NXC>
+__global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a, const NmAsync q) {
+    extern __shared__ double smem[];
+    __shared__ double r_f[4];
+    __shared__ int r_t[4], r_s[4], r_k[4], r_cnt[4], r_ev[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+    const int nx = NXC ? NXC : sc.nx, np = nx + 1;
+    const int ts = (nx + 2) & ~1;
+    double* sbl = smem;
+    double* sbu = sbl + ts;
+    double* saux = sbu + ts;
+    double* yv = saux + ts;
+    double* yx = yv + ts;
+    double* st = yx + 8;                        /* the blended start of the current restart */
+    double* mine = st + ts + (size_t)w * (5 * ts + (size_t)np * nx);
+    for (int i = tid; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
+    __syncthreads();
+    const tk_obj_ctx ctx = tk_make_ctx(sc, nx, sbl, sbu, saux);
+    const int s = (int)blockIdx.x, P = (int)gridDim.x - 1;
+    const int c0 = q.c0, cb = q.cb;
+    /* The last block is the time keeper: one warp folds the P clocks into their minimum (the global virtual time, a lower bound of
+     * every finish event still to come) and publishes it in TK_GVT_COPIES words on different lines.  Instances wait on ONE word:
+     * hundreds of blocks polling all P clocks saturate the L2 slice that holds them, and the runners' ticks queue up behind the
+     * polls (measured: C3 with 592 instances 155 ms, of which 90 % waiting). */
+    if (s == P) {
+        if (w != 0) return;
+        int* gvt = q.clk + P + 32;
+        for (;;) {
+            int m = 0x7fffffff;
+            for (int i = lane; i < P; i += 32) m = min(m, ld_vol(q.clk + i));
+            m = (int)__reduce_min_sync(0xffffffffu, (unsigned)m);
+            if (lane < TK_GVT_COPIES) st_vol(gvt + lane * 32, m);
+            if (m == 0x7fffffff) return;
+            __nanosleep(100);
+        }
+    }
+    long long dbg_wait = 0, dbg_scan = 0, dbg_run = 0, dbg_n = 0, dbg_polls = 0;
+    int k = q.first_k + s, Tv = 0; /* the first P restarts start at virtual time 0 and see the rows known before the launch */
+    for (;;) {
+        const long long t_scan0 = clock64();
+        /* one pass over the rows handed out so far: finish events in front of (Tv, s) -> which restart this instance takes; the best
+         * visible row.  (Plain L2 loads: every record with a finish time <= Tv was complete before the wait below ended.) */
+        int cnt_ev = 0, cnt_vis = 0, bt = 0, bs = 0, bk = -1;
+        double bf = 0.0;
+        const int hi = min(q.last_k, __ldcg(q.clk + P));
+        for (int jj = tid; jj <= hi; jj += 128) {
+            const int4 raw = __ldcg(reinterpret_cast<const int4*>(q.ev + jj));
+            const int tj = raw.z, sj = raw.w;
+            if (tj < 0 || tj > Tv) continue;
+            if (jj >= q.first_k && (tj < Tv || sj < s)) cnt_ev++;
+            const double fj = __hiloint2double(raw.y, raw.x);
+            if (!(fj == fj)) continue; /* a NaN value is no row (ingest_kernel) */
+            cnt_vis++;
+            if (bk < 0 || nm_row_before(fj, tj, sj, jj, bf, bt, bs, bk)) { bf = fj; bt = tj; bs = sj; bk = jj; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double f2 = __shfl_xor_sync(0xffffffffu, bf, o);
+            const int t2 = __shfl_xor_sync(0xffffffffu, bt, o), s2 = __shfl_xor_sync(0xffffffffu, bs, o), k2 = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (k2 >= 0 && (bk < 0 || nm_row_before(f2, t2, s2, k2, bf, bt, bs, bk))) { bf = f2; bt = t2; bs = s2; bk = k2; }
+            cnt_ev += __shfl_xor_sync(0xffffffffu, cnt_ev, o);
+            cnt_vis += __shfl_xor_sync(0xffffffffu, cnt_vis, o);
+        }
+        __syncthreads(); /* (the r_* of the previous restart have been read by everybody) */
+        if (lane == 0) { r_f[w] = bf; r_t[w] = bt; r_s[w] = bs; r_k[w] = bk; r_cnt[w] = cnt_vis; r_ev[w] = cnt_ev; }
+        __syncthreads();
+        bf = r_f[0]; bt = r_t[0]; bs = r_s[0]; bk = r_k[0]; cnt_vis = r_cnt[0]; cnt_ev = r_ev[0];
+        for (int o = 1; o < 4; o++) {
+            if (r_k[o] >= 0 && (bk < 0 || nm_row_before(r_f[o], r_t[o], r_s[o], r_k[o], bf, bt, bs, bk))) { bf = r_f[o]; bt = r_t[o]; bs = r_s[o]; bk = r_k[o]; }
+            cnt_vis += r_cnt[o]; cnt_ev += r_ev[o];
+        }
+        if (Tv > 0) k = q.first_k + P + cnt_ev; /* P restarts were taken at time 0, one more at every finish event */
+        if (k > q.last_k) {
+            if (tid == 0) { st_vol(q.clk + s, 0x7fffffff); if (q.dbg) { q.dbg[s * 5] = dbg_wait; q.dbg[s * 5 + 1] = dbg_scan; q.dbg[s * 5 + 2] = dbg_run; q.dbg[s * 5 + 3] = dbg_n; q.dbg[s * 5 + 4] = dbg_polls; } }
+            return;
+        }
+        if (tid == 0 && Tv > 0) atomicMax(q.clk + P, k);
+        /* getModifiedParam (:683-720), unfused; the searchStart.dat row */
+        for (int d = tid; d < nx; d += 128) {
+            const double ev = q.xs[(size_t)(d + 1) * q.K + (k - 1)];
+            double out = ev;
+            if (cnt_vis > 1 && bk >= 0) { /* count <= 1: no finished local minimisation yet (:701) */
+                const double wgt = q.w11[k];
+                out = TK_ADD(TK_MUL(wgt, q.res[(size_t)bk * (nx + 1) + 1 + d]), TK_MUL(TK_SUB(1.0, wgt), ev));
+            }
+            st[d] = out;
+            q.arch_starts[(size_t)d * q.K + (k - 1)] = out;
+        }
+        __syncthreads();
+        const int T0 = Tv;
+        const long long t_run0 = clock64();
+        dbg_scan += t_run0 - t_scan0;
+        const NmQuadOut o = nm_quad_search<Obj, NXC>(ctx, a, nx, false, sbl, sbu, yv, yx, mine, [&](int i) { return st[i]; },
+                                                     [&](int trips, int shrinks) { if (tid == 0) st_vol(q.clk + s, T0 + cb + c0 + trips + shrinks * c0); });
+        const int F = T0 + cb + c0 + o.trips + o.shrinks * c0;
+        /* completeSearch :582-597: the row of restart k (through the f40.20 record when the text round trip is on) */
+        if (w == 0) {
+            double* dst = q.res + (size_t)k * (nx + 1);
+            const double frt = q.roundtrip ? tk_f4020_roundtrip(o.ylo) : o.ylo;
+            if (lane < nx) { const double xv = o.p[o.ilo * nx + lane]; dst[1 + lane] = q.roundtrip ? tk_f4020_roundtrip(xv) : xv; }
+            if (lane == 0) {
+                dst[0] = frt;
+                q.ev[k].fv = frt;
+                q.ev[k].slt = s;
+                q.valid[k] = (frt == frt) ? 1 : 0;
+                q.arch_evals[k] = np + o.iter + 1;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                st_vol(&q.ev[k].fin, F);            /* the finish event exists from here on ... */
+                __threadfence();
+                st_vol(q.clk + s, F + cb + c0);     /* ... and this instance's next one cannot come before F + cb + c0 */
+            }
+        }
+        const long long t_wait0 = clock64();
+        dbg_run += t_wait0 - t_run0; dbg_n++;
+        /* act at virtual time F only when nobody else can still finish at or before it */
+        if (w == 0) { /* one warp polls one word; the others park at the barrier */
+            const int* gvt = q.clk + P + 32 + (s % TK_GVT_COPIES) * 32;
+            unsigned ns = 100;
+            for (;;) {
+                dbg_polls++;
+                if (ld_vol(gvt) > F) break;
+                __nanosleep(ns);
+                if (ns < 800) ns += ns;
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        dbg_wait += clock64() - t_wait0;
+        Tv = F;
     }
 }
 
@@ -1194,6 +1416,54 @@ static int nm_launch_warp(tiktak_handle* h, const TkTablesG& T, const NmArgs& a,
     return TIKTAK_OK;
 }
 
+/* best row of the table by (value, virtual finish time, instance, k): getBestLine on the file an asynchronous run would have written */
+__global__ void best_async_kernel(const double* res, const int* valid, const TkAsyncRow* ev, int nrows, int nx, double* best) {
+    __shared__ double sf[256];
+    __shared__ int st_[256], ss[256], sk[256], sc[256];
+    double bf = 0.0; int bt = 0, bs = 0, bk = -1, cnt = 0;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+        if (!valid[r]) continue;
+        cnt++;
+        const double f = res[(size_t)r * (nx + 1)];
+        const int t = r == 0 ? 0 : max(ev[r].fin, 0), s_ = r == 0 ? -1 : ev[r].slt;
+        if (bk < 0 || nm_row_before(f, t, s_, r, bf, bt, bs, bk)) { bf = f; bt = t; bs = s_; bk = r; }
+    }
+    sf[threadIdx.x] = bf; st_[threadIdx.x] = bt; ss[threadIdx.x] = bs; sk[threadIdx.x] = bk; sc[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const int i2 = threadIdx.x + o;
+            if (sk[i2] >= 0 && (sk[threadIdx.x] < 0 || nm_row_before(sf[i2], st_[i2], ss[i2], sk[i2], sf[threadIdx.x], st_[threadIdx.x], ss[threadIdx.x], sk[threadIdx.x]))) {
+                sf[threadIdx.x] = sf[i2]; st_[threadIdx.x] = st_[i2]; ss[threadIdx.x] = ss[i2]; sk[threadIdx.x] = sk[i2];
+            }
+            sc[threadIdx.x] += sc[i2];
+        }
+        __syncthreads();
+    }
+    const int b = sk[0];
+    if (threadIdx.x == 0) { best[0] = sf[0]; best[1] = (double)b; best[2] = (double)sc[0]; }
+    if (b >= 0)
+        for (int d = threadIdx.x; d < nx; d += blockDim.x) best[3 + d] = res[(size_t)b * (nx + 1) + 1 + d];
+}
+
+template <class Obj, int NXC>
+static int nm_launch_async(tiktak_handle* h, const TkTablesG& T, const NmArgs& a, NmAsync q, size_t shmem, int want, int* used) {
+    auto kern = nm_quad_async_kernel<Obj, NXC>;
+    TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    int per_sm = 0;
+    TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, shmem));
+    const int n = q.last_k - q.first_k + 1;
+    const int P = std::max(1, std::min(std::min(want, n), per_sm * h->sm_count - 1)); /* every instance and the time keeper must be resident (they wait for one another) */
+    if (!h->d_async_clk) TK_CUDA(cudaMalloc(&h->d_async_clk, (size_t)64 * 1024 * sizeof(int)));
+    q.clk = h->d_async_clk;
+    nm_async_init_kernel<<<(std::max(q.K + 1, P + 1) + 255) / 256, 256, 0, h->stream>>>(q, P);
+    void* args[] = {(void*)&T, (void*)&h->sc, (void*)&a, (void*)&q};
+    TK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)P + 1), dim3(128), args, shmem, h->stream));
+    h->launches += 2;
+    *used = P;
+    return TIKTAK_OK;
+}
+
 int tk_launch_nm_vec(tiktak_handle* h, const NmArgs& a);
 bool tk_nm_w4_supported(tiktak_handle* h);
 int tk_nm_w4_capacity(tiktak_handle* h);
@@ -1303,4 +1573,56 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size) 
         TK_CUDA(cudaGetLastError());
         return TIKTAK_OK;
     });
+}
+
+
+/* Asynchronous instances (nm_quad_async_kernel): restarts first_k .. first_k + n_k - 1 by min(instances, resident blocks) instances;
+ * rows, evaluation counts, searchStart rows and the best row are on the device when the stream has drained. */
+bool tk_nm_async_supported(tiktak_handle* h) {
+    const int nx = h->cfg.nx;
+    if (h->cfg.world != 1 || h->cfg.search_type != 0 || h->cfg.nm_shrink_mode != 0 || h->cfg.objective_id == TIKTAK_OBJ_SMM || nx > 31) return false;
+    bool ok = false;
+    tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int { ok = Obj::nterms(nx) <= nx; return 0; });
+    return ok;
+}
+
+int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used) {
+    const int nx = h->cfg.nx, np = nx + 1, K = h->cfg.maxpoints_plus1;
+    if (!tk_nm_async_supported(h)) { tk_set_error("local_async: Nelder-Mead with a scalar objective, nx <= 31, search_type 0, nm_shrink_mode 0, one GPU"); return TIKTAK_ERR_UNSUPPORTED; }
+    NmArgs a;
+    a.n_k = n_k; a.rank = 0; a.world = 1; a.n_run = n_k; a.first_k = first_k; a.K = K;
+    a.starts = nullptr; a.width = h->d_width; a.wshr = nullptr; a.shr_have = nullptr;
+    a.simplex = h->d_simplex; a.scale = h->nm_scale; a.ftol = h->cfg.nm_ftol; a.itmax = h->cfg.nm_itmax;
+    const double ndim = (double)nx;
+    a.fac1r = (1.0 - (-1.0)) / ndim; a.fac2r = a.fac1r - (-1.0);
+    a.fac1e = (1.0 - 2.0) / ndim;    a.fac2e = a.fac1e - 2.0;
+    a.fac1c = (1.0 - 0.5) / ndim;    a.fac2c = a.fac1c - 0.5;
+    a.tiny = (double)1.0e-10f;
+    a.out_x = nullptr; a.out_f = nullptr; a.out_evals = nullptr;
+    if (!h->d_async_ev) TK_CUDA(cudaMalloc(&h->d_async_ev, (size_t)(K + 1) * sizeof(TkAsyncRow)));
+    NmAsync q;
+    q.first_k = first_k; q.last_k = first_k + n_k - 1; q.K = K; q.nx = nx; q.roundtrip = h->cfg.text_roundtrip;
+    q.xs = h->d_xstarts; q.w11 = h->d_w11; q.res = h->d_res; q.valid = h->d_res_valid; q.arch_evals = h->d_arch_evals;
+    q.arch_starts = h->d_arch_starts; q.ev = h->d_async_ev; q.clk = nullptr;
+    q.dbg = nullptr;
+    if (getenv("TIKTAK_ASYNC_DEBUG")) { static long long* d = nullptr; if (!d) cudaMalloc(&d, 5 * 2048 * sizeof(long long)); q.dbg = d; h->async_dbg = d; }
+    q.c0 = (np + 3) / 4; q.cb = TIKTAK_ASYNC_PICKUP_TICKS;
+    if (const char* e = getenv("TIKTAK_ASYNC_CB")) q.cb = atoi(e); /* experiment */
+    const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
+    const int ts = (nx + 2) & ~1;
+    const size_t shmem = (size_t)(4 * ts + 8 + ts + 4 * (5 * ts + np * nx)) * sizeof(double);
+    int rc = tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
+        switch (nx) {
+            case 4: return nm_launch_async<Obj, 4>(h, T, a, q, shmem, instances, used);
+            case 10: return nm_launch_async<Obj, 10>(h, T, a, q, shmem, instances, used);
+            case 20: return nm_launch_async<Obj, 20>(h, T, a, q, shmem, instances, used);
+            default: return nm_launch_async<Obj, 0>(h, T, a, q, shmem, instances, used);
+        }
+    });
+    if (rc) return rc;
+    TK_CUDA(cudaGetLastError());
+    best_async_kernel<<<1, 256, 0, h->stream>>>(h->d_res, h->d_res_valid, h->d_async_ev, K + 1, nx, h->d_best);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
 }

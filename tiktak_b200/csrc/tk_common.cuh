@@ -60,6 +60,9 @@ __host__ __device__ inline int64_t tk_local_index(int64_t n, int world) {
     return (cb / world) * TIKTAK_SOBOL_BLOCK + (n % TIKTAK_SOBOL_BLOCK);
 }
 
+/* one row of an asynchronous run as the scans of nm_quad_async_kernel read it */
+struct alignas(16) TkAsyncRow { double fv; int fin; int slt; };
+
 struct tiktak_handle {
     tiktak_config cfg;
     std::vector<double> range, init, bound, aux;
@@ -143,6 +146,10 @@ struct tiktak_handle {
     bool counts_global = false;       /* d_counts holds the all-reduced (global) per-block counts */
     int* d_nmq = nullptr;             /* control words of the throughput Nelder-Mead kernel's restart queue (nm_common.cuh) */
     int blend_w_idx = -1;             /* > 0: the next launch blends with the weight of restart number blend_w_idx (missing-search sweep) */
+    TkAsyncRow* d_async_ev = nullptr; /* asynchronous instances (kernels_nm.cu): value, virtual finish time and instance of row k */
+    int* d_async_clk = nullptr;       /* ... and the instances' clocks */
+    long long* async_dbg = nullptr;   /* experiment counters (TIKTAK_ASYNC_DEBUG) */
+    bool async_rows = false;          /* the rows of the table were written by an asynchronous run: local_fetch orders them by (finish time, instance) */
     int nm_form = -1;                 /* 1: one warp per restart (kernels_nm_w4.cu), 0: four warps per restart (kernels_nm.cu), -1: not decided yet */
     double *d_objfun_x = nullptr, *d_objfun_f = nullptr; /* staging of tiktak_cuda_objfun for host arguments */
     int64_t objfun_scratch_pts = 0;
@@ -170,6 +177,8 @@ int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k, int w_idx = -1);
 int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count, int w_idx = -1);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size = 0);
+int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used);
+bool tk_nm_async_supported(tiktak_handle* h);
 bool tk_nm_use_w4(tiktak_handle* h);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
 int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, const double* pack, int* d_accepted);

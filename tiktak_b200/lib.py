@@ -39,6 +39,8 @@ SIGNATURES = {
     "tiktak_cuda_local_missing": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p]),
     "tiktak_cuda_local_status": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_nrescue": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int32_p]),
+    "tiktak_cuda_local_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p]),
+    "tiktak_cuda_local_async_supported": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_ingest_rounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_int32_p]),
     "tiktak_cuda_local_capacity": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_launch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p]),

@@ -254,6 +254,31 @@ class TikTakSearch:
         self.nrescue = nr  # RESCUE_H calls per restart (DFNLS)
         return True
 
+    def asyncSupported(self, algor="a"):
+        yes = C.c_int32()
+        _lib.check(self._L.tiktak_cuda_local_async_supported(self._h, _ALG[algor], C.byref(yes)), "local_async_supported")
+        return bool(yes.value)
+
+    def LocalMinimizationsAsync(self, algor="a", instances=None):
+        """Every restart by `instances` asynchronous instances (default: cfg.round_size) -- the reference's multi-process mode on
+        one GPU, one kernel launch (tiktak_cuda_local_async; DESIGN.md "asynchronous instances").  Sets searchStart,
+        searchResults, evals and `instances_used`."""
+        alg = _ALG[algor]
+        K, nx = self.K, self.cfg.nx
+        P = max(1, int(self.cfg.round_size if instances is None else instances))
+        used = C.c_int32()
+        _lib.check(self._L.tiktak_cuda_local_async(self._h, alg, 1, K, P, C.byref(used)), "LocalMinimizationsAsync")
+        self.instances_used = used.value
+        self.local_launches = 1
+        s = np.empty((nx, K), dtype=np.float64)
+        r = np.empty((nx + 4, K), dtype=np.float64)
+        e = np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_fetch(self._h, 1, K, s.ctypes.data, r.ctypes.data, e.ctypes.data), "LocalMinimizationsAsync")
+        self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
+        self.status = np.zeros(K, dtype=np.int32)
+        self.nrescue = np.zeros(K, dtype=np.int32)
+        return True
+
     def pushResults(self, rows):
         """rows (n, nx+4) = seqNo, k, #improvements, fval, x re-read from searchResults.dat (options 3, missing-work sweep)"""
         rows = np.asarray(rows, dtype=np.float64)
