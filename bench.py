@@ -42,6 +42,9 @@ F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905}
 OBJ_NAME = {"C1": "template", "C2": "Griewank", "C3": "Rastrigin", "C4": "Rosenbrock", "C5": "synthetic SMM"}
 # restarts per round (all blended against the best row of the round's start)
 ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 1184, "C5": 128}
+# asynchronous instances (restart stage, one GPU): how many blocks play the reference's processes -- about four restarts per instance at
+# C2, every resident block at C3 (887) and C5 (147: one block per SM, one SM keeps the time); the library clamps to what is resident
+ASYNC_INSTANCES = {"C1": 4, "C2": 256, "C3": 1024, "C4": 1184, "C5": 147}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage's kernel, from the committed `ncu --set full` captures
 TRAFFIC = {"C2": (25088, "profiles/r01d_full_c2_sobol.csv"), "C3": (742264320, "profiles/r01d_full_c3_sobol.csv"),
            "C4": (21494528, "profiles/r01d_full_c4_sobol.csv"), "C5": (1020513512, "profiles/r01c_full_c5_smm.csv (1184 evaluations)")}
@@ -321,7 +324,7 @@ class Job:
         t3 = time.perf_counter()
         if not self.no_local:
             if self.local_async:
-                s.LocalMinimizationsAsync(self.alg)
+                s.LocalMinimizationsAsync(self.alg, instances=ASYNC_INSTANCES[self.name])
             else:
                 s.LocalMinimizations(self.alg)
         e4 = self.mark()

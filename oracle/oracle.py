@@ -158,13 +158,13 @@ class Oracle:
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
         return True
 
-    def LocalMinimizationsAsync(self, instances):
+    def LocalMinimizationsAsync(self, instances, algor=1):
         """the asynchronous-instances run (Oracle::local_async); sets searchStart / searchResults / evals / fin / inst"""
         K, nx = self.K, self.cfg.nx
         s = np.empty((nx, K)); r = np.empty((nx + 4, K)); e = np.zeros(K, dtype=np.int32)
         fin = np.zeros(K, dtype=np.int32); inst = np.zeros(K, dtype=np.int32)
-        self.L.orc_local_async.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]
-        rc = self.L.orc_local_async(self.h, instances, dptr(s), dptr(r), e.ctypes.data_as(c_int32_p), fin.ctypes.data_as(c_int32_p),
+        self.L.orc_local_async.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]
+        rc = self.L.orc_local_async(self.h, algor, instances, dptr(s), dptr(r), e.ctypes.data_as(c_int32_p), fin.ctypes.data_as(c_int32_p),
                                     inst.ctypes.data_as(c_int32_p))
         assert rc == 0, rc
         self.searchStart, self.searchResults, self.evals, self.fin, self.inst = s.T.copy(), r.T.copy(), e, fin, inst

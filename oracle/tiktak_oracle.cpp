@@ -648,7 +648,7 @@ struct Oracle {
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first = 1);
-    int local_async(int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out);
+    int local_async(int alg, int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out);
     int missing_search(int alg, int k, double* start_out, double* row_out, int32_t* evals_out);
     int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
     int dfnls_force_first = 0, dfnls_force_every = 0; /* test hook (orc_set_dfnls_force_rescue) */
@@ -789,10 +789,11 @@ int Oracle::local(int alg, int round_size, double* starts_out, double* results_o
  * amoeba's loop; c0 = ceil((nx+1)/4): what the initial simplex and a shrink step cost four warps).  Restart numbers go out in the order of the finish times, ties by instance number; a start sees the
  * rows with finish time <= its start time; the best row is the lowest value, ties by the order of the file (finish time, instance, k).
  * Nelder-Mead, search_type 0, nm_shrink_mode 0. */
-int Oracle::local_async(int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out) {
+int Oracle::local_async(int alg, int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out) {
     const int K = c.maxpoints_plus1, nx = c.nx;
     if ((int)x_starts.size() != K * (nx + 1)) return -1;
-    if (c.search_type != 0 || c.nm_shrink_mode != 0) return -2;
+    if (c.search_type != 0 || (alg == TIKTAK_ALG_AMOEBA && c.nm_shrink_mode != 0)) return -2;
+    if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) return -2;
     const int P = std::max(1, std::min(instances, K));
     const int c0 = (nx + 1 + 3) / 4;
     const int seqNo = 1;
@@ -832,12 +833,26 @@ int Oracle::local_async(int instances, double* starts_out, double* results_out, 
         }
         if (starts_out) for (int d = 0; d < nx; d++) starts_out[(size_t)d * K + (k - 1)] = evalParam[d];
         const long nfev0 = nfev;
-        std::vector<double> width;
-        simplex_width(k, rows, 1, width);
-        int iters = 0;
-        runAmoeba(evalParam, width, iters);
-        const int steps = TIKTAK_ASYNC_PICKUP_TICKS + c0 + amoeba_trips + amoeba_shrinks * c0;
+        int steps;
+        if (alg == TIKTAK_ALG_AMOEBA) {
+            std::vector<double> width;
+            simplex_width(k, rows, 1, width);
+            int iters = 0;
+            runAmoeba(evalParam, width, iters);
+            steps = TIKTAK_ASYNC_PICKUP_TICKS + c0 + amoeba_trips + amoeba_shrinks * c0;
+        } else { /* DFNLS: the tick is one objective evaluation (for the SMM objective: one pass over the panel) */
+            const double itratio = (double)((float)k / (float)K);
+            double mn = bu()[0] - bl()[0];
+            for (int d = 1; d < nx; d++) mn = std::min(mn, bu()[d] - bl()[d]);
+            double rhobeg, rhoend;
+            if (itratio > 0.5) { rhobeg = (mn / 2.5) / (4 * itratio); rhoend = 1.0e-3 / (4 * itratio); }
+            else { rhobeg = mn / 2.50; rhoend = 1.0e-3; }
+            int nf = 0, nresc = 0;
+            dfnls(evalParam, rhobeg, rhoend, c.maxeval, nf, nresc);
+            steps = 0;
+        }
         const double fn_val = objFun(evalParam.data()); /* :582 */
+        if (alg == TIKTAK_ALG_DFNLS) steps = TIKTAK_ASYNC_PICKUP_TICKS + (int)(nfev - nfev0);
         if (evals_out) evals_out[k - 1] = (int32_t)(nfev - nfev0);
         Row r;
         r.seq = seqNo; r.k = k; r.imp = 0;
@@ -1052,8 +1067,8 @@ long orc_nfev(void* h) { return ((Oracle*)h)->nfev; }
 long orc_best_tie_events(void* h) { return ((Oracle*)h)->best_tie_events; }
 
 /* one Nelder-Mead restart from `start` exactly as runAmoeba does it for restart k (width = p_range) */
-int orc_local_async(void* h, int instances, double* starts, double* results, int32_t* evals, int32_t* fin, int32_t* inst) {
-    return ((Oracle*)h)->local_async(instances, starts, results, evals, fin, inst);
+int orc_local_async(void* h, int alg, int instances, double* starts, double* results, int32_t* evals, int32_t* fin, int32_t* inst) {
+    return ((Oracle*)h)->local_async(alg, instances, starts, results, evals, fin, inst);
 }
 int orc_run_amoeba(void* h, double* pt, int32_t* iters) {
     Oracle* o = (Oracle*)h;

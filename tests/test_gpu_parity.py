@@ -198,6 +198,43 @@ def test_asynchronous_instances(built, name, P, nm, K):
             assert np.any(np.diff(o.fin) < 0)
 
 
+@pytest.mark.parametrize("name,P,nm,K", [("template4", 3, 8, 9), ("griewank7", 4, 3, 10), ("griewank10", 16, 6, 40), ("rosenbrock33", 5, 4, 12)])
+def test_asynchronous_instances_dfnls(built, name, P, nm, K):
+    """the same scheme for DFNLS (dfnls_kernel with DfArgs.async): the tick of the virtual clock is one objective evaluation"""
+    cfg = cfg_of(name, nm=nm, maxpoints=K, round_size=P)
+    with TikTakSearch(cfg) as s:
+        assert s.asyncSupported("b")
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizationsAsync("b")
+        gs, gr, ge, used = s.searchStart, s.searchResults, s.evals, s.instances_used
+        gbest = s.getBestLine()
+    assert used == min(P, cfg.p_maxpoints)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizationsAsync(used, algor=0)
+    assert np.array_equal(gs, o.searchStart), "blended start points differ"
+    assert np.array_equal(ge, o.evals)
+    assert np.array_equal(gr, o.searchResults)
+    assert gbest[0] == o.getBestLine()[0]
+
+
+def test_asynchronous_instances_smm_dfnls(built):
+    """BASELINE config 5 at reduced panel size, DFNLS by asynchronous instances (the form bench.py times at full size)"""
+    cfg = smm_config(np_persons=1024, T=20, qr_ndraw=300, legitimate=40, maxpoints=11, fvalmax=20000.0, round_size=4)
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizationsAsync("b")
+        gs, gr, ge, used = s.searchStart, s.searchResults, s.evals, s.instances_used
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizationsAsync(used, algor=0)
+    assert used == 4 and np.array_equal(gs, o.searchStart) and np.array_equal(ge, o.evals) and np.array_equal(gr, o.searchResults)
+
+
 def test_one_asynchronous_instance_is_the_sequential_run(built):
     """P = 1: the instance sees every earlier row -- the reference's single-process run, i.e. rounds of one restart"""
     cfg = cfg_of("griewank10", maxpoints=25, round_size=1)

@@ -1074,7 +1074,7 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
 int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used) {
     if (!h || !used || first_k < 1 || n_k < 0 || instances < 1 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
     *used = 0;
-    if (alg != TIKTAK_ALG_AMOEBA) { tk_set_error("local_async: Nelder-Mead only"); return TIKTAK_ERR_UNSUPPORTED; }
+    if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) { tk_set_error("local_async: Nelder-Mead or DFNLS"); return TIKTAK_ERR_UNSUPPORTED; }
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
     if (n_k == 0) return TIKTAK_OK;
     TK_CUDA(cudaSetDevice(h->device));
@@ -1083,7 +1083,7 @@ int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int3
         h->local_timing_open = true;
     }
     int u = 0;
-    int rc = tk_launch_nm_async(h, first_k, n_k, instances, &u);
+    int rc = alg == TIKTAK_ALG_AMOEBA ? tk_launch_nm_async(h, first_k, n_k, instances, &u) : tk_launch_dfnls(h, first_k, n_k, instances, &u);
     if (rc) return rc;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
     h->async_rows = true;
@@ -1103,7 +1103,8 @@ extern "C" int tiktak_cuda_debug_async(tiktak_handle* h, long long* out, int n) 
 /* which instances tiktak_cuda_local_async would run: 0 = the configuration is not built for it */
 int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* yes) {
     if (!h || !yes) return TIKTAK_ERR_ARG;
-    *yes = (alg == TIKTAK_ALG_AMOEBA && tk_nm_async_supported(h)) ? 1 : 0;
+    *yes = ((alg == TIKTAK_ALG_AMOEBA && tk_nm_async_supported(h)) ||
+            (alg == TIKTAK_ALG_DFNLS && h->cfg.world == 1 && h->cfg.search_type == 0 && h->cfg.nx <= 100)) ? 1 : 0;
     return TIKTAK_OK;
 }
 

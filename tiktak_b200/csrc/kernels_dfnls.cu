@@ -34,7 +34,7 @@ namespace {
 enum DfOp : int {
     OP_EXIT = 0, OP_DFOVEC, OP_PRELIM_ZERO, OP_PRELIM_STORE, OP_PRELIM_G, OP_PRELIM_H, OP_PRELIM_SWAP,
     OP_L20_HQV, OP_L20_PQV, OP_SHIFT, OP_VQUAD, OP_UPDATE_MODEL, OP_GQV_W, OP_OPT_MOVE, OP_LFN, OP_TRS_MODEL, OP_FINAL,
-    OP_RESC_SHIFT, OP_RESC_NEWPT, OP_RESC_MODEL
+    OP_RESC_SHIFT, OP_RESC_NEWPT, OP_RESC_MODEL, OP_ASYNC_PICK
 };
 
 struct DfArgs {
@@ -51,6 +51,9 @@ struct DfArgs {
     int* out_status;
     int force_first, force_every; /* test hook: treat the denominator test as failed when NF reaches force_first (+ k force_every) */
     int big_in_global;    /* XPT, BMAT, ZMAT live in the slab instead of shared memory (nx > ~55) */
+    int async;            /* asynchronous instances (nm_common.cuh): block r is instance r, block n_run keeps the time; rhobeg / rhoend are
+                             indexed by k - aq.first_k */
+    tknm::NmAsync aq;
 };
 
 struct DfCtl { /* master <-> workers */
@@ -76,6 +79,11 @@ struct Df {
     bool model_update, opt_update;
     int nrescue;
     int force_first, force_every, forced_at;
+    /* asynchronous instances */
+    const tknm::NmAsync* aq;
+    int a_t0, a_nev;      /* virtual time at which the running restart's evaluations start; evaluations so far */
+    int* a_clk;           /* this instance's clock (NULL: rounds) */
+    double* pk_f; int *pk_t, *pk_s, *pk_k, *pk_v, *pk_e; /* per-warp results of OP_ASYNC_PICK */
 
 #define XPT_(k, j) XPT[((j)-1) * NPT + ((k)-1)]
 #define BMAT_(i, j) BMAT[((j)-1) * NDIM + ((i)-1)]
@@ -450,6 +458,42 @@ struct Df {
                 break;
             }
             case OP_RESC_SHIFT: case OP_RESC_NEWPT: case OP_RESC_MODEL: run_op_rescue(op); break;
+            case OP_ASYNC_PICK: { /* asynchronous instances: finish events in front of (Tv, s), the best visible row (kernels_nm.cu has the same pass) */
+                const tknm::NmAsync& q = *aq;
+                const int Tv = c.i0, s_ = c.i1, P = c.i2;
+                const int lane = tid & 31, wp = tid >> 5, nw = (nthr + 31) >> 5;
+                int cnt_ev = 0, cnt_vis = 0, bt = 0, bs = 0, bk = -1;
+                double bf = 0.0;
+                const int hi = min(q.last_k, __ldcg(q.clk + P));
+                for (int jj = tid; jj <= hi; jj += nthr) {
+                    const int4 raw = __ldcg(reinterpret_cast<const int4*>(q.ev + jj));
+                    const int tj = raw.z, sj = raw.w;
+                    if (tj < 0 || tj > Tv) continue;
+                    if (jj >= q.first_k && (tj < Tv || sj < s_)) cnt_ev++;
+                    const double fj = __hiloint2double(raw.y, raw.x);
+                    if (!(fj == fj)) continue;
+                    cnt_vis++;
+                    if (bk < 0 || tknm::nm_row_before(fj, tj, sj, jj, bf, bt, bs, bk)) { bf = fj; bt = tj; bs = sj; bk = jj; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double f2 = __shfl_xor_sync(0xffffffffu, bf, o);
+                    const int t2 = __shfl_xor_sync(0xffffffffu, bt, o), s2 = __shfl_xor_sync(0xffffffffu, bs, o), k2 = __shfl_xor_sync(0xffffffffu, bk, o);
+                    if (k2 >= 0 && (bk < 0 || tknm::nm_row_before(f2, t2, s2, k2, bf, bt, bs, bk))) { bf = f2; bt = t2; bs = s2; bk = k2; }
+                    cnt_ev += __shfl_xor_sync(0xffffffffu, cnt_ev, o);
+                    cnt_vis += __shfl_xor_sync(0xffffffffu, cnt_vis, o);
+                }
+                if (lane == 0) { pk_f[wp] = bf; pk_t[wp] = bt; pk_s[wp] = bs; pk_k[wp] = bk; pk_v[wp] = cnt_vis; pk_e[wp] = cnt_ev; }
+                bar();
+                if (tid == 0) {
+                    bf = pk_f[0]; bt = pk_t[0]; bs = pk_s[0]; bk = pk_k[0]; cnt_vis = pk_v[0]; cnt_ev = pk_e[0];
+                    for (int o = 1; o < nw; o++) {
+                        if (pk_k[o] >= 0 && (bk < 0 || tknm::nm_row_before(pk_f[o], pk_t[o], pk_s[o], pk_k[o], bf, bt, bs, bk))) { bf = pk_f[o]; bt = pk_t[o]; bs = pk_s[o]; bk = pk_k[o]; }
+                        cnt_vis += pk_v[o]; cnt_ev += pk_e[o];
+                    }
+                    ctl->i3 = cnt_ev; ctl->i0 = cnt_vis; ctl->i1 = bk;
+                }
+                break;
+            }
             case OP_FINAL:
             default: break;
         }
@@ -473,6 +517,8 @@ struct Df {
 
     /* F = sum v_err^2 in index order (f_value :1173-1183) + getPenalty; master only, after OP_DFOVEC */
     __device__ double eval_at_XC() {
+        a_nev++;
+        if (a_clk) tknm::st_vol(a_clk, a_t0 + a_nev); /* the restart cannot finish before this evaluation has */
         par(OP_DFOVEC);
         double F = 0.0;
         if constexpr (Obj::kVector) {
@@ -1554,15 +1600,35 @@ struct Df {
     }
 };
 
-template <class Obj>
+/* BIG: XPT, BMAT and ZMAT live in the restart's slab of global memory (nx > ~55).  A template parameter, not a run-time choice of
+ * pointer: with the three matrices carved from `sm` the compiler knows they are shared memory and reads them with LDS; a pointer
+ * that may be either makes every access a generic load (measured: the C5 stage 5.8 -> 7.3 s). */
+template <class Obj, bool BIG>
 __global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const TkTablesG T, const TkScalars sc, const DfArgs a) {
     extern __shared__ double sm[];
     __shared__ DfCtl ctl;
     __shared__ tk_obj_ctx sctx;
+    __shared__ double pk_f[16];
+    __shared__ int pk_i[5][16];
     const int r = blockIdx.x;
+    if (a.async && r == a.n_run) { /* the time keeper of an asynchronous run (see nm_quad_async_kernel) */
+        if (threadIdx.x >= 32) return;
+        const int P = a.n_run, lane = threadIdx.x;
+        int* gvt = a.aq.clk + P + 32;
+        for (;;) {
+            int m = 0x7fffffff;
+            for (int i = lane; i < P; i += 32) m = min(m, tknm::ld_vol(a.aq.clk + i));
+            m = (int)__reduce_min_sync(0xffffffffu, (unsigned)m);
+            if (lane < TK_GVT_COPIES) tknm::st_vol(gvt + lane * 32, m);
+            if (m == 0x7fffffff) return;
+            __nanosleep(100);
+        }
+    }
     if (r >= a.n_run) return;
     const int slot = a.rank + r * a.world;
     Df<Obj> d;
+    d.aq = &a.aq; d.a_t0 = 0; d.a_nev = 0; d.a_clk = nullptr;
+    d.pk_f = pk_f; d.pk_t = pk_i[0]; d.pk_s = pk_i[1]; d.pk_k = pk_i[2]; d.pk_v = pk_i[3]; d.pk_e = pk_i[4];
     d.tid = threadIdx.x; d.nthr = blockDim.x;
     d.N = sc.nx; d.NPT = a.npt; d.mv = a.mv; d.NDIM = d.NPT + d.N; d.NP = d.N + 1; d.NPTM = d.NPT - d.NP; d.NH = (d.N * d.NP) / 2;
     d.eps = 2.220446049250313e-16;
@@ -1575,9 +1641,11 @@ __global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const T
     double* sbl = take(N); double* sbu = take(N); double* saux = take(N);
     d.XL = sbl; d.XU = sbu;
     const int nzm = NPT * (d.NPTM > 0 ? d.NPTM : 1);
-    const bool big_sh = !a.big_in_global; /* XPT, BMAT and ZMAT in shared memory (else in the slab: 560 KB at nx = 100) */
-    d.XBASE = take(N); d.XPT = big_sh ? take(NPT * N) : nullptr; d.FVAL = take(NPT); d.XOPT = take(N); d.GOPT = take(N); d.HQ = take(NH);
-    d.BMAT = big_sh ? take(NDIM * N) : nullptr; d.ZMAT = big_sh ? take(nzm) : nullptr; d.SL = take(N); d.SU = take(N); d.XNEW = take(N);
+    d.XBASE = take(N);
+    if constexpr (!BIG) d.XPT = take(NPT * N);
+    d.FVAL = take(NPT); d.XOPT = take(N); d.GOPT = take(N); d.HQ = take(NH);
+    if constexpr (!BIG) { d.BMAT = take(NDIM * N); d.ZMAT = take(nzm); }
+    d.SL = take(N); d.SU = take(N); d.XNEW = take(N);
     d.XALT = take(N); d.D = take(N); d.VLAG = take(NDIM); d.W = take(2 * NDIM + 6 * N + 2 * NPT + 16); d.HD1 = take(N);
     d.TK = take(NDIM + NPT + 8); d.XC = take(N); d.VBUF = take(blockDim.x);
     d.VSH = nullptr; d.YSH = nullptr;
@@ -1588,40 +1656,94 @@ __global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const T
     d.GQV = g; g += mv * N; d.HQV = g; g += mv * NH; d.PQV = g; g += mv * NPT; d.FVAL_V = g; g += mv * NPT; d.WV = g; g += mv * N;
     d.v_sumpq = g; g += mv; d.v_err = g; g += mv; d.v_beg = g; g += mv; d.v_temp = g; g += mv; d.v_diff = g; g += mv;
     d.v_vquad = g; g += mv; d.PQVold = g; g += mv; d.v_fbase = g; g += mv; d.v_itest = (int*)g; g += mv;
-    if (!big_sh) { d.XPT = g; g += (size_t)NPT * N; d.BMAT = g; g += (size_t)NDIM * N; d.ZMAT = g; g += nzm; }
+    if constexpr (BIG) { d.XPT = g; g += (size_t)NPT * N; d.BMAT = g; g += (size_t)NDIM * N; d.ZMAT = g; g += nzm; }
     d.nrescue = 0; d.force_first = a.force_first; d.force_every = a.force_every > 0 ? a.force_every : 1 << 30; d.forced_at = -1;
     for (int i = threadIdx.x; i < N; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
     if (threadIdx.x == 0) { sctx = tk_make_ctx(sc, N, sbl, sbu, saux); ctl.op = -1; ctl.model_update = 0; }
     __syncthreads();
     if (threadIdx.x != 0) { d.worker_loop(); return; }
-    /* ---- master: BOBYQA_H :354-396 ---- */
-    const double RHOBEG = a.rhobeg[slot], RHOEND = a.rhoend[slot];
-    int NF = 0, status = 0;
-    bool ok = !(NPT < N + 2 || NPT > 2 * N + 1);
-    for (int J = 1; J <= N && ok; J++) {
-        double xj = a.starts[(size_t)(J - 1) * a.n_k + slot];
-        const double TEMP = sbu[J - 1] - sbl[J - 1];
-        if (TEMP < RHOBEG + RHOBEG) { ok = false; d.XC[J - 1] = xj; break; }
-        double sl = sbl[J - 1] - xj, su = sbu[J - 1] - xj;
-        if (sl >= -RHOBEG) {
-            if (sl >= 0.0) { xj = sbl[J - 1]; sl = 0.0; su = TEMP; }
-            else { xj = sbl[J - 1] + RHOBEG; sl = -RHOBEG; su = fmax(sbu[J - 1] - xj, RHOBEG); }
-        } else if (su <= RHOBEG) {
-            if (su <= 0.0) { xj = sbu[J - 1]; sl = -TEMP; su = 0.0; }
-            else { xj = sbu[J - 1] - RHOBEG; sl = fmin(sbl[J - 1] - xj, -RHOBEG); su = RHOBEG; }
+    /* ---- master: BOBYQA_H :354-396 for one start; returns objFun at the result (completeSearch :582) ---- */
+    auto search = [&](auto start, double RHOBEG, double RHOEND, int& NF, int& status) -> double {
+        NF = 0; status = 0;
+        d.nrescue = 0; d.forced_at = -1;
+        ctl.model_update = 0;
+        bool ok = !(NPT < N + 2 || NPT > 2 * N + 1);
+        for (int J = 1; J <= N && ok; J++) {
+            double xj = start(J - 1);
+            const double TEMP = sbu[J - 1] - sbl[J - 1];
+            if (TEMP < RHOBEG + RHOBEG) { ok = false; d.XC[J - 1] = xj; break; }
+            double sl = sbl[J - 1] - xj, su = sbu[J - 1] - xj;
+            if (sl >= -RHOBEG) {
+                if (sl >= 0.0) { xj = sbl[J - 1]; sl = 0.0; su = TEMP; }
+                else { xj = sbl[J - 1] + RHOBEG; sl = -RHOBEG; su = fmax(sbu[J - 1] - xj, RHOBEG); }
+            } else if (su <= RHOBEG) {
+                if (su <= 0.0) { xj = sbu[J - 1]; sl = -TEMP; su = 0.0; }
+                else { xj = sbu[J - 1] - RHOBEG; sl = fmin(sbl[J - 1] - xj, -RHOBEG); su = RHOBEG; }
+            }
+            d.XC[J - 1] = xj; d.SL[J - 1] = sl; d.SU[J - 1] = su;
         }
-        d.XC[J - 1] = xj; d.SL[J - 1] = sl; d.SU[J - 1] = su;
-    }
-    if (ok) d.BOBYQB_H(RHOBEG, RHOEND, a.maxfun, NF, status);
-    else { status = 2; for (int J = 1; J <= N; J++) d.XC[J - 1] = a.starts[(size_t)(J - 1) * a.n_k + slot]; }
-    /* completeSearch :582: fn_val = objFun(evalParam) */
-    const double fn = d.eval_at_XC();
-    for (int J = 0; J < N; J++) a.out_x[(size_t)J * a.n_k + slot] = d.XC[J];
-    a.out_f[slot] = fn;
+        if (ok) d.BOBYQB_H(RHOBEG, RHOEND, a.maxfun, NF, status);
+        else { status = 2; for (int J = 1; J <= N; J++) d.XC[J - 1] = start(J - 1); }
+        return d.eval_at_XC();
+    };
     /* status (2 bits) and the number of RESCUE_H calls (5 bits, saturating) travel with the evaluation count (pack rows, ingest,
      * local_fetch / local_status / local_nrescue) */
-    a.out_evals[slot] = (NF + 1) | ((status | ((d.nrescue < 31 ? d.nrescue : 31) << 2)) << 24);
-    a.out_status[slot] = status;
+    auto packed_evals = [&](int NF, int status) { return (NF + 1) | ((status | ((d.nrescue < 31 ? d.nrescue : 31) << 2)) << 24); };
+    if (!a.async) {
+        int NF, status;
+        const double fn = search([&](int j) { return a.starts[(size_t)j * a.n_k + slot]; }, a.rhobeg[slot], a.rhoend[slot], NF, status);
+        for (int J = 0; J < N; J++) a.out_x[(size_t)J * a.n_k + slot] = d.XC[J];
+        a.out_f[slot] = fn;
+        a.out_evals[slot] = packed_evals(NF, status);
+        a.out_status[slot] = status;
+    } else {
+        /* asynchronous instances: the scheme of nm_quad_async_kernel with the evaluation (one pass over the panel: the unit
+         * every instance spends the same real time on) as the tick of the virtual clock: a restart costs cb + #evaluations */
+        const tknm::NmAsync& q = a.aq;
+        const int P = a.n_run, cb = q.cb;
+        int k = q.first_k + r, Tv = 0;
+        d.a_clk = q.clk + r;
+        for (;;) {
+            ctl.i0 = Tv; ctl.i1 = r; ctl.i2 = P;
+            d.par(OP_ASYNC_PICK);
+            const int cnt_vis = ctl.i0, bk = ctl.i1;
+            double stv[100]; /* the blended start (nx <= 100) */
+            if (Tv > 0) k = q.first_k + P + ctl.i3;
+            if (k > q.last_k) { tknm::st_vol(q.clk + r, 0x7fffffff); break; }
+            if (Tv > 0) atomicMax(q.clk + P, k);
+            for (int dd = 0; dd < N; dd++) { /* getModifiedParam :683-720 */
+                const double ev = q.xs[(size_t)(dd + 1) * q.K + (k - 1)];
+                double out = ev;
+                if (cnt_vis > 1 && bk >= 0) {
+                    const double wgt = q.w11[k];
+                    out = TK_ADD(TK_MUL(wgt, q.res[(size_t)bk * (N + 1) + 1 + dd]), TK_MUL(TK_SUB(1.0, wgt), ev));
+                }
+                stv[dd] = out;
+                q.arch_starts[(size_t)dd * q.K + (k - 1)] = out;
+            }
+            d.a_t0 = Tv + cb; d.a_nev = 0;
+            int NF, status;
+            const double fn = search([&](int j) { return stv[j]; }, a.rhobeg[k - q.first_k], a.rhoend[k - q.first_k], NF, status);
+            const int F = Tv + cb + d.a_nev;
+            double* dst = q.res + (size_t)k * (N + 1);
+            const double frt = q.roundtrip ? tk_f4020_roundtrip(fn) : fn;
+            dst[0] = frt;
+            for (int dd = 0; dd < N; dd++) dst[1 + dd] = q.roundtrip ? tk_f4020_roundtrip(d.XC[dd]) : d.XC[dd];
+            q.ev[k].fv = frt;
+            q.ev[k].slt = r;
+            q.valid[k] = (frt == frt) ? 1 : 0;
+            q.arch_evals[k] = packed_evals(NF, status);
+            __threadfence();
+            tknm::st_vol(&q.ev[k].fin, F);
+            __threadfence();
+            tknm::st_vol(q.clk + r, F + cb + 1);
+            const int* gvt = q.clk + P + 32 + (r % TK_GVT_COPIES) * 32;
+            unsigned ns = 100;
+            while (!(tknm::ld_vol(gvt) > F)) { __nanosleep(ns); if (ns < 1600) ns += ns; }
+            __threadfence();
+            Tv = F;
+        }
+    }
     ctl.op = OP_EXIT;
     d.bar();
 }
@@ -1732,12 +1854,19 @@ int tk_launch_nm_vec(tiktak_handle* h, const tknm::NmArgs& a) {
     return TIKTAK_OK;
 }
 
-int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
+/* instances > 0: asynchronous instances (one cooperative launch for all n_k restarts, rows committed by the kernel; *used = instances run) */
+int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k, int instances, int* used) {
     const int nx = h->cfg.nx, mv = h->cfg.nm, npt = 2 * nx + 1; /* p_ninterppt, genericParams.f90:311 */
     const int ndim = npt + nx, nh = nx * (nx + 1) / 2, nptm = npt - nx - 1;
     DfArgs a;
     a.n_k = n_k; a.rank = h->cfg.rank; a.world = h->cfg.world;
     a.n_run = (n_k > a.rank) ? (n_k - a.rank + a.world - 1) / a.world : 0;
+    a.async = 0;
+    if (instances > 0) {
+        if (h->cfg.world != 1 || h->cfg.search_type != 0) { tk_set_error("local_async (DFNLS): one GPU, search_type 0"); return TIKTAK_ERR_UNSUPPORTED; }
+        a.async = 1;
+        a.n_run = std::min(instances, n_k); /* clamped to the resident blocks below */
+    }
     if (a.n_run <= 0) return TIKTAK_OK;
     if (nx > 100) { tk_set_error("DFNLS supports nx <= 100 (nmax of minimize.f90:416)"); return TIKTAK_ERR_UNSUPPORTED; }
     /* rhobeg / rhoend per restart k (completeSearch :564-571): itratio is a single-precision quotient.
@@ -1789,20 +1918,34 @@ int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k) {
     const size_t shd = (small + (a.big_in_global ? 0 : big)) * sizeof(double);
     if (shd > 226 * 1024) { tk_set_error("DFNLS small matrices do not fit in shared memory (nx=%d)", nx); return TIKTAK_ERR_UNSUPPORTED; }
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
+    /* rounds: one block per restart of the launch.  Asynchronous instances: min(instances, resident blocks - 1) blocks + the time
+     * keeper, launched cooperatively (the instances wait for one another) */
+    auto go = [&](auto kern, size_t sh) -> int {
+        TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        if (!a.async) {
+            kern<<<a.n_run, threads, sh, h->stream>>>(T, h->sc, a);
+        } else {
+            int per_sm = 0;
+            TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, sh));
+            a.n_run = std::max(1, std::min(a.n_run, per_sm * h->sm_count - 1));
+            int rc = tk_async_setup(h, first_k, n_k, 1, &a.aq);
+            if (rc) return rc;
+            if ((rc = tk_async_init(h, a.aq, a.n_run))) return rc;
+            void* args[] = {(void*)&T, (void*)&h->sc, (void*)&a};
+            TK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)a.n_run + 1), dim3((unsigned)threads), args, sh, h->stream));
+            if (used) *used = a.n_run;
+        }
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+        return a.async ? tk_async_best(h) : TIKTAK_OK;
+    };
     if (h->cfg.objective_id == TIKTAK_OBJ_SMM) {
         const size_t shv = shd + (size_t)(mv + 2 * TK_SMM_SMEM_DOUBLES(h->smm_T)) * sizeof(double);
         if (shv > 226 * 1024) { tk_set_error("DFNLS+SMM shared memory"); return TIKTAK_ERR_UNSUPPORTED; }
-        TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<ObjSmm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shv));
-        dfnls_kernel<ObjSmm><<<a.n_run, threads, shv, h->stream>>>(T, h->sc, a);
-        h->launches++;
-        TK_CUDA(cudaGetLastError());
-        return TIKTAK_OK;
+        if (a.big_in_global) { tk_set_error("DFNLS+SMM: the small matrices must fit in shared memory"); return TIKTAK_ERR_UNSUPPORTED; }
+        return go(dfnls_kernel<ObjSmm, false>, shv);
     }
     return tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
-        TK_CUDA(cudaFuncSetAttribute(dfnls_kernel<Obj>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shd));
-        dfnls_kernel<Obj><<<a.n_run, threads, shd, h->stream>>>(T, h->sc, a);
-        h->launches++;
-        TK_CUDA(cudaGetLastError());
-        return TIKTAK_OK;
+        return a.big_in_global ? go(dfnls_kernel<Obj, true>, shd) : go(dfnls_kernel<Obj, false>, shd);
     });
 }

@@ -558,33 +558,6 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_kernel(const TkTable
  * asks the occupancy calculator and launches cooperatively.
  * The block itself writes the row (completeSearch :582-597 through the f40.20 record), so there is no ingest kernel.
  * --------------------------------------------------------------------------------------------- */
-struct NmAsync {
-    int first_k, last_k;   /* restarts of the launch */
-    int K, nx, roundtrip;
-    const double* xs;      /* x_starts (K, nx+1) column-major */
-    const double* w11;     /* blend weight per restart number */
-    double* res;           /* (K+1) x (nx+1) result rows [fval, x] */
-    int* valid;
-    int* arch_evals;
-    double* arch_starts;   /* (K, nx) column-major */
-    TkAsyncRow* ev;        /* [K+1] value, virtual finish time (-1: not finished; 0: rows known before the launch) and instance (-1: known
-                              before) of row k, one 16-byte record per row for the scans */
-    int* clk;              /* [P] lower bound of the instance's next finish time; clk[P]: highest restart number handed out */
-    long long* dbg;        /* experiment: per instance [wait cycles, scan cycles, run cycles, restarts, polls] or NULL */
-    int c0, cb;            /* ticks of the initial simplex / of a shrink step; ticks an instance needs between two restarts */
-};
-
-#define TK_GVT_COPIES 16
-__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-__device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
-/* (f, fin, slt, k) of row A before row B: lower value first, then the order of the (virtual) file */
-__device__ __forceinline__ bool nm_row_before(double fa, int ta, int sa, int ka, double fb, int tb, int sb, int kb) {
-    if (fa != fb) return fa < fb;
-    if (ta != tb) return ta < tb;
-    if (sa != sb) return sa < sb;
-    return ka < kb;
-}
-
 __global__ void nm_async_init_kernel(const NmAsync q, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= q.K) {
@@ -1454,12 +1427,11 @@ static int nm_launch_async(tiktak_handle* h, const TkTablesG& T, const NmArgs& a
     TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, shmem));
     const int n = q.last_k - q.first_k + 1;
     const int P = std::max(1, std::min(std::min(want, n), per_sm * h->sm_count - 1)); /* every instance and the time keeper must be resident (they wait for one another) */
-    if (!h->d_async_clk) TK_CUDA(cudaMalloc(&h->d_async_clk, (size_t)64 * 1024 * sizeof(int)));
-    q.clk = h->d_async_clk;
-    nm_async_init_kernel<<<(std::max(q.K + 1, P + 1) + 255) / 256, 256, 0, h->stream>>>(q, P);
+    int rc = tk_async_init(h, q, P);
+    if (rc) return rc;
     void* args[] = {(void*)&T, (void*)&h->sc, (void*)&a, (void*)&q};
     TK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)P + 1), dim3(128), args, shmem, h->stream));
-    h->launches += 2;
+    h->launches++;
     *used = P;
     return TIKTAK_OK;
 }
@@ -1599,15 +1571,9 @@ int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, in
     a.fac1c = (1.0 - 0.5) / ndim;    a.fac2c = a.fac1c - 0.5;
     a.tiny = (double)1.0e-10f;
     a.out_x = nullptr; a.out_f = nullptr; a.out_evals = nullptr;
-    if (!h->d_async_ev) TK_CUDA(cudaMalloc(&h->d_async_ev, (size_t)(K + 1) * sizeof(TkAsyncRow)));
     NmAsync q;
-    q.first_k = first_k; q.last_k = first_k + n_k - 1; q.K = K; q.nx = nx; q.roundtrip = h->cfg.text_roundtrip;
-    q.xs = h->d_xstarts; q.w11 = h->d_w11; q.res = h->d_res; q.valid = h->d_res_valid; q.arch_evals = h->d_arch_evals;
-    q.arch_starts = h->d_arch_starts; q.ev = h->d_async_ev; q.clk = nullptr;
-    q.dbg = nullptr;
-    if (getenv("TIKTAK_ASYNC_DEBUG")) { static long long* d = nullptr; if (!d) cudaMalloc(&d, 5 * 2048 * sizeof(long long)); q.dbg = d; h->async_dbg = d; }
-    q.c0 = (np + 3) / 4; q.cb = TIKTAK_ASYNC_PICKUP_TICKS;
-    if (const char* e = getenv("TIKTAK_ASYNC_CB")) q.cb = atoi(e); /* experiment */
+    int rc0 = tk_async_setup(h, first_k, n_k, (np + 3) / 4, &q);
+    if (rc0) return rc0;
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     const int ts = (nx + 2) & ~1;
     const size_t shmem = (size_t)(4 * ts + 8 + ts + 4 * (5 * ts + np * nx)) * sizeof(double);
@@ -1621,7 +1587,31 @@ int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, in
     });
     if (rc) return rc;
     TK_CUDA(cudaGetLastError());
-    best_async_kernel<<<1, 256, 0, h->stream>>>(h->d_res, h->d_res_valid, h->d_async_ev, K + 1, nx, h->d_best);
+    return tk_async_best(h);
+}
+
+/* the bookkeeping both asynchronous kernels (Nelder-Mead here, DFNLS in kernels_dfnls.cu) share */
+int tk_async_setup(tiktak_handle* h, int first_k, int n_k, int c0, NmAsync* q) {
+    const int K = h->cfg.maxpoints_plus1;
+    if (!h->d_async_ev) TK_CUDA(cudaMalloc(&h->d_async_ev, (size_t)(K + 1) * sizeof(TkAsyncRow)));
+    if (!h->d_async_clk) TK_CUDA(cudaMalloc(&h->d_async_clk, (size_t)64 * 1024 * sizeof(int)));
+    q->first_k = first_k; q->last_k = first_k + n_k - 1; q->K = K; q->nx = h->cfg.nx; q->roundtrip = h->cfg.text_roundtrip;
+    q->xs = h->d_xstarts; q->w11 = h->d_w11; q->res = h->d_res; q->valid = h->d_res_valid; q->arch_evals = h->d_arch_evals;
+    q->arch_starts = h->d_arch_starts; q->ev = h->d_async_ev; q->clk = h->d_async_clk;
+    q->dbg = nullptr;
+    if (getenv("TIKTAK_ASYNC_DEBUG")) { static long long* d = nullptr; if (!d) cudaMalloc(&d, 5 * 2048 * sizeof(long long)); q->dbg = d; h->async_dbg = d; }
+    q->c0 = c0; q->cb = TIKTAK_ASYNC_PICKUP_TICKS;
+    if (const char* e = getenv("TIKTAK_ASYNC_CB")) q->cb = atoi(e); /* experiment */
+    return TIKTAK_OK;
+}
+int tk_async_init(tiktak_handle* h, const NmAsync& q, int P) {
+    nm_async_init_kernel<<<(std::max(q.K + 1, P + 1) + 255) / 256, 256, 0, h->stream>>>(q, P);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TIKTAK_OK;
+}
+int tk_async_best(tiktak_handle* h) {
+    best_async_kernel<<<1, 256, 0, h->stream>>>(h->d_res, h->d_res_valid, h->d_async_ev, h->cfg.maxpoints_plus1 + 1, h->cfg.nx, h->d_best);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return TIKTAK_OK;

@@ -62,4 +62,37 @@ __device__ __forceinline__ bool nm_converged(const NmArgs& a, double ylo, double
     return conv;
 }
 
+/* ---- asynchronous instances (kernels_nm.cu: nm_quad_async_kernel; kernels_dfnls.cu: dfnls_kernel with DfArgs.aq) ---- */
+struct NmAsync {
+    int first_k, last_k;   /* restarts of the launch */
+    int K, nx, roundtrip;
+    const double* xs;      /* x_starts (K, nx+1) column-major */
+    const double* w11;     /* blend weight per restart number */
+    double* res;           /* (K+1) x (nx+1) result rows [fval, x] */
+    int* valid;
+    int* arch_evals;
+    double* arch_starts;   /* (K, nx) column-major */
+    TkAsyncRow* ev;        /* [K+1] value, virtual finish time (-1: not finished; 0: rows known before the launch) and instance (-1: known
+                              before) of row k, one 16-byte record per row for the scans */
+    int* clk;              /* [P] lower bound of the instance's next finish time; clk[P]: highest restart number handed out */
+    long long* dbg;        /* experiment: per instance [wait cycles, scan cycles, run cycles, restarts, polls] or NULL */
+    int c0, cb;            /* ticks of the initial simplex / of a shrink step; ticks an instance needs between two restarts */
+};
+
+#define TK_GVT_COPIES 16
+__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+/* (f, fin, slt, k) of row A before row B: lower value first, then the order of the (virtual) file */
+__device__ __forceinline__ bool nm_row_before(double fa, int ta, int sa, int ka, double fb, int tb, int sb, int kb) {
+    if (fa != fb) return fa < fb;
+    if (ta != tb) return ta < tb;
+    if (sa != sb) return sa < sb;
+    return ka < kb;
+}
+
+
 } /* namespace tknm */
+
+int tk_async_setup(tiktak_handle* h, int first_k, int n_k, int c0, tknm::NmAsync* q);
+int tk_async_init(tiktak_handle* h, const tknm::NmAsync& q, int P);
+int tk_async_best(tiktak_handle* h);

@@ -180,7 +180,7 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size =
 int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used);
 bool tk_nm_async_supported(tiktak_handle* h);
 bool tk_nm_use_w4(tiktak_handle* h);
-int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k);
+int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k, int instances = 0, int* used = nullptr);
 int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, const double* pack, int* d_accepted);
 int tk_nm_wave_capacity(tiktak_handle* h);
 int tk_launch_pack(tiktak_handle* h, int n_k, double* pack);

@@ -275,8 +275,11 @@ class TikTakSearch:
         e = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_local_fetch(self._h, 1, K, s.ctypes.data, r.ctypes.data, e.ctypes.data), "LocalMinimizationsAsync")
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
-        self.status = np.zeros(K, dtype=np.int32)
-        self.nrescue = np.zeros(K, dtype=np.int32)
+        st = np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_status(self._h, 1, K, st.ctypes.data_as(C.POINTER(C.c_int32))), "local_status")
+        nr = np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_nrescue(self._h, 1, K, nr.ctypes.data_as(C.POINTER(C.c_int32))), "local_nrescue")
+        self.status, self.nrescue = st, nr
         return True
 
     def pushResults(self, rows):
