@@ -320,6 +320,18 @@ int main(int argc, char** argv) {
         CHECK(tiktak_cuda_local_capacity(h, alg, &window));
         const int per_launch = std::max(B, (window / B) * B);
         const int kfirst = k0;
+        /* TIKTAK_ASYNC_INSTANCES=<n> (one GPU): the restarts as n asynchronous instances -- the reference's multi-process mode in one
+         * kernel launch (tiktak_cuda_local_async) -- instead of rounds.  Rows are written in restart order; their #improvements
+         * column counts in the order the instances finished (the order of the file n processes would have written). */
+        if (const char* ea = getenv("TIKTAK_ASYNC_INSTANCES")) {
+            int32_t yes = 0, used = 0;
+            CHECK(tiktak_cuda_local_async_supported(h, alg, &yes));
+            if (yes && atoi(ea) > 0 && option != 5 && k0 <= kend) {
+                CHECK(tiktak_cuda_local_async(h, alg, k0, kend - k0 + 1, atoi(ea), &used));
+                char b[200]; snprintf(b, sizeof b, "%d runs restarts %d..%d as %d asynchronous instances", seqNo, k0, kend, (int)used); logmsg(b);
+                k0 = kend + 1;
+            }
+        }
         while (k0 <= kend) {
             const int nk = std::min(per_launch, kend - k0 + 1);
             int32_t acc = 0;

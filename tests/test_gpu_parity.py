@@ -435,6 +435,23 @@ def test_cli_driver_writes_reference_files(built, tmp_path):
     assert int(open(tmp_path / "lastSobol.dat").read()) == 11 and int(open(tmp_path / "legitSobol.dat").read()) == 10
 
 
+def test_cli_driver_asynchronous_instances(built, tmp_path, monkeypatch):
+    """TIKTAK_ASYNC_INSTANCES=3: the CLI driver runs state 7 through tiktak_cuda_local_async; rows as the oracle's event simulation"""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "driver", "TiktakGlobalSearch")
+    cfgfile = os.path.join(root, "tests", "golden", "config_c1.txt")
+    monkeypatch.setenv("TIKTAK_ASYNC_INSTANCES", "3")
+    r = subprocess.run([exe, "0", cfgfile, "a"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(tmp_path / "searchResults.dat")
+    o = Oracle(baseline_config("C1"), MATH_TK)
+    o.solveAtSobolPoints(); o.chooseSobol(mode=1); o.LocalMinimizationsAsync(3)
+    assert rows.shape == (5, 8) and rows[0, 1] == 0
+    assert np.allclose(rows[1:], o.searchResults, rtol=1e-15, atol=1e-19)
+    assert "as 3 asynchronous instances" in open(tmp_path / "logFile.txt").read()
+
+
 def test_start_selection_large_m(built):
     """more winners than one sort chunk (1024): chunk sort + merge-by-rank passes, odd and even pass counts"""
     for maxpoints, nd in ((1500, 4000), (3000, 20000), (5000, 6000)):

@@ -80,9 +80,9 @@ struct Df {
     int nrescue;
     int force_first, force_every, forced_at;
     /* asynchronous instances */
-    const tknm::NmAsync* aq;
-    int a_t0, a_nev;      /* virtual time at which the running restart's evaluations start; evaluations so far */
-    int* a_clk;           /* this instance's clock (NULL: rounds) */
+    const tknm::NmAsync* aq = nullptr;
+    int a_t0 = 0, a_nev = 0; /* virtual time at which the running restart's evaluations start; evaluations so far */
+    int* a_clk = nullptr;    /* this instance's clock (NULL: rounds, and the Nelder-Mead kernel for vector objectives) */
     double* pk_f; int *pk_t, *pk_s, *pk_k, *pk_v, *pk_e; /* per-warp results of OP_ASYNC_PICK */
 
 #define XPT_(k, j) XPT[((j)-1) * NPT + ((k)-1)]
