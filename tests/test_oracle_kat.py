@@ -214,6 +214,52 @@ def test_round_schedule_and_counter_column(built):
     assert np.array_equal(o.searchStart[1:], o.x_starts[1:, 1:])
 
 
+def test_asynchronous_instances_event_simulation(built):
+    """Oracle::local_async, the model nm_quad_async_kernel / dfnls_kernel reproduce on the device, checked against its own
+    definition with numpy: (1) one instance is the sequential run (rounds of one restart); (2) for P instances, replaying the
+    schedule from the reported finish times and instance numbers gives back every start row: restart k starts when the
+    earliest-free instance is free (lowest number among equals), sees exactly the rows with a finish time <= that, and is
+    blended toward the lowest of them (ties in file order) with the single-precision weight of k; (3) the #improvements column
+    counts along the file order (finish time, instance)."""
+    cfg = make_config(nx=6, nm=2, qr_ndraw=900, maxpoints=29, lo=-40.0, hi=60.0, init=[10.0] * 6, objective_id=OBJ_GRIEWANK)
+    K, nx = cfg.p_maxpoints, cfg.nx
+    o1 = Oracle(cfg, MATH_TK)
+    o1.solveAtSobolPoints(); o1.chooseSobol(mode=1); o1.LocalMinimizations(1, round_size=1)
+    oa = Oracle(cfg, MATH_TK)
+    oa.solveAtSobolPoints(); xs = oa.chooseSobol(mode=1); oa.LocalMinimizationsAsync(1)
+    assert np.array_equal(o1.searchStart, oa.searchStart) and np.array_equal(o1.searchResults, oa.searchResults) and np.array_equal(o1.evals, oa.evals)
+    assert np.all(np.diff(oa.fin) > 0) and np.all(oa.inst == 0)
+    for alg, P in ((1, 5), (1, 12), (0, 4)):
+        o = Oracle(cfg, MATH_TK)
+        o.solveAtSobolPoints(); xs = o.chooseSobol(mode=1); o.LocalMinimizationsAsync(P, algor=alg)
+        fin, inst, res, st = o.fin.astype(np.int64), o.inst, o.searchResults, o.searchStart
+        f0 = xs[0, 0]                                    # the k = 0 record: the value of the initial guess
+        free = np.zeros(P, dtype=np.int64)
+        for k in range(1, K + 1):
+            i = int(np.argmin(free))                     # earliest free instance, lowest number among equals
+            assert inst[k - 1] == i
+            T = free[i]
+            vis = [j for j in range(1, k) if fin[j - 1] <= T]
+            cand = [(f0, 0, -1, 0)] + [(res[j - 1, 3], fin[j - 1], inst[j - 1], j) for j in vis]
+            best = min(cand)
+            if len(cand) <= 1:
+                want = xs[k - 1, 1:]
+            else:
+                w = np.float64(min(max(np.float32(0.10), np.sqrt(np.float32(k) / np.float32(K))), np.float32(0.95)))
+                base = xs[0, 1:] if best[3] == 0 else res[best[3] - 1, 4:]
+                want = w * base + (1.0 - w) * xs[k - 1, 1:]
+            assert np.array_equal(st[k - 1], want), (alg, P, k)
+            assert fin[k - 1] > T + 32                   # pickup ticks + at least one tick of work
+            free[i] = fin[k - 1]
+        order = np.lexsort((inst, fin))                  # file order: finish time, then instance
+        best_f, imp = f0, 0
+        for j in order:
+            if res[j, 3] < best_f:
+                best_f, imp = res[j, 3], imp + 1
+            assert res[j, 2] == imp
+        assert P == 1 or len(set(inst.tolist())) == P
+
+
 def test_legitimate_cut_prefix_semantics(built):
     cfg = make_config(10, 1, 5000, 10, -400.0, 600.0, objective_id=OBJ_GRIEWANK)
     o = Oracle(cfg, MATH_TK); o.solveAtSobolPoints()
