@@ -38,8 +38,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 # algorithmic FP64 flops per Sobol evaluation, SURVEY.md section 8(d) / BASELINE.md section 3
-F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905}
-OBJ_NAME = {"C1": "template", "C2": "Griewank", "C3": "Rastrigin", "C4": "Rosenbrock", "C5": "synthetic SMM"}
+F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905, "X7": 383}  # X7: Griewank 7-D by the same per-coordinate count (54 nx + 5)
+OBJ_NAME = {"C1": "template", "C2": "Griewank", "C3": "Rastrigin", "C4": "Rosenbrock", "C5": "synthetic SMM", "X7": "Griewank"}
 # restarts per round (all blended against the best row of the round's start)
 ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 1184, "C5": 128}
 # asynchronous instances (restart stage, one GPU): how many blocks play the reference's processes -- about four restarts per instance at
@@ -531,6 +531,18 @@ def run_graft(args, rank, world, local_rank):
                 per_workload[wn] = wm
                 if wn == "C3":
                     strong = dict(wm, n_gpus=1)
+            # a dimension WITHOUT a compiled-in instantiation of the Sobol kernel: the library compiles the fixed-nx kernel for it
+            # at run time (NVRTC, csrc/rtc.cu); Sobol stage + selection only
+            from tiktak_b200 import OBJ_GRIEWANK, make_config
+            xcfg = make_config(7, 1, 1_000_000, 1000, -400.0, 600.0, init=[100.0] * 7, objective_id=OBJ_GRIEWANK, round_size=128)
+            xj = Job("X7", xcfg, rank, 1, local_rank, None, no_local=True)
+            xm = xj.measure(flush, 3, 3, sampler)
+            xj.close()
+            xroof, _ = rooflines("X7", xcfg, xm, 1, peak_tf, hbm_gbs, hbm_src)
+            L.tiktak_cuda_debug_rtc_kernels.restype = C.c_int
+            xroof["kernel"] = "sobol_eval_kernel<ObjGriewank, 7, ...> compiled at run time" if L.tiktak_cuda_debug_rtc_kernels() > 0 else "sobol_eval_generic_kernel (runtime nx)"
+            xm.update(roofline=xroof, rtc_kernels_loaded=int(L.tiktak_cuda_debug_rtc_kernels()))
+            per_workload["X7"] = xm
         else:
             scfg = workload_config("C3", world, weak=False)
             sj = Job("C3", scfg, rank, world, local_rank, dist, local_mode=args.local_mode)

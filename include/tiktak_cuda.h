@@ -24,7 +24,9 @@
 #ifndef TIKTAK_CUDA_H
 #define TIKTAK_CUDA_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {

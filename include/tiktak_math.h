@@ -18,9 +18,13 @@
 #ifndef TIKTAK_MATH_H
 #define TIKTAK_MATH_H
 
+#ifndef __CUDACC_RTC__ /* NVRTC (the run-time compiled Sobol kernel, tiktak_b200/csrc/rtc.cu) has these built in */
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#else
+typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long long uint64_t; typedef long long int64_t;
+#endif
 
 #if defined(__CUDACC__)
 #define TK_HD __host__ __device__ __forceinline__

@@ -149,3 +149,22 @@ def test_fortran_patch_applies_to_the_reference(tmp_path):
     f90 = open(os.path.join(ROOT, "fortran", "tiktak_cuda_mod.f90")).read()
     for name in re.findall(r"(tiktak_cuda_\w+)\(", out):
         assert f"NAME='{name}'" in f90, name  # every call of the patched driver is bound by the interface module
+
+
+def test_run_time_compiled_sobol_kernel_sources_build():
+    """rtc.cu: the sources of the fixed-nx Sobol kernel that travel inside the library compile with NVRTC for (objective, nx)
+    pairs that have no compiled-in instantiation -- no device needed for that (libnvrtc cross-compiles for sm_100a)"""
+    import ctypes as C
+
+    from tiktak_b200 import lib
+
+    L = lib.load()
+    L.tiktak_cuda_debug_rtc_compile.restype = C.c_long
+    L.tiktak_cuda_debug_rtc_compile.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    log = C.create_string_buffer(8000)
+    if L.tiktak_cuda_debug_rtc_compile(1, 7, 8, 1, 0, log, 8000) == -1:
+        import pytest
+        pytest.skip("libnvrtc is not installed here")
+    for obj, nx, P, inb, G in ((1, 7, 8, 1, 0), (0, 12, 4, 1, 4), (2, 33, 16, 0, 0), (3, 64, 32, 1, 0), (1, 15, 8, 1, 5), (2, 1, 4, 1, 0)):
+        size = L.tiktak_cuda_debug_rtc_compile(obj, nx, P, inb, G, log, 8000)
+        assert size > 10000, (obj, nx, P, inb, G, size, log.value.decode()[:2000])

@@ -452,6 +452,33 @@ def test_cli_driver_asynchronous_instances(built, tmp_path, monkeypatch):
     assert "as 3 asynchronous instances" in open(tmp_path / "logFile.txt").read()
 
 
+def test_run_time_compiled_sobol_kernel_is_used_and_agrees_with_the_runtime_nx_kernel(built, tmp_path):
+    """(objective, nx) pairs without a compiled-in instantiation get the fixed-nx kernel through NVRTC (rtc.cu); TIKTAK_NO_RTC=1
+    keeps the runtime-nx kernel.  Both against the oracle, bit for bit, with the Sobol box inside and outside the bounds."""
+    import ctypes as C, os, subprocess, sys
+    from tiktak_b200 import lib
+    L = lib.load()
+    for name, kw in (("griewank7", {}), ("rosenbrock33", {}), ("griewank7", dict(bound=[[-30.0, 50.0]] * 7, fvalmax=1e4, legitimate=-1))):
+        cfg = cfg_of(name, **kw)
+        with TikTakSearch(cfg) as s:
+            s.solveAtSobolPoints()
+            f = s.sobolFnVal()
+        o = Oracle(cfg, MATH_TK)
+        o.solveAtSobolPoints()
+        assert np.array_equal(f, o.sobolFnVal()), name
+    assert L.tiktak_cuda_debug_rtc_kernels() >= 3  # (cached per process: earlier tests may have compiled the same kernels)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')\n"
+            "from tiktak_b200 import TikTakSearch, lib\nfrom test_gpu_parity import cfg_of\n"
+            "s = TikTakSearch(cfg_of('griewank7')); s.solveAtSobolPoints(); np.save(%r, s.sobolFnVal()); "
+            "print('rtc kernels', lib.load().tiktak_cuda_debug_rtc_kernels())\n") % (root, root, str(tmp_path / "f.npy"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, TIKTAK_NO_RTC="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "rtc kernels 0" in r.stdout, r.stdout + r.stderr
+    o = Oracle(cfg_of("griewank7"), MATH_TK)
+    o.solveAtSobolPoints()
+    assert np.array_equal(np.load(tmp_path / "f.npy"), o.sobolFnVal())
+
+
 def test_start_selection_large_m(built):
     """more winners than one sort chunk (1024): chunk sort + merge-by-rank passes, odd and even pass counts"""
     for maxpoints, nd in ((1500, 4000), (3000, 20000), (5000, 6000)):

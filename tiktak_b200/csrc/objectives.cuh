@@ -6,10 +6,12 @@
  * order, v_err = f(x) + 1 "for relative criterion" (objective.f90:111).
  */
 #pragma once
+#ifndef __CUDACC_RTC__ /* (the run-time compiled Sobol kernel gets these files pasted in front of this one, rtc.cu) */
 #include <math.h>
 
 #include "../../include/tiktak_cuda.h"
 #include "../../include/tiktak_obj.cuh"
+#endif
 
 struct ObjTemplate { /* val1 = sum x^2/200 ; val2 = cos(x1) * prod cos(x_i/sqrt(i)) ; v = val1 - val2 + 1 + 1 */
     static constexpr int kId = TIKTAK_OBJ_TEMPLATE;
