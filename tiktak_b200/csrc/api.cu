@@ -291,7 +291,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
                     h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_nmq, h->d_counts_spare,
-                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
+                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_nm_pslab, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

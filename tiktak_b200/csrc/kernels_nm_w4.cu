@@ -453,6 +453,17 @@ __device__ void nm_try_commit(const NmArgs& a, const NmQueue& q, int lane) {
     }
 }
 
+/* Where a warp's simplex lives.  In shared memory a 50-D simplex is 20 KB: 10 warps fit an SM, and a single in-order warp per
+ * scheduler exposes every latency (ncu: 14 % warps active, issue slots 27 % busy).  One coordinate pair per lane and one row per
+ * evaluation are all a warp touches between shrinks, coalesced -- so for nx >= 32 (two or more coordinates per lane) the simplex
+ * goes to a per-warp slab of global memory (L1/L2 resident) and the registers, not the shared memory, bound the occupancy
+ * (94 registers: 20 warps per SM).  TK_NMW4_PGLOBAL=0 keeps it in shared memory (experiments). */
+#ifndef TK_NMW4_PGLOBAL
+#define TK_NMW4_PGLOBAL 1
+#endif
+template <int CJ, int LP>
+__host__ __device__ constexpr bool w4_pglobal() { return TK_NMW4_PGLOBAL && LP == 32 && CJ >= 2; }
+
 #ifndef TK_NMW4_MINB
 #define TK_NMW4_MINB 1
 #endif
@@ -477,13 +488,16 @@ __global__ void __launch_bounds__(128, TK_NMW4_MINB) nm_w4_kernel(const TkTables
     NmWarpMem m;
     {
         constexpr int NA = 2 + (nm_uses_b<Obj>() ? 1 : 0) + (Obj::kTermLocal ? 0 : 1); /* arrays of NPT*ts: ta, pn, [tb], [cand] */
-        double* mine = saux + ts + (size_t)w * ((NPT * NA + 1) * ts + (size_t)np * nx);
+        constexpr bool PG = w4_pglobal<CJ, LP>();
+        double* mine = saux + ts + (size_t)w * ((NPT * NA + 1) * ts + (PG ? (size_t)0 : (size_t)np * nx));
         m.ta = mine; m.pn = mine + NPT * ts;
         double* nxt = mine + 2 * NPT * ts;
         m.tb = m.ta; m.cand = m.ta;
         if (nm_uses_b<Obj>()) { m.tb = nxt; nxt += NPT * ts; }
         if (!Obj::kTermLocal) { m.cand = nxt; nxt += NPT * ts; }
-        m.yv = nxt; m.p = nxt + ts;
+        m.yv = nxt;
+        if constexpr (PG) m.p = q.pslab + ((size_t)blockIdx.x * (blockDim.x >> 5) + w) * ((size_t)np * nx);
+        else m.p = nxt + ts;
         m.ts = ts;
     }
     for (int i = threadIdx.x; i < nx; i += blockDim.x) { sbl[i] = T.bl[i]; sbu[i] = T.bu[i]; saux[i] = T.aux[i]; }
@@ -909,7 +923,8 @@ inline size_t w4_warp_doubles(int nx) {
     const int ts = (nx + 2) & ~1;
     const int na = 2 + (nm_uses_b<Obj>() ? 1 : 0) + (Obj::kTermLocal ? 0 : 1);
     const int npt = (32 / w4_lp<Obj>(nx)) * (w4_mode(nx) % 10);
-    return (size_t)(npt * na + 1) * ts + (size_t)(nx + 1) * nx;
+    const bool pg = TK_NMW4_PGLOBAL && w4_lp<Obj>(nx) == 32 && (nx + 1 + 31) / 32 >= 2; /* = w4_pglobal<CJ, LP>() */
+    return (size_t)(npt * na + 1) * ts + (pg ? 0 : (size_t)(nx + 1) * nx);
 }
 /* warps per block: as many as keep a block's shared memory small enough for many blocks per SM, at least one */
 template <class Obj>
@@ -999,7 +1014,19 @@ int tk_launch_nm_w4(tiktak_handle* h, const NmArgs& a, const NmQueue& q) {
             const int useful = q.commit ? std::min(a.n_run, std::max(4 * q.depth0, q.round_size)) : a.n_run;
             const int need = (useful + wpb - 1) / wpb;
             const int grid = std::max(1, std::min(need, bps * h->sm_count));
-            nm_w4_kernel<Obj, CJ, NXC, LP, NC><<<grid, wpb * 32, w4_shmem<Obj>(nx, wpb), h->stream>>>(T, h->sc, a, q);
+            NmQueue qq = q;
+            qq.pslab = nullptr;
+            if (w4_pglobal<CJ, LP>()) { /* the warps' simplices in global memory */
+                const size_t doubles = (size_t)grid * wpb * (size_t)(nx + 1) * nx;
+                if (h->nm_pslab_doubles < doubles) {
+                    if (h->d_nm_pslab) cudaFree(h->d_nm_pslab);
+                    h->d_nm_pslab = nullptr; h->nm_pslab_doubles = 0;
+                    TK_CUDA(cudaMalloc(&h->d_nm_pslab, doubles * sizeof(double)));
+                    h->nm_pslab_doubles = doubles;
+                }
+                qq.pslab = h->d_nm_pslab;
+            }
+            nm_w4_kernel<Obj, CJ, NXC, LP, NC><<<grid, wpb * 32, w4_shmem<Obj>(nx, wpb), h->stream>>>(T, h->sc, a, qq);
             h->launches++;
             TK_CUDA(cudaGetLastError());
             return TIKTAK_OK;

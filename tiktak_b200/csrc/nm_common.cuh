@@ -46,6 +46,7 @@ struct NmQueue {
     int* valid;
     int* arch_evals;
     double* best;     /* [0] fval [1] k [2] #rows [3..] x */
+    double* pslab;    /* simplices of the resident warps when they live in global memory (nm_w4_kernel, nx >= 32): (nx+1)*nx doubles per warp */
 };
 enum { NMQ_HEAD = 0, NMQ_COMMIT = 1, NMQ_LOCK = 2, NMQ_GATE = 3, NMQ_ACCEPTED = 4, NMQ_STREAK = 5, NMQ_DONE0 = 8 };
 

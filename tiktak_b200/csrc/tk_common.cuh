@@ -109,6 +109,8 @@ struct tiktak_handle {
     double *d_xsend = nullptr, *d_xrecv = nullptr;
     size_t xbuf_doubles = 0;
     bool counts_global = false;       /* d_counts holds the all-reduced (global) per-block counts */
+    double* d_nm_pslab = nullptr;     /* simplices of nm_w4_kernel's resident warps (nx >= 32) */
+    size_t nm_pslab_doubles = 0;
     int* d_nmq = nullptr;             /* control words of the throughput Nelder-Mead kernel's restart queue (nm_common.cuh) */
     int blend_w_idx = -1;             /* > 0: the next launch blends with the weight of restart number blend_w_idx (missing-search sweep) */
     TkAsyncRow* d_async_ev = nullptr; /* asynchronous instances (kernels_nm.cu): value, virtual finish time and instance of row k */
