@@ -41,10 +41,10 @@ import numpy as np  # noqa: E402
 F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905, "X7": 383}  # X7: Griewank 7-D by the same per-coordinate count (54 nx + 5)
 OBJ_NAME = {"C1": "template", "C2": "Griewank", "C3": "Rastrigin", "C4": "Rosenbrock", "C5": "synthetic SMM", "X7": "Griewank"}
 # restarts per round (all blended against the best row of the round's start)
-ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 2368, "C5": 128}  # C4: 16 warps per SM of the one-warp kernel (round 1: 1184)
+ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 3552, "C5": 128}  # C4: the 24 warps per SM the one-warp kernel keeps resident (round 1: 1184)
 # asynchronous instances (restart stage, one GPU): how many blocks play the reference's processes -- about four restarts per instance at
 # C2, every resident block at C3 (887) and C5 (147: one block per SM, one SM keeps the time); the library clamps to what is resident
-ASYNC_INSTANCES = {"C1": 4, "C2": 256, "C3": 1024, "C4": 2368, "C5": 147}
+ASYNC_INSTANCES = {"C1": 4, "C2": 256, "C3": 1024, "C4": 3552, "C5": 147}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage's kernel, from the committed `ncu --set full` captures
 TRAFFIC = {"C2": (25088, "profiles/r01d_full_c2_sobol.csv"), "C3": (742264320, "profiles/r01d_full_c3_sobol.csv"),
            "C4": (21494528, "profiles/r01d_full_c4_sobol.csv"), "C5": (1020513512, "profiles/r01c_full_c5_smm.csv (1184 evaluations)")}

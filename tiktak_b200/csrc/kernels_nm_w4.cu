@@ -472,8 +472,14 @@ __host__ __device__ constexpr bool w4_pglobal() { return TK_NMW4_PGLOBAL && LP =
  * (reflection, then expansion OR contraction as minimize.f90:97-105 orders them), for objectives and dimensions where
  * most iterations are a plain accepted reflection and the speculative points would be wasted work (C4: 1.18 evaluations
  * counted per iteration).  CJ = coordinates per lane = ceil((nx+1) / LP). */
+/* resident blocks the kernel is compiled for: with the simplex in global memory (two coordinates per lane: nx = 32..63, C4) the
+ * registers bound the occupancy; 6 blocks of four warps = 80 registers, no spills, 24 warps per SM (measured at C4: 73.7 ms against
+ * 85 ms at 124 registers / 16 warps; 64 registers / 32 warps spill: 83 ms) */
+template <int CJ, int LP, int NC>
+__host__ __device__ constexpr int w4_minb() { return (w4_pglobal<CJ, LP>() && CJ == 2 && NC == 1) ? 6 : TK_NMW4_MINB; }
+
 template <class Obj, int CJ, int NXC, int LP, int NC>
-__global__ void __launch_bounds__(128, TK_NMW4_MINB) nm_w4_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a, const NmQueue q) {
+__global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a, const NmQueue q) {
     extern __shared__ double smem[];
     constexpr int NPT = (32 / LP) * NC; /* points per evaluation pass: four sub-groups (LP = 8), or NC points as parallel chains of one lane */
     static_assert(NC == 1 || (NC == 4 && LP == 32), "NC = 4 goes with LP = 32");

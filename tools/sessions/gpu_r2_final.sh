@@ -10,5 +10,6 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/r2f_smoke.log 2>&1; echo
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-extra"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file $O/r2f_launches_c2.csv $CMD > $O/r2f_ncu1.log 2>&1; echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nm_quad_async_kernel -s 3 -c 1 -o $O/r2f_c2_async $CMD > $O/r2f_ncu2.log 2>&1; echo "c2 async rc=$?"
-C5="python bench.py --workload C5 --steps 1 --warmup 3 --no-cpu --no-extra"
+C4="python bench.py --workload C4 --steps 1 --warmup 3 --no-cpu --no-extra"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:nm_w4_kernel -s 20 -c 1 -o $O/r2f_c4_w4 $C4 > $O/r2f_ncu3.log 2>&1; echo "c4 w4 rc=$?"
 ls -la $O/r2f_*
