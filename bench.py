@@ -324,7 +324,12 @@ class Job:
         t3 = time.perf_counter()
         if not self.no_local:
             if self.local_async:
-                s.LocalMinimizationsAsync(self.alg, instances=ASYNC_INSTANCES[self.name])
+                try:
+                    s.LocalMinimizationsAsync(self.alg, instances=ASYNC_INSTANCES[self.name])
+                except Exception as exc:  # e.g. no cooperative launch on this device: the rounds form always exists
+                    print(f"bench: asynchronous instances unavailable ({exc}); using rounds", file=sys.stderr)
+                    self.local_async = False
+                    s.LocalMinimizations(self.alg)
             else:
                 s.LocalMinimizations(self.alg)
         e4 = self.mark()

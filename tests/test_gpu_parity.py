@@ -479,6 +479,21 @@ def test_run_time_compiled_sobol_kernel_is_used_and_agrees_with_the_runtime_nx_k
     assert np.array_equal(np.load(tmp_path / "f.npy"), o.sobolFnVal())
 
 
+def test_repeated_jobs_on_one_handle_through_the_stage_graph(built):
+    """the one-wave pre-test stage is captured as a CUDA graph on its second and third run (the two counts buffers alternate)
+    and launched as a graph from the fourth on: values, counts and the selection stay those of the first run / the oracle"""
+    cfg = cfg_of("griewank10")
+    o = Oracle(cfg, MATH_TK)
+    _, one, onl = o.solveAtSobolPoints()
+    oxs = o.chooseSobol(mode=1)
+    with TikTakSearch(cfg) as s:
+        for rep in range(6):
+            _, ne, nl = s.solveAtSobolPoints(wait=(rep % 2 == 0))
+            assert ne == one and s.n_legit == onl
+            assert np.array_equal(s.sobolFnVal(), o.sobolFnVal())
+            assert np.array_equal(s.chooseSobol(), oxs)
+
+
 def test_start_selection_large_m(built):
     """more winners than one sort chunk (1024): chunk sort + merge-by-rank passes, odd and even pass counts"""
     for maxpoints, nd in ((1500, 4000), (3000, 20000), (5000, 6000)):

@@ -1180,6 +1180,9 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
     std::vector<int> order(last + 1);
     for (int k = 0; k <= last; k++) order[k] = k;
     if (h->async_rows) { /* the file of an asynchronous run is in the order of the (virtual) finish times, ties by instance */
+        int aerr = 0;
+        TK_CUDA(cudaMemcpy(&aerr, h->d_async_clk + 60 * 1024, sizeof(int), cudaMemcpyDeviceToHost));
+        if (aerr) { tk_set_error("local_async: an instance gave up waiting for the others (the launch was not resident as a whole?)"); return TIKTAK_ERR_STATE; }
         std::vector<TkAsyncRow> ev(last + 1);
         TK_CUDA(cudaMemcpy(ev.data(), h->d_async_ev, ev.size() * sizeof(TkAsyncRow), cudaMemcpyDeviceToHost));
         std::vector<int> fin(last + 1), slt(last + 1);

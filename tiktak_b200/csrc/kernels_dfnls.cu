@@ -1739,8 +1739,14 @@ __global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const T
             tknm::st_vol(q.clk + r, F + cb + 1);
             const int* gvt = q.clk + P + 32 + (r % TK_GVT_COPIES) * 32;
             unsigned ns = 100;
-            while (!(tknm::ld_vol(gvt) > F)) { __nanosleep(ns); if (ns < 1600) ns += ns; }
+            const long long t_wait0 = clock64();
+            while (!(tknm::ld_vol(gvt) > F)) {
+                if (clock64() - t_wait0 > TK_ASYNC_PATIENCE) { atomicExch(q.err, 1); break; } /* never in a healthy run */
+                __nanosleep(ns);
+                if (ns < 1600) ns += ns;
+            }
             __threadfence();
+            if (tknm::ld_vol(q.err)) { tknm::st_vol(q.clk + r, 0x7fffffff); break; }
             Tv = F;
         }
     }

@@ -572,6 +572,7 @@ __global__ void nm_async_init_kernel(const NmAsync q, int P) {
     if (i < P) q.clk[i] = q.cb + q.c0;
     if (i == P) q.clk[P] = min(q.last_k, q.first_k + P - 1);
     if (i < TK_GVT_COPIES) q.clk[P + 32 + i * 32] = 0; /* the time keeper's words */
+    if (i == 0) *q.err = 0;
 }
 
 template <class Obj, int NXC>
@@ -697,11 +698,13 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
             for (;;) {
                 dbg_polls++;
                 if (ld_vol(gvt) > F) break;
+                if (clock64() - t_wait0 > TK_ASYNC_PATIENCE) { if (lane == 0) atomicExch(q.err, 1); break; } /* never in a healthy run */
                 __nanosleep(ns);
                 if (ns < 800) ns += ns;
             }
         }
         __syncthreads();
+        if (ld_vol(q.err)) { if (tid == 0) st_vol(q.clk + s, 0x7fffffff); return; }
         __threadfence();
         dbg_wait += clock64() - t_wait0;
         Tv = F;
@@ -1598,6 +1601,7 @@ int tk_async_setup(tiktak_handle* h, int first_k, int n_k, int c0, NmAsync* q) {
     q->first_k = first_k; q->last_k = first_k + n_k - 1; q->K = K; q->nx = h->cfg.nx; q->roundtrip = h->cfg.text_roundtrip;
     q->xs = h->d_xstarts; q->w11 = h->d_w11; q->res = h->d_res; q->valid = h->d_res_valid; q->arch_evals = h->d_arch_evals;
     q->arch_starts = h->d_arch_starts; q->ev = h->d_async_ev; q->clk = h->d_async_clk;
+    q->err = h->d_async_clk + 60 * 1024; /* (the clock array is 64 K ints: far behind the clocks and the time keeper's words) */
     q->dbg = nullptr;
     if (getenv("TIKTAK_ASYNC_DEBUG")) { static long long* d = nullptr; if (!d) cudaMalloc(&d, 5 * 2048 * sizeof(long long)); q->dbg = d; h->async_dbg = d; }
     q->c0 = c0; q->cb = TIKTAK_ASYNC_PICKUP_TICKS;

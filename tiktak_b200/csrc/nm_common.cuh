@@ -76,11 +76,14 @@ struct NmAsync {
     TkAsyncRow* ev;        /* [K+1] value, virtual finish time (-1: not finished; 0: rows known before the launch) and instance (-1: known
                               before) of row k, one 16-byte record per row for the scans */
     int* clk;              /* [P] lower bound of the instance's next finish time; clk[P]: highest restart number handed out */
+    int* err;              /* set when an instance gave up waiting (TK_ASYNC_PATIENCE cycles without the global time passing its own):
+                              the launch ends instead of hanging the GPU, tiktak_cuda_local_fetch reports it */
     long long* dbg;        /* experiment: per instance [wait cycles, scan cycles, run cycles, restarts, polls] or NULL */
     int c0, cb;            /* ticks of the initial simplex / of a shrink step; ticks an instance needs between two restarts */
 };
 
 #define TK_GVT_COPIES 16
+#define TK_ASYNC_PATIENCE (1ll << 34) /* SM cycles (~9 s) an instance waits for the others before it gives up */
 __device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ void st_vol(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 /* (f, fin, slt, k) of row A before row B: lower value first, then the order of the (virtual) file */
