@@ -283,6 +283,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     for (auto& g : h->stage_graph) if (g) cudaGraphExecDestroy(g);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_fetch) cudaFreeHost(h->h_fetch);
     tk_comm_destroy(h);
     tk_smm_free(h);
     void* ptrs[] = {h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux, h->d_init, h->d_simplex, h->d_w11, h->d_fval,
@@ -1164,12 +1165,24 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
     if (n_k == 0) return TIKTAK_OK;
     const int nx = h->cfg.nx, K = h->cfg.maxpoints_plus1, last = first_k + n_k - 1;
     TK_CUDA(cudaSetDevice(h->device));
-    std::vector<double> hres((size_t)(last + 1) * (nx + 1)), hst((size_t)K * nx);
-    std::vector<int> hval(last + 1), hev(last + 1);
-    TK_CUDA(cudaMemcpyAsync(hres.data(), h->d_res, hres.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaMemcpyAsync(hval.data(), h->d_res_valid, hval.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaMemcpyAsync(hev.data(), h->d_arch_evals, hev.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (starts) TK_CUDA(cudaMemcpyAsync(hst.data(), h->d_arch_starts, hst.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    /* one pinned staging area per handle: the four tables (and the rows of an asynchronous run) come over in one go, asynchronously
+     * (pageable destinations made every copy a staged, synchronous one: 4.5 ms of C3's restart stage) */
+    const size_t n_res = (size_t)(K + 1) * (nx + 1), n_st = (size_t)K * nx, n_i = (size_t)K + 1;
+    if (!h->h_fetch) TK_CUDA(cudaMallocHost(&h->h_fetch, (n_res + n_st) * sizeof(double) + 2 * n_i * sizeof(int) + n_i * sizeof(TkAsyncRow) + 64));
+    double* hres = (double*)h->h_fetch;
+    double* hst = hres + n_res;
+    TkAsyncRow* hrow = (TkAsyncRow*)(hst + n_st + (n_st & 1)); /* 16-byte aligned */
+    int* hval = (int*)(hrow + n_i);
+    int* hev = hval + n_i;
+    int* herr = hev + n_i;
+    TK_CUDA(cudaMemcpyAsync(hres, h->d_res, (size_t)(last + 1) * (nx + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hval, h->d_res_valid, (size_t)(last + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaMemcpyAsync(hev, h->d_arch_evals, (size_t)(last + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (starts) TK_CUDA(cudaMemcpyAsync(hst, h->d_arch_starts, n_st * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h->async_rows) {
+        TK_CUDA(cudaMemcpyAsync(herr, h->d_async_clk + 60 * 1024, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaMemcpyAsync(hrow, h->d_async_ev, (size_t)(last + 1) * sizeof(TkAsyncRow), cudaMemcpyDeviceToHost, h->stream));
+    }
     TK_CUDA(cudaStreamSynchronize(h->stream));
     /* the #improvements column (completeSearch :585-589): previous best row's counter, +1 when strictly lower;
      * rows are taken in restart order k = 0, 1, 2, ... (ties: the earlier row stays the best) */
@@ -1180,13 +1193,9 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
     std::vector<int> order(last + 1);
     for (int k = 0; k <= last; k++) order[k] = k;
     if (h->async_rows) { /* the file of an asynchronous run is in the order of the (virtual) finish times, ties by instance */
-        int aerr = 0;
-        TK_CUDA(cudaMemcpy(&aerr, h->d_async_clk + 60 * 1024, sizeof(int), cudaMemcpyDeviceToHost));
-        if (aerr) { tk_set_error("local_async: an instance gave up waiting for the others (the launch was not resident as a whole?)"); return TIKTAK_ERR_STATE; }
-        std::vector<TkAsyncRow> ev(last + 1);
-        TK_CUDA(cudaMemcpy(ev.data(), h->d_async_ev, ev.size() * sizeof(TkAsyncRow), cudaMemcpyDeviceToHost));
+        if (*herr) { tk_set_error("local_async: an instance gave up waiting for the others (the launch was not resident as a whole?)"); return TIKTAK_ERR_STATE; }
         std::vector<int> fin(last + 1), slt(last + 1);
-        for (int k = 0; k <= last; k++) { fin[k] = ev[k].fin; slt[k] = ev[k].slt; }
+        for (int k = 0; k <= last; k++) { fin[k] = hrow[k].fin; slt[k] = hrow[k].slt; }
         std::stable_sort(order.begin() + 1, order.end(), [&](int x, int y) {
             const int fx = std::max(fin[x], 0), fy = std::max(fin[y], 0);
             if (fx != fy) return fx < fy;
@@ -1213,10 +1222,20 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
         for (int d = 0; d < nx; d++) rows[(size_t)(4 + d) * n_k + s] = valid ? hres[(size_t)k * (nx + 1) + 1 + d] : NAN;
         if (starts) for (int d = 0; d < nx; d++) st[(size_t)d * n_k + s] = hst[(size_t)d * K + (k - 1)];
     }
-    if (starts) TK_CUDA(cudaMemcpy(starts, st.data(), st.size() * 8, cudaMemcpyDefault));
-    if (results) TK_CUDA(cudaMemcpy(results, rows.data(), rows.size() * 8, cudaMemcpyDefault));
-    for (int& e : hev) e &= 0xffffff; /* the high byte is the local search's status (tiktak_cuda_local_status) */
-    if (evals) TK_CUDA(cudaMemcpy(evals, hev.data() + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDefault));
+    /* caller buffers: host memory (the usual case: a plain memcpy) or device memory */
+    auto put = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!is_device_ptr(dst)) { memcpy(dst, src, bytes); return TIKTAK_OK; }
+        TK_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+        return TIKTAK_OK;
+    };
+    int rcp = TIKTAK_OK;
+    if (starts && (rcp = put(starts, st.data(), st.size() * 8))) return rcp;
+    if (results && (rcp = put(results, rows.data(), rows.size() * 8))) return rcp;
+    if (evals) {
+        std::vector<int> ev2(n_k);
+        for (int s = 0; s < n_k; s++) ev2[s] = hev[first_k + s] & 0xffffff; /* the high byte is the local search's status (tiktak_cuda_local_status) */
+        if ((rcp = put(evals, ev2.data(), (size_t)n_k * sizeof(int)))) return rcp;
+    }
     return TIKTAK_OK;
 }
 

@@ -56,6 +56,7 @@ struct tiktak_handle {
     unsigned long long* d_counts = nullptr; /* [n_cblocks] */
     unsigned long long* d_counts_spare = nullptr; /* zeroed twin: the next job swaps to it */
     unsigned long long* h_counts = nullptr; /* pinned host mirror of d_counts */
+    void* h_fetch = nullptr;                /* pinned staging of tiktak_cuda_local_fetch */
     bool counts_copied = false;            /* the whole-stage path has queued the copy of all counts to h_counts already */
     int64_t cblocks_done = 0;
     int64_t kcut = -1, nlegit = 0;
