@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
             __nanosleep(100);
         }
     }
-    long long dbg_wait = 0, dbg_scan = 0, dbg_run = 0, dbg_n = 0, dbg_polls = 0;
+    long long dbg_wait = 0, dbg_scan = 0, dbg_run = 0, dbg_n = 0, dbg_polls = 0, dbg_trips = 0;
     int k = q.first_k + s, Tv = 0; /* the first P restarts start at virtual time 0 and see the rows known before the launch */
     for (;;) {
         const long long t_scan0 = clock64();
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
         }
         if (Tv > 0) k = q.first_k + P + cnt_ev; /* P restarts were taken at time 0, one more at every finish event */
         if (k > q.last_k) {
-            if (tid == 0) { st_vol(q.clk + s, 0x7fffffff); if (q.dbg) { q.dbg[s * 5] = dbg_wait; q.dbg[s * 5 + 1] = dbg_scan; q.dbg[s * 5 + 2] = dbg_run; q.dbg[s * 5 + 3] = dbg_n; q.dbg[s * 5 + 4] = dbg_polls; } }
+            if (tid == 0) { st_vol(q.clk + s, 0x7fffffff); if (q.dbg) { q.dbg[s * 5] = dbg_wait; q.dbg[s * 5 + 1] = dbg_scan; q.dbg[s * 5 + 2] = dbg_run; q.dbg[s * 5 + 3] = dbg_n; q.dbg[s * 5 + 4] = dbg_trips; } }
             return;
         }
         if (tid == 0 && Tv > 0) atomicMax(q.clk + P, k);
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
             }
         }
         const long long t_wait0 = clock64();
-        dbg_run += t_wait0 - t_run0; dbg_n++;
+        dbg_run += t_wait0 - t_run0; dbg_n++; dbg_trips += c0 + o.trips + o.shrinks * c0;
         /* act at virtual time F only when nobody else can still finish at or before it */
         if (w == 0) { /* one warp polls one word; the others park at the barrier */
             const int* gvt = q.clk + P + 32 + (s % TK_GVT_COPIES) * 32;
