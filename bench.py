@@ -309,9 +309,7 @@ class Job:
         flush.zero_()  # evict L2 between steps (untimed)
         self.barrier()
         t0 = time.perf_counter()
-        e0 = self.mark()
         _, ne, nl = s.solveAtSobolPoints(wait=e2e)  # e2e: the stage's counters (lastSobol / legitSobol) are read back
-        e1 = self.mark()
         d2h = 0
         if e2e:  # every stored value streams to pinned host memory on a second stream, beside selection and restarts
             if self.pinned is None:
@@ -377,6 +375,7 @@ class Job:
                "mean_evals_per_restart": float(np.mean(s.evals)) if s.evals is not None else None,
                "evals_in_restarts": float(np.sum(s.evals)) if s.evals is not None else None,
                "local_launches": getattr(s, "local_launches", None), "gpu_launches": int(launches),
+               "rescue_calls": int(np.sum(s.nrescue)) if (self.name == "C5" and getattr(s, "nrescue", None) is not None) else None,  # RESCUE_H entries (DFNLS)
                "local_mode": "async" if self.local_async else "rounds",
                "instances": getattr(s, "instances_used", None) if self.local_async else None,
                "pretest_ms_steps": [round(float(d["pretest_ms"]), 5) for d in dev],
