@@ -386,6 +386,16 @@ class Job:
             self.local_async = True
             out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_launches": getattr(s, "local_launches", None),
                              "restarts_per_s": cfg.p_maxpoints / (np.mean([d["local_ms"] for d in rd]) * 1e-3), "best_fval": s.getBestLine()[0]}
+        if self.local_async and not self.no_local and self.alg == "a":  # ... and as free-running instances (not reproducible: beside, untimed steps)
+            fr = []
+            for _ in range(2):
+                flush.zero_(); self.barrier()
+                s.solveAtSobolPoints(wait=False); s.chooseSobol()
+                ea = self.mark(); s.LocalMinimizationsAsync(self.alg, instances=ASYNC_INSTANCES[self.name], free_running=True); eb = self.mark()
+                self.ext.synchronize()
+                fr.append(ea.elapsed_time(eb))
+            out["free_running"] = {"local_ms": float(np.mean(fr)), "restarts_per_s": cfg.p_maxpoints / (np.mean(fr) * 1e-3), "best_fval": s.getBestLine()[0],
+                                   "note": "no virtual clock: the reference's multi-process semantics literally; verified restart by restart (tests), not reproducible as a whole"}
         if e2e:
             out["e2e_sobol_s"] = self.mx(np.mean([d["wall_pretest"] for d in e2e]))
             out["e2e_step_s"] = self.mx(np.mean([d["wall"] for d in e2e]))
@@ -572,7 +582,7 @@ def run_graft(args, rank, world, local_rank):
                                  "stage's own device work; choose/local: events bracketing the host calls)"},
             "restarts_per_s": m["restarts_per_s"], "mean_evals_per_restart": m["mean_evals_per_restart"],
             "stage_ms": m["stage_ms"], "pretest_ms_steps": m["pretest_ms_steps"], "local_launches": m["local_launches"],
-            "local_mode": m["local_mode"], "instances": m["instances"], "rounds": m.get("rounds"),
+            "local_mode": m["local_mode"], "instances": m["instances"], "rounds": m.get("rounds"), "free_running": m.get("free_running"),
             "roofline": roof, "roofline_local": rl, "cpu_baseline": cpu,
             "e2e": {"value": m["n_evaluated"] / m["e2e_sobol_s"], "unit": "evals/s",
                     "h2d_bytes_per_step": tables_bytes, "d2h_bytes_per_step": m["d2h_total"],

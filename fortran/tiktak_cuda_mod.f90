@@ -69,6 +69,10 @@ MODULE tiktak_cuda_mod
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, first_k, n_k, instances
        INTEGER(C_INT32_T), INTENT(OUT) :: used
      END FUNCTION
+     ! which row each start of an asynchronous run was blended toward (-1: none) and the restart's place in the order of the file
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_async_info(h, first_k, n_k, base, order) BIND(C, NAME='tiktak_cuda_local_async_info')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: base(*), order(*)
+     END FUNCTION
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_async_supported(h, alg, yes) BIND(C, NAME='tiktak_cuda_local_async_supported')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg; INTEGER(C_INT32_T), INTENT(OUT) :: yes
      END FUNCTION

@@ -202,6 +202,12 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
 #define TIKTAK_ASYNC_PICKUP_TICKS 32 /* virtual ticks an instance spends between two restarts (reading the rows, blending the start) */
 int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used);
 int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* yes);
+/* instances < 0 in tiktak_cuda_local_async: |instances| FREE-RUNNING instances (Nelder-Mead) -- no virtual clock: an instance takes the
+ * next restart number from a counter and blends toward the best row committed at that moment, exactly as the reference's processes do
+ * with searchResults.dat.  Like a multi-process run of the reference it is not reproducible run to run; every restart is still the
+ * reference's search from its recorded start.  tiktak_cuda_local_async_info tells, for either form, which row each start was blended
+ * toward (-1: none) and the restart's place in the order of the file. */
+int tiktak_cuda_local_async_info(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* base, int32_t* order);
 /* how each restart's local search ended: 0 = as the reference's would; 2 = DFNLS refused the start (bounds closer than
  * 2 rhobeg, minimize.f90:354-362).  (1 was "stopped where the reference calls RESCUE_H" while RESCUE_H was not on the device.) */
 int tiktak_cuda_local_status(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* status);

@@ -235,6 +235,43 @@ def test_asynchronous_instances_smm_dfnls(built):
     assert used == 4 and np.array_equal(gs, o.searchStart) and np.array_equal(ge, o.evals) and np.array_equal(gr, o.searchResults)
 
 
+def test_free_running_instances_restart_by_restart(built):
+    """instances < 0: no virtual clock -- like the reference's processes, an instance blends toward whatever row is the best one
+    committed when it takes its next restart, so the run is not reproducible as a whole.  Checked restart by restart: every restart
+    ran once; its start is the blend of its Sobol start with the row the library says it used (a row committed before it, or none);
+    and the search from that start is the oracle's, bit for bit (minimum, value, evaluation count)."""
+    import ctypes as C
+    from tiktak_b200._abi import dptr
+    cfg = cfg_of("griewank10", maxpoints=150, round_size=48, text_roundtrip=0)  # (rows as computed, not through the f40.20 record)
+    K, nx = cfg.p_maxpoints, cfg.nx
+    with TikTakSearch(cfg) as s:
+        s.solveAtSobolPoints()
+        xs = s.chooseSobol()
+        s.LocalMinimizationsAsync("a", free_running=True)
+        st, res, ev, base, order, used = s.searchStart, s.searchResults, s.evals, s.async_base, s.async_order, s.instances_used
+    assert used == 48 and sorted(order.tolist()) == list(range(1, K + 1))
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    assert np.array_equal(xs, o.chooseSobol(mode=1))
+    blended = 0
+    for k in range(1, K + 1):
+        b = int(base[k - 1])
+        if b < 0:
+            want = xs[k - 1, 1:]
+        else:
+            assert b == 0 or order[b - 1] < order[k - 1]
+            w = np.float64(min(max(np.float32(0.10), np.sqrt(np.float32(k) / np.float32(K))), np.float32(0.95)))
+            bx = xs[0, 1:] if b == 0 else res[b - 1, 4:]
+            want = w * bx + (1.0 - w) * xs[k - 1, 1:]
+            blended += 1
+        assert np.array_equal(st[k - 1], want), k
+        pt = np.ascontiguousarray(st[k - 1].copy())
+        it = C.c_int32()
+        assert o.L.orc_run_amoeba(o.h, dptr(pt), C.byref(it)) == 0
+        assert np.array_equal(pt, res[k - 1, 4:]) and o.objFun(pt)[0] == res[k - 1, 3] and ev[k - 1] == nx + 1 + it.value + 1, k
+    assert blended >= K - 48  # everything after the first pick-up of each instance saw at least one finished row
+
+
 def test_one_asynchronous_instance_is_the_sequential_run(built):
     """P = 1: the instance sees every earlier row -- the reference's single-process run, i.e. rounds of one restart"""
     cfg = cfg_of("griewank10", maxpoints=25, round_size=1)

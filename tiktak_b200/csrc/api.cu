@@ -292,7 +292,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
                     h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_nmq, h->d_counts_spare,
-                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_nm_pslab, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
+                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_async_base, h->d_nm_pslab, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1073,8 +1073,11 @@ int tiktak_cuda_local_launch(tiktak_handle* h, int32_t alg, int32_t first_k, int
  * (TiktakGlobalSearch.f90:546-600), made reproducible by a virtual clock (kernels_nm.cu, nm_quad_async_kernel).
  * One launch, no rounds, no host round trip; *used = instances actually run (<= the number of resident blocks). */
 int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used) {
-    if (!h || !used || first_k < 1 || n_k < 0 || instances < 1 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (!h || !used || first_k < 1 || n_k < 0 || instances == 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
     *used = 0;
+    const bool free_run = instances < 0; /* -n: n free-running instances (no virtual clock: not reproducible, see the header) */
+    if (free_run) instances = -instances;
+    if (free_run && alg != TIKTAK_ALG_AMOEBA) { tk_set_error("local_async: free-running instances are built for Nelder-Mead"); return TIKTAK_ERR_UNSUPPORTED; }
     if (alg != TIKTAK_ALG_AMOEBA && alg != TIKTAK_ALG_DFNLS) { tk_set_error("local_async: Nelder-Mead or DFNLS"); return TIKTAK_ERR_UNSUPPORTED; }
     if (!h->starts_ready) { tk_set_error("local: choose has not run"); return TIKTAK_ERR_STATE; }
     if (n_k == 0) return TIKTAK_OK;
@@ -1084,13 +1087,32 @@ int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int3
         h->local_timing_open = true;
     }
     int u = 0;
-    int rc = alg == TIKTAK_ALG_AMOEBA ? tk_launch_nm_async(h, first_k, n_k, instances, &u) : tk_launch_dfnls(h, first_k, n_k, instances, &u);
+    int rc = alg == TIKTAK_ALG_AMOEBA ? tk_launch_nm_async(h, first_k, n_k, instances, &u, free_run) : tk_launch_dfnls(h, first_k, n_k, instances, &u);
     if (rc) return rc;
     TK_CUDA(cudaEventRecord(h->evl1, h->stream));
     h->async_rows = true;
     h->best_dirty = false;
     h->n_rows = first_k + n_k; /* (rows with a NaN value are not rows; the exact count is d_best[2]) */
     *used = u;
+    return TIKTAK_OK;
+}
+
+/* what an asynchronous run did with restart k: the row its start was blended toward (-1: none, the raw Sobol start) and its place in
+ * the order of the commits / virtual finish times (the order of the file; ties of the virtual clock share a value) */
+int tiktak_cuda_local_async_info(tiktak_handle* h, int32_t first_k, int32_t n_k, int32_t* base, int32_t* order) {
+    if (!h || first_k < 1 || n_k < 0 || first_k + n_k - 1 > h->cfg.maxpoints_plus1) return TIKTAK_ERR_ARG;
+    if (!h->async_rows || !h->d_async_base) { tk_set_error("local_async_info: the rows are not those of an asynchronous run"); return TIKTAK_ERR_STATE; }
+    if (n_k == 0) return TIKTAK_OK;
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (base) TK_CUDA(cudaMemcpy(base, h->d_async_base + first_k, (size_t)n_k * sizeof(int), cudaMemcpyDefault));
+    if (order) {
+        std::vector<TkAsyncRow> ev(n_k);
+        TK_CUDA(cudaMemcpy(ev.data(), h->d_async_ev + first_k, (size_t)n_k * sizeof(TkAsyncRow), cudaMemcpyDeviceToHost));
+        std::vector<int> o(n_k);
+        for (int i = 0; i < n_k; i++) o[i] = ev[i].fin;
+        TK_CUDA(cudaMemcpy(order, o.data(), (size_t)n_k * sizeof(int), cudaMemcpyDefault));
+    }
     return TIKTAK_OK;
 }
 

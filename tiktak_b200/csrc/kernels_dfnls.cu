@@ -1711,6 +1711,7 @@ __global__ void __launch_bounds__(Obj::kVector ? 512 : 256) dfnls_kernel(const T
             if (Tv > 0) k = q.first_k + P + ctl.i3;
             if (k > q.last_k) { tknm::st_vol(q.clk + r, 0x7fffffff); break; }
             if (Tv > 0) atomicMax(q.clk + P, k);
+            q.base[k] = (cnt_vis > 1 && bk >= 0) ? bk : -1;
             for (int dd = 0; dd < N; dd++) { /* getModifiedParam :683-720 */
                 const double ev = q.xs[(size_t)(dd + 1) * q.K + (k - 1)];
                 double out = ev;

@@ -570,7 +570,7 @@ __global__ void nm_async_init_kernel(const NmAsync q, int P) {
         if (i >= q.first_k && i <= q.last_k) q.valid[i] = 0;
     }
     if (i < P) q.clk[i] = q.cb + q.c0;
-    if (i == P) q.clk[P] = min(q.last_k, q.first_k + P - 1);
+    if (i == P) { q.clk[P] = min(q.last_k, q.first_k + P - 1); q.clk[P + 1] = 0; /* commits so far (free-running) */ }
     if (i < TK_GVT_COPIES) q.clk[P + 32 + i * 32] = 0; /* the time keeper's words */
     if (i == 0) *q.err = 0;
 }
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
         for (int jj = tid; jj <= hi; jj += 128) {
             const int4 raw = __ldcg(reinterpret_cast<const int4*>(q.ev + jj));
             const int tj = raw.z, sj = raw.w;
-            if (tj < 0 || tj > Tv) continue;
+            if (tj < 0 || (!q.free_run && tj > Tv)) continue;
             if (jj >= q.first_k && (tj < Tv || sj < s)) cnt_ev++;
             const double fj = __hiloint2double(raw.y, raw.x);
             if (!(fj == fj)) continue; /* a NaN value is no row (ingest_kernel) */
@@ -645,12 +645,20 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
             if (r_k[o] >= 0 && (bk < 0 || nm_row_before(r_f[o], r_t[o], r_s[o], r_k[o], bf, bt, bs, bk))) { bf = r_f[o]; bt = r_t[o]; bs = r_s[o]; bk = r_k[o]; }
             cnt_vis += r_cnt[o]; cnt_ev += r_ev[o];
         }
-        if (Tv > 0) k = q.first_k + P + cnt_ev; /* P restarts were taken at time 0, one more at every finish event */
+        if (q.free_run) { /* the next number from the counter (clk[P]: highest number handed out) */
+            if (Tv > 0) {
+                __syncthreads();
+                if (tid == 0) r_ev[0] = atomicAdd(q.clk + P, 1) + 1;
+                __syncthreads();
+                k = r_ev[0];
+            }
+        } else if (Tv > 0) k = q.first_k + P + cnt_ev; /* P restarts were taken at time 0, one more at every finish event */
         if (k > q.last_k) {
             if (tid == 0) { st_vol(q.clk + s, 0x7fffffff); if (q.dbg) { q.dbg[s * 5] = dbg_wait; q.dbg[s * 5 + 1] = dbg_scan; q.dbg[s * 5 + 2] = dbg_run; q.dbg[s * 5 + 3] = dbg_n; q.dbg[s * 5 + 4] = dbg_trips; } }
             return;
         }
-        if (tid == 0 && Tv > 0) atomicMax(q.clk + P, k);
+        if (tid == 0 && Tv > 0 && !q.free_run) atomicMax(q.clk + P, k);
+        if (tid == 0) q.base[k] = (cnt_vis > 1 && bk >= 0) ? bk : -1;
         /* getModifiedParam (:683-720), unfused; the searchStart.dat row */
         for (int d = tid; d < nx; d += 128) {
             const double ev = q.xs[(size_t)(d + 1) * q.K + (k - 1)];
@@ -668,7 +676,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
         dbg_scan += t_run0 - t_scan0;
         const NmQuadOut o = nm_quad_search<Obj, NXC>(ctx, a, nx, false, sbl, sbu, yv, yx, mine, [&](int i) { return st[i]; },
                                                      [&](int trips, int shrinks) { if (tid == 0) st_vol(q.clk + s, T0 + cb + c0 + trips + shrinks * c0); });
-        const int F = T0 + cb + c0 + o.trips + o.shrinks * c0;
+        int F = T0 + cb + c0 + o.trips + o.shrinks * c0;
         /* completeSearch :582-597: the row of restart k (through the f40.20 record when the text round trip is on) */
         if (w == 0) {
             double* dst = q.res + (size_t)k * (nx + 1);
@@ -682,6 +690,8 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
                 q.arch_evals[k] = np + o.iter + 1;
             }
             __syncwarp();
+            if (q.free_run) F = 1 + (lane == 0 ? atomicAdd(q.clk + P + 1, 1) : 0); /* the order of the commits is the order of the file */
+            F = __shfl_sync(0xffffffffu, F, 0);
             if (lane == 0) {
                 __threadfence();
                 st_vol(&q.ev[k].fin, F);            /* the finish event exists from here on ... */
@@ -692,6 +702,12 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
         const long long t_wait0 = clock64();
         dbg_run += t_wait0 - t_run0; dbg_n++; dbg_trips += c0 + o.trips + o.shrinks * c0;
         /* act at virtual time F only when nobody else can still finish at or before it */
+        if (q.free_run) { /* nobody waits for anybody */
+            __syncthreads();
+            __threadfence();
+            Tv = 1;
+            continue;
+        }
         if (w == 0) { /* one warp polls one word; the others park at the barrier */
             const int* gvt = q.clk + P + 32 + (s % TK_GVT_COPIES) * 32;
             unsigned ns = 100;
@@ -1561,7 +1577,7 @@ bool tk_nm_async_supported(tiktak_handle* h) {
     return ok;
 }
 
-int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used) {
+int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used, bool free_run) {
     const int nx = h->cfg.nx, np = nx + 1, K = h->cfg.maxpoints_plus1;
     if (!tk_nm_async_supported(h)) { tk_set_error("local_async: Nelder-Mead with a scalar objective, nx <= 31, search_type 0, nm_shrink_mode 0, one GPU"); return TIKTAK_ERR_UNSUPPORTED; }
     NmArgs a;
@@ -1577,6 +1593,7 @@ int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, in
     NmAsync q;
     int rc0 = tk_async_setup(h, first_k, n_k, (np + 3) / 4, &q);
     if (rc0) return rc0;
+    q.free_run = free_run ? 1 : 0;
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     const int ts = (nx + 2) & ~1;
     const size_t shmem = (size_t)(4 * ts + 8 + ts + 4 * (5 * ts + np * nx)) * sizeof(double);
@@ -1604,6 +1621,9 @@ int tk_async_setup(tiktak_handle* h, int first_k, int n_k, int c0, NmAsync* q) {
     q->err = h->d_async_clk + 60 * 1024; /* (the clock array is 64 K ints: far behind the clocks and the time keeper's words) */
     q->dbg = nullptr;
     if (getenv("TIKTAK_ASYNC_DEBUG")) { static long long* d = nullptr; if (!d) cudaMalloc(&d, 5 * 2048 * sizeof(long long)); q->dbg = d; h->async_dbg = d; }
+    if (!h->d_async_base) TK_CUDA(cudaMalloc(&h->d_async_base, (size_t)(K + 1) * sizeof(int)));
+    q->base = h->d_async_base;
+    q->free_run = 0;
     q->c0 = c0; q->cb = TIKTAK_ASYNC_PICKUP_TICKS;
     if (const char* e = getenv("TIKTAK_ASYNC_CB")) q->cb = atoi(e); /* experiment */
     return TIKTAK_OK;

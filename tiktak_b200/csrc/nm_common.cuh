@@ -79,6 +79,9 @@ struct NmAsync {
     int* err;              /* set when an instance gave up waiting (TK_ASYNC_PATIENCE cycles without the global time passing its own):
                               the launch ends instead of hanging the GPU, tiktak_cuda_local_fetch reports it */
     long long* dbg;        /* experiment: per instance [wait cycles, scan cycles, run cycles, restarts, polls] or NULL */
+    int free_run;          /* 1: no virtual clock -- an instance takes the next restart number from a counter and sees whatever rows are
+                              committed at that moment, like the reference's processes (not reproducible run to run); fin = commit order */
+    int* base;             /* [K+1] the row restart k was blended toward (-1: none): lets a free-running run be verified restart by restart */
     int c0, cb;            /* ticks of the initial simplex / of a shrink step; ticks an instance needs between two restarts */
 };
 

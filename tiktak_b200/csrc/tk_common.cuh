@@ -116,6 +116,7 @@ struct tiktak_handle {
     int blend_w_idx = -1;             /* > 0: the next launch blends with the weight of restart number blend_w_idx (missing-search sweep) */
     TkAsyncRow* d_async_ev = nullptr; /* asynchronous instances (kernels_nm.cu): value, virtual finish time and instance of row k */
     int* d_async_clk = nullptr;       /* ... and the instances' clocks */
+    int* d_async_base = nullptr;      /* ... and the row each restart was blended toward */
     long long* async_dbg = nullptr;   /* experiment counters (TIKTAK_ASYNC_DEBUG) */
     bool async_rows = false;          /* the rows of the table were written by an asynchronous run: local_fetch orders them by (finish time, instance) */
     int nm_form = -1;                 /* 1: one warp per restart (kernels_nm_w4.cu), 0: four warps per restart (kernels_nm.cu), -1: not decided yet */
@@ -147,7 +148,7 @@ int tk_launch_best(tiktak_handle* h);
 int tk_launch_blend(tiktak_handle* h, int first_k, int n_k, int w_idx = -1);
 int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count, int w_idx = -1);
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size = 0);
-int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used);
+int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used, bool free_run = false);
 bool tk_nm_async_supported(tiktak_handle* h);
 bool tk_nm_use_w4(tiktak_handle* h);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k, int instances = 0, int* used = nullptr);

@@ -259,7 +259,7 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_local_async_supported(self._h, _ALG[algor], C.byref(yes)), "local_async_supported")
         return bool(yes.value)
 
-    def LocalMinimizationsAsync(self, algor="a", instances=None):
+    def LocalMinimizationsAsync(self, algor="a", instances=None, free_running=False):
         """Every restart by `instances` asynchronous instances (default: cfg.round_size) -- the reference's multi-process mode on
         one GPU, one kernel launch (tiktak_cuda_local_async; DESIGN.md "asynchronous instances").  Sets searchStart,
         searchResults, evals and `instances_used`."""
@@ -267,8 +267,12 @@ class TikTakSearch:
         K, nx = self.K, self.cfg.nx
         P = max(1, int(self.cfg.round_size if instances is None else instances))
         used = C.c_int32()
-        _lib.check(self._L.tiktak_cuda_local_async(self._h, alg, 1, K, P, C.byref(used)), "LocalMinimizationsAsync")
+        _lib.check(self._L.tiktak_cuda_local_async(self._h, alg, 1, K, -P if free_running else P, C.byref(used)), "LocalMinimizationsAsync")
         self.instances_used = used.value
+        base, order = np.zeros(K, dtype=np.int32), np.zeros(K, dtype=np.int32)
+        _lib.check(self._L.tiktak_cuda_local_async_info(self._h, 1, K, base.ctypes.data_as(C.POINTER(C.c_int32)), order.ctypes.data_as(C.POINTER(C.c_int32))),
+                   "local_async_info")
+        self.async_base, self.async_order = base, order  # the row each start was blended toward (-1: none); place in the file order
         self.local_launches = 1
         s = np.empty((nx, K), dtype=np.float64)
         r = np.empty((nx + 4, K), dtype=np.float64)
