@@ -575,7 +575,8 @@ __global__ void nm_async_init_kernel(const NmAsync q, int P) {
     if (i == 0) *q.err = 0;
 }
 
-template <class Obj, int NXC>
+/* FREE: free-running instances (a template parameter: the reproducible form keeps its 84 registers = six blocks per SM) */
+template <class Obj, int NXC, bool FREE>
 __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a, const NmAsync q) {
     extern __shared__ double smem[];
     __shared__ double r_f[4];
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
         for (int jj = tid; jj <= hi; jj += 128) {
             const int4 raw = __ldcg(reinterpret_cast<const int4*>(q.ev + jj));
             const int tj = raw.z, sj = raw.w;
-            if (tj < 0 || (!q.free_run && tj > Tv)) continue;
+            if (tj < 0 || (!FREE && tj > Tv)) continue;
             if (jj >= q.first_k && (tj < Tv || sj < s)) cnt_ev++;
             const double fj = __hiloint2double(raw.y, raw.x);
             if (!(fj == fj)) continue; /* a NaN value is no row (ingest_kernel) */
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
             if (r_k[o] >= 0 && (bk < 0 || nm_row_before(r_f[o], r_t[o], r_s[o], r_k[o], bf, bt, bs, bk))) { bf = r_f[o]; bt = r_t[o]; bs = r_s[o]; bk = r_k[o]; }
             cnt_vis += r_cnt[o]; cnt_ev += r_ev[o];
         }
-        if (q.free_run) { /* the next number from the counter (clk[P]: highest number handed out) */
+        if (FREE) { /* the next number from the counter (clk[P]: highest number handed out) */
             if (Tv > 0) {
                 __syncthreads();
                 if (tid == 0) r_ev[0] = atomicAdd(q.clk + P, 1) + 1;
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
             if (tid == 0) { st_vol(q.clk + s, 0x7fffffff); if (q.dbg) { q.dbg[s * 5] = dbg_wait; q.dbg[s * 5 + 1] = dbg_scan; q.dbg[s * 5 + 2] = dbg_run; q.dbg[s * 5 + 3] = dbg_n; q.dbg[s * 5 + 4] = dbg_trips; } }
             return;
         }
-        if (tid == 0 && Tv > 0 && !q.free_run) atomicMax(q.clk + P, k);
+        if (tid == 0 && Tv > 0 && !FREE) atomicMax(q.clk + P, k);
         if (tid == 0) q.base[k] = (cnt_vis > 1 && bk >= 0) ? bk : -1;
         /* getModifiedParam (:683-720), unfused; the searchStart.dat row */
         for (int d = tid; d < nx; d += 128) {
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
                 q.arch_evals[k] = np + o.iter + 1;
             }
             __syncwarp();
-            if (q.free_run) F = 1 + (lane == 0 ? atomicAdd(q.clk + P + 1, 1) : 0); /* the order of the commits is the order of the file */
+            if (FREE) F = 1 + (lane == 0 ? atomicAdd(q.clk + P + 1, 1) : 0); /* the order of the commits is the order of the file */
             F = __shfl_sync(0xffffffffu, F, 0);
             if (lane == 0) {
                 __threadfence();
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(128, TK_NMQ_MINB) nm_quad_async_kernel(const T
         const long long t_wait0 = clock64();
         dbg_run += t_wait0 - t_run0; dbg_n++; dbg_trips += c0 + o.trips + o.shrinks * c0;
         /* act at virtual time F only when nobody else can still finish at or before it */
-        if (q.free_run) { /* nobody waits for anybody */
+        if (FREE) { /* nobody waits for anybody */
             __syncthreads();
             __threadfence();
             Tv = 1;
@@ -1440,7 +1441,7 @@ __global__ void best_async_kernel(const double* res, const int* valid, const TkA
 
 template <class Obj, int NXC>
 static int nm_launch_async(tiktak_handle* h, const TkTablesG& T, const NmArgs& a, NmAsync q, size_t shmem, int want, int* used) {
-    auto kern = nm_quad_async_kernel<Obj, NXC>;
+    auto kern = q.free_run ? nm_quad_async_kernel<Obj, NXC, true> : nm_quad_async_kernel<Obj, NXC, false>;
     TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     int per_sm = 0;
     TK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, shmem));
