@@ -43,8 +43,9 @@ OBJ_NAME = {"C1": "template", "C2": "Griewank", "C3": "Rastrigin", "C4": "Rosenb
 # restarts per round (all blended against the best row of the round's start)
 ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 3552, "C5": 128}  # C4: the 24 warps per SM the one-warp kernel keeps resident (round 1: 1184)
 # asynchronous instances (restart stage, one GPU): how many blocks play the reference's processes -- about four restarts per instance at
-# C2, every resident block at C3 (887) and C5 (147: one block per SM, one SM keeps the time); the library clamps to what is resident
-ASYNC_INSTANCES = {"C1": 4, "C2": 256, "C3": 1024, "C4": 3552, "C5": 147}
+# C2 (four-warp blocks), every resident WARP at C3 (2956) and C4 (3548) -- asking for at least 12 per SM selects the one-warp instances
+# (tiktak_cuda_local_async_clock) -- and C5 (147: one block per SM, one SM keeps the time); the library clamps to what is resident
+ASYNC_INSTANCES = {"C1": 4, "C2": 256, "C3": 4096, "C4": 4096, "C5": 147}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage's kernel, from the committed `ncu --set full` captures
 TRAFFIC = {"C2": (25088, "profiles/r01d_full_c2_sobol.csv"), "C3": (742264320, "profiles/r01d_full_c3_sobol.csv"),
            "C4": (21494528, "profiles/r01d_full_c4_sobol.csv"), "C5": (1020513512, "profiles/r01c_full_c5_smm.csv (1184 evaluations)")}
@@ -378,6 +379,9 @@ class Job:
                "rescue_calls": int(np.sum(s.nrescue)) if (self.name == "C5" and getattr(s, "nrescue", None) is not None) else None,  # RESCUE_H entries (DFNLS)
                "local_mode": "async" if self.local_async else "rounds",
                "instances": getattr(s, "instances_used", None) if self.local_async else None,
+               "instance_form": (("one warp (nm_w4_kernel), tick = objective evaluation" if s.asyncClock(self.alg, ASYNC_INSTANCES[self.name]) == 1 and self.alg == "a"
+                                  else "four-warp block (nm_quad_async_kernel), tick = loop trip" if self.alg == "a" else "block (dfnls_kernel), tick = objective evaluation")
+                                 if self.local_async else None),
                "pretest_ms_steps": [round(float(d["pretest_ms"]), 5) for d in dev],
                "best_fval": None if self.no_local else s.getBestLine()[0]}
         if self.local_async and not self.no_local:  # the same restarts as rounds of round_size, beside (untimed steps)
@@ -386,7 +390,7 @@ class Job:
             self.local_async = True
             out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_launches": getattr(s, "local_launches", None),
                              "restarts_per_s": cfg.p_maxpoints / (np.mean([d["local_ms"] for d in rd]) * 1e-3), "best_fval": s.getBestLine()[0]}
-        if self.local_async and not self.no_local and self.alg == "a":  # ... and as free-running instances (not reproducible: beside, untimed steps)
+        if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31:  # ... and as free-running instances (not reproducible: beside, untimed steps)
             fr = []
             for _ in range(3):
                 flush.zero_(); self.barrier()
@@ -438,7 +442,9 @@ def rooflines(name, cfg, m, world, peak_tf, hbm_gbs, hbm_src):
     if m.get("evals_in_restarts") and m["stage_ms"]["local"] > 0 and name != "C5":
         ach = m["evals_in_restarts"] * F_ALG[name] / (m["stage_ms"]["local"] * 1e-3) / 1e12
         asy = m.get("local_mode") == "async"
-        local = {"bound": "latency", "kernel": ("nm_quad_async_kernel (four warps per restart, %s asynchronous instances, one launch)" % m.get("instances")) if asy else
+        w1 = asy and "one warp" in (m.get("instance_form") or "")
+        local = {"bound": "latency", "kernel": (("nm_w4_kernel (one warp per restart, %s asynchronous instances, one launch)" if w1 else
+                                                 "nm_quad_async_kernel (four warps per restart, %s asynchronous instances, one launch)") % m.get("instances")) if asy else
                  ("nm_quad_kernel (four warps per restart)" if cfg.nx <= 31 else "nm_w4_kernel (one warp per restart, device-side restart queue)"),
                  "achieved": ach, "peak": peak_tf * world, "unit": "TFLOP/s", "frac": ach / (peak_tf * world),
                  "objective_evals_per_step": m["evals_in_restarts"], "share_of_step": m["stage_ms"]["local"] / step_ms,
@@ -488,7 +494,7 @@ def parity_block(rank, world, local_rank):
                     s.chooseSobol()
                     s.LocalMinimizationsAsync("a")
                     res, st, ev, best, used = s.searchResults, s.searchStart, s.evals, s.getBestLine(), s.instances_used
-                    o.LocalMinimizationsAsync(used)
+                    o.LocalMinimizationsAsync(used, clock=s.asyncClock("a"))
                     checks = {"starts": bool(np.array_equal(st, o.searchStart)), "results": bool(np.array_equal(res, o.searchResults)),
                               "evals": bool(np.array_equal(ev, o.evals)), "best": best[0] == o.getBestLine()[0], "instances": int(used)}
                     detail[cname + "_async"] = checks

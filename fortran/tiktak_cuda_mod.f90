@@ -76,6 +76,10 @@ MODULE tiktak_cuda_mod
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_async_supported(h, alg, yes) BIND(C, NAME='tiktak_cuda_local_async_supported')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg; INTEGER(C_INT32_T), INTENT(OUT) :: yes
      END FUNCTION
+     ! the tick of the virtual clock: 0 = pass of amoeba's loop (four-warp instances), 1 = objective evaluation (one-warp instances, DFNLS)
+     INTEGER(C_INT) FUNCTION tiktak_cuda_local_async_clock(h, alg, instances, clock) BIND(C, NAME='tiktak_cuda_local_async_clock')
+       IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: alg, instances; INTEGER(C_INT32_T), INTENT(OUT) :: clock
+     END FUNCTION
      ! RESCUE_H calls of each restart's DFNLS search (minimize.f90:643-650)
      INTEGER(C_INT) FUNCTION tiktak_cuda_local_nrescue(h, first_k, n_k, nrescue) BIND(C, NAME='tiktak_cuda_local_nrescue')
        IMPORT; TYPE(C_PTR), VALUE :: h; INTEGER(C_INT32_T), VALUE :: first_k, n_k; INTEGER(C_INT32_T) :: nrescue(*)

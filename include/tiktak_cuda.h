@@ -202,6 +202,15 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
 #define TIKTAK_ASYNC_PICKUP_TICKS 32 /* virtual ticks an instance spends between two restarts (reading the rows, blending the start) */
 int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used);
 int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* yes);
+/* The tick of the virtual clock.  TRIPS: Nelder-Mead with a block of four warps as the instance (nx <= 31, the default there): a restart
+ * costs PICKUP + c0 + trips + shrinks * c0 ticks, c0 = ceil((nx+1)/4).  EVALS: a restart costs PICKUP + its objective evaluations --
+ * DFNLS, and Nelder-Mead with ONE WARP as the instance (the throughput form: 3.3 times as many instances per GPU, less than half the
+ * instructions per evaluation) -- taken for nx 32..127 and whenever `instances` is at least twice what the GPU holds as four-warp
+ * blocks (12 per SM: 1776 on a B200); TIKTAK_ASYNC_FORM=quad|w4 in the environment overrides.  Positive `instances` only (free-running
+ * instances have no clock). */
+#define TIKTAK_ASYNC_CLOCK_TRIPS 0
+#define TIKTAK_ASYNC_CLOCK_EVALS 1
+int tiktak_cuda_local_async_clock(tiktak_handle* h, int32_t alg, int32_t instances, int32_t* clock);
 /* instances < 0 in tiktak_cuda_local_async: |instances| FREE-RUNNING instances (Nelder-Mead) -- no virtual clock: an instance takes the
  * next restart number from a counter and blends toward the best row committed at that moment, exactly as the reference's processes do
  * with searchResults.dat.  Like a multi-process run of the reference it is not reproducible run to run; every restart is still the

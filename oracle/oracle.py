@@ -158,9 +158,13 @@ class Oracle:
         self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
         return True
 
-    def LocalMinimizationsAsync(self, instances, algor=1):
-        """the asynchronous-instances run (Oracle::local_async); sets searchStart / searchResults / evals / fin / inst"""
+    def LocalMinimizationsAsync(self, instances, algor=1, clock=0):
+        """the asynchronous-instances run (Oracle::local_async); sets searchStart / searchResults / evals / fin / inst.
+        clock (Nelder-Mead): 0 = a tick per pass of amoeba's loop, 1 = a tick per objective evaluation (tiktak_cuda_local_async_clock)"""
         K, nx = self.K, self.cfg.nx
+        self.L.orc_set_async_clock.argtypes = [C.c_void_p, C.c_int]
+        self.L.orc_set_async_clock.restype = None
+        self.L.orc_set_async_clock(self.h, int(clock))
         s = np.empty((nx, K)); r = np.empty((nx + 4, K)); e = np.zeros(K, dtype=np.int32)
         fin = np.zeros(K, dtype=np.int32); inst = np.zeros(K, dtype=np.int32)
         self.L.orc_local_async.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]

@@ -648,6 +648,7 @@ struct Oracle {
     /* LocalMinimizations (:473-544) + getModifiedParam (:683-720) + completeSearch (:546-600),
      * restarts 1..K, `round_size` restarts share the best-so-far of the round's start. */
     int local(int alg, int round_size, double* starts_out, double* results_out, int32_t* evals_out, int k_first = 1);
+    int async_clock = TIKTAK_ASYNC_CLOCK_TRIPS; /* Nelder-Mead: the tick of local_async's virtual clock (tiktak_cuda_local_async_clock) */
     int local_async(int alg, int instances, double* starts_out, double* results_out, int32_t* evals_out, int32_t* fin_out, int32_t* inst_out);
     int missing_search(int alg, int k, double* start_out, double* row_out, int32_t* evals_out);
     int dfnls(std::vector<double>& x, double rhobeg, double rhoend, int maxfun, int& nf, int& nrescue);
@@ -839,7 +840,7 @@ int Oracle::local_async(int alg, int instances, double* starts_out, double* resu
             simplex_width(k, rows, 1, width);
             int iters = 0;
             runAmoeba(evalParam, width, iters);
-            steps = TIKTAK_ASYNC_PICKUP_TICKS + c0 + amoeba_trips + amoeba_shrinks * c0;
+            steps = TIKTAK_ASYNC_PICKUP_TICKS + c0 + amoeba_trips + amoeba_shrinks * c0; /* TIKTAK_ASYNC_CLOCK_TRIPS; EVALS: below */
         } else { /* DFNLS: the tick is one objective evaluation (for the SMM objective: one pass over the panel) */
             const double itratio = (double)((float)k / (float)K);
             double mn = bu()[0] - bl()[0];
@@ -852,7 +853,7 @@ int Oracle::local_async(int alg, int instances, double* starts_out, double* resu
             steps = 0;
         }
         const double fn_val = objFun(evalParam.data()); /* :582 */
-        if (alg == TIKTAK_ALG_DFNLS) steps = TIKTAK_ASYNC_PICKUP_TICKS + (int)(nfev - nfev0);
+        if (alg == TIKTAK_ALG_DFNLS || async_clock == TIKTAK_ASYNC_CLOCK_EVALS) steps = TIKTAK_ASYNC_PICKUP_TICKS + (int)(nfev - nfev0);
         if (evals_out) evals_out[k - 1] = (int32_t)(nfev - nfev0);
         Row r;
         r.seq = seqNo; r.k = k; r.imp = 0;
@@ -1067,6 +1068,7 @@ long orc_nfev(void* h) { return ((Oracle*)h)->nfev; }
 long orc_best_tie_events(void* h) { return ((Oracle*)h)->best_tie_events; }
 
 /* one Nelder-Mead restart from `start` exactly as runAmoeba does it for restart k (width = p_range) */
+void orc_set_async_clock(void* h, int clock) { ((Oracle*)h)->async_clock = clock; }
 int orc_local_async(void* h, int alg, int instances, double* starts, double* results, int32_t* evals, int32_t* fin, int32_t* inst) {
     return ((Oracle*)h)->local_async(alg, instances, starts, results, evals, fin, inst);
 }

@@ -180,13 +180,13 @@ def test_asynchronous_instances(built, name, P, nm, K):
         s.solveAtSobolPoints()
         s.chooseSobol()
         s.LocalMinimizationsAsync("a")
-        gs, gr, ge, used = s.searchStart, s.searchResults, s.evals, s.instances_used
+        gs, gr, ge, used, clock = s.searchStart, s.searchResults, s.evals, s.instances_used, s.asyncClock("a")
         gbest = s.getBestLine()
     assert used == min(P, cfg.p_maxpoints)
     o = Oracle(cfg, MATH_TK)
     o.solveAtSobolPoints()
     o.chooseSobol(mode=1)
-    o.LocalMinimizationsAsync(used)
+    o.LocalMinimizationsAsync(used, clock=clock)
     assert np.array_equal(gs, o.searchStart), "blended start points differ"
     assert np.array_equal(ge, o.evals)
     assert np.array_equal(gr, o.searchResults)
@@ -196,6 +196,39 @@ def test_asynchronous_instances(built, name, P, nm, K):
         assert len(set(o.inst.tolist())) == used
         if cfg.p_maxpoints > 2 * used:
             assert np.any(np.diff(o.fin) < 0)
+
+
+@pytest.mark.parametrize("name,P,nm,K,mode", [("griewank10", 16, 3, 40, None), ("griewank10", 64, 1, 200, None), ("rastrigin20", 30, 2, 30, None),
+                                               ("rastrigin20", 200, 1, 600, None), ("template4", 3, 8, 3, None), ("griewank7", 1, 1, 10, None),
+                                               ("rosenbrock33", 5, 1, 12, None), ("rosenbrock50", 40, 1, 90, None), ("rastrigin20", 30, 1, 60, "324"),
+                                               ("griewank10", 20, 1, 50, "81")])
+def test_asynchronous_instances_one_warp(built, monkeypatch, name, P, nm, K, mode):
+    """the throughput form of the asynchronous run: ONE WARP is the instance (nm_w4_kernel with NmQueue.aq; nx 32..127 by default,
+    TIKTAK_ASYNC_FORM=w4 below that), the tick of the virtual clock is one objective evaluation (TIKTAK_ASYNC_CLOCK_EVALS) --
+    against the oracle's event simulation on that clock, bit for bit"""
+    monkeypatch.setenv("TIKTAK_ASYNC_FORM", "w4")
+    if mode:
+        monkeypatch.setenv("TIKTAK_ASYNC_MODE", mode)
+    cfg = cfg_of(name, nm=nm, maxpoints=K, round_size=P)
+    with TikTakSearch(cfg) as s:
+        assert s.asyncSupported("a") and s.asyncClock("a") == 1
+        s.solveAtSobolPoints()
+        s.chooseSobol()
+        s.LocalMinimizationsAsync("a")
+        gs, gr, ge, used = s.searchStart, s.searchResults, s.evals, s.instances_used
+        gbest = s.getBestLine()
+    assert used == min(P, cfg.p_maxpoints)
+    o = Oracle(cfg, MATH_TK)
+    o.solveAtSobolPoints()
+    o.chooseSobol(mode=1)
+    o.LocalMinimizationsAsync(used, clock=1)
+    assert np.array_equal(gs, o.searchStart), "blended start points differ"
+    assert np.array_equal(ge, o.evals)
+    assert np.array_equal(gr, o.searchResults)
+    ob = o.getBestLine()
+    assert gbest[0] == ob[0] and gbest[2] == ob[2]
+    if used > 1:
+        assert len(set(o.inst.tolist())) == used
 
 
 @pytest.mark.parametrize("name,P,nm,K", [("template4", 3, 8, 9), ("griewank7", 4, 3, 10), ("griewank10", 16, 6, 40), ("rosenbrock33", 5, 4, 12)])

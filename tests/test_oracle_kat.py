@@ -229,9 +229,9 @@ def test_asynchronous_instances_event_simulation(built):
     oa.solveAtSobolPoints(); xs = oa.chooseSobol(mode=1); oa.LocalMinimizationsAsync(1)
     assert np.array_equal(o1.searchStart, oa.searchStart) and np.array_equal(o1.searchResults, oa.searchResults) and np.array_equal(o1.evals, oa.evals)
     assert np.all(np.diff(oa.fin) > 0) and np.all(oa.inst == 0)
-    for alg, P in ((1, 5), (1, 12), (0, 4)):
+    for alg, P, clock in ((1, 5, 0), (1, 12, 0), (0, 4, 0), (1, 5, 1), (1, 12, 1)):  # clock 1: the one-warp instances' (tick = evaluation)
         o = Oracle(cfg, MATH_TK)
-        o.solveAtSobolPoints(); xs = o.chooseSobol(mode=1); o.LocalMinimizationsAsync(P, algor=alg)
+        o.solveAtSobolPoints(); xs = o.chooseSobol(mode=1); o.LocalMinimizationsAsync(P, algor=alg, clock=clock)
         fin, inst, res, st = o.fin.astype(np.int64), o.inst, o.searchResults, o.searchStart
         f0 = xs[0, 0]                                    # the k = 0 record: the value of the initial guess
         free = np.zeros(P, dtype=np.int64)
@@ -250,6 +250,8 @@ def test_asynchronous_instances_event_simulation(built):
                 want = w * base + (1.0 - w) * xs[k - 1, 1:]
             assert np.array_equal(st[k - 1], want), (alg, P, k)
             assert fin[k - 1] > T + 32                   # pickup ticks + at least one tick of work
+            if clock == 1 or alg == 0:
+                assert fin[k - 1] == T + 32 + o.evals[k - 1]  # a restart costs the pickup + its objective evaluations
             free[i] = fin[k - 1]
         order = np.lexsort((inst, fin))                  # file order: finish time, then instance
         best_f, imp = f0, 0

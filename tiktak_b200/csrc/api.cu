@@ -292,7 +292,7 @@ void tiktak_cuda_destroy(tiktak_handle* h) {
                     h->d_out_f, h->d_width, h->d_out_evals, h->d_dfnls_slab, h->d_rho, h->d_out_status, h->d_wshr,
                     h->d_shr_have, h->d_arch_starts, h->d_arch_evals, h->d_lot_f, h->d_lot_sf, h->d_lot_cum,
                     h->d_lot_k, h->d_lot_sk, h->d_lot_point, h->d_ticket, h->d_accepted, h->d_nmq, h->d_counts_spare,
-                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_async_base, h->d_nm_pslab, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
+                    h->d_objfun_x, h->d_objfun_f, h->d_async_ev, h->d_async_clk, h->d_async_base, h->d_async_desc, h->d_nm_pslab, h->d_sobtab, h->d_sel_list_key, h->d_sel_list_n, h->d_xsend, h->d_xrecv};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1128,6 +1128,17 @@ int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* ye
     if (!h || !yes) return TIKTAK_ERR_ARG;
     *yes = ((alg == TIKTAK_ALG_AMOEBA && tk_nm_async_supported(h)) ||
             (alg == TIKTAK_ALG_DFNLS && h->cfg.world == 1 && h->cfg.search_type == 0 && h->cfg.nx <= 100)) ? 1 : 0;
+    return TIKTAK_OK;
+}
+
+/* the virtual clock tiktak_cuda_local_async(h, alg, ., ., instances, .) runs on (what a model of the run has to charge a restart) */
+int tiktak_cuda_local_async_clock(tiktak_handle* h, int32_t alg, int32_t instances, int32_t* clock) {
+    if (!h || !clock) return TIKTAK_ERR_ARG;
+    int32_t yes = 0;
+    int rc = tiktak_cuda_local_async_supported(h, alg, &yes);
+    if (rc) return rc;
+    if (!yes) { tk_set_error("local_async_clock: asynchronous instances are not built for this configuration"); return TIKTAK_ERR_UNSUPPORTED; }
+    *clock = (alg == TIKTAK_ALG_DFNLS || tk_nm_async_form(h, instances) == 1) ? TIKTAK_ASYNC_CLOCK_EVALS : TIKTAK_ASYNC_CLOCK_TRIPS;
     return TIKTAK_OK;
 }
 

@@ -1570,17 +1570,36 @@ int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size) 
 
 /* Asynchronous instances (nm_quad_async_kernel): restarts first_k .. first_k + n_k - 1 by min(instances, resident blocks) instances;
  * rows, evaluation counts, searchStart rows and the best row are on the device when the stream has drained. */
-bool tk_nm_async_supported(tiktak_handle* h) {
+int tk_launch_nm_w4_async(tiktak_handle* h, const NmArgs& a, const NmAsync& aq, int want, int* used);
+
+/* which instance runs: -1 = none built for the configuration; 0 = a block of four warps (nm_quad_async_kernel, nx <= 31), tick = pass
+ * of amoeba's loop; 1 = one warp (nm_w4_kernel), tick = objective evaluation.  The four-warp block is the latency form: it wins while
+ * the run has fewer restarts in flight than the GPU has room for; with every SM full the one-warp form spends less than half the
+ * instructions per counted evaluation and the GPU holds 3.3 times as many instances (C3: 887 blocks 19.4 ms, 2956 warps
+ * 14.8 ms).  So: one warp above nx = 31 and whenever the caller asks for at least twice the blocks the four-warp form keeps resident;
+ * TIKTAK_ASYNC_FORM=quad|w4 overrides. */
+int tk_nm_async_form(tiktak_handle* h, int instances) {
     const int nx = h->cfg.nx;
-    if (h->cfg.world != 1 || h->cfg.search_type != 0 || h->cfg.nm_shrink_mode != 0 || h->cfg.objective_id == TIKTAK_OBJ_SMM || nx > 31) return false;
-    bool ok = false;
-    tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int { ok = Obj::nterms(nx) <= nx; return 0; });
-    return ok;
+    if (h->cfg.world != 1 || h->cfg.search_type != 0 || h->cfg.nm_shrink_mode != 0 || h->cfg.objective_id == TIKTAK_OBJ_SMM) return -1;
+    bool scalar = false;
+    tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int { scalar = Obj::nterms(nx) <= nx; return 0; });
+    if (!scalar) return -1;
+    const bool quad_ok = nx <= 31, w4_ok = tk_nm_w4_supported(h);
+    if (!quad_ok && !w4_ok) return -1;
+    const char* e = getenv("TIKTAK_ASYNC_FORM");
+    if (e && !strcmp(e, "quad") && quad_ok) return 0;
+    if (e && !strcmp(e, "w4") && w4_ok) return 1;
+    if (!quad_ok) return 1;
+    return (w4_ok && instances >= 12 * h->sm_count /* twice the six blocks per SM */) ? 1 : 0;
 }
+bool tk_nm_async_supported(tiktak_handle* h) { return tk_nm_async_form(h, 0) >= 0; }
 
 int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used, bool free_run) {
     const int nx = h->cfg.nx, np = nx + 1, K = h->cfg.maxpoints_plus1;
-    if (!tk_nm_async_supported(h)) { tk_set_error("local_async: Nelder-Mead with a scalar objective, nx <= 31, search_type 0, nm_shrink_mode 0, one GPU"); return TIKTAK_ERR_UNSUPPORTED; }
+    int form = tk_nm_async_form(h, instances);
+    if (form == 1 && free_run && nx <= 31) form = 0; /* free-running instances exist as four-warp blocks only */
+    if (form < 0) { tk_set_error("local_async: Nelder-Mead with a scalar objective, nx <= 127, search_type 0, nm_shrink_mode 0, one GPU"); return TIKTAK_ERR_UNSUPPORTED; }
+    if (form == 1 && free_run) { tk_set_error("local_async: free-running instances are built for the four-warp form (nx <= 31)"); return TIKTAK_ERR_UNSUPPORTED; }
     NmArgs a;
     a.n_k = n_k; a.rank = 0; a.world = 1; a.n_run = n_k; a.first_k = first_k; a.K = K;
     a.starts = nullptr; a.width = h->d_width; a.wshr = nullptr; a.shr_have = nullptr;
@@ -1592,9 +1611,15 @@ int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, in
     a.tiny = (double)1.0e-10f;
     a.out_x = nullptr; a.out_f = nullptr; a.out_evals = nullptr;
     NmAsync q;
-    int rc0 = tk_async_setup(h, first_k, n_k, (np + 3) / 4, &q);
+    int rc0 = tk_async_setup(h, first_k, n_k, form == 1 ? np + 1 : (np + 3) / 4, &q); /* (one-warp form: c0 = the least a restart evaluates) */
     if (rc0) return rc0;
     q.free_run = free_run ? 1 : 0;
+    if (form == 1) {
+        int rc = tk_launch_nm_w4_async(h, a, q, instances, used);
+        if (rc) return rc;
+        TK_CUDA(cudaGetLastError());
+        return tk_async_best(h);
+    }
     const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
     const int ts = (nx + 2) & ~1;
     const size_t shmem = (size_t)(4 * ts + 8 + ts + 4 * (5 * ts + np * nx)) * sizeof(double);

@@ -514,12 +514,61 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
 #pragma unroll
     for (int k = 0; k < CJ; k++) jj[k] = (l8 + LP * k < nx) ? l8 + LP * k : 0;
 
+    /* ---- asynchronous instances (nm_common.cuh; the scheme of nm_quad_async_kernel with a warp as the instance and the objective
+     * evaluation as the tick of the virtual clock: a restart costs cb + #evaluations) ---- */
+    const tknm::NmAsync* aq = q.aq;
+    const int AP = q.aq_P;
+    const int inst = (int)blockIdx.x * (int)(blockDim.x >> 5) + w;
+    if (aq && blockIdx.x == gridDim.x - 1) { /* the time keeper */
+        if (w != 0) return;
+        int* gvt = aq->clk + AP + 32;
+        for (;;) {
+            int mn = 0x7fffffff;
+            for (int i = lane; i < AP; i += 32) mn = min(mn, tknm::ld_vol(aq->clk + i));
+            mn = (int)__reduce_min_sync(FULL, (unsigned)mn);
+            if (lane < TK_GVT_COPIES) tknm::st_vol(gvt + lane * 32, mn);
+            if (mn == 0x7fffffff) return;
+            __nanosleep(100);
+        }
+    }
+    if (aq && inst >= AP) return;
+    int ak = aq ? aq->first_k + inst : 0, aTv = 0, a_bk = -1, a_vis = 0;
+
     for (;;) { /* ------------------------------ one restart per trip ------------------------------ */
         int ticket = 0;
+        if (aq) { /* which restart, and the best row visible at its (virtual) start */
+            int cnt_ev = 0, cnt_vis = 0, bt = 0, bs = 0, bk = -1;
+            double bf = 0.0;
+            const int hi = min(aq->last_k, __ldcg(aq->clk + AP));
+            for (int jr = lane; jr <= hi; jr += 32) {
+                const int4 raw = __ldcg(reinterpret_cast<const int4*>(aq->ev + jr));
+                const int tj = raw.z, sj = raw.w;
+                if (tj < 0 || tj > aTv) continue;
+                if (jr >= aq->first_k && (tj < aTv || sj < inst)) cnt_ev++;
+                const double fj = __hiloint2double(raw.y, raw.x);
+                if (!(fj == fj)) continue;
+                cnt_vis++;
+                if (bk < 0 || tknm::nm_row_before(fj, tj, sj, jr, bf, bt, bs, bk)) { bf = fj; bt = tj; bs = sj; bk = jr; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double f2 = __shfl_xor_sync(FULL, bf, o);
+                const int t2 = __shfl_xor_sync(FULL, bt, o), s2 = __shfl_xor_sync(FULL, bs, o), k2 = __shfl_xor_sync(FULL, bk, o);
+                if (k2 >= 0 && (bk < 0 || tknm::nm_row_before(f2, t2, s2, k2, bf, bt, bs, bk))) { bf = f2; bt = t2; bs = s2; bk = k2; }
+                cnt_ev += __shfl_xor_sync(FULL, cnt_ev, o);
+                cnt_vis += __shfl_xor_sync(FULL, cnt_vis, o);
+            }
+            if (aTv > 0) ak = aq->first_k + AP + cnt_ev;
+            if (ak > aq->last_k) { if (lane == 0) tknm::st_vol(aq->clk + inst, 0x7fffffff); break; }
+            a_bk = bk; a_vis = cnt_vis;
+            if (lane == 0) { if (aTv > 0) atomicMax(aq->clk + AP, ak); aq->base[ak] = (cnt_vis > 1 && bk >= 0) ? bk : -1; }
+            ticket = ak - aq->first_k;
+        } else {
+        ticket = 0;
         if (lane == 0) ticket = (ctl[NMQ_GATE] < 0) ? 0x7fffffff : atomicAdd(q.ctl + NMQ_HEAD, 1);
         ticket = __shfl_sync(FULL, ticket, 0);
         if (ticket >= a.n_run) break;
-        if (q.commit) { /* early starts are bounded: wait until the ticket is inside the window */
+        }
+        if (q.commit && !aq) { /* early starts are bounded: wait until the ticket is inside the window */
             bool stopped = false;
             for (;;) {
                 int gate = 0;
@@ -539,7 +588,17 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
             const double* wsrc = shr ? a.wshr : a.width;
             for (int e = lane; e < np * nx; e += 32) {
                 const int ia = e / nx, i = e - ia * nx;
-                double tt = TK_ADD(a.starts[(size_t)i * a.n_k + slot], TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
+                double st_i;
+                if (aq) { /* getModifiedParam (:683-720), unfused; the searchStart.dat row */
+                    const double ev = aq->xs[(size_t)(i + 1) * aq->K + (ak - 1)];
+                    st_i = ev;
+                    if (a_vis > 1 && a_bk >= 0) {
+                        const double wgt = aq->w11[ak];
+                        st_i = TK_ADD(TK_MUL(wgt, aq->res[(size_t)a_bk * (nx + 1) + 1 + i]), TK_MUL(TK_SUB(1.0, wgt), ev));
+                    }
+                    if (ia == 0) aq->arch_starts[(size_t)i * aq->K + (ak - 1)] = st_i;
+                } else st_i = a.starts[(size_t)i * a.n_k + slot];
+                double tt = TK_ADD(st_i, TK_DIV(TK_MUL(a.simplex[(size_t)ia * nx + i], wsrc[i]), a.scale));
                 tt = fmax(fmin(tt, sbu[i]), sbl[i]);
                 m.p[e] = tt;
             }
@@ -587,6 +646,7 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
             const double ynhi = nm_w4_y<CJ, LP>(ys, nx - 1);
             const int ihi = nm_w4_r<CJ, LP>(rows, nx);
             if (nm_converged(a, ylo, yhi) || iter >= a.itmax) break;
+            if (aq && lane == 0) tknm::st_vol(aq->clk + inst, aTv + aq->cb + np + iter + 1); /* the restart cannot finish before the evaluations made so far + the final one */
             if (q.commit && ((++chk) & 31) == 0) { /* a committed round changed the best row: this restart is void */
                 if (ctl[NMQ_GATE] < 0) { discard = true; break; }
             }
@@ -889,6 +949,42 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
          * same value */
         {
             const int il = nm_w4_ilo<CJ, LP>(ys, rows, ylo, np, l8);
+            if (aq) { /* completeSearch :582-597: the row of restart ak, then the finish event, then the wait for the global time */
+                const int F = aTv + aq->cb + np + iter + 1;
+                double* dst = aq->res + (size_t)ak * (nx + 1);
+                const double frt = aq->roundtrip ? tk_f4020_roundtrip(ylo) : ylo;
+                for (int j = lane; j < nx; j += 32) { const double xv = m.p[il * nx + j]; dst[1 + j] = aq->roundtrip ? tk_f4020_roundtrip(xv) : xv; }
+                if (lane == 0) {
+                    dst[0] = frt;
+                    aq->ev[ak].fv = frt;
+                    aq->ev[ak].slt = inst;
+                    aq->valid[ak] = (frt == frt) ? 1 : 0;
+                    aq->arch_evals[ak] = np + iter + 1;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    tknm::st_vol(&aq->ev[ak].fin, F);
+                    __threadfence();
+                    tknm::st_vol(aq->clk + inst, F + aq->cb + np + 1);
+                    const int* gvt = aq->clk + AP + 32 + (inst % TK_GVT_COPIES) * 32;
+                    unsigned ns = 100;
+                    const long long t0w = clock64();
+                    while (!(tknm::ld_vol(gvt) > F)) {
+                        if (clock64() - t0w > TK_ASYNC_PATIENCE) { atomicExch(aq->err, 1); break; }
+                        __nanosleep(ns);
+                        if (ns < 800) ns += ns;
+                    }
+                    __threadfence();
+                }
+                __syncwarp();
+                int bad = 0;
+                if (lane == 0) bad = tknm::ld_vol(aq->err);
+                bad = __shfl_sync(FULL, bad, 0);
+                if (bad) { if (lane == 0) tknm::st_vol(aq->clk + inst, 0x7fffffff); break; }
+                aTv = F;
+                continue;
+            }
             for (int j = lane; j < nx; j += 32) a.out_x[(size_t)j * a.n_k + slot] = m.p[il * nx + j];
             if (lane == 0) {
                 a.out_f[slot] = ylo;
@@ -915,7 +1011,9 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
 
 /* which form: four candidates per pass (LP = 8) unless most of them would be wasted */
 /* mode = LP * 10 + NC: 81 = four sub-groups of eight lanes, 321 = one point at a time, 324 = four points as parallel chains */
+static int g_w4_mode_force = 0; /* the asynchronous launcher's choice while it configures and launches */
 inline int w4_mode(int nx) {
+    if (g_w4_mode_force) return (g_w4_mode_force == 81 && nx > 63) ? 321 : g_w4_mode_force;
     const char* e = getenv("TIKTAK_NM_MODE");
     int mode = (nx > 31) ? 321 : 324;
     if (e && (atoi(e) == 81 || atoi(e) == 321 || atoi(e) == 324)) mode = atoi(e);
@@ -1038,4 +1136,58 @@ int tk_launch_nm_w4(tiktak_handle* h, const NmArgs& a, const NmQueue& q) {
             return TIKTAK_OK;
         });
     });
+}
+
+/* Asynchronous instances with a WARP as the instance (nm_common.cuh; tk_launch_nm_async in kernels_nm.cu decides between this and
+ * the four-warp blocks of nm_quad_async_kernel): the tick of the virtual clock is one objective evaluation, a restart costs
+ * cb + its evaluation count.  One cooperative launch: every instance and the time keeper's block must be resident. */
+int tk_launch_nm_w4_async(tiktak_handle* h, const NmArgs& a, const NmAsync& aq, int want, int* used) {
+    const int nx = h->cfg.nx;
+    const TkTablesG T{h->d_V, h->d_lo, h->d_w, h->d_bl, h->d_bu, h->d_aux};
+    /* one point at a time (mode 321) spends the fewest instructions per counted evaluation: what a throughput-bound run wants */
+    int mode = 321;
+    if (const char* e = getenv("TIKTAK_ASYNC_MODE")) { if (atoi(e) == 81 || atoi(e) == 321 || atoi(e) == 324) mode = atoi(e); }
+    g_w4_mode_force = mode;
+    int rc = tk_dispatch_obj(h->cfg.objective_id, [&]<class Obj>() -> int {
+        int wpb = w4_wpb<Obj>(nx);
+        if (const char* e = getenv("TIKTAK_ASYNC_WPB")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) wpb = std::min(wpb, v); }
+        return w4_dispatch<Obj>(nx, [&]<int CJ, int NXC, int LP, int NC>() -> int {
+            int bps = 0;
+            int rc = w4_configure<Obj, CJ, NXC, LP, NC>(nx, wpb, &bps);
+            if (rc) return rc;
+            if (bps < 1) { tk_set_error("nx=%d: the Nelder-Mead simplex does not fit in shared memory", nx); return TIKTAK_ERR_UNSUPPORTED; }
+            const int n = aq.last_k - aq.first_k + 1;
+            const int P = std::max(1, std::min(std::min(want, n), (bps * h->sm_count - 1) * wpb));
+            const int grid = (P + wpb - 1) / wpb + 1; /* + the time keeper */
+            NmQueue qq;
+            memset(&qq, 0, sizeof(qq));
+            if (!h->d_nmq) TK_CUDA(cudaMalloc(&h->d_nmq, (size_t)(NMQ_DONE0 + h->cfg.maxpoints_plus1 + 1) * sizeof(int)));
+            qq.ctl = h->d_nmq; qq.round_size = n; qq.n_rounds = 1; qq.roundtrip = h->cfg.text_roundtrip; qq.nx = nx;
+            qq.res = h->d_res; qq.valid = h->d_res_valid; qq.arch_evals = h->d_arch_evals; qq.best = h->d_best;
+            if (w4_pglobal<CJ, LP>()) {
+                const size_t doubles = (size_t)grid * wpb * (size_t)(nx + 1) * nx;
+                if (h->nm_pslab_doubles < doubles) {
+                    if (h->d_nm_pslab) cudaFree(h->d_nm_pslab);
+                    h->d_nm_pslab = nullptr; h->nm_pslab_doubles = 0;
+                    TK_CUDA(cudaMalloc(&h->d_nm_pslab, doubles * sizeof(double)));
+                    h->nm_pslab_doubles = doubles;
+                }
+                qq.pslab = h->d_nm_pslab;
+            }
+            rc = tk_async_init(h, aq, P);
+            if (rc) return rc;
+            if (!h->d_async_desc) TK_CUDA(cudaMalloc(&h->d_async_desc, sizeof(NmAsync)));
+            TK_CUDA(cudaMemcpyAsync(h->d_async_desc, &aq, sizeof(NmAsync), cudaMemcpyHostToDevice, h->stream)); /* (pageable source: staged before the call returns) */
+            qq.aq = (const NmAsync*)h->d_async_desc;
+            qq.aq_P = P;
+            void* args[] = {(void*)&T, (void*)&h->sc, (void*)&a, (void*)&qq};
+            TK_CUDA(cudaLaunchCooperativeKernel((const void*)nm_w4_kernel<Obj, CJ, NXC, LP, NC>, dim3((unsigned)grid), dim3((unsigned)wpb * 32), args,
+                                                w4_shmem<Obj>(nx, wpb), h->stream));
+            h->launches++;
+            *used = P;
+            return TIKTAK_OK;
+        });
+    });
+    g_w4_mode_force = 0;
+    return rc;
 }

@@ -117,6 +117,7 @@ struct tiktak_handle {
     TkAsyncRow* d_async_ev = nullptr; /* asynchronous instances (kernels_nm.cu): value, virtual finish time and instance of row k */
     int* d_async_clk = nullptr;       /* ... and the instances' clocks */
     int* d_async_base = nullptr;      /* ... and the row each restart was blended toward */
+    void* d_async_desc = nullptr;     /* ... and the device copy of the run's descriptor (one-warp instances, kernels_nm_w4.cu) */
     long long* async_dbg = nullptr;   /* experiment counters (TIKTAK_ASYNC_DEBUG) */
     bool async_rows = false;          /* the rows of the table were written by an asynchronous run: local_fetch orders them by (finish time, instance) */
     int nm_form = -1;                 /* 1: one warp per restart (kernels_nm_w4.cu), 0: four warps per restart (kernels_nm.cu), -1: not decided yet */
@@ -150,6 +151,7 @@ int tk_launch_blend_lottery(tiktak_handle* h, int first_k, int n_k, int count, i
 int tk_launch_nm(tiktak_handle* h, int first_k, int n_k, int commit_round_size = 0);
 int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used, bool free_run = false);
 bool tk_nm_async_supported(tiktak_handle* h);
+int tk_nm_async_form(tiktak_handle* h, int instances); /* -1: not built for the configuration; 0: four-warp blocks, tick = loop trip; 1: one warp, tick = evaluation */
 bool tk_nm_use_w4(tiktak_handle* h);
 int tk_launch_dfnls(tiktak_handle* h, int first_k, int n_k, int instances = 0, int* used = nullptr);
 int tk_launch_ingest(tiktak_handle* h, int first_k, int n_k, int round_size, const double* pack, int* d_accepted);

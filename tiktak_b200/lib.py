@@ -41,6 +41,7 @@ SIGNATURES = {
     "tiktak_cuda_local_nrescue": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_async_supported": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
+    "tiktak_cuda_local_async_clock": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int32_p]),
     "tiktak_cuda_local_async_info": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int32_p, c_int32_p]),
     "tiktak_cuda_local_ingest_rounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_int32_p]),
     "tiktak_cuda_local_capacity": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),

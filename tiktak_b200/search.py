@@ -259,6 +259,14 @@ class TikTakSearch:
         _lib.check(self._L.tiktak_cuda_local_async_supported(self._h, _ALG[algor], C.byref(yes)), "local_async_supported")
         return bool(yes.value)
 
+    def asyncClock(self, algor="a", instances=None):
+        """the virtual clock of LocalMinimizationsAsync(algor, instances): 0 = a restart costs PICKUP + c0 + trips + shrinks*c0 ticks
+        (four-warp instances); 1 = PICKUP + its evaluations (one-warp instances, DFNLS)"""
+        c = C.c_int32()
+        P = max(1, int(self.cfg.round_size if instances is None else instances))
+        _lib.check(self._L.tiktak_cuda_local_async_clock(self._h, _ALG[algor], P, C.byref(c)), "local_async_clock")
+        return c.value
+
     def LocalMinimizationsAsync(self, algor="a", instances=None, free_running=False):
         """Every restart by `instances` asynchronous instances (default: cfg.round_size) -- the reference's multi-process mode on
         one GPU, one kernel launch (tiktak_cuda_local_async; DESIGN.md "asynchronous instances").  Sets searchStart,
