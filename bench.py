@@ -379,9 +379,9 @@ class Job:
                "rescue_calls": int(np.sum(s.nrescue)) if (self.name == "C5" and getattr(s, "nrescue", None) is not None) else None,  # RESCUE_H entries (DFNLS)
                "local_mode": "async" if self.local_async else "rounds",
                "instances": getattr(s, "instances_used", None) if self.local_async else None,
-               "instance_form": (("one warp (nm_w4_kernel), tick = objective evaluation" if s.asyncClock(self.alg, ASYNC_INSTANCES[self.name]) == 1 and self.alg == "a"
+               "instance_form": (("one warp (nm_w4_kernel), tick = objective evaluation" if self.alg == "a" and s.asyncClock(self.alg, ASYNC_INSTANCES.get(self.name, 256)) == 1
                                   else "four-warp block (nm_quad_async_kernel), tick = loop trip" if self.alg == "a" else "block (dfnls_kernel), tick = objective evaluation")
-                                 if self.local_async else None),
+                                 if (self.local_async and not self.no_local) else None),
                "pretest_ms_steps": [round(float(d["pretest_ms"]), 5) for d in dev],
                "best_fval": None if self.no_local else s.getBestLine()[0]}
         if self.local_async and not self.no_local:  # the same restarts as rounds of round_size, beside (untimed steps)
@@ -390,6 +390,18 @@ class Job:
             self.local_async = True
             out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_launches": getattr(s, "local_launches", None),
                              "restarts_per_s": cfg.p_maxpoints / (np.mean([d["local_ms"] for d in rd]) * 1e-3), "best_fval": s.getBestLine()[0]}
+        if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31 and "one warp" in (out["instance_form"] or ""):
+            # ... and as four-warp blocks (the latency form: a third of the instances, each ~2x as fast), beside (untimed steps)
+            fw = []
+            for _ in range(3):
+                flush.zero_(); self.barrier()
+                s.solveAtSobolPoints(wait=False); s.chooseSobol()
+                ea = self.mark(); s.LocalMinimizationsAsync(self.alg, instances=6 * 148); eb = self.mark()
+                self.ext.synchronize()
+                fw.append(ea.elapsed_time(eb))
+            fw = fw[1:]
+            out["four_warp_blocks"] = {"local_ms": float(np.mean(fw)), "instances": s.instances_used, "restarts_per_s": cfg.p_maxpoints / (np.mean(fw) * 1e-3),
+                                       "best_fval": s.getBestLine()[0]}
         if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31:  # ... and as free-running instances (not reproducible: beside, untimed steps)
             fr = []
             for _ in range(3):

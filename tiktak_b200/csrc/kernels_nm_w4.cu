@@ -1159,8 +1159,7 @@ int tk_launch_nm_w4_async(tiktak_handle* h, const NmArgs& a, const NmAsync& aq, 
             const int n = aq.last_k - aq.first_k + 1;
             const int P = std::max(1, std::min(std::min(want, n), (bps * h->sm_count - 1) * wpb));
             const int grid = (P + wpb - 1) / wpb + 1; /* + the time keeper */
-            NmQueue qq;
-            memset(&qq, 0, sizeof(qq));
+            NmQueue qq{};
             if (!h->d_nmq) TK_CUDA(cudaMalloc(&h->d_nmq, (size_t)(NMQ_DONE0 + h->cfg.maxpoints_plus1 + 1) * sizeof(int)));
             qq.ctl = h->d_nmq; qq.round_size = n; qq.n_rounds = 1; qq.roundtrip = h->cfg.text_roundtrip; qq.nx = nx;
             qq.res = h->d_res; qq.valid = h->d_res_valid; qq.arch_evals = h->d_arch_evals; qq.best = h->d_best;

@@ -47,9 +47,9 @@ struct NmQueue {
     int* arch_evals;
     double* best;     /* [0] fval [1] k [2] #rows [3..] x */
     double* pslab;    /* simplices of the resident warps when they live in global memory (nm_w4_kernel, nx >= 32): (nx+1)*nx doubles per warp */
-    const struct NmAsync* aq; /* not NULL: asynchronous instances, one warp = one instance, ticks = objective evaluations (device copy of the
+    const struct NmAsync* aq = nullptr; /* not NULL: asynchronous instances, one warp = one instance, ticks = objective evaluations (device copy of the
                                  descriptor; the last block of the grid keeps the time) */
-    int aq_P;         /* instances (warps) of the asynchronous run */
+    int aq_P = 0;     /* instances (warps) of the asynchronous run */
 };
 enum { NMQ_HEAD = 0, NMQ_COMMIT = 1, NMQ_LOCK = 2, NMQ_GATE = 3, NMQ_ACCEPTED = 4, NMQ_STREAK = 5, NMQ_DONE0 = 8 };
 
