@@ -376,6 +376,9 @@ class Job:
                "mean_evals_per_restart": float(np.mean(s.evals)) if s.evals is not None else None,
                "evals_in_restarts": float(np.sum(s.evals)) if s.evals is not None else None,
                "local_launches": getattr(s, "local_launches", None), "gpu_launches": int(launches),
+               # the restart kernels alone (events around the launches, last step); stage_ms.local also holds the fetch of every row
+               # (searchStart, searchResults, evaluation counts) into host arrays, which is what the caller gets back
+               "local_kernels_ms": None if self.no_local else float(s.stage_ms("local")),
                "rescue_calls": int(np.sum(s.nrescue)) if (self.name == "C5" and getattr(s, "nrescue", None) is not None) else None,  # RESCUE_H entries (DFNLS)
                "local_mode": "async" if self.local_async else "rounds",
                "instances": getattr(s, "instances_used", None) if self.local_async else None,
@@ -388,7 +391,7 @@ class Job:
             self.local_async = False
             rd = [self.step(flush, False) for _ in range(3)][1:]  # (the first pass loads the rounds kernels: CUDA loads modules lazily)
             self.local_async = True
-            out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_launches": getattr(s, "local_launches", None),
+            out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_kernels_ms": float(s.stage_ms("local")), "local_launches": getattr(s, "local_launches", None),
                              "restarts_per_s": cfg.p_maxpoints / (np.mean([d["local_ms"] for d in rd]) * 1e-3), "best_fval": s.getBestLine()[0]}
         if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31 and "one warp" in (out["instance_form"] or ""):
             # ... and as four-warp blocks (the latency form: a third of the instances, each ~2x as fast), beside (untimed steps)
@@ -400,7 +403,7 @@ class Job:
                 self.ext.synchronize()
                 fw.append(ea.elapsed_time(eb))
             fw = fw[1:]
-            out["four_warp_blocks"] = {"local_ms": float(np.mean(fw)), "instances": s.instances_used, "restarts_per_s": cfg.p_maxpoints / (np.mean(fw) * 1e-3),
+            out["four_warp_blocks"] = {"local_ms": float(np.mean(fw)), "local_kernels_ms": float(s.stage_ms("local")), "instances": s.instances_used, "restarts_per_s": cfg.p_maxpoints / (np.mean(fw) * 1e-3),
                                        "best_fval": s.getBestLine()[0]}
         if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31:  # ... and as free-running instances (not reproducible: beside, untimed steps)
             fr = []

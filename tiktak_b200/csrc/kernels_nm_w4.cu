@@ -474,9 +474,10 @@ __host__ __device__ constexpr bool w4_pglobal() { return TK_NMW4_PGLOBAL && LP =
  * counted per iteration).  CJ = coordinates per lane = ceil((nx+1) / LP). */
 /* resident blocks the kernel is compiled for: with the simplex in global memory (two coordinates per lane: nx = 32..63, C4) the
  * registers bound the occupancy; 6 blocks of four warps = 80 registers, no spills, 24 warps per SM (measured at C4: 73.7 ms against
- * 85 ms at 124 registers / 16 warps; 64 registers / 32 warps spill: 83 ms) */
+ * 85 ms at 124 registers / 16 warps; 64 registers / 32 warps spill: 83 ms).  The same bound for one point at a time with one coordinate
+ * per lane (nx <= 31: the instance of the asynchronous run at C3) -- no spills at 80 registers, 24 instead of 20 warps per SM */
 template <int CJ, int LP, int NC>
-__host__ __device__ constexpr int w4_minb() { return (w4_pglobal<CJ, LP>() && CJ == 2 && NC == 1) ? 6 : TK_NMW4_MINB; }
+__host__ __device__ constexpr int w4_minb() { return ((w4_pglobal<CJ, LP>() && CJ == 2 && NC == 1) || (LP == 32 && CJ == 1 && NC == 1)) ? 6 : TK_NMW4_MINB; }
 
 template <class Obj, int CJ, int NXC, int LP, int NC>
 __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const TkTablesG T, const TkScalars sc, const NmArgs a, const NmQueue q) {
