@@ -338,7 +338,7 @@ class Job:
             s.sobolFnValWait()
         t5 = time.perf_counter()
         return dict(pretest_ms=s.stage_ms("pretest"), choose_ms=e2.elapsed_time(e3),
-                    local_ms=0.0 if self.no_local else e3.elapsed_time(e4), pretest_eval_ms=s.stage_ms("pretest_eval"),
+                    local_ms=0.0 if self.no_local else e3.elapsed_time(e4), local_kernels_ms=None if self.no_local else s.stage_ms("local"), pretest_eval_ms=s.stage_ms("pretest_eval"),
                     wall_pretest=t1 - t0, wall_choose=t3 - t1, wall_local=t4 - t3, wall=t5 - t0, copy_tail=t5 - t4,
                     ne=ne, nl=s.n_legit, d2h=d2h)
 
@@ -378,7 +378,7 @@ class Job:
                "local_launches": getattr(s, "local_launches", None), "gpu_launches": int(launches),
                # the restart kernels alone (events around the launches, last step); stage_ms.local also holds the fetch of every row
                # (searchStart, searchResults, evaluation counts) into host arrays, which is what the caller gets back
-               "local_kernels_ms": None if self.no_local else float(s.stage_ms("local")),
+               "local_kernels_ms": None if self.no_local else float(np.mean([d["local_kernels_ms"] for d in dev])),
                "rescue_calls": int(np.sum(s.nrescue)) if (self.name == "C5" and getattr(s, "nrescue", None) is not None) else None,  # RESCUE_H entries (DFNLS)
                "local_mode": "async" if self.local_async else "rounds",
                "instances": getattr(s, "instances_used", None) if self.local_async else None,
@@ -391,7 +391,7 @@ class Job:
             self.local_async = False
             rd = [self.step(flush, False) for _ in range(3)][1:]  # (the first pass loads the rounds kernels: CUDA loads modules lazily)
             self.local_async = True
-            out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_kernels_ms": float(s.stage_ms("local")), "local_launches": getattr(s, "local_launches", None),
+            out["rounds"] = {"local_ms": float(np.mean([d["local_ms"] for d in rd])), "local_kernels_ms": float(np.mean([d["local_kernels_ms"] for d in rd])), "local_launches": getattr(s, "local_launches", None),
                              "restarts_per_s": cfg.p_maxpoints / (np.mean([d["local_ms"] for d in rd]) * 1e-3), "best_fval": s.getBestLine()[0]}
         if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31 and "one warp" in (out["instance_form"] or ""):
             # ... and as four-warp blocks (the latency form: a third of the instances, each ~2x as fast), beside (untimed steps)
@@ -402,8 +402,9 @@ class Job:
                 ea = self.mark(); s.LocalMinimizationsAsync(self.alg, instances=6 * 148); eb = self.mark()
                 self.ext.synchronize()
                 fw.append(ea.elapsed_time(eb))
+                fwk = s.stage_ms("local")
             fw = fw[1:]
-            out["four_warp_blocks"] = {"local_ms": float(np.mean(fw)), "local_kernels_ms": float(s.stage_ms("local")), "instances": s.instances_used, "restarts_per_s": cfg.p_maxpoints / (np.mean(fw) * 1e-3),
+            out["four_warp_blocks"] = {"local_ms": float(np.mean(fw)), "local_kernels_ms": float(fwk), "instances": s.instances_used, "restarts_per_s": cfg.p_maxpoints / (np.mean(fw) * 1e-3),
                                        "best_fval": s.getBestLine()[0]}
         if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31:  # ... and as free-running instances (not reproducible: beside, untimed steps)
             fr = []
@@ -413,8 +414,9 @@ class Job:
                 ea = self.mark(); s.LocalMinimizationsAsync(self.alg, instances=ASYNC_INSTANCES[self.name], free_running=True); eb = self.mark()
                 self.ext.synchronize()
                 fr.append(ea.elapsed_time(eb))
+                frk = s.stage_ms("local")
             fr = fr[1:]  # (first pass: lazy module load)
-            out["free_running"] = {"local_ms": float(np.mean(fr)), "restarts_per_s": cfg.p_maxpoints / (np.mean(fr) * 1e-3), "best_fval": s.getBestLine()[0],
+            out["free_running"] = {"local_ms": float(np.mean(fr)), "local_kernels_ms": float(frk), "restarts_per_s": cfg.p_maxpoints / (np.mean(fr) * 1e-3), "best_fval": s.getBestLine()[0],
                                    "note": "no virtual clock: the reference's multi-process semantics literally; verified restart by restart (tests), not reproducible as a whole"}
         if e2e:
             out["e2e_sobol_s"] = self.mx(np.mean([d["wall_pretest"] for d in e2e]))

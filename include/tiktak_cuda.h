@@ -193,12 +193,12 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
                             int32_t* evals);
 /* Asynchronous instances -- the reference's own parallel mode (N processes that each take the next restart number when they
  * finish one and blend the new start toward the best row of searchResults.dat as it is then, TiktakGlobalSearch.f90:546-600,
- * 683-720), with `instances` blocks of one GPU as the processes and a virtual clock (one tick per loop trip of amoeba) in place
- * of wall time, so that the run is reproducible: restart numbers are handed out in the order of the virtual finish times
+ * 683-720), with `instances` blocks (or warps: tiktak_cuda_local_async_clock below) of one GPU as the processes and a virtual clock
+ * in place of wall time, so that the run is reproducible: restart numbers are handed out in the order of the virtual finish times
  * (ties: lower instance number first) and a start sees exactly the rows that finished at or before its virtual start time.
  * One kernel launch for restarts first_k .. first_k + n_k - 1, rows committed on the device; *used = instances run
- * (min(instances, n_k, resident blocks)).  Nelder-Mead with a scalar objective, nx <= 31, search_type 0, nm_shrink_mode 0,
- * world 1 (local_async_supported tells); tiktak_cuda_local_fetch then numbers the #improvements column in that file order. */
+ * (min(instances, n_k, what is resident)).  Nelder-Mead with a scalar objective (nx <= 127) or DFNLS (nx <= 100), search_type 0,
+ * nm_shrink_mode 0, world 1 (local_async_supported tells); tiktak_cuda_local_fetch then numbers the #improvements column in that file order. */
 #define TIKTAK_ASYNC_PICKUP_TICKS 32 /* virtual ticks an instance spends between two restarts (reading the rows, blending the start) */
 int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used);
 int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* yes);
