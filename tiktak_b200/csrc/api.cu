@@ -1222,8 +1222,19 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
     double best_f = 1.0e7; /* pos_miss, getBestLine :791-796 */
     int best_imp = 0;
     bool any = false;
-    std::vector<double> rows((size_t)n_k * (nx + 4)), st((size_t)n_k * nx);
-    std::vector<int> order(last + 1);
+    /* caller buffers: host memory (the usual case: written in place) or device memory (staged) */
+    auto put = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!is_device_ptr(dst)) { memcpy(dst, src, bytes); return TIKTAK_OK; }
+        TK_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+        return TIKTAK_OK;
+    };
+    const bool res_host = results && !is_device_ptr(results), st_host = starts && !is_device_ptr(starts);
+    std::vector<double> rows_v, st_v;
+    if (!res_host) rows_v.resize((size_t)n_k * (nx + 4));
+    if (starts && !st_host) st_v.resize((size_t)n_k * nx);
+    double* rows = res_host ? results : rows_v.data();
+    double* st = st_host ? starts : st_v.data();
+    std::vector<int> order(last + 1), impv(last + 1, 0);
     for (int k = 0; k <= last; k++) order[k] = k;
     if (h->async_rows) { /* the file of an asynchronous run is in the order of the (virtual) finish times, ties by instance */
         if (*herr) { tk_set_error("local_async: an instance gave up waiting for the others (the launch was not resident as a whole?)"); return TIKTAK_ERR_STATE; }
@@ -1236,34 +1247,41 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
             return x < y;
         });
     }
-    for (int kk = 0; kk <= last; kk++) {
+    for (int kk = 0; kk <= last; kk++) { /* the counters, along the file */
         const int k = order[kk];
-        const bool valid = hval[k] != 0;
+        if (hval[k] == 0) continue;
         const double fv = hres[(size_t)k * (nx + 1)];
         int imp = best_imp;
-        if (valid) {
-            if (k > 0 && fv < best_f) imp = best_imp + 1;
-            if (!any || fv < best_f) { best_f = fv; best_imp = imp; any = true; }
-            h->h_res_f[k] = fv; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
-        }
-        if (k < first_k) continue;
-        const int s = k - first_k;
-        rows[(size_t)0 * n_k + s] = 1.0; /* seqNo */
-        rows[(size_t)1 * n_k + s] = (double)k;
-        rows[(size_t)2 * n_k + s] = valid ? (double)imp : 0.0;
-        rows[(size_t)3 * n_k + s] = valid ? fv : NAN;
-        for (int d = 0; d < nx; d++) rows[(size_t)(4 + d) * n_k + s] = valid ? hres[(size_t)k * (nx + 1) + 1 + d] : NAN;
-        if (starts) for (int d = 0; d < nx; d++) st[(size_t)d * n_k + s] = hst[(size_t)d * K + (k - 1)];
+        if (k > 0 && fv < best_f) imp = best_imp + 1;
+        if (!any || fv < best_f) { best_f = fv; best_imp = imp; any = true; }
+        h->h_res_f[k] = fv; h->h_res_valid[k] = 1; h->h_res_imp[k] = imp;
+        impv[k] = imp;
     }
-    /* caller buffers: host memory (the usual case: a plain memcpy) or device memory */
-    auto put = [&](void* dst, const void* src, size_t bytes) -> int {
-        if (!is_device_ptr(dst)) { memcpy(dst, src, bytes); return TIKTAK_OK; }
-        TK_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
-        return TIKTAK_OK;
-    };
+    /* the rows, (n_k, nx+4) column-major: a block of restarts at a time, so that the transposition reads from cache and writes runs */
+    constexpr int KB = 128;
+    for (int s0 = 0; s0 < n_k; s0 += KB) {
+        const int s1 = std::min(n_k, s0 + KB);
+        for (int s_ = s0; s_ < s1; s_++) {
+            const int k = first_k + s_;
+            const bool valid = hval[k] != 0;
+            rows[(size_t)0 * n_k + s_] = 1.0; /* seqNo */
+            rows[(size_t)1 * n_k + s_] = (double)k;
+            rows[(size_t)2 * n_k + s_] = valid ? (double)impv[k] : 0.0;
+            rows[(size_t)3 * n_k + s_] = valid ? hres[(size_t)k * (nx + 1)] : NAN;
+        }
+        for (int d = 0; d < nx; d++) {
+            double* dst = rows + (size_t)(4 + d) * n_k;
+            for (int s_ = s0; s_ < s1; s_++) {
+                const int k = first_k + s_;
+                dst[s_] = hval[k] != 0 ? hres[(size_t)k * (nx + 1) + 1 + d] : NAN;
+            }
+        }
+    }
+    if (starts) /* (K, nx) column-major on the device, (n_k, nx) column-major for the caller: a run per coordinate */
+        for (int d = 0; d < nx; d++) memcpy(st + (size_t)d * n_k, hst + (size_t)d * K + (first_k - 1), (size_t)n_k * 8);
     int rcp = TIKTAK_OK;
-    if (starts && (rcp = put(starts, st.data(), st.size() * 8))) return rcp;
-    if (results && (rcp = put(results, rows.data(), rows.size() * 8))) return rcp;
+    if (starts && !st_host && (rcp = put(starts, st_v.data(), st_v.size() * 8))) return rcp;
+    if (results && !res_host && (rcp = put(results, rows_v.data(), rows_v.size() * 8))) return rcp;
     if (evals) {
         std::vector<int> ev2(n_k);
         for (int s = 0; s < n_k; s++) ev2[s] = hev[first_k + s] & 0xffffff; /* the high byte is the local search's status (tiktak_cuda_local_status) */

@@ -245,7 +245,7 @@ class TikTakSearch:
         e = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_local_fetch(self._h, 1, K, s.ctypes.data, r.ctypes.data, e.ctypes.data),
                    "LocalMinimizations")
-        self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
+        self.searchStart, self.searchResults, self.evals = s.T, r.T, e  # (K, nx) / (K, nx+4) views of the column-major buffers: no host transposition
         st = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_local_status(self._h, 1, K, st.ctypes.data_as(C.POINTER(C.c_int32))), "local_status")
         self.status = st  # 0 = ended like the reference's search; 2 = DFNLS refused the start
@@ -286,7 +286,7 @@ class TikTakSearch:
         r = np.empty((nx + 4, K), dtype=np.float64)
         e = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_local_fetch(self._h, 1, K, s.ctypes.data, r.ctypes.data, e.ctypes.data), "LocalMinimizationsAsync")
-        self.searchStart, self.searchResults, self.evals = s.T.copy(), r.T.copy(), e
+        self.searchStart, self.searchResults, self.evals = s.T, r.T, e  # (K, nx) / (K, nx+4) views of the column-major buffers: no host transposition
         st = np.zeros(K, dtype=np.int32)
         _lib.check(self._L.tiktak_cuda_local_status(self._h, 1, K, st.ctypes.data_as(C.POINTER(C.c_int32))), "local_status")
         nr = np.zeros(K, dtype=np.int32)
