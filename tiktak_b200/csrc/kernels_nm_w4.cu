@@ -520,15 +520,22 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
     const tknm::NmAsync* aq = q.aq;
     const int AP = q.aq_P;
     const int inst = (int)blockIdx.x * (int)(blockDim.x >> 5) + w;
-    if (aq && blockIdx.x == gridDim.x - 1) { /* the time keeper */
-        if (w != 0) return;
+    if (aq && blockIdx.x == gridDim.x - 1) { /* the time keeper: every warp of the block folds its share of the clocks (thousands of them:
+                                                one warp's sweep made the global time ~50 us stale) */
+        __shared__ int km[4];
+        const int nw = (int)(blockDim.x >> 5);
         int* gvt = aq->clk + AP + 32;
         for (;;) {
             int mn = 0x7fffffff;
-            for (int i = lane; i < AP; i += 32) mn = min(mn, tknm::ld_vol(aq->clk + i));
+            for (int i = (int)threadIdx.x; i < AP; i += (int)blockDim.x) mn = min(mn, tknm::ld_vol(aq->clk + i));
             mn = (int)__reduce_min_sync(FULL, (unsigned)mn);
-            if (lane < TK_GVT_COPIES) tknm::st_vol(gvt + lane * 32, mn);
-            if (mn == 0x7fffffff) return;
+            if (lane == 0) km[w] = mn;
+            __syncthreads();
+            int g = km[0];
+            for (int j = 1; j < nw; j++) g = min(g, km[j]);
+            __syncthreads();
+            if (w == 0 && lane < TK_GVT_COPIES) tknm::st_vol(gvt + lane * 32, g);
+            if (g == 0x7fffffff) return;
             __nanosleep(100);
         }
     }
@@ -647,7 +654,7 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
             const double ynhi = nm_w4_y<CJ, LP>(ys, nx - 1);
             const int ihi = nm_w4_r<CJ, LP>(rows, nx);
             if (nm_converged(a, ylo, yhi) || iter >= a.itmax) break;
-            if (aq && lane == 0) tknm::st_vol(aq->clk + inst, aTv + aq->cb + np + iter + 1); /* the restart cannot finish before the evaluations made so far + the final one */
+            if (aq && lane == 0) tknm::st_vol(aq->clk + inst, aTv + aq->cb + np + iter + 2); /* not converged: this pass evaluates at least one more point; then the final one */
             if (q.commit && ((++chk) & 31) == 0) { /* a committed round changed the best row: this restart is void */
                 if (ctl[NMQ_GATE] < 0) { discard = true; break; }
             }
