@@ -42,10 +42,11 @@ F_ALG = {"C1": 237, "C2": 545, "C3": 1105, "C4": 905, "X7": 383}  # X7: Griewank
 OBJ_NAME = {"C1": "template", "C2": "Griewank", "C3": "Rastrigin", "C4": "Rosenbrock", "C5": "synthetic SMM", "X7": "Griewank"}
 # restarts per round (all blended against the best row of the round's start)
 ROUND_SIZE = {"C1": 4, "C2": 128, "C3": 1024, "C4": 3552, "C5": 128}  # C4: the 24 warps per SM the one-warp kernel keeps resident (round 1: 1184)
-# asynchronous instances (restart stage, one GPU): how many blocks play the reference's processes -- about four restarts per instance at
-# C2 (four-warp blocks), every resident WARP at C3 (2956) and C4 (3548) -- asking for at least 12 per SM selects the one-warp instances
-# (tiktak_cuda_local_async_clock) -- and C5 (147: one block per SM, one SM keeps the time); the library clamps to what is resident
-ASYNC_INSTANCES = {"C1": 4, "C2": 256, "C3": 4096, "C4": 4096, "C5": 147}
+# asynchronous instances (restart stage, one GPU): how many blocks / warps play the reference's processes -- about two restarts per
+# instance: 512 four-warp blocks at C2 (1.3 ms; 256: 1.9 ms, the same best value), every resident WARP at C3 (4096) and C4 (3548) -- asking
+# for at least 12 per SM selects the one-warp instances (tiktak_cuda_local_async_clock) -- and C5 (147: one block per SM, one SM keeps the
+# time); the library clamps to what is resident
+ASYNC_INSTANCES = {"C1": 4, "C2": 512, "C3": 4096, "C4": 4096, "C5": 147}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage's kernel, from the committed `ncu --set full` captures
 TRAFFIC = {"C2": (25088, "profiles/r01d_full_c2_sobol.csv"), "C3": (742264320, "profiles/r01d_full_c3_sobol.csv"),
            "C4": (21494528, "profiles/r01d_full_c4_sobol.csv"), "C5": (1020513512, "profiles/r01c_full_c5_smm.csv (1184 evaluations)")}
