@@ -407,7 +407,7 @@ class Job:
             fw = fw[1:]
             out["four_warp_blocks"] = {"local_ms": float(np.mean(fw)), "local_kernels_ms": float(fwk), "instances": s.instances_used, "restarts_per_s": cfg.p_maxpoints / (np.mean(fw) * 1e-3),
                                        "best_fval": s.getBestLine()[0]}
-        if self.local_async and not self.no_local and self.alg == "a" and cfg.nx <= 31:  # ... and as free-running instances (not reproducible: beside, untimed steps)
+        if self.local_async and not self.no_local and self.alg == "a":  # ... and as free-running instances (not reproducible: beside, untimed steps)
             fr = []
             for _ in range(3):
                 flush.zero_(); self.barrier()

@@ -268,13 +268,15 @@ def test_asynchronous_instances_smm_dfnls(built):
     assert used == 4 and np.array_equal(gs, o.searchStart) and np.array_equal(ge, o.evals) and np.array_equal(gr, o.searchResults)
 
 
-def test_free_running_instances_restart_by_restart(built):
-    """instances < 0: no virtual clock -- like the reference's processes, an instance blends toward whatever row is the best one
+@pytest.mark.parametrize("form", ["quad", "w4"])
+def test_free_running_instances_restart_by_restart(built, monkeypatch, form):
+    """(as four-warp blocks and as one-warp instances)  instances < 0: no virtual clock -- like the reference's processes, an instance blends toward whatever row is the best one
     committed when it takes its next restart, so the run is not reproducible as a whole.  Checked restart by restart: every restart
     ran once; its start is the blend of its Sobol start with the row the library says it used (a row committed before it, or none);
     and the search from that start is the oracle's, bit for bit (minimum, value, evaluation count)."""
     import ctypes as C
     from tiktak_b200._abi import dptr
+    monkeypatch.setenv("TIKTAK_ASYNC_FORM", form)
     cfg = cfg_of("griewank10", maxpoints=150, round_size=48, text_roundtrip=0)  # (rows as computed, not through the f40.20 record)
     K, nx = cfg.p_maxpoints, cfg.nx
     with TikTakSearch(cfg) as s:

@@ -1597,9 +1597,7 @@ bool tk_nm_async_supported(tiktak_handle* h) { return tk_nm_async_form(h, 0) >= 
 int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, int* used, bool free_run) {
     const int nx = h->cfg.nx, np = nx + 1, K = h->cfg.maxpoints_plus1;
     int form = tk_nm_async_form(h, instances);
-    if (form == 1 && free_run && nx <= 31) form = 0; /* free-running instances exist as four-warp blocks only */
     if (form < 0) { tk_set_error("local_async: Nelder-Mead with a scalar objective, nx <= 127, search_type 0, nm_shrink_mode 0, one GPU"); return TIKTAK_ERR_UNSUPPORTED; }
-    if (form == 1 && free_run) { tk_set_error("local_async: free-running instances are built for the four-warp form (nx <= 31)"); return TIKTAK_ERR_UNSUPPORTED; }
     NmArgs a;
     a.n_k = n_k; a.rank = 0; a.world = 1; a.n_run = n_k; a.first_k = first_k; a.K = K;
     a.starts = nullptr; a.width = h->d_width; a.wshr = nullptr; a.shr_have = nullptr;

@@ -520,6 +520,8 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
     const tknm::NmAsync* aq = q.aq;
     const int AP = q.aq_P;
     const int inst = (int)blockIdx.x * (int)(blockDim.x >> 5) + w;
+    const bool fr = aq && aq->free_run; /* free-running instances: no virtual clock, nobody waits (nm_common.cuh) */
+    if (fr && blockIdx.x == gridDim.x - 1) return; /* (no time to keep) */
     if (aq && blockIdx.x == gridDim.x - 1) { /* the time keeper: every warp of the block folds its share of the clocks (thousands of them:
                                                 one warp's sweep made the global time ~50 us stale) */
         __shared__ int km[4];
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
             for (int jr = lane; jr <= hi; jr += 32) {
                 const int4 raw = __ldcg(reinterpret_cast<const int4*>(aq->ev + jr));
                 const int tj = raw.z, sj = raw.w;
-                if (tj < 0 || tj > aTv) continue;
+                if (tj < 0 || (!fr && tj > aTv)) continue;
                 if (jr >= aq->first_k && (tj < aTv || sj < inst)) cnt_ev++;
                 const double fj = __hiloint2double(raw.y, raw.x);
                 if (!(fj == fj)) continue;
@@ -565,10 +567,16 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
                 cnt_ev += __shfl_xor_sync(FULL, cnt_ev, o);
                 cnt_vis += __shfl_xor_sync(FULL, cnt_vis, o);
             }
-            if (aTv > 0) ak = aq->first_k + AP + cnt_ev;
+            if (aTv > 0) {
+                if (fr) { /* the next number from the counter (clk[AP]: highest number handed out) */
+                    int nk = 0;
+                    if (lane == 0) nk = atomicAdd(aq->clk + AP, 1) + 1;
+                    ak = __shfl_sync(FULL, nk, 0);
+                } else ak = aq->first_k + AP + cnt_ev;
+            }
             if (ak > aq->last_k) { if (lane == 0) tknm::st_vol(aq->clk + inst, 0x7fffffff); break; }
             a_bk = bk; a_vis = cnt_vis;
-            if (lane == 0) { if (aTv > 0) atomicMax(aq->clk + AP, ak); aq->base[ak] = (cnt_vis > 1 && bk >= 0) ? bk : -1; }
+            if (lane == 0) { if (aTv > 0 && !fr) atomicMax(aq->clk + AP, ak); aq->base[ak] = (cnt_vis > 1 && bk >= 0) ? bk : -1; }
             ticket = ak - aq->first_k;
         } else {
         ticket = 0;
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
             const double ynhi = nm_w4_y<CJ, LP>(ys, nx - 1);
             const int ihi = nm_w4_r<CJ, LP>(rows, nx);
             if (nm_converged(a, ylo, yhi) || iter >= a.itmax) break;
-            if (aq && lane == 0) tknm::st_vol(aq->clk + inst, aTv + aq->cb + np + iter + 2); /* not converged: this pass evaluates at least one more point; then the final one */
+            if (aq && !fr && lane == 0) tknm::st_vol(aq->clk + inst, aTv + aq->cb + np + iter + 2); /* not converged: this pass evaluates at least one more point; then the final one */
             if (q.commit && ((++chk) & 31) == 0) { /* a committed round changed the best row: this restart is void */
                 if (ctl[NMQ_GATE] < 0) { discard = true; break; }
             }
@@ -958,7 +966,7 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
         {
             const int il = nm_w4_ilo<CJ, LP>(ys, rows, ylo, np, l8);
             if (aq) { /* completeSearch :582-597: the row of restart ak, then the finish event, then the wait for the global time */
-                const int F = aTv + aq->cb + np + iter + 1;
+                int F = aTv + aq->cb + np + iter + 1;
                 double* dst = aq->res + (size_t)ak * (nx + 1);
                 const double frt = aq->roundtrip ? tk_f4020_roundtrip(ylo) : ylo;
                 for (int j = lane; j < nx; j += 32) { const double xv = m.p[il * nx + j]; dst[1 + j] = aq->roundtrip ? tk_f4020_roundtrip(xv) : xv; }
@@ -970,6 +978,17 @@ __global__ void __launch_bounds__(128, w4_minb<CJ, LP, NC>()) nm_w4_kernel(const
                     aq->arch_evals[ak] = np + iter + 1;
                 }
                 __syncwarp();
+                if (fr) { /* the order of the commits is the order of the file; nobody waits for anybody */
+                    if (lane == 0) {
+                        F = 1 + atomicAdd(aq->clk + AP + 1, 1);
+                        __threadfence();
+                        tknm::st_vol(&aq->ev[ak].fin, F);
+                        __threadfence();
+                    }
+                    __syncwarp();
+                    aTv = 1;
+                    continue;
+                }
                 if (lane == 0) {
                     __threadfence();
                     tknm::st_vol(&aq->ev[ak].fin, F);
