@@ -211,7 +211,8 @@ int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* ye
 #define TIKTAK_ASYNC_CLOCK_TRIPS 0
 #define TIKTAK_ASYNC_CLOCK_EVALS 1
 int tiktak_cuda_local_async_clock(tiktak_handle* h, int32_t alg, int32_t instances, int32_t* clock);
-/* instances < 0 in tiktak_cuda_local_async: |instances| FREE-RUNNING instances (Nelder-Mead) -- no virtual clock: an instance takes the
+/* instances < 0 in tiktak_cuda_local_async: |instances| FREE-RUNNING instances (Nelder-Mead, four-warp blocks or one warp by the same rule as
+ * the reproducible form) -- no virtual clock: an instance takes the
  * next restart number from a counter and blends toward the best row committed at that moment, exactly as the reference's processes do
  * with searchResults.dat.  Like a multi-process run of the reference it is not reproducible run to run; every restart is still the
  * reference's search from its recorded start.  tiktak_cuda_local_async_info tells, for either form, which row each start was blended
