@@ -200,6 +200,9 @@ int tiktak_cuda_local_fetch(tiktak_handle* h, int32_t first_k, int32_t n_k, doub
  * (min(instances, n_k, what is resident)).  Nelder-Mead with a scalar objective (nx <= 127) or DFNLS (nx <= 100), search_type 0,
  * nm_shrink_mode 0, world 1 (local_async_supported tells); tiktak_cuda_local_fetch then numbers the #improvements column in that file order. */
 #define TIKTAK_ASYNC_PICKUP_TICKS 32 /* virtual ticks an instance spends between two restarts (reading the rows, blending the start) */
+#define TIKTAK_ASYNC_PICKUP_TICKS_NM_EVALS 128 /* ... on the evaluation clock of the one-warp Nelder-Mead instances: an evaluation is a much
+                                                 shorter tick than a pass of the four-warp block, and the pickup is the lookahead every other
+                                                 instance gets after a finish event (C3, 4140 instances: 32 ticks 13.4 ms, 128: 8.4 ms, 512: 8.3 ms) */
 int tiktak_cuda_local_async(tiktak_handle* h, int32_t alg, int32_t first_k, int32_t n_k, int32_t instances, int32_t* used);
 int tiktak_cuda_local_async_supported(tiktak_handle* h, int32_t alg, int32_t* yes);
 /* The tick of the virtual clock.  TRIPS: Nelder-Mead with a block of four warps as the instance (nx <= 31, the default there): a restart

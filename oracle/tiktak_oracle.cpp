@@ -853,7 +853,8 @@ int Oracle::local_async(int alg, int instances, double* starts_out, double* resu
             steps = 0;
         }
         const double fn_val = objFun(evalParam.data()); /* :582 */
-        if (alg == TIKTAK_ALG_DFNLS || async_clock == TIKTAK_ASYNC_CLOCK_EVALS) steps = TIKTAK_ASYNC_PICKUP_TICKS + (int)(nfev - nfev0);
+        if (alg == TIKTAK_ALG_DFNLS) steps = TIKTAK_ASYNC_PICKUP_TICKS + (int)(nfev - nfev0);
+        else if (async_clock == TIKTAK_ASYNC_CLOCK_EVALS) steps = TIKTAK_ASYNC_PICKUP_TICKS_NM_EVALS + (int)(nfev - nfev0);
         if (evals_out) evals_out[k - 1] = (int32_t)(nfev - nfev0);
         Row r;
         r.seq = seqNo; r.k = k; r.imp = 0;

@@ -1613,6 +1613,7 @@ int tk_launch_nm_async(tiktak_handle* h, int first_k, int n_k, int instances, in
     if (rc0) return rc0;
     q.free_run = free_run ? 1 : 0;
     if (form == 1) {
+        if (!getenv("TIKTAK_ASYNC_CB")) q.cb = TIKTAK_ASYNC_PICKUP_TICKS_NM_EVALS;
         int rc = tk_launch_nm_w4_async(h, a, q, instances, used);
         if (rc) return rc;
         TK_CUDA(cudaGetLastError());
